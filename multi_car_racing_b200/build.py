@@ -1,0 +1,61 @@
+"""Build libmcr.so (hand-written sm_100a CUDA + the C-ABI of include/mcr.h) in-tree with nvcc.
+
+    python -m multi_car_racing_b200.build [--force] [--verbose]
+
+The library is compiled for sm_100a only (B200).  -fmad=false keeps fp32 arithmetic
+un-contracted so the rigid-body solver and the rasteriser reproduce the reference's
+(Box2D's) operation-by-operation IEEE results.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libmcr.so")
+SOURCES = ["api.cu", "physics.cu", "contacts.cu", "raster.cu", "reset.cu"]
+HEADERS = [os.path.join(CSRC, "mcr_internal.h"), os.path.join(HERE, "..", "include", "mcr.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+    "--cudart", "static", "-shared",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-O2",
+]
+
+
+def nvcc_path():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(p) > t for p in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    tmp = LIB + ".tmp%d" % os.getpid()
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout)
+        raise RuntimeError("nvcc failed building libmcr.so")
+    if verbose:
+        print(proc.stdout)
+    os.replace(tmp, LIB)
+    return LIB
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(path)

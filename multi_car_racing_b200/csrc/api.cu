@@ -1,0 +1,646 @@
+// api.cu -- host side of libmcr.so: the C-ABI of include/mcr.h.
+//
+// Host restatements (product code, independent of oracle/):
+//   * Box2D b2PolygonShape::Set / ComputeMass and b2Body::ResetMassData for the fixed
+//     car_dynamics.Car geometry (gym 0.17.2) -> CarConst
+//   * numpy legacy RandomState (MT19937) + MultiCarRacing._create_track (mcr:183-338) and the
+//     reset() spawn grid (mcr:366-393), float64 with the reference's operation order
+// "mcr" = gym_multi_car_racing/multi_car_racing.py of the reference.
+#include "mcr_internal.h"
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return code;
+}
+#define CUDA_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail(-100, "%s: %s", #expr, cudaGetErrorString(e_)); } while (0)
+
+// ---------------------------------------------------------------------------------------
+// Box2D polygon set-up (fp32)
+// ---------------------------------------------------------------------------------------
+namespace {
+
+struct P2 { float x, y; };
+inline P2 operator-(P2 a, P2 b) { return P2{a.x - b.x, a.y - b.y}; }
+inline P2 operator+(P2 a, P2 b) { return P2{a.x + b.x, a.y + b.y}; }
+inline P2 operator*(float s, P2 a) { return P2{s * a.x, s * a.y}; }
+inline float dot(P2 a, P2 b) { return a.x * b.x + a.y * b.y; }
+inline float cross(P2 a, P2 b) { return a.x * b.y - a.y * b.x; }
+
+// b2PolygonShape::Set: weld, gift-wrap from the right-most vertex, counter-clockwise.
+std::vector<P2> b2_polygon_set(const std::vector<P2>& in) {
+    std::vector<P2> ps;
+    for (const P2& v : in) {
+        bool uniq = true;
+        for (const P2& u : ps) { P2 dd = v - u; if (dot(dd, dd) < 0.5f * B2_LINEAR_SLOP) { uniq = false; break; } }
+        if (uniq) ps.push_back(v);
+    }
+    const int n = (int)ps.size();
+    if (n < 3) return {};
+    int i0 = 0; float x0 = ps[0].x;
+    for (int i = 1; i < n; ++i) {
+        const float x = ps[i].x;
+        if (x > x0 || (x == x0 && ps[i].y < ps[i0].y)) { i0 = i; x0 = x; }
+    }
+    std::vector<int> hull; int ih = i0;
+    for (;;) {
+        hull.push_back(ih);
+        int ie = 0;
+        for (int j = 1; j < n; ++j) {
+            if (ie == ih) { ie = j; continue; }
+            const P2 r = ps[ie] - ps[hull.back()], v = ps[j] - ps[hull.back()];
+            const float c = cross(r, v);
+            if (c < 0.0f) ie = j;
+            if (c == 0.0f && dot(v, v) > dot(r, r)) ie = j;
+        }
+        ih = ie;
+        if (ie == i0) break;
+        if ((int)hull.size() > n) return {};
+    }
+    std::vector<P2> out;
+    for (int id : hull) out.push_back(ps[id]);
+    return out;
+}
+
+struct Mass { float mass; P2 center; float I; };
+
+// b2PolygonShape::ComputeMass
+Mass b2_polygon_mass(const std::vector<P2>& v, float density) {
+    const int n = (int)v.size();
+    P2 center{0.0f, 0.0f}; float area = 0.0f, I = 0.0f;
+    P2 s{0.0f, 0.0f};
+    for (int i = 0; i < n; ++i) s = s + v[i];
+    s = (1.0f / n) * s;
+    const float k_inv3 = 1.0f / 3.0f;
+    for (int i = 0; i < n; ++i) {
+        const P2 e1 = v[i] - s, e2 = (i + 1 < n ? v[i + 1] : v[0]) - s;
+        const float D = cross(e1, e2);
+        const float tri = 0.5f * D;
+        area += tri;
+        center = center + (tri * k_inv3) * (e1 + e2);
+        const float intx2 = e1.x * e1.x + e2.x * e1.x + e2.x * e2.x;
+        const float inty2 = e1.y * e1.y + e2.y * e1.y + e2.y * e2.y;
+        I += (0.25f * k_inv3 * D) * (intx2 + inty2);
+    }
+    Mass m;
+    m.mass = density * area;
+    center = (1.0f / area) * center;
+    m.center = center + s;
+    m.I = density * I;
+    m.I += m.mass * (dot(m.center, m.center) - dot(center, center));
+    return m;
+}
+
+void to_poly8(const std::vector<P2>& v, Poly8& out) {
+    out.n = (int)v.size();
+    for (int i = 0; i < MCR_MAXV; ++i) { out.x[i] = i < out.n ? v[i].x : 0.0f; out.y[i] = i < out.n ? v[i].y : 0.0f; }
+}
+
+// car_dynamics.py geometry (gym 0.17.2), units of SIZE
+const double kSIZE = 0.02;
+const double kWHEEL_R = 27, kWHEEL_W = 14;
+const double kWHEELPOS[4][2] = {{-55, +80}, {+55, +80}, {-55, -82}, {+55, -82}};
+const std::vector<std::vector<std::pair<double, double>>> kHULL = {
+    {{-60, +130}, {+60, +130}, {+60, +110}, {-60, +110}},
+    {{-15, +120}, {+15, +120}, {+20, +20}, {-20, 20}},
+    {{+25, +20}, {+50, -10}, {+50, -40}, {+20, -90}, {-20, -90}, {-50, -40}, {-50, -10}, {-25, +20}},
+    {{-50, -120}, {+50, -120}, {+50, -90}, {-50, -90}}};
+
+bool build_car_const(CarConst& cc) {
+    std::vector<P2> hull[4];
+    for (int f = 0; f < 4; ++f) {
+        std::vector<P2> raw;
+        for (auto& p : kHULL[f]) raw.push_back(P2{(float)(p.first * kSIZE), (float)(p.second * kSIZE)});
+        hull[f] = b2_polygon_set(raw);
+        if (hull[f].size() != kHULL[f].size()) return false;
+        to_poly8(hull[f], cc.hull_poly[f]);
+    }
+    const double front_k = 1.0;
+    const double wp[4][2] = {{-kWHEEL_W, +kWHEEL_R}, {+kWHEEL_W, +kWHEEL_R}, {+kWHEEL_W, -kWHEEL_R}, {-kWHEEL_W, -kWHEEL_R}};
+    std::vector<P2> raw;
+    for (int i = 0; i < 4; ++i) raw.push_back(P2{(float)(wp[i][0] * front_k * kSIZE), (float)(wp[i][1] * front_k * kSIZE)});
+    std::vector<P2> wheel = b2_polygon_set(raw);
+    if (wheel.size() != 4) return false;
+    to_poly8(wheel, cc.wheel_poly);
+    // b2Body::ResetMassData -- the fixture list is walked newest first
+    {
+        float mass = 0.0f, I = 0.0f; P2 lc{0.0f, 0.0f};
+        for (int f = 3; f >= 0; --f) {
+            const Mass md = b2_polygon_mass(hull[f], 1.0f);
+            mass += md.mass; lc = lc + md.mass * md.center; I += md.I;
+        }
+        const float inv = 1.0f / mass;
+        lc = inv * lc;
+        I -= mass * dot(lc, lc);
+        cc.hull_mass = mass; cc.hull_invMass = inv; cc.hull_I = I; cc.hull_invI = 1.0f / I;
+        cc.hull_lcx = lc.x; cc.hull_lcy = lc.y;
+    }
+    {
+        const Mass md = b2_polygon_mass(wheel, 0.1f);
+        const float mass = md.mass; P2 lc = md.mass * md.center; float I = md.I;
+        const float inv = 1.0f / mass;
+        lc = inv * lc;
+        I -= mass * dot(lc, lc);
+        cc.wheel_mass = mass; cc.wheel_invMass = inv; cc.wheel_I = I; cc.wheel_invI = 1.0f / I;
+        // the solver drops every rB term: that is only exact if the wheel's centre of mass is its origin
+        if (lc.x != 0.0f || lc.y != 0.0f) return false;
+    }
+    for (int w = 0; w < 4; ++w) { cc.anchor_x[w] = (float)(kWHEELPOS[w][0] * kSIZE); cc.anchor_y[w] = (float)(kWHEELPOS[w][1] * kSIZE); }
+    cc.max_motor_torque = (float)(180 * 900 * kSIZE * kSIZE);
+    cc.lower = (float)-0.4; cc.upper = (float)+0.4;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// numpy legacy RandomState: MT19937
+// ---------------------------------------------------------------------------------------
+struct MT {
+    uint32_t* mt; uint32_t& pos;
+    explicit MT(uint32_t* st) : mt(st), pos(st[624]) {}
+    void regen() {
+        const uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, MATRIX_A = 0x9908b0dfu;
+        int kk; uint32_t y;
+        for (kk = 0; kk < 624 - 397; ++kk) { y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER); mt[kk] = mt[kk + 397] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MATRIX_A); }
+        for (; kk < 623; ++kk) { y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER); mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MATRIX_A); }
+        y = (mt[623] & UPPER) | (mt[0] & LOWER); mt[623] = mt[396] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MATRIX_A);
+        pos = 0;
+    }
+    uint32_t next32() {
+        if (pos >= 624) regen();
+        uint32_t y = mt[pos++];
+        y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
+        return y;
+    }
+    double next_double() { const uint32_t a = next32() >> 5, b = next32() >> 6; return (a * 67108864.0 + b) / 9007199254740992.0; }
+    double uniform(double lo, double hi) { return lo + (hi - lo) * next_double(); }
+};
+
+inline double npsign(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : 0.0); }
+inline int pyidx(int i, int n) { return i < 0 ? i + n : i; }
+
+}  // namespace
+
+extern "C" int mcr_mt_seed(uint32_t* st, const uint32_t* key, int32_t key_len) {
+    if (!st || !key || key_len < 1) return fail(-1, "mcr_mt_seed: bad arguments");
+    // init_genrand(19650218)
+    st[0] = 19650218u;
+    for (int i = 1; i < 624; ++i) st[i] = 1812433253u * (st[i - 1] ^ (st[i - 1] >> 30)) + (uint32_t)i;
+    int i = 1, j = 0;
+    int k = 624 > key_len ? 624 : key_len;
+    for (; k; --k) {
+        st[i] = (st[i] ^ ((st[i - 1] ^ (st[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+        ++i; ++j;
+        if (i >= 624) { st[0] = st[623]; i = 1; }
+        if (j >= key_len) j = 0;
+    }
+    for (k = 623; k; --k) {
+        st[i] = (st[i] ^ ((st[i - 1] ^ (st[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+        ++i;
+        if (i >= 624) { st[0] = st[623]; i = 1; }
+    }
+    st[0] = 0x80000000u;
+    st[624] = 624;
+    return 0;
+}
+
+// One attempt of _create_track (mcr:183-338).
+extern "C" int mcr_track_generate(uint32_t* mt_state, int32_t max_tiles, int32_t max_quads, double* h_nodes,
+                                  double* h_quads, float* h_quad_rgb, int32_t* h_quad_tile, int32_t* out_q,
+                                  int32_t* idx_range) {
+    if (!mt_state || !h_nodes || !h_quads || !h_quad_rgb || !h_quad_tile || !out_q) return fail(-1, "mcr_track_generate: null argument");
+    MT rng(mt_state);
+    const double PI = M_PI, SCALE = 6.0, TRACK_RAD = 900 / SCALE, TRACK_DETAIL_STEP = 21 / SCALE;
+    const double TRACK_TURN_RATE = 0.31, TRACK_WIDTH = 40 / SCALE, BORDER = 8 / SCALE;
+    const int CHECKPOINTS = 12, BORDER_MIN_COUNT = 4;
+    struct CP { double alpha, x, y; } cp[CHECKPOINTS];
+    double start_alpha = 0;
+    for (int c = 0; c < CHECKPOINTS; ++c) {
+        double alpha = 2 * PI * c / CHECKPOINTS + rng.uniform(0, 2 * PI * 1 / CHECKPOINTS);
+        double rad = rng.uniform(TRACK_RAD / 3, TRACK_RAD);
+        if (c == 0) { alpha = 0; rad = 1.5 * TRACK_RAD; }
+        if (c == CHECKPOINTS - 1) { alpha = 2 * PI * c / CHECKPOINTS; start_alpha = 2 * PI * (-0.5) / CHECKPOINTS; rad = 1.5 * TRACK_RAD; }
+        cp[c] = CP{alpha, rad * std::cos(alpha), rad * std::sin(alpha)};
+    }
+    struct Node { double alpha, beta, x, y; };
+    std::vector<Node> path; path.reserve(2600);
+    double x = 1.5 * TRACK_RAD, y = 0, beta = 0;
+    long dest_i = 0; int laps = 0, no_freeze = 2500; bool visited_other_side = false;
+    for (;;) {
+        double alpha = std::atan2(y, x);
+        if (visited_other_side && alpha > 0) { ++laps; visited_other_side = false; }
+        if (alpha < 0) { visited_other_side = true; alpha += 2 * PI; }
+        double dest_alpha, dest_x, dest_y;
+        for (;;) {
+            bool failed = true;
+            for (;;) {
+                const CP& d = cp[dest_i % CHECKPOINTS];
+                dest_alpha = d.alpha; dest_x = d.x; dest_y = d.y;
+                if (alpha <= dest_alpha) { failed = false; break; }
+                ++dest_i;
+                if (dest_i % CHECKPOINTS == 0) break;
+            }
+            if (!failed) break;
+            alpha -= 2 * PI;
+        }
+        const double r1x = std::cos(beta), r1y = std::sin(beta);
+        const double p1x = -r1y, p1y = r1x;
+        const double dest_dx = dest_x - x, dest_dy = dest_y - y;
+        double proj = r1x * dest_dx + r1y * dest_dy;
+        while (beta - alpha > 1.5 * PI) beta -= 2 * PI;
+        while (beta - alpha < -1.5 * PI) beta += 2 * PI;
+        const double prev_beta = beta;
+        proj *= SCALE;
+        if (proj > 0.3) beta -= std::fmin(TRACK_TURN_RATE, std::fabs(0.001 * proj));
+        if (proj < -0.3) beta += std::fmin(TRACK_TURN_RATE, std::fabs(0.001 * proj));
+        x += p1x * TRACK_DETAIL_STEP;
+        y += p1y * TRACK_DETAIL_STEP;
+        path.push_back(Node{alpha, prev_beta * 0.5 + beta * 0.5, x, y});
+        if (laps > 4) break;
+        if (--no_freeze == 0) break;
+    }
+    int i1 = -1, i2 = -1;
+    int i = (int)path.size();
+    for (;;) {
+        --i;
+        if (i == 0) return 0;   // "return False  # Failed"
+        const bool pass = path[i].alpha > start_alpha && path[i - 1].alpha <= start_alpha;
+        if (pass && i2 == -1) i2 = i;
+        else if (pass && i1 == -1) { i1 = i; break; }
+    }
+    if (idx_range) { idx_range[0] = i1; idx_range[1] = i2; }
+    const int n = (i2 - 1) - i1;
+    if (n <= 0) return 0;
+    const Node* tr = path.data() + i1;
+    {
+        const double fb = tr[0].beta, fpx = std::cos(fb), fpy = std::sin(fb);
+        const double a = fpx * (tr[0].x - tr[n - 1].x), bq = fpy * (tr[0].y - tr[n - 1].y);
+        const double glued = std::sqrt(a * a + bq * bq);
+        if (glued > TRACK_DETAIL_STEP) return 0;
+    }
+    if (n > max_tiles) return fail(-2, "track has %d tiles, max_tiles is %d", n, max_tiles);
+    std::vector<char> border(n, 0);
+    for (int k = 0; k < n; ++k) {
+        bool good = true; double oneside = 0;
+        for (int neg = 0; neg < BORDER_MIN_COUNT; ++neg) {
+            const double b1 = tr[pyidx(k - neg - 0, n)].beta, b2 = tr[pyidx(k - neg - 1, n)].beta;
+            good &= std::fabs(b1 - b2) > TRACK_TURN_RATE * 0.2;
+            oneside += npsign(b1 - b2);
+        }
+        good &= std::fabs(oneside) == BORDER_MIN_COUNT;
+        border[k] = good;
+    }
+    for (int k = 0; k < n; ++k)
+        for (int neg = 0; neg < BORDER_MIN_COUNT; ++neg) border[pyidx(k - neg, n)] |= border[k];
+    int q = 0;
+    auto put = [&](const double v[8], float r, float g, float bl, int tile) -> bool {
+        if (q >= max_quads) return false;
+        std::memcpy(h_quads + (size_t)q * 8, v, sizeof(double) * 8);
+        h_quad_rgb[3 * q] = r; h_quad_rgb[3 * q + 1] = g; h_quad_rgb[3 * q + 2] = bl;
+        h_quad_tile[q] = tile; ++q; return true;
+    };
+    for (int k = 0; k < n; ++k) {
+        const Node& n1 = tr[k]; const Node& n2 = tr[pyidx(k - 1, n)];
+        const double b1 = n1.beta, x1 = n1.x, y1 = n1.y, b2 = n2.beta, x2 = n2.x, y2 = n2.y;
+        const double road[8] = {x1 - TRACK_WIDTH * std::cos(b1), y1 - TRACK_WIDTH * std::sin(b1),
+                                x1 + TRACK_WIDTH * std::cos(b1), y1 + TRACK_WIDTH * std::sin(b1),
+                                x2 + TRACK_WIDTH * std::cos(b2), y2 + TRACK_WIDTH * std::sin(b2),
+                                x2 - TRACK_WIDTH * std::cos(b2), y2 - TRACK_WIDTH * std::sin(b2)};
+        const double c = 0.01 * (k % 3);
+        if (!put(road, (float)(0.4 + c), (float)(0.4 + c), (float)(0.4 + c), k)) return fail(-3, "max_quads too small");
+        if (border[k]) {
+            const double side = npsign(b2 - b1);
+            const double bq[8] = {x1 + side * TRACK_WIDTH * std::cos(b1), y1 + side * TRACK_WIDTH * std::sin(b1),
+                                  x1 + side * (TRACK_WIDTH + BORDER) * std::cos(b1), y1 + side * (TRACK_WIDTH + BORDER) * std::sin(b1),
+                                  x2 + side * (TRACK_WIDTH + BORDER) * std::cos(b2), y2 + side * (TRACK_WIDTH + BORDER) * std::sin(b2),
+                                  x2 + side * TRACK_WIDTH * std::cos(b2), y2 + side * TRACK_WIDTH * std::sin(b2)};
+            const bool white = k % 2 == 0;
+            if (!put(bq, 1.0f, white ? 1.0f : 0.0f, white ? 1.0f : 0.0f, -1)) return fail(-3, "max_quads too small");
+        }
+    }
+    for (int k = 0; k < n; ++k) { h_nodes[4 * k] = tr[k].alpha; h_nodes[4 * k + 1] = tr[k].beta; h_nodes[4 * k + 2] = tr[k].x; h_nodes[4 * k + 3] = tr[k].y; }
+    *out_q = q;
+    return n;
+}
+
+// reset() spawn grid, mcr:366-393
+extern "C" int mcr_spawn_poses(const double* nodes, int32_t T, const int32_t* car_order, int32_t A, int32_t cw, double* poses) {
+    if (!nodes || !car_order || !poses || T < 1 || A < 1) return fail(-1, "mcr_spawn_poses: bad arguments");
+    const double PI = M_PI;
+    const int LINE_SPACING = 5; const double LATERAL_SPACING = 3;
+    const double pos_x = nodes[2], pos_y = nodes[3];
+    for (int c = 0; c < A; ++c) {
+        const int line_number = car_order[c] / 2;
+        const int side = 2 * (car_order[c] % 2) - 1;
+        int idx = -line_number * LINE_SPACING;
+        if (idx < 0) idx += T;
+        if (idx < 0 || idx >= T) return fail(-2, "mcr_spawn_poses: track too short for %d agents", A);
+        const double dx = nodes[4 * idx + 2] - pos_x, dy = nodes[4 * idx + 3] - pos_y;
+        double angle = nodes[4 * idx + 1];
+        if (cw) angle -= PI;
+        const double norm_theta = angle - PI / 2;
+        poses[3 * c + 0] = angle;
+        poses[3 * c + 1] = pos_x + dx + (LATERAL_SPACING * std::sin(norm_theta) * side);
+        poses[3 * c + 2] = pos_y + dy + (LATERAL_SPACING * std::cos(norm_theta) * side);
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------
+struct BufSpec { const char* name; int dtype; int ndim; int64_t dims[4]; };
+
+struct mcr_handle_t {
+    mcr_config cfg;
+    Dims d;
+    CarConst cc;
+    DevBuffers buf;
+    void* ptr[BUF_COUNT];
+    BufSpec spec[BUF_COUNT];
+    int64_t launches;
+    uint8_t palette[PAL_COUNT][4];
+    bool palette_ready;
+};
+
+
+static void set_spec(mcr_handle_t* h, int id, const char* name, int dtype, std::initializer_list<int64_t> dims) {
+    BufSpec& s = h->spec[id];
+    s.name = name; s.dtype = dtype; s.ndim = (int)dims.size();
+    int k = 0; for (int64_t v : dims) s.dims[k++] = v;
+    for (; k < 4; ++k) s.dims[k] = 1;
+}
+
+extern "C" int mcr_abi_version(void) { return MCR_ABI_VERSION; }
+extern "C" const char* mcr_last_error(void) { return g_err; }
+
+extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
+    if (!cfg || !out) return fail(-1, "mcr_create: null argument");
+    if (cfg->batch_envs < 1) return fail(-1, "batch_envs must be >= 1");
+    if (cfg->num_agents < 1 || cfg->num_agents > MCR_MAX_AGENTS) return fail(-1, "num_agents must be in [1, %d]", MCR_MAX_AGENTS);
+    if (cfg->max_tiles < 16 || cfg->max_tiles > 32768) return fail(-1, "max_tiles out of range");
+    if (cfg->max_quads < cfg->max_tiles || cfg->max_quads > 32767) return fail(-1, "max_quads must be in [max_tiles, 32767]");
+    if (cfg->pool_tracks < 1) return fail(-1, "pool_tracks must be >= 1");
+    mcr_handle_t* h = new mcr_handle_t();
+    h->cfg = *cfg;
+    h->d = Dims{cfg->batch_envs, cfg->num_agents, cfg->batch_envs * cfg->num_agents, cfg->max_tiles, cfg->max_quads, cfg->pool_tracks};
+    if (!build_car_const(h->cc)) { delete h; return fail(-2, "car geometry set-up failed"); }
+    std::memset(&h->buf, 0, sizeof(h->buf));
+    std::memset(h->ptr, 0, sizeof(h->ptr));
+    h->launches = 0; h->palette_ready = false;
+    const int64_t N = h->d.N, B = h->d.B, A = h->d.A, T = h->d.Tmax, Q = h->d.Qmax, P = h->d.P;
+    set_spec(h, BUF_BODY, "body", MCR_F32, {5, BODY_FIELDS, N});
+    set_spec(h, BUF_SLEEP_TIME, "sleep_time", MCR_F32, {5, N});
+    set_spec(h, BUF_AWAKE, "awake", MCR_U8, {5, N});
+    set_spec(h, BUF_JOINT, "joint", MCR_F32, {4, JOINT_FIELDS, N});
+    set_spec(h, BUF_LIMIT_STATE, "limit_state", MCR_U8, {4, N});
+    set_spec(h, BUF_WHEEL, "wheel", MCR_F64, {4, WHEEL_FIELDS, N});
+    set_spec(h, BUF_CTRL, "ctrl", MCR_F64, {CTRL_FIELDS, N});
+    set_spec(h, BUF_ON_ROAD, "on_road", MCR_U8, {4, N});
+    set_spec(h, BUF_ON_ROAD_NEXT, "on_road_next", MCR_U8, {4, N});
+    set_spec(h, BUF_REWARD, "reward", MCR_F64, {N});
+    set_spec(h, BUF_PREV_REWARD, "prev_reward", MCR_F64, {N});
+    set_spec(h, BUF_VISIT_COUNT, "visit_count", MCR_I32, {N});
+    set_spec(h, BUF_BACKWARD, "backward", MCR_U8, {N});
+    set_spec(h, BUF_TIME, "time", MCR_F64, {N});
+    set_spec(h, BUF_STEPS, "steps", MCR_I32, {N});
+    set_spec(h, BUF_CAMERA, "camera", MCR_F32, {6, N});
+    set_spec(h, BUF_STRIPE, "stripe", MCR_F32, {8, N});
+    set_spec(h, BUF_HEADING, "heading", MCR_F64, {N});
+    set_spec(h, BUF_ENV_TRACK, "env_track", MCR_I32, {B});
+    set_spec(h, BUF_ENV_CW, "env_cw", MCR_U8, {B});
+    set_spec(h, BUF_ENV_EPISODE, "env_episode", MCR_U32, {B});
+    set_spec(h, BUF_VISITED, "visited", MCR_U32, {B, T});
+    set_spec(h, BUF_TOUCHED, "touched", MCR_U8, {B, T});
+    set_spec(h, BUF_RESET_MASK, "reset_mask", MCR_U8, {B});
+    set_spec(h, BUF_STATUS, "status", MCR_I32, {STATUS_WORDS});
+    set_spec(h, BUF_TRK_T, "trk_T", MCR_I32, {P});
+    set_spec(h, BUF_TRK_Q, "trk_Q", MCR_I32, {P});
+    set_spec(h, BUF_TRK_NODE, "trk_node", MCR_F64, {P, T, 3});
+    set_spec(h, BUF_TRK_TILE, "trk_tile", MCR_F32, {P, T, 8});
+    set_spec(h, BUF_TRK_TILE_AABB, "trk_tile_aabb", MCR_F32, {P, T, 4});
+    set_spec(h, BUF_TRK_QUAD, "trk_quad", MCR_F32, {P, Q, 8});
+    set_spec(h, BUF_TRK_QUAD_COL, "trk_quad_col", MCR_U8, {P, Q});
+    set_spec(h, BUF_TRK_QUAD_TILE, "trk_quad_tile", MCR_I16, {P, Q});
+    set_spec(h, BUF_TRK_SLOT_POSE, "trk_slot_pose", MCR_F64, {P, 2, A, 3});
+    *out = h;
+    return 0;
+}
+
+extern "C" int mcr_destroy(mcr_handle h) { delete h; return 0; }
+
+extern "C" int mcr_buffer_count(mcr_handle h) { return h ? BUF_COUNT : fail(-1, "null handle"); }
+
+extern "C" int mcr_buffer_spec(mcr_handle h, int i, const char** name, int32_t* dtype, int32_t* ndim, int64_t dims[4]) {
+    if (!h || i < 0 || i >= BUF_COUNT) return fail(-1, "mcr_buffer_spec: bad index");
+    const BufSpec& s = h->spec[i];
+    if (name) *name = s.name;
+    if (dtype) *dtype = s.dtype;
+    if (ndim) *ndim = s.ndim;
+    if (dims) for (int k = 0; k < 4; ++k) dims[k] = s.dims[k];
+    return 0;
+}
+
+extern "C" int mcr_bind_buffer(mcr_handle h, int i, void* p) {
+    if (!h || i < 0 || i >= BUF_COUNT) return fail(-1, "mcr_bind_buffer: bad index");
+    if (!p || ((uintptr_t)p & 15)) return fail(-1, "mcr_bind_buffer(%s): pointer must be non-null and 16-byte aligned", h->spec[i].name);
+    h->ptr[i] = p;
+    DevBuffers& b = h->buf;
+    switch (i) {
+        case BUF_BODY: b.body = (float*)p; break;
+        case BUF_SLEEP_TIME: b.sleep_time = (float*)p; break;
+        case BUF_AWAKE: b.awake = (uint8_t*)p; break;
+        case BUF_JOINT: b.joint = (float*)p; break;
+        case BUF_LIMIT_STATE: b.limit_state = (uint8_t*)p; break;
+        case BUF_WHEEL: b.wheel = (double*)p; break;
+        case BUF_CTRL: b.ctrl = (double*)p; break;
+        case BUF_ON_ROAD: b.on_road = (uint8_t*)p; break;
+        case BUF_ON_ROAD_NEXT: b.on_road_next = (uint8_t*)p; break;
+        case BUF_REWARD: b.reward = (double*)p; break;
+        case BUF_PREV_REWARD: b.prev_reward = (double*)p; break;
+        case BUF_VISIT_COUNT: b.visit_count = (int32_t*)p; break;
+        case BUF_BACKWARD: b.backward = (uint8_t*)p; break;
+        case BUF_TIME: b.time = (double*)p; break;
+        case BUF_STEPS: b.steps = (int32_t*)p; break;
+        case BUF_CAMERA: b.camera = (float*)p; break;
+        case BUF_STRIPE: b.stripe = (float*)p; break;
+        case BUF_HEADING: b.heading = (double*)p; break;
+        case BUF_ENV_TRACK: b.env_track = (int32_t*)p; break;
+        case BUF_ENV_CW: b.env_cw = (uint8_t*)p; break;
+        case BUF_ENV_EPISODE: b.env_episode = (uint32_t*)p; break;
+        case BUF_VISITED: b.visited = (uint32_t*)p; break;
+        case BUF_TOUCHED: b.touched = (uint8_t*)p; break;
+        case BUF_RESET_MASK: b.reset_mask = (uint8_t*)p; break;
+        case BUF_STATUS: b.status = (int32_t*)p; break;
+        case BUF_TRK_T: b.trk_T = (int32_t*)p; break;
+        case BUF_TRK_Q: b.trk_Q = (int32_t*)p; break;
+        case BUF_TRK_NODE: b.trk_node = (double*)p; break;
+        case BUF_TRK_TILE: b.trk_tile = (float*)p; break;
+        case BUF_TRK_TILE_AABB: b.trk_tile_aabb = (float*)p; break;
+        case BUF_TRK_QUAD: b.trk_quad = (float*)p; break;
+        case BUF_TRK_QUAD_COL: b.trk_quad_col = (uint8_t*)p; break;
+        case BUF_TRK_QUAD_TILE: b.trk_quad_tile = (int16_t*)p; break;
+        case BUF_TRK_SLOT_POSE: b.trk_slot_pose = (double*)p; break;
+    }
+    return 0;
+}
+
+static int check_bound(mcr_handle h) {
+    if (!h) return fail(-1, "null handle");
+    for (int i = 0; i < BUF_COUNT; ++i)
+        if (!h->ptr[i]) return fail(-3, "buffer '%s' is not bound (mcr_bind_buffer)", h->spec[i].name);
+    return 0;
+}
+
+extern "C" int mcr_get_mass(mcr_handle h, float* o) {
+    if (!h || !o) return fail(-1, "mcr_get_mass: null argument");
+    const CarConst& c = h->cc;
+    o[0] = c.hull_mass; o[1] = c.hull_invMass; o[2] = c.hull_I; o[3] = c.hull_invI; o[4] = c.hull_lcx; o[5] = c.hull_lcy;
+    o[6] = c.wheel_mass; o[7] = c.wheel_invMass; o[8] = c.wheel_I; o[9] = c.wheel_invI; o[10] = 0.0f; o[11] = 0.0f;
+    return 0;
+}
+
+extern "C" int mcr_get_shape(mcr_handle h, int32_t which, float* o) {
+    if (!h || !o || which < 0 || which > 4) return fail(-1, "mcr_get_shape: bad argument");
+    const Poly8& P = which < 4 ? h->cc.hull_poly[which] : h->cc.wheel_poly;
+    for (int i = 0; i < P.n; ++i) { o[2 * i] = P.x[i]; o[2 * i + 1] = P.y[i]; }
+    return P.n;
+}
+
+extern "C" int64_t mcr_launch_count(mcr_handle h) { return h ? h->launches : -1; }
+
+// ---------------------------------------------------------------------------------------
+// tracks
+// ---------------------------------------------------------------------------------------
+static inline uint8_t col_u8(float c) { return (uint8_t)(int)std::floor(c * 255.0f + 0.5f); }
+
+extern "C" int mcr_load_track(mcr_handle h, int32_t slot, int32_t T, const double* nodes, int32_t Q, const double* quads,
+                              const float* quad_rgb, const int32_t* quad_tile, void* stream) {
+    int rc = check_bound(h); if (rc) return rc;
+    const Dims& d = h->d;
+    if (slot < 0 || slot >= d.P) return fail(-1, "mcr_load_track: slot %d out of range", slot);
+    if (T < 1 || T > d.Tmax) return fail(-1, "mcr_load_track: T=%d exceeds max_tiles=%d", T, d.Tmax);
+    if (Q < T || Q > d.Qmax) return fail(-1, "mcr_load_track: Q=%d exceeds max_quads=%d", Q, d.Qmax);
+    CUDA_OK(cudaSetDevice(h->cfg.device));
+    if (!h->palette_ready) { std::memcpy(h->palette, mcr_host_palette(), sizeof(h->palette)); h->palette_ready = true; }
+    std::vector<double> node3((size_t)T * 3);
+    for (int i = 0; i < T; ++i) { node3[3 * i] = nodes[4 * i + 1]; node3[3 * i + 1] = nodes[4 * i + 2]; node3[3 * i + 2] = nodes[4 * i + 3]; }
+    std::vector<float> quadf((size_t)Q * 8), tile((size_t)T * 8, 0.0f), aabb((size_t)T * 4, 0.0f);
+    std::vector<uint8_t> qcol(Q); std::vector<int16_t> qtile(Q);
+    std::vector<char> seen(T, 0);
+    for (int q = 0; q < Q; ++q) {
+        for (int k = 0; k < 8; ++k) quadf[(size_t)q * 8 + k] = (float)quads[(size_t)q * 8 + k];   // glVertex3f / b2Vec2
+        const uint8_t r = col_u8(quad_rgb[3 * q]), g = col_u8(quad_rgb[3 * q + 1]), bl = col_u8(quad_rgb[3 * q + 2]);
+        int pal = -1;
+        for (int p = 0; p < PAL_COUNT; ++p) if (h->palette[p][0] == r && h->palette[p][1] == g && h->palette[p][2] == bl) { pal = p; break; }
+        if (pal < 0) return fail(-4, "mcr_load_track: quad %d colour (%d,%d,%d) is not in the palette", q, r, g, bl);
+        qcol[q] = (uint8_t)pal;
+        const int t = quad_tile[q];
+        if (t >= T) return fail(-4, "mcr_load_track: quad %d refers to tile %d >= T", q, t);
+        qtile[q] = (int16_t)(t < 0 ? -1 : t);
+        if (t >= 0) {
+            std::vector<P2> raw;
+            for (int k = 0; k < 4; ++k) raw.push_back(P2{quadf[(size_t)q * 8 + 2 * k], quadf[(size_t)q * 8 + 2 * k + 1]});
+            const std::vector<P2> poly = b2_polygon_set(raw);      // fd_tile.shape.vertices = ..., mcr:318
+            if (poly.size() != 4) return fail(-5, "mcr_load_track: tile %d is not a proper quad after b2PolygonShape::Set", t);
+            float lx = poly[0].x, ly = poly[0].y, hx = lx, hy = ly;
+            for (int k = 0; k < 4; ++k) {
+                tile[(size_t)t * 8 + 2 * k] = poly[k].x; tile[(size_t)t * 8 + 2 * k + 1] = poly[k].y;
+                lx = std::fmin(lx, poly[k].x); ly = std::fmin(ly, poly[k].y); hx = std::fmax(hx, poly[k].x); hy = std::fmax(hy, poly[k].y);
+            }
+            aabb[(size_t)t * 4] = lx; aabb[(size_t)t * 4 + 1] = ly; aabb[(size_t)t * 4 + 2] = hx; aabb[(size_t)t * 4 + 3] = hy;
+            seen[t] = 1;
+        }
+    }
+    for (int t = 0; t < T; ++t) if (!seen[t]) return fail(-4, "mcr_load_track: tile %d has no quad", t);
+    // spawn pose of every grid position for the device-side auto reset
+    const int A = d.A;
+    std::vector<double> slot_pose((size_t)2 * A * 3);
+    std::vector<int32_t> ident(A);
+    for (int c = 0; c < A; ++c) ident[c] = c;
+    for (int cw = 0; cw < 2; ++cw) {
+        rc = mcr_spawn_poses(nodes, T, ident.data(), A, cw, slot_pose.data() + (size_t)cw * A * 3);
+        if (rc) return rc;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const DevBuffers& b = h->buf;
+    const int32_t Ti = T, Qi = Q;
+    CUDA_OK(cudaMemcpyAsync(b.trk_T + slot, &Ti, 4, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(b.trk_Q + slot, &Qi, 4, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(b.trk_node + (size_t)slot * d.Tmax * 3, node3.data(), node3.size() * 8, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(b.trk_tile + (size_t)slot * d.Tmax * 8, tile.data(), tile.size() * 4, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(b.trk_tile_aabb + (size_t)slot * d.Tmax * 4, aabb.data(), aabb.size() * 4, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(b.trk_quad + (size_t)slot * d.Qmax * 8, quadf.data(), quadf.size() * 4, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(b.trk_quad_col + (size_t)slot * d.Qmax, qcol.data(), qcol.size(), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(b.trk_quad_tile + (size_t)slot * d.Qmax, qtile.data(), qtile.size() * 2, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(b.trk_slot_pose + (size_t)slot * 2 * A * 3, slot_pose.data(), slot_pose.size() * 8, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaStreamSynchronize(s));   // the staging vectors die with this frame
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// reset / step
+// ---------------------------------------------------------------------------------------
+#define LAUNCH(expr) do { int n_ = (expr); if (n_ < 0) return fail(-101, "kernel launch failed in %s: %s", #expr, cudaGetErrorString(cudaGetLastError())); h->launches += n_; } while (0)
+
+extern "C" int mcr_contacts(mcr_handle h, const uint8_t* mask, void* stream) {
+    int rc = check_bound(h); if (rc) return rc;
+    LAUNCH(launch_contacts(h->d, h->buf, h->cc, mask, stream));
+    return 0;
+}
+
+extern "C" int mcr_physics(mcr_handle h, const uint8_t* mask, const void* action, int32_t action_dtype, void* stream) {
+    int rc = check_bound(h); if (rc) return rc;
+    if (action && action_dtype != MCR_F32 && action_dtype != MCR_F64) return fail(-1, "action dtype must be MCR_F32 or MCR_F64");
+    LAUNCH(launch_physics(h->d, h->buf, h->cc, mask, action, action_dtype, h->cfg.h_ratio, stream));
+    return 0;
+}
+
+extern "C" int mcr_render(mcr_handle h, const uint8_t* mask, uint8_t* obs, double* reward, uint8_t* done, int32_t post_step, void* stream) {
+    int rc = check_bound(h); if (rc) return rc;
+    if (!obs) return fail(-1, "mcr_render: d_obs is null");
+    if (post_step && (!reward || !done)) return fail(-1, "mcr_render: post_step needs d_reward and d_done");
+    LAUNCH(launch_render(h->d, h->buf, h->cc, mask, obs, reward, done, post_step, h->cfg.backwards_flag,
+                         h->cfg.use_ego_color, h->cfg.max_episode_steps, stream));
+    return 0;
+}
+
+extern "C" int mcr_reset(mcr_handle h, const uint8_t* mask, const int32_t* track_slot, const uint8_t* cw,
+                         const double* spawn_pose, uint8_t* obs, void* stream) {
+    int rc = check_bound(h); if (rc) return rc;
+    if (!track_slot || !cw || !spawn_pose || !obs) return fail(-1, "mcr_reset: null argument");
+    LAUNCH(launch_spawn(h->d, h->buf, h->cc, mask, track_slot, cw, spawn_pose, stream));
+    // the implicit step(None), mcr:408
+    LAUNCH(launch_contacts(h->d, h->buf, h->cc, mask, stream));
+    LAUNCH(launch_physics(h->d, h->buf, h->cc, mask, nullptr, MCR_F32, h->cfg.h_ratio, stream));
+    LAUNCH(launch_render(h->d, h->buf, h->cc, mask, obs, nullptr, nullptr, 0, h->cfg.backwards_flag,
+                         h->cfg.use_ego_color, h->cfg.max_episode_steps, stream));
+    return 0;
+}
+
+extern "C" int mcr_step(mcr_handle h, const void* action, int32_t action_dtype, uint8_t* obs, double* reward,
+                        uint8_t* done, int32_t flags, void* stream) {
+    int rc = check_bound(h); if (rc) return rc;
+    if (!action || !obs || !reward || !done) return fail(-1, "mcr_step: null argument");
+    if (action_dtype != MCR_F32 && action_dtype != MCR_F64) return fail(-1, "action dtype must be MCR_F32 or MCR_F64");
+    LAUNCH(launch_contacts(h->d, h->buf, h->cc, nullptr, stream));
+    LAUNCH(launch_physics(h->d, h->buf, h->cc, nullptr, action, action_dtype, h->cfg.h_ratio, stream));
+    LAUNCH(launch_render(h->d, h->buf, h->cc, nullptr, obs, reward, done, 1, h->cfg.backwards_flag,
+                         h->cfg.use_ego_color, h->cfg.max_episode_steps, stream));
+    if (flags & 1) {
+        AutoResetCfg ar{h->cfg.use_random_direction, h->cfg.direction_cw, (unsigned long long)h->cfg.seed};
+        LAUNCH(launch_auto_reset(h->d, h->buf, h->cc, done, ar, stream));
+        const uint8_t* m = h->buf.reset_mask;
+        LAUNCH(launch_contacts(h->d, h->buf, h->cc, m, stream));
+        LAUNCH(launch_physics(h->d, h->buf, h->cc, m, nullptr, MCR_F32, h->cfg.h_ratio, stream));
+        LAUNCH(launch_render(h->d, h->buf, h->cc, m, obs, nullptr, nullptr, 0, h->cfg.backwards_flag,
+                             h->cfg.use_ego_color, h->cfg.max_episode_steps, stream));
+    }
+    return 0;
+}

@@ -1,0 +1,100 @@
+// mcr_internal.h -- layouts shared by the host API and the three kernels of libmcr.so.
+// Product code: nothing here (or anywhere under multi_car_racing_b200/) touches oracle/.
+#pragma once
+#include <stdint.h>
+#include "../../include/mcr.h"
+
+// ---------------------------------------------------------------------------------------
+// Box2D 2.3.x constants (b2Settings.h) used by the specialised solver
+// ---------------------------------------------------------------------------------------
+#define B2_PI 3.14159265359f
+#define B2_LINEAR_SLOP 0.005f
+#define B2_ANGULAR_SLOP (2.0f / 180.0f * B2_PI)
+#define B2_POLYGON_RADIUS (2.0f * B2_LINEAR_SLOP)
+#define B2_MAX_ANGULAR_CORRECTION (8.0f / 180.0f * B2_PI)
+#define B2_MAX_TRANSLATION 2.0f
+#define B2_MAX_ROTATION (0.5f * B2_PI)
+#define B2_TIME_TO_SLEEP 0.5f
+#define B2_LINEAR_SLEEP_TOL 0.01f
+#define B2_ANGULAR_SLEEP_TOL (2.0f / 180.0f * B2_PI)
+#define B2_EPS 1.1920928955078125e-7f
+
+#define MCR_VEL_ITERS 180   // world.Step(1/FPS, 6*30, 2*30), mcr:428
+#define MCR_POS_ITERS 60
+#define MCR_MAXV 8
+
+// body SoA: body[(b * BODY_FIELDS + f) * N + car], b = 0 hull, 1..4 wheels
+enum { BF_CX = 0, BF_CY, BF_A, BF_VX, BF_VY, BF_W, BF_PX, BF_PY, BF_QS, BF_QC, BODY_FIELDS };
+// joint SoA: joint[(w * JOINT_FIELDS + f) * N + car]
+enum { JF_IX = 0, JF_IY, JF_IZ, JF_MOTOR, JOINT_FIELDS };
+// wheel SoA (f64): wheel[(w * WHEEL_FIELDS + f) * N + car]
+enum { WF_OMEGA = 0, WF_PHASE, WHEEL_FIELDS };
+// ctrl SoA (f64): ctrl[f * N + car]
+enum { CF_GAS = 0, CF_BRAKE, CF_STEER, CTRL_FIELDS };
+enum { LIM_INACTIVE = 0, LIM_LOWER = 1, LIM_UPPER = 2, LIM_EQUAL = 3 };
+
+// buffer ids (order == mcr_buffer_spec index)
+enum {
+    BUF_BODY = 0, BUF_SLEEP_TIME, BUF_AWAKE, BUF_JOINT, BUF_LIMIT_STATE, BUF_WHEEL, BUF_CTRL,
+    BUF_ON_ROAD, BUF_ON_ROAD_NEXT, BUF_REWARD, BUF_PREV_REWARD, BUF_VISIT_COUNT, BUF_BACKWARD,
+    BUF_TIME, BUF_STEPS, BUF_CAMERA, BUF_STRIPE, BUF_HEADING,
+    BUF_ENV_TRACK, BUF_ENV_CW, BUF_ENV_EPISODE,
+    BUF_VISITED, BUF_TOUCHED, BUF_RESET_MASK, BUF_STATUS,
+    BUF_TRK_T, BUF_TRK_Q, BUF_TRK_NODE, BUF_TRK_TILE, BUF_TRK_TILE_AABB, BUF_TRK_QUAD, BUF_TRK_QUAD_COL,
+    BUF_TRK_QUAD_TILE, BUF_TRK_SLOT_POSE,
+    BUF_COUNT
+};
+
+// status words
+enum { ST_EVENT_OVERFLOW = 0, ST_NAN = 1, ST_RASTER_OVERFLOW = 2, ST_RESERVED = 3, STATUS_WORDS = 4 };
+
+// palette indices (rgb values in raster.cu)
+enum {
+    PAL_BLACK = 0, PAL_GRASS, PAL_GRASS_LIGHT, PAL_ROAD0, PAL_ROAD1, PAL_ROAD2, PAL_WHITE, PAL_RED,
+    PAL_WHEEL_WHITE, PAL_CAR0, /* 8 car colours: PAL_CAR0 .. PAL_CAR0+7 */
+    PAL_IND_BLUE = PAL_CAR0 + 8, PAL_IND_BLUE2, PAL_IND_GREEN, PAL_FLAG_BLUE, PAL_COUNT
+};
+
+struct Poly8 { int n; float x[MCR_MAXV]; float y[MCR_MAXV]; };
+
+// car_dynamics.Car rigid-body constants, computed on the host at mcr_create (fp32, Box2D's
+// ComputeMass / ResetMassData) and passed to the kernels by value.
+struct CarConst {
+    float hull_invMass, hull_invI, hull_lcx, hull_lcy;
+    float wheel_invMass, wheel_invI;
+    float anchor_x[4], anchor_y[4];       // localAnchorA on the hull
+    float max_motor_torque, lower, upper;
+    Poly8 hull_poly[4];
+    Poly8 wheel_poly;
+    float hull_mass, hull_I, wheel_mass, wheel_I;
+};
+
+struct DevBuffers {
+    float* body; float* sleep_time; uint8_t* awake; float* joint; uint8_t* limit_state;
+    double* wheel; double* ctrl; uint8_t* on_road; uint8_t* on_road_next;
+    double* reward; double* prev_reward; int32_t* visit_count; uint8_t* backward;
+    double* time; int32_t* steps;        // per car (all cars of an env hold identical values)
+    float* camera;                       // [6][N] world -> viewport-pixel affine of each car's view
+    float* stripe;                       // [4*2][N] wheel stripe y extents (NaN = hidden)
+    double* heading;                     // [N] car_angle of mcr:449-456
+    int32_t* env_track; uint8_t* env_cw; uint32_t* env_episode;
+    uint32_t* visited; uint8_t* touched; uint8_t* reset_mask; int32_t* status;
+    int32_t* trk_T; int32_t* trk_Q; double* trk_node; float* trk_tile; float* trk_tile_aabb;
+    float* trk_quad; uint8_t* trk_quad_col; int16_t* trk_quad_tile; double* trk_slot_pose;
+};
+
+struct Dims { int B, A, N, Tmax, Qmax, P; };
+
+// kernel launchers (each returns the number of kernels it launched, or < 0 on error)
+int launch_contacts(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, void* stream);
+int launch_physics(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
+                   const void* action, int action_dtype, double h_ratio, void* stream);
+int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* obs,
+                  double* reward, uint8_t* done, int post_step, int backwards_flag,
+                  int use_ego_color, int max_episode_steps, void* stream);
+const uint8_t (*mcr_host_palette())[4];
+int launch_spawn(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
+                 const int32_t* track_slot, const uint8_t* cw, const double* spawn_pose, void* stream);
+struct AutoResetCfg { int use_random_direction, direction_cw; unsigned long long seed; };
+int launch_auto_reset(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* done,
+                      const AutoResetCfg& cfg, void* stream);

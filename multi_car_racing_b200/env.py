@@ -1,0 +1,466 @@
+"""Host-side mirror of the reference's env surface for the B200 step+render path.
+
+Two classes:
+  * BatchedMultiCarRacing -- B independent MultiCarRacing-v0 envs on one GPU; torch tensors in
+    and out, state held in a torch SoA that libmcr.so's kernels read and write in place.
+  * MultiCarRacing        -- the reference's single-env API (same kwargs, defaults, shapes,
+    dtypes and RNG usage; reference gym_multi_car_racing/multi_car_racing.py:125-674) on top of
+    a batch of one: numpy observations (num_agents, 96, 96, 3) uint8, rewards (num_agents,)
+    float64, done bool, info {}.
+
+All compute goes through the C-ABI of include/mcr.h; this module owns memory (torch), streams
+and RNG plumbing only.  It raises if CUDA or libmcr.so is unavailable -- there is no fallback.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .track import TrackGenerator, np_random, MAX_TILES_DEFAULT, MAX_QUADS_DEFAULT
+
+STATE_W = 96
+STATE_H = 96
+FPS = 50
+PLAYFIELD = 2000 / 6.0
+
+_TORCH_DTYPES = None
+
+
+def _torch():
+    import torch
+    global _TORCH_DTYPES
+    if _TORCH_DTYPES is None:
+        _TORCH_DTYPES = {_lib.MCR_U8: torch.uint8, _lib.MCR_I32: torch.int32, _lib.MCR_U32: torch.int32,
+                         _lib.MCR_F32: torch.float32, _lib.MCR_F64: torch.float64, _lib.MCR_I16: torch.int16}
+    return torch
+
+
+class Box:
+    """Minimal stand-in for gym.spaces.Box (gym is an optional dependency)."""
+
+    def __init__(self, low, high, shape=None, dtype=np.float32):
+        self.dtype = np.dtype(dtype)
+        if shape is None:
+            low = np.asarray(low)
+            shape = low.shape
+        self.shape = tuple(shape)
+        self.low = np.broadcast_to(np.asarray(low, dtype=self.dtype), self.shape).copy()
+        self.high = np.broadcast_to(np.asarray(high, dtype=self.dtype), self.shape).copy()
+        self._rng = np.random.RandomState()
+
+    def seed(self, seed=None):
+        self._rng.seed(seed)
+        return [seed]
+
+    def sample(self):
+        if self.dtype.kind == "f":
+            return self._rng.uniform(self.low, self.high).astype(self.dtype)
+        return self._rng.randint(self.low, self.high.astype(np.int64) + 1).astype(self.dtype)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.shape and np.all(x >= self.low) and np.all(x <= self.high)
+
+    def __repr__(self):
+        return "Box(%s, %s, %s, %s)" % (self.low.min(), self.high.max(), self.shape, self.dtype)
+
+
+def _make_box(low, high, shape=None, dtype=np.float32):
+    try:  # use the real thing when a gym is installed, so isinstance checks downstream work
+        from gym import spaces  # type: ignore
+        return spaces.Box(low, high, shape=shape, dtype=dtype) if shape is not None else spaces.Box(low, high, dtype=dtype)
+    except Exception:
+        return Box(low, high, shape=shape, dtype=dtype)
+
+
+class BatchedMultiCarRacing:
+    """B independent MultiCarRacing-v0 environments stepped by three CUDA kernels.
+
+    Constructor kwargs mirror MultiCarRacing.__init__ (reference :131-133); `batch_envs`,
+    `device`, the pool/capacity knobs and `max_episode_steps` (the gym registration's TimeLimit,
+    reference __init__.py:8) are additions.
+    """
+
+    def __init__(self, batch_envs, num_agents=2, verbose=0, direction='CCW', use_random_direction=True,
+                 backwards_flag=True, h_ratio=0.25, use_ego_color=False, device=None,
+                 max_tiles=MAX_TILES_DEFAULT, max_quads=MAX_QUADS_DEFAULT, pool_tracks=None,
+                 max_episode_steps=1000, auto_reset=True, seed=None):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.McrError("multi_car_racing_b200 needs a CUDA device (B200, sm_100a); none is visible")
+        self.L = _lib.load()
+        self.device = torch.device(device if device is not None else "cuda:0")
+        if self.device.type != "cuda":
+            raise _lib.McrError("device must be a CUDA device")
+        self.batch_envs, self.num_agents = int(batch_envs), int(num_agents)
+        self.verbose = verbose
+        self.direction, self.use_random_direction = direction, use_random_direction
+        self.backwards_flag, self.h_ratio, self.use_ego_color = backwards_flag, h_ratio, use_ego_color
+        self.max_episode_steps = int(max_episode_steps or 0)
+        self.auto_reset = bool(auto_reset)
+        self.pool_tracks = int(pool_tracks) if pool_tracks else self.batch_envs
+        if self.pool_tracks < self.batch_envs:
+            raise ValueError("pool_tracks must be >= batch_envs")
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        cfg = _lib.McrConfig(self.batch_envs, self.num_agents, max_tiles, max_quads, self.pool_tracks,
+                             int(bool(backwards_flag)), int(bool(use_ego_color)), self.max_episode_steps,
+                             float(h_ratio), dev_index, int(bool(use_random_direction)),
+                             int(direction == 'CW'), 0, int(seed if seed is not None else 0) & (2 ** 64 - 1))
+        self._h = ctypes.c_void_p()
+        _lib.check(self.L.mcr_create(ctypes.byref(cfg), ctypes.byref(self._h)), "mcr_create")
+        self.max_tiles, self.max_quads = max_tiles, max_quads
+        # ---- torch-owned SoA state, bound once ------------------------------------------------
+        self.buffers = {}
+        with torch.cuda.device(self.device):
+            n = self.L.mcr_buffer_count(self._h)
+            for i in range(n):
+                name, dt, nd = ctypes.c_char_p(), ctypes.c_int32(), ctypes.c_int32()
+                dims = (ctypes.c_int64 * 4)()
+                _lib.check(self.L.mcr_buffer_spec(self._h, i, ctypes.byref(name), ctypes.byref(dt), ctypes.byref(nd),
+                                                  ctypes.byref(dims)), "mcr_buffer_spec")
+                shape = tuple(int(dims[k]) for k in range(nd.value))
+                t = torch.zeros(shape, dtype=_TORCH_DTYPES[dt.value], device=self.device)
+                self.buffers[name.value.decode()] = t
+                _lib.check(self.L.mcr_bind_buffer(self._h, i, t.data_ptr()), "mcr_bind_buffer")
+            B, A = self.batch_envs, self.num_agents
+            self.obs = torch.zeros((B, A, STATE_H, STATE_W, 3), dtype=torch.uint8, device=self.device)
+            self.reward_out = torch.zeros((B, A), dtype=torch.float64, device=self.device)
+            self.done_out = torch.zeros((B,), dtype=torch.uint8, device=self.device)
+            self._slot = torch.zeros((B,), dtype=torch.int32, device=self.device)
+            self._cw = torch.zeros((B,), dtype=torch.uint8, device=self.device)
+            self._pose = torch.zeros((B, A, 3), dtype=torch.float64, device=self.device)
+        self._gen = TrackGenerator(max_tiles, max_quads)
+        self.tracks = [None] * self.pool_tracks          # HostTrack per pool slot
+        self.episode_direction = [direction] * self.batch_envs
+        self.car_order = [None] * self.batch_envs
+        self.action_space = _make_box(np.array([-1, 0, 0]), np.array([+1, +1, +1]), dtype=np.float32)
+        self.observation_space = _make_box(0, 255, shape=(STATE_H, STATE_W, 3), dtype=np.uint8)
+        self.seed(seed)
+
+    # ---- plumbing ---------------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                self.L.mcr_destroy(self._h)
+                self._h = ctypes.c_void_p()
+        except Exception:
+            pass
+
+    def close(self):
+        self.__del__()
+
+    @property
+    def launch_count(self):
+        return int(self.L.mcr_launch_count(self._h))
+
+    def seed(self, seed=None):
+        """Per-env RandomState streams: env i is seeded like the reference's env.seed(seed + i)."""
+        self.np_randoms, seeds = [], []
+        for i in range(self.batch_envs):
+            rng, s = np_random(None if seed is None else int(seed) + i)
+            self.np_randoms.append(rng)
+            seeds.append(s)
+        return seeds
+
+    def load_track(self, slot, track):
+        """Upload a HostTrack (or any object with nodes/quads/quad_rgb/quad_tile) into a pool slot."""
+        nodes = np.ascontiguousarray(track.nodes, np.float64)
+        quads = np.ascontiguousarray(track.quads, np.float64).reshape(-1, 8)
+        rgb = np.ascontiguousarray(track.quad_rgb, np.float32)
+        qt = np.ascontiguousarray(track.quad_tile, np.int32)
+        with _torch().cuda.device(self.device):
+            _lib.check(self.L.mcr_load_track(self._h, int(slot), len(nodes), nodes.ctypes.data, len(quads),
+                                             quads.ctypes.data, rgb.ctypes.data, qt.ctypes.data, self._stream()),
+                       "mcr_load_track")
+        self.tracks[slot] = track
+
+    # ---- reset, reference :340-408 ---------------------------------------------------------------
+    def reset(self, tracks=None, car_orders=None, directions=None):
+        """Reset every env.  RNG usage per env follows the reference: direction and car order from
+        the GLOBAL numpy RNG (:351-357), the track from the env's own RandomState (:359-364).
+        `tracks` / `car_orders` / `directions` inject host-made values (parity tests)."""
+        torch = _torch()
+        B, A = self.batch_envs, self.num_agents
+        poses = np.empty((B, A, 3), np.float64)
+        cws = np.empty((B,), np.uint8)
+        for e in range(B):
+            if directions is not None:
+                self.episode_direction[e] = directions[e]
+            elif self.use_random_direction:
+                self.episode_direction[e] = str(np.random.choice(['CW', 'CCW']))
+            if car_orders is not None:
+                order = np.asarray(car_orders[e])
+            else:
+                order = np.random.choice([i for i in range(A)], size=A, replace=False)
+            self.car_order[e] = {i: order[i] for i in range(A)}
+            tr = tracks[e] if tracks is not None else self._gen.generate(self.np_randoms[e], self.verbose)
+            self.load_track(e, tr)
+            cws[e] = self.episode_direction[e] == 'CW'
+            poses[e] = self._gen.spawn_poses(tr.nodes, order, cws[e])
+        # extra pool slots (device-side auto reset draws from the whole pool)
+        for s in range(B, self.pool_tracks):
+            if self.tracks[s] is None:
+                self.load_track(s, self._gen.generate(self.np_randoms[s % B], 0))
+        with torch.cuda.device(self.device):
+            self._slot.copy_(torch.arange(B, dtype=torch.int32))
+            self._cw.copy_(torch.from_numpy(cws))
+            self._pose.copy_(torch.from_numpy(poses))
+            _lib.check(self.L.mcr_reset(self._h, None, self._slot.data_ptr(), self._cw.data_ptr(),
+                                        self._pose.data_ptr(), self.obs.data_ptr(), self._stream()), "mcr_reset")
+        return self.obs
+
+    # ---- step, reference :410-509 ------------------------------------------------------------------
+    def step(self, action):
+        """action: (B, A, 3) torch tensor on this device (float32 or float64), or anything
+        np.reshape can bring to that shape.  Returns (obs u8 (B,A,96,96,3), reward f64 (B,A),
+        done u8 (B,) [bit0 done, bit1 TimeLimit], {}) -- views of buffers reused every step."""
+        torch = _torch()
+        B, A = self.batch_envs, self.num_agents
+        if not isinstance(action, torch.Tensor):
+            action = torch.from_numpy(np.ascontiguousarray(np.reshape(action, (B, A, -1)))).to(self.device)
+        if action.dtype not in (torch.float32, torch.float64):
+            action = action.to(torch.float32)
+        action = action.reshape(B, A, -1)
+        if action.shape[-1] != 3 or action.device != self.device:
+            raise ValueError("action must have shape (batch_envs, num_agents, 3) on %s" % self.device)
+        action = action.contiguous()
+        dt = _lib.MCR_F32 if action.dtype == torch.float32 else _lib.MCR_F64
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.mcr_step(self._h, action.data_ptr(), dt, self.obs.data_ptr(), self.reward_out.data_ptr(),
+                                       self.done_out.data_ptr(), 1 if self.auto_reset else 0, self._stream()), "mcr_step")
+        return self.obs, self.reward_out, self.done_out, {}
+
+    def render(self, mode='state_pixels'):
+        assert mode in ['human', 'state_pixels', 'rgb_array']
+        if mode != 'state_pixels':
+            raise NotImplementedError("only the 'state_pixels' observation path is built (SURVEY.md §8: other modes are out of scope)")
+        with _torch().cuda.device(self.device):
+            _lib.check(self.L.mcr_render(self._h, None, self.obs.data_ptr(), None, None, 0, self._stream()), "mcr_render")
+        return self.obs
+
+    # ---- split entry points (bench / ncu / tests) ------------------------------------------------
+    def contacts_only(self):
+        _lib.check(self.L.mcr_contacts(self._h, None, self._stream()), "mcr_contacts")
+
+    def physics_only(self, action):
+        dt = _lib.MCR_F32 if action.dtype == _torch().float32 else _lib.MCR_F64
+        _lib.check(self.L.mcr_physics(self._h, None, action.data_ptr(), dt, self._stream()), "mcr_physics")
+
+    def render_only(self):
+        _lib.check(self.L.mcr_render(self._h, None, self.obs.data_ptr(), None, None, 0, self._stream()), "mcr_render")
+
+    # ---- state views for tests / users ----------------------------------------------------------
+    def bodies(self):
+        """(B, A, 5, 10) float32: cx cy angle vx vy w px py sin cos for hull + 4 wheels."""
+        b = self.buffers["body"]                      # (5, 10, N)
+        return b.permute(2, 0, 1).reshape(self.batch_envs, self.num_agents, 5, 10)
+
+    def status(self):
+        return self.buffers["status"].cpu().numpy()
+
+    def mass(self):
+        out = np.empty(12, np.float32)
+        _lib.check(self.L.mcr_get_mass(self._h, out.ctypes.data), "mcr_get_mass")
+        return out
+
+    def shape(self, which):
+        out = np.empty(16, np.float32)
+        n = _lib.check(self.L.mcr_get_shape(self._h, which, out.ctypes.data), "mcr_get_shape")
+        return out[:2 * n].reshape(n, 2).copy()
+
+
+class _Vec2(tuple):
+    @property
+    def x(self):
+        return self[0]
+
+    @property
+    def y(self):
+        return self[1]
+
+
+class _JointView:
+    def __init__(self, env, car, wheel):
+        self._e, self._c, self._w = env, car, wheel
+
+    @property
+    def angle(self):
+        b = self._e._batch.bodies()[0, self._c].cpu().numpy()
+        return float(np.float32(b[1 + self._w, 2]) - np.float32(b[0, 2]))
+
+
+class _WheelView:
+    def __init__(self, env, car, wheel):
+        self._e, self._c, self._w = env, car, wheel
+        self.joint = _JointView(env, car, wheel)
+        self.car_id = car
+
+    @property
+    def omega(self):
+        return float(self._e._batch.buffers["wheel"][self._w, 0, self._c].item())
+
+    @property
+    def phase(self):
+        return float(self._e._batch.buffers["wheel"][self._w, 1, self._c].item())
+
+
+class _HullView:
+    def __init__(self, env, car):
+        self._e, self._c = env, car
+
+    def _row(self):
+        return self._e._batch.bodies()[0, self._c, 0].cpu().numpy()
+
+    @property
+    def position(self):
+        r = self._row()
+        return _Vec2((float(r[6]), float(r[7])))
+
+    @property
+    def angle(self):
+        return float(self._row()[2])
+
+    @property
+    def linearVelocity(self):
+        r = self._row()
+        return _Vec2((float(r[3]), float(r[4])))
+
+    @property
+    def angularVelocity(self):
+        return float(self._row()[5])
+
+
+class _CarView:
+    def __init__(self, env, car):
+        self.hull = _HullView(env, car)
+        self.wheels = [_WheelView(env, car, w) for w in range(4)]
+
+
+class MultiCarRacing:
+    """Single-env drop-in for the reference class (same kwargs/defaults, reference :131-133).
+
+    step()/reset() return host numpy arrays exactly shaped like the reference's
+    (reference :408, :509, :518).  `device` is the only extra kwarg.
+    """
+    metadata = {'render.modes': ['human', 'rgb_array', 'state_pixels'], 'video.frames_per_second': FPS}
+
+    def __init__(self, num_agents=2, verbose=1, direction='CCW', use_random_direction=True,
+                 backwards_flag=True, h_ratio=0.25, use_ego_color=False, device=None,
+                 max_tiles=MAX_TILES_DEFAULT, max_quads=MAX_QUADS_DEFAULT):
+        self.num_agents = num_agents
+        self.verbose = verbose
+        self.use_random_direction = use_random_direction
+        self.episode_direction = direction
+        if self.use_random_direction:                       # reference :156-157 (global numpy RNG)
+            self.episode_direction = str(np.random.choice(['CW', 'CCW']))
+        self.backwards_flag, self.h_ratio, self.use_ego_color = backwards_flag, h_ratio, use_ego_color
+        self._batch = BatchedMultiCarRacing(1, num_agents=num_agents, verbose=verbose, direction=direction,
+                                            use_random_direction=use_random_direction, backwards_flag=backwards_flag,
+                                            h_ratio=h_ratio, use_ego_color=use_ego_color, device=device,
+                                            max_tiles=max_tiles, max_quads=max_quads, pool_tracks=1,
+                                            max_episode_steps=0, auto_reset=False)
+        self.action_space = self._batch.action_space
+        self.observation_space = self._batch.observation_space
+        self.car_order = None
+        self.track = None
+        self.road_poly = []
+        self.state = None
+        self._has_reset = False
+        self.cars = [_CarView(self, c) for c in range(num_agents)]
+        self.seed()
+
+    def seed(self, seed=None):
+        self.np_random, seed = np_random(seed)
+        self._batch.np_randoms = [self.np_random]
+        return [seed]
+
+    def reset(self):
+        if self.use_random_direction:                       # reference :351-352
+            self.episode_direction = str(np.random.choice(['CW', 'CCW']))
+        ids = [i for i in range(self.num_agents)]           # reference :355-357
+        shuffle_ids = np.random.choice(ids, size=self.num_agents, replace=False)
+        self.car_order = {i: shuffle_ids[i] for i in range(self.num_agents)}
+        tr = self._batch._gen.generate(self.np_random, self.verbose)
+        self.track = [tuple(r) for r in tr.nodes]
+        self.road_poly = [([tuple(p) for p in q], tuple(c)) for q, c in zip(tr.quads, tr.quad_rgb)]
+        obs = self._batch.reset(tracks=[tr], car_orders=[shuffle_ids], directions=[self.episode_direction])
+        self._has_reset = True
+        self.state = obs[0].cpu().numpy()
+        return self.state
+
+    def step(self, action):
+        if action is None:
+            raise ValueError("step(None) is reset()'s internal call (reference :408); call reset()")
+        action = np.reshape(action, (self.num_agents, -1))   # reference :420 (raises on a wrong size)
+        if action.shape[1] != 3:
+            raise ValueError("cannot reshape action into (num_agents, 3)")
+        if action.dtype != np.float32:
+            action = action.astype(np.float64)
+        obs, rew, done, _ = self._batch.step(action.reshape(1, self.num_agents, 3))
+        self.state = obs[0].cpu().numpy()
+        return self.state, rew[0].cpu().numpy(), bool(done[0].item() & 1), {}
+
+    def render(self, mode='human'):
+        assert mode in ['human', 'state_pixels', 'rgb_array']
+        if mode != 'state_pixels':
+            raise NotImplementedError("only mode='state_pixels' is built on the B200 path")
+        if not self._has_reset:
+            return None
+        return self._batch.render('state_pixels')[0].cpu().numpy()
+
+    def close(self):
+        pass
+
+    # attributes users of the reference poke at
+    @property
+    def reward(self):
+        return self._batch.buffers["reward"].cpu().numpy().copy()
+
+    @property
+    def prev_reward(self):
+        return self._batch.buffers["prev_reward"].cpu().numpy().copy()
+
+    @property
+    def tile_visited_count(self):
+        return [int(v) for v in self._batch.buffers["visit_count"].cpu().numpy()]
+
+    @property
+    def driving_backward(self):
+        return self._batch.buffers["backward"].cpu().numpy().astype(bool)
+
+    @property
+    def t(self):
+        return float(self._batch.buffers["time"][0].item())
+
+
+class TimeLimit:
+    """gym.wrappers.TimeLimit semantics (gym 0.17.2) for make(): done at max_episode_steps with
+    info['TimeLimit.truncated'] = not done (reference __init__.py:5-10)."""
+
+    def __init__(self, env, max_episode_steps):
+        self.env = env
+        self._max_episode_steps = max_episode_steps
+        self._elapsed_steps = None
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)
+
+    @property
+    def unwrapped(self):
+        return self.env
+
+    def reset(self, **kw):
+        self._elapsed_steps = 0
+        return self.env.reset(**kw)
+
+    def step(self, action):
+        assert self._elapsed_steps is not None, "Cannot call env.step() before calling reset()"
+        obs, rew, done, info = self.env.step(action)
+        self._elapsed_steps += 1
+        if self._elapsed_steps >= self._max_episode_steps:
+            info['TimeLimit.truncated'] = not done
+            done = True
+        return obs, rew, done, info

@@ -1,0 +1,126 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the CPU oracle, same seeded inputs.
+
+Bars (BASELINE.json north_star): tile-visit flags / counts bit-exact, rewards bit-exact
+(float64, same accumulation order), car pose within 1e-4 relative after 1000 steps (in
+practice bit-exact: both sides run the same un-contracted fp32 operation sequence),
+observations bit-exact against the oracle rasteriser."""
+import numpy as np
+import pytest
+
+from helpers import action_tape, make_oracle_worlds, gpu_state, oracle_state, visited_bits
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(oracle, mcr, B, A, seed, directions=None, **kw):
+    tracks, orders = [], []
+    rs = np.random.RandomState(1000 + seed)
+    for e in range(B):
+        tr, _ = oracle.generate_track(np.random.RandomState(seed * 100 + e))
+        tracks.append(tr)
+        orders.append(rs.permutation(A))
+    if directions is None:
+        directions = ['CW' if rs.uniform() < 0.5 else 'CCW' for _ in range(B)]
+    venv = mcr.BatchedMultiCarRacing(B, num_agents=A, auto_reset=False, max_episode_steps=0, **kw)
+    obs0 = venv.reset(tracks=tracks, car_orders=orders, directions=directions).cpu().numpy()
+    okw = dict(h_ratio=kw.get("h_ratio", 0.25), backwards_flag=kw.get("backwards_flag", True),
+               use_ego_color=kw.get("use_ego_color", False))
+    worlds = make_oracle_worlds(oracle, tracks, orders, directions, A, **okw)
+    oobs0 = np.stack([w.step(None)[0] for w in worlds])
+    return venv, worlds, tracks, obs0, oobs0
+
+
+def _compare_state(venv, worlds, tracks, step, exact=True):
+    g, o = gpu_state(venv), oracle_state(worlds)
+    A = venv.num_agents
+    for e, tr in enumerate(tracks):
+        assert np.array_equal(visited_bits(g["visited"][e], tr.T, A), o["visited"][e]), "visited flags, step %d env %d" % (step, e)
+        assert np.array_equal(g["touched"][e][:tr.T], o["touched"][e]), "tile colour flags, step %d env %d" % (step, e)
+    assert np.array_equal(g["counts"], o["counts"]), "tile_visited_count, step %d" % step
+    assert np.array_equal(g["reward"], o["reward"]), "reward (float64, bit-exact), step %d" % step
+    assert np.array_equal(g["backward"], o["backward"]), "driving_backward, step %d" % step
+    if exact:
+        for k in ("bodies", "wheels", "joints"):
+            assert np.array_equal(g[k], o[k]), "%s differ at step %d: max abs %g" % (k, step, np.abs(g[k].astype(np.float64) - o[k]).max())
+    else:
+        pose_g, pose_o = g["bodies"][..., :3].astype(np.float64), o["bodies"][..., :3].astype(np.float64)
+        rel = np.abs(pose_g - pose_o) / np.maximum(np.abs(pose_o), 1.0)
+        assert rel.max() <= 1e-4, "pose relative error %g > 1e-4 at step %d" % (rel.max(), step)
+
+
+def test_reset_matches_oracle(oracle, mcr):
+    venv, worlds, tracks, obs0, oobs0 = _setup(oracle, mcr, B=3, A=2, seed=1)
+    _compare_state(venv, worlds, tracks, -1)
+    assert np.array_equal(obs0, oobs0)
+    assert venv.status().tolist() == [0, 0, 0, 0]
+
+
+@pytest.mark.parametrize("A,B,seed", [(1, 2, 2), (2, 4, 3), (4, 2, 4)])
+def test_step_parity_300(oracle, mcr, A, B, seed):
+    import torch
+    venv, worlds, tracks, obs0, oobs0 = _setup(oracle, mcr, B=B, A=A, seed=seed)
+    tape = action_tape(seed, 300, B, A)
+    for s in range(300):
+        obs, rew, done, _ = venv.step(torch.from_numpy(tape[s]).to(venv.device))
+        oo = [w.step(tape[s, e].astype(np.float64)) for e, w in enumerate(worlds)]
+        assert np.array_equal(rew.cpu().numpy(), np.stack([x[1] for x in oo])), "step_reward, step %d" % s
+        assert np.array_equal(done.cpu().numpy() & 1, np.array([x[2] for x in oo], np.uint8)), "done, step %d" % s
+        if s % 10 == 0 or s > 290:
+            _compare_state(venv, worlds, tracks, s)
+            assert np.array_equal(obs.cpu().numpy(), np.stack([x[0] for x in oo])), "observation pixels, step %d" % s
+    assert venv.status().tolist() == [0, 0, 0, 0]
+
+
+def test_pose_after_1000_steps(oracle, mcr):
+    """north_star: tile visits + rewards bit-exact and pose within 1e-4 relative after 1000 steps."""
+    import torch
+    B, A = 8, 2
+    venv, worlds, tracks, _, _ = _setup(oracle, mcr, B=B, A=A, seed=7)
+    tape = action_tape(7, 1000, B, A, brake_p=0.1)
+    total_g = np.zeros((B, A)); total_o = np.zeros((B, A))
+    for s in range(1000):
+        obs, rew, done, _ = venv.step(torch.from_numpy(tape[s]).to(venv.device))
+        total_g += rew.cpu().numpy()
+        for e, w in enumerate(worlds):
+            total_o[e] += w.step(tape[s, e].astype(np.float64), render=False)[1]
+    assert np.array_equal(total_g, total_o)
+    _compare_state(venv, worlds, tracks, 1000, exact=False)
+    _compare_state(venv, worlds, tracks, 1000, exact=True)
+
+
+@pytest.mark.parametrize("kw", [dict(use_ego_color=True), dict(h_ratio=0.5, backwards_flag=False)])
+def test_render_options(oracle, mcr, kw):
+    import torch
+    venv, worlds, tracks, obs0, oobs0 = _setup(oracle, mcr, B=2, A=3, seed=11, **kw)
+    assert np.array_equal(obs0, oobs0)
+    tape = action_tape(11, 80, 2, 3)
+    for s in range(80):
+        obs, _, _, _ = venv.step(torch.from_numpy(tape[s]).to(venv.device))
+        oo = [w.step(tape[s, e].astype(np.float64)) for e, w in enumerate(worlds)]
+        if s % 8 == 0:
+            assert np.array_equal(obs.cpu().numpy(), np.stack([x[0] for x in oo])), "pixels, step %d" % s
+
+
+def test_single_env_dropin_matches_oracle_env(oracle, mcr):
+    """The reference-shaped API end to end: same seeds -> same tracks, spawn, rewards, frames."""
+    np.random.seed(5)
+    ref = oracle.OracleMultiCarRacing(num_agents=2, verbose=0)
+    ref.seed(42)
+    o0 = ref.reset()
+    np.random.seed(5)
+    env = mcr.MultiCarRacing(num_agents=2, verbose=0)
+    assert env.seed(42) == [42]
+    g0 = env.reset()
+    assert g0.shape == (2, 96, 96, 3) and g0.dtype == np.uint8
+    assert np.array_equal(g0, o0)
+    assert env.episode_direction == ref.episode_direction
+    assert len(env.track) == len(ref.track)
+    rs = np.random.RandomState(9)
+    for s in range(60):
+        a = np.stack([rs.uniform(-1, 1, 2), rs.uniform(0, 1, 2), np.zeros(2)], 1)
+        go, gr, gd, gi = env.step(a)
+        oo, orr, od, _ = ref.step(a)
+        assert gr.dtype == np.float64 and gr.shape == (2,) and gi == {} and isinstance(gd, bool)
+        assert np.array_equal(gr, orr) and gd == od
+        assert np.array_equal(go, oo), "pixels at step %d" % s
+    assert env.tile_visited_count == [int(v) for v in ref.tile_visited_count]
