@@ -30,13 +30,15 @@
 #define LIST_CAP 384
 #define MASK_WORDS (LIST_CAP / 32)
 #define SPAN_POOL 4096
+#define N_CHECKER 400   // range(-20, 20, 2) squared
 #define SW MCR_STATE_W
 #define SH MCR_STATE_H
 
+// initial values are documentation; launch_render overwrites them with mcr_host_palette()
 __constant__ uint8_t c_palette[PAL_COUNT][4] = {
     {0, 0, 0, 0},       // PAL_BLACK
     {102, 204, 102, 0}, // PAL_GRASS        (0.4, 0.8, 0.4)
-    {102, 229, 102, 0}, // PAL_GRASS_LIGHT  (0.4, 0.9, 0.4)
+    {102, 230, 102, 0}, // PAL_GRASS_LIGHT  (0.4, 0.9, 0.4): 0.9f*255 = 229.5 in fp32 -> 230
     {102, 102, 102, 0}, // PAL_ROAD0        0.40
     {105, 105, 105, 0}, // PAL_ROAD1        0.41
     {107, 107, 107, 0}, // PAL_ROAD2        0.42
@@ -51,9 +53,21 @@ __constant__ uint8_t c_palette[PAL_COUNT][4] = {
     {0, 0, 255, 0},     // PAL_FLAG_BLUE    c3B (0, 0, 255)
 };
 
+// Host copy of the palette, derived from the reference's float colours with the GL rule
+// u8 = floor(c * 255 + 0.5) evaluated in fp32; launch_render checks c_palette against it.
+static const float h_palette_f[PAL_COUNT][3] = {
+    {0, 0, 0}, {0.4f, 0.8f, 0.4f}, {0.4f, 0.9f, 0.4f}, {0.4f, 0.4f, 0.4f}, {0.41f, 0.41f, 0.41f}, {0.42f, 0.42f, 0.42f},
+    {1, 1, 1}, {1, 0, 0}, {0.3f, 0.3f, 0.3f},
+    {0.8f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.8f}, {0.0f, 0.8f, 0.0f}, {0.0f, 0.8f, 0.8f},
+    {0.8f, 0.8f, 0.8f}, {0.0f, 0.0f, 0.0f}, {0.8f, 0.0f, 0.8f}, {0.8f, 0.8f, 0.0f},
+    {0, 0, 1}, {0.2f, 0, 1}, {0, 1, 0}, {0, 0, 1}};
+
 const uint8_t (*mcr_host_palette())[4] {
     static uint8_t pal[PAL_COUNT][4];
-    cudaMemcpyFromSymbol(pal, c_palette, sizeof(pal));
+    for (int i = 0; i < PAL_COUNT; ++i) {
+        for (int c = 0; c < 3; ++c) pal[i][c] = (uint8_t)(int)floorf(h_palette_f[i][c] * 255.0f + 0.5f);
+        pal[i][3] = 0;
+    }
     return pal;
 }
 
@@ -110,16 +124,16 @@ __device__ int gen_candidate(int i, const View& V, const Affine& M, const CarCon
         col = PAL_GRASS; return 4;
     }
     i -= 1;
-    if (i < 100) {                                  // checker quads, mcr:620-627
+    if (i < N_CHECKER) {                            // 20 x 20 checker quads, mcr:620-627
         const double k = PLAYFIELD / 20.0;
-        const int x = -20 + 2 * (i / 10), y = -20 + 2 * (i % 10);
+        const int x = -20 + 2 * (i / 20), y = -20 + 2 * (i % 20);
         xf_pt(M, (float)(k * x + k), (float)(k * y + 0), px[0], py[0]);
         xf_pt(M, (float)(k * x + 0), (float)(k * y + 0), px[1], py[1]);
         xf_pt(M, (float)(k * x + 0), (float)(k * y + k), px[2], py[2]);
         xf_pt(M, (float)(k * x + k), (float)(k * y + k), px[3], py[3]);
         col = PAL_GRASS_LIGHT; return 4;
     }
-    i -= 100;
+    i -= N_CHECKER;
     if (i < V.Q) {                                  // road_poly, mcr:628-631
         const float4 a = *(const float4*)(V.quad + (size_t)i * 8);
         const float4 b = *(const float4*)(V.quad + (size_t)i * 8 + 4);
@@ -325,7 +339,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     const Affine M = S.M;
 
     // ---- candidates -> ordered display list -> flush -----------------------------------------
-    const int NC = 1 + 100 + Q + 12 * d.A + 9;
+    const int NC = 1 + N_CHECKER + Q + 12 * d.A + 9;
     int base = 0;
     while (base < NC) {
         const int i = base + tid;
@@ -484,6 +498,7 @@ int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const 
     static bool configured = false;
     const size_t smem = sizeof(RasterSmem);
     if (!configured) {
+        if (cudaMemcpyToSymbol(c_palette, mcr_host_palette(), sizeof(uint8_t) * PAL_COUNT * 4) != cudaSuccess) return -1;
         if (cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         configured = true;
     }
