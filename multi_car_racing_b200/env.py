@@ -233,6 +233,65 @@ class BatchedMultiCarRacing:
                                        self.done_out.data_ptr(), 1 if self.auto_reset else 0, self._stream()), "mcr_step")
         return self.obs, self.reward_out, self.done_out, {}
 
+    def step_host(self, action):
+        """The reference-facing call with HOST buffers: `action` is a (B, A, 3) float32/float64
+        numpy array (ideally a view of pinned memory, see host_buffers()); returns numpy views
+        of pinned host buffers (obs, reward, done) valid until the next call.  Host->device and
+        device->host copies and the synchronisation happen inside this call."""
+        torch = _torch()
+        B, A = self.batch_envs, self.num_agents
+        hb = self.host_buffers()
+        a = np.reshape(action, (B, A, 3))
+        if a.dtype == np.float64:
+            hb["action64"].numpy()[...] = a
+            src = hb["action64"]
+        else:
+            if a.ctypes.data != hb["action"].data_ptr():
+                hb["action"].numpy()[...] = a
+            src = hb["action"]
+        with torch.cuda.device(self.device):
+            dev_a = self._dev_action64 if src.dtype == torch.float64 else self._dev_action
+            dev_a.copy_(src, non_blocking=True)
+            self.step(dev_a)
+            hb["obs"].copy_(self.obs, non_blocking=True)
+            hb["reward"].copy_(self.reward_out, non_blocking=True)
+            hb["done"].copy_(self.done_out, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        return hb["obs"].numpy(), hb["reward"].numpy(), hb["done"].numpy(), {}
+
+    def host_buffers(self):
+        """Pinned host staging buffers of step_host (allocated on first use)."""
+        if getattr(self, "_host", None) is None:
+            torch = _torch()
+            B, A = self.batch_envs, self.num_agents
+            self._host = dict(
+                action=torch.zeros((B, A, 3), dtype=torch.float32).pin_memory(),
+                action64=torch.zeros((B, A, 3), dtype=torch.float64).pin_memory(),
+                obs=torch.zeros((B, A, STATE_H, STATE_W, 3), dtype=torch.uint8).pin_memory(),
+                reward=torch.zeros((B, A), dtype=torch.float64).pin_memory(),
+                done=torch.zeros((B,), dtype=torch.uint8).pin_memory())
+            self._dev_action = torch.zeros((B, A, 3), dtype=torch.float32, device=self.device)
+            self._dev_action64 = torch.zeros((B, A, 3), dtype=torch.float64, device=self.device)
+        return self._host
+
+    def step_split(self, action, events=None):
+        """mcr_step without auto reset, issued as its three kernels through the split entry
+        points; `events` (4 torch.cuda.Event) are recorded around them (bench.py's per-kernel
+        timing).  Identical results to step()."""
+        torch = _torch()
+        dt = _lib.MCR_F32 if action.dtype == torch.float32 else _lib.MCR_F64
+        st = self._stream()
+        cur = torch.cuda.current_stream(self.device)
+        if events: events[0].record(cur)
+        _lib.check(self.L.mcr_contacts(self._h, None, st), "mcr_contacts")
+        if events: events[1].record(cur)
+        _lib.check(self.L.mcr_physics(self._h, None, action.data_ptr(), dt, st), "mcr_physics")
+        if events: events[2].record(cur)
+        _lib.check(self.L.mcr_render(self._h, None, self.obs.data_ptr(), self.reward_out.data_ptr(),
+                                     self.done_out.data_ptr(), 1, st), "mcr_render")
+        if events: events[3].record(cur)
+        return self.obs, self.reward_out, self.done_out, {}
+
     def render(self, mode='state_pixels'):
         assert mode in ['human', 'state_pixels', 'rgb_array']
         if mode != 'state_pixels':
