@@ -16,7 +16,7 @@ MAX_AGENTS = 16
 EXPORTS = [
     "mcr_create", "mcr_destroy", "mcr_last_error", "mcr_abi_version", "mcr_buffer_count",
     "mcr_buffer_spec", "mcr_bind_buffer", "mcr_track_generate", "mcr_mt_seed", "mcr_spawn_poses",
-    "mcr_load_track", "mcr_reset", "mcr_step", "mcr_contacts", "mcr_physics", "mcr_render",
+    "mcr_load_track", "mcr_reset", "mcr_step", "mcr_simulate", "mcr_contacts", "mcr_physics", "mcr_render",
     "mcr_get_mass", "mcr_get_shape", "mcr_launch_count",
 ]
 
@@ -81,6 +81,8 @@ def load():
     L.mcr_contacts.argtypes = [vp, vp, vp]
     L.mcr_physics.restype = i32
     L.mcr_physics.argtypes = [vp, vp, vp, i32, vp]
+    L.mcr_simulate.restype = i32
+    L.mcr_simulate.argtypes = [vp, vp, vp, i32, vp]
     L.mcr_render.restype = i32
     L.mcr_render.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     L.mcr_get_mass.restype = i32

@@ -155,6 +155,8 @@ bool build_car_const(CarConst& cc) {
     for (int w = 0; w < 4; ++w) { cc.anchor_x[w] = (float)(kWHEELPOS[w][0] * kSIZE); cc.anchor_y[w] = (float)(kWHEELPOS[w][1] * kSIZE); }
     cc.max_motor_torque = (float)(180 * 900 * kSIZE * kSIZE);
     cc.lower = (float)-0.4; cc.upper = (float)+0.4;
+    // the sweep kernels have no e_equalLimits path (b2RevoluteJoint: |upper - lower| < 2 * angularSlop)
+    if (std::fabs(cc.upper - cc.lower) < 2.0f * B2_ANGULAR_SLOP) return false;
     return true;
 }
 
@@ -602,6 +604,13 @@ extern "C" int mcr_physics(mcr_handle h, const uint8_t* mask, const void* action
     return 0;
 }
 
+extern "C" int mcr_simulate(mcr_handle h, const uint8_t* mask, const void* action, int32_t action_dtype, void* stream) {
+    int rc = check_bound(h); if (rc) return rc;
+    if (action && action_dtype != MCR_F32 && action_dtype != MCR_F64) return fail(-1, "action dtype must be MCR_F32 or MCR_F64");
+    LAUNCH(launch_simulate(h->d, h->buf, h->cc, mask, action, action_dtype, h->cfg.h_ratio, stream));
+    return 0;
+}
+
 extern "C" int mcr_render(mcr_handle h, const uint8_t* mask, uint8_t* obs, double* reward, uint8_t* done, int32_t post_step, void* stream) {
     int rc = check_bound(h); if (rc) return rc;
     if (!obs) return fail(-1, "mcr_render: d_obs is null");
@@ -617,8 +626,7 @@ extern "C" int mcr_reset(mcr_handle h, const uint8_t* mask, const int32_t* track
     if (!track_slot || !cw || !spawn_pose || !obs) return fail(-1, "mcr_reset: null argument");
     LAUNCH(launch_spawn(h->d, h->buf, h->cc, mask, track_slot, cw, spawn_pose, stream));
     // the implicit step(None), mcr:408
-    LAUNCH(launch_contacts(h->d, h->buf, h->cc, mask, stream));
-    LAUNCH(launch_physics(h->d, h->buf, h->cc, mask, nullptr, MCR_F32, h->cfg.h_ratio, stream));
+    LAUNCH(launch_simulate(h->d, h->buf, h->cc, mask, nullptr, MCR_F32, h->cfg.h_ratio, stream));
     LAUNCH(launch_render(h->d, h->buf, h->cc, mask, obs, nullptr, nullptr, 0, h->cfg.backwards_flag,
                          h->cfg.use_ego_color, h->cfg.max_episode_steps, stream));
     return 0;
@@ -629,16 +637,14 @@ extern "C" int mcr_step(mcr_handle h, const void* action, int32_t action_dtype, 
     int rc = check_bound(h); if (rc) return rc;
     if (!action || !obs || !reward || !done) return fail(-1, "mcr_step: null argument");
     if (action_dtype != MCR_F32 && action_dtype != MCR_F64) return fail(-1, "action dtype must be MCR_F32 or MCR_F64");
-    LAUNCH(launch_contacts(h->d, h->buf, h->cc, nullptr, stream));
-    LAUNCH(launch_physics(h->d, h->buf, h->cc, nullptr, action, action_dtype, h->cfg.h_ratio, stream));
+    LAUNCH(launch_simulate(h->d, h->buf, h->cc, nullptr, action, action_dtype, h->cfg.h_ratio, stream));
     LAUNCH(launch_render(h->d, h->buf, h->cc, nullptr, obs, reward, done, 1, h->cfg.backwards_flag,
                          h->cfg.use_ego_color, h->cfg.max_episode_steps, stream));
     if (flags & 1) {
         AutoResetCfg ar{h->cfg.use_random_direction, h->cfg.direction_cw, (unsigned long long)h->cfg.seed};
         LAUNCH(launch_auto_reset(h->d, h->buf, h->cc, done, ar, stream));
         const uint8_t* m = h->buf.reset_mask;
-        LAUNCH(launch_contacts(h->d, h->buf, h->cc, m, stream));
-        LAUNCH(launch_physics(h->d, h->buf, h->cc, m, nullptr, MCR_F32, h->cfg.h_ratio, stream));
+        LAUNCH(launch_simulate(h->d, h->buf, h->cc, m, nullptr, MCR_F32, h->cfg.h_ratio, stream));
         LAUNCH(launch_render(h->d, h->buf, h->cc, m, obs, nullptr, nullptr, 0, h->cfg.backwards_flag,
                              h->cfg.use_ego_color, h->cfg.max_episode_steps, stream));
     }

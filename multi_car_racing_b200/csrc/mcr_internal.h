@@ -89,6 +89,8 @@ struct Dims { int B, A, N, Tmax, Qmax, P; };
 int launch_contacts(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, void* stream);
 int launch_physics(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
                    const void* action, int action_dtype, double h_ratio, void* stream);
+int launch_simulate(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
+                    const void* action, int action_dtype, double h_ratio, void* stream);
 int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* obs,
                   double* reward, uint8_t* done, int post_step, int backwards_flag,
                   int use_ego_color, int max_episode_steps, void* stream);

@@ -4,7 +4,7 @@
 //   mcr:511-604  render("state_pixels") / _render_window: camera from ego pose/velocity/t,
 //                glViewport(0,0,96,96) under glOrtho(0,1000,0,800), colour-buffer read-back,
 //                row flip, alpha drop
-//   mcr:613-632  render_road (playfield quad, 100 checker quads, road + border quads)
+//   mcr:613-632  render_road (playfield quad, 20x20 checker quads, road + border quads)
 //   gym Car.draw (wheels, wheel stripes from phase, 4 hull fixtures), all cars in every view
 //   mcr:634-674  render_indicators (HUD bar, 7 indicator quads, score, backward flag)
 //   mcr:433-507  reward -= 0.1, step_reward, driving_backward, done / out-of-field (post_step)
@@ -12,27 +12,33 @@
 // spans, every edge evaluated from its lower to its upper endpoint (shared edges are
 // watertight and bit-reproducible); painter's order is the reference's draw order.
 //
-// Mapping: one CTA (256 threads) per agent-frame.
-//   1. candidate polygons are generated one per thread in painter's order, projected with the
-//      fp32 affine camera, culled against the 96x96 viewport and compacted IN ORDER into a
-//      shared-memory display list (block scan);
-//   2. span generation: warp per polygon, lane per row -> (x0,x1) byte pairs in a shared span
-//      pool + a per-row polygon bitmask;
-//   3. fill: warp per row walks that row's bitmask top-down with early exit once all 96 pixels
-//      are resolved, writing 1-byte palette indices into a 96x96 shared tile;
-//   4. the tile is expanded to RGB and written to HBM with 16-byte vector stores (1728 uint4
-//      per frame) -- the only HBM traffic that scales with the frame count.
+// Mapping: one CTA of 288 threads (= 96 rows x 3 segments of 32 pixels) per agent-frame.
+//   1. candidates: one polygon per thread in painter's order (checker squares are enumerated
+//      only over the index range the camera can see), projected with the fp32 affine camera,
+//      culled against the viewport and compacted IN ORDER (block scan) into a shared-memory
+//      display list of canonical edges (lower endpoint, upper y, slope) -- the one IEEE
+//      division per edge is paid once per polygon, not once per row;
+//   2. spans: one thread per (polygon,row) slot (binary search slot -> polygon) writes the
+//      half-open pixel span [x0,x1) into a shared pool and sets the polygon's bit in the row's
+//      bitmask;
+//   3. fill: one thread per (row, 32-pixel segment) walks the row's bitmask top-most polygon
+//      first with a 32-bit "still uncovered" mask, so every pixel is written exactly once and
+//      the walk stops as soon as the segment is resolved;
+//   4. the palette-index tile is expanded to RGB and stored with 16-byte vector stores
+//      (1728 uint4 per frame) -- the only HBM traffic that scales with the frame count.
 #include "mcr_internal.h"
 #include <cuda_runtime.h>
 
-#define RS_THREADS 256
+#define RS_THREADS 288
 #define RS_WARPS (RS_THREADS / 32)
-#define LIST_CAP 384
+#define LIST_CAP 256
 #define MASK_WORDS (LIST_CAP / 32)
 #define SPAN_POOL 4096
-#define N_CHECKER 400   // range(-20, 20, 2) squared
+#define N_CHECKER_AXIS 20   // range(-20, 20, 2)
+#define CAR_PARTS 12        // 4 x (wheel, stripe) + 4 hull fixtures
 #define SW MCR_STATE_W
 #define SH MCR_STATE_H
+#define IMG_STRIDE 104      // bytes per tile row: 26 words -> rows land in different banks
 
 // initial values are documentation; launch_render overwrites them with mcr_host_palette()
 __constant__ uint8_t c_palette[PAL_COUNT][4] = {
@@ -54,7 +60,7 @@ __constant__ uint8_t c_palette[PAL_COUNT][4] = {
 };
 
 // Host copy of the palette, derived from the reference's float colours with the GL rule
-// u8 = floor(c * 255 + 0.5) evaluated in fp32; launch_render checks c_palette against it.
+// u8 = floor(c * 255 + 0.5) evaluated in fp32; launch_render uploads it into c_palette.
 static const float h_palette_f[PAL_COUNT][3] = {
     {0, 0, 0}, {0.4f, 0.8f, 0.4f}, {0.4f, 0.9f, 0.4f}, {0.4f, 0.4f, 0.4f}, {0.41f, 0.41f, 0.41f}, {0.42f, 0.42f, 0.42f},
     {1, 1, 1}, {1, 0, 0}, {0.3f, 0.3f, 0.3f},
@@ -79,31 +85,37 @@ __constant__ uint8_t c_font[11][5] = {
 
 struct Affine { float m00, m01, m02, m10, m11, m12; };
 
+// One display-list entry = 4 canonical edges.  The hull octagon takes two consecutive
+// entries (ne = 8 on the first, a row-less continuation after it).
 struct __align__(16) RasterSmem {
-    float vx[MCR_MAXV][LIST_CAP];
-    float vy[MCR_MAXV][LIST_CAP];
-    uint16_t off[LIST_CAP];
-    uint8_t n[LIST_CAP], col[LIST_CAP], y0[LIST_CAP], y1[LIST_CAP];
+    float e_ax[4][LIST_CAP];      // x at the lower endpoint
+    float e_ay[4][LIST_CAP];      // y of the lower endpoint (+inf: unused / horizontal edge)
+    float e_by[4][LIST_CAP];      // y of the upper endpoint
+    float e_sl[4][LIST_CAP];      // (bx - ax) / (by - ay)
+    int base[LIST_CAP];           // span pool offset of viewport row 0 of this polygon: off - y0
+    uint16_t off[LIST_CAP];       // first span slot (continuations: the next polygon's)
+    uint8_t ne[LIST_CAP], col[LIST_CAP];
     uchar2 span[SPAN_POOL];
     uint32_t rowmask[SH][MASK_WORDS];
-    uint8_t img[SH * SW];            // palette indices, row 0 = TOP row of the observation
+    uint8_t img[SH * IMG_STRIDE];  // palette indices, row 0 = TOP row of the observation
     Affine M;
     int list_count, pool_count, first_bad;
+    int ck_j0x, ck_nx, ck_j0y, ck_ny;   // visible checker index range
     int warp_cnt[RS_WARPS], warp_rows[RS_WARPS];
     double red_d[RS_WARPS]; int red_i[RS_WARPS];
-    char glyph[4];
+    signed char glyph[4];
     uint32_t pal32[32];
 };
 
-__device__ __forceinline__ double sign_d(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : 0.0); }
 __device__ __forceinline__ double py_mod(double a, double m) {
     double r = fmod(a, m);
     if (r != 0 && ((r < 0) != (m < 0))) r += m;
     return r;
 }
 
-struct View {              // everything candidate generation needs, in registers/params
-    int env, agent, A, N, Q, slot;
+struct View {
+    int env, agent, A, N, Q;
+    int n_checker, ck_j0x, ck_j0y, ck_ny;
     const float* body; const double* wheel; const float* stripe;
     const float* quad; const uint8_t* quad_col; const int16_t* quad_tile; const uint8_t* touched;
     int use_ego_color, backward_flag_on;
@@ -114,8 +126,9 @@ __device__ __forceinline__ void xf_pt(const Affine& M, float x, float y, float& 
     oy = (M.m10 * x + M.m11 * y) + M.m12;
 }
 
-// Generate candidate polygon i (painter's order).  Returns vertex count (0 = nothing to draw).
-__device__ int gen_candidate(int i, const View& V, const Affine& M, const CarConst& cc, float* px, float* py, int& col) {
+// Candidate polygon i in painter's order.  Returns the vertex count (0 = nothing to draw).
+__device__ int gen_candidate(int i, const View& V, const Affine& M, const CarConst& cc, float (&px)[MCR_MAXV],
+                             float (&py)[MCR_MAXV], int& col) {
     const double PLAYFIELD = 2000 / 6.0;
     if (i == 0) {                                   // playfield, mcr:615-619
         const float pf = (float)PLAYFIELD;
@@ -124,16 +137,16 @@ __device__ int gen_candidate(int i, const View& V, const Affine& M, const CarCon
         col = PAL_GRASS; return 4;
     }
     i -= 1;
-    if (i < N_CHECKER) {                            // 20 x 20 checker quads, mcr:620-627
+    if (i < V.n_checker) {                          // checker quads that can be in view, mcr:620-627
         const double k = PLAYFIELD / 20.0;
-        const int x = -20 + 2 * (i / 20), y = -20 + 2 * (i % 20);
+        const int x = -20 + 2 * (V.ck_j0x + i / V.ck_ny), y = -20 + 2 * (V.ck_j0y + i % V.ck_ny);
         xf_pt(M, (float)(k * x + k), (float)(k * y + 0), px[0], py[0]);
         xf_pt(M, (float)(k * x + 0), (float)(k * y + 0), px[1], py[1]);
         xf_pt(M, (float)(k * x + 0), (float)(k * y + k), px[2], py[2]);
         xf_pt(M, (float)(k * x + k), (float)(k * y + k), px[3], py[3]);
         col = PAL_GRASS_LIGHT; return 4;
     }
-    i -= N_CHECKER;
+    i -= V.n_checker;
     if (i < V.Q) {                                  // road_poly, mcr:628-631
         const float4 a = *(const float4*)(V.quad + (size_t)i * 8);
         const float4 b = *(const float4*)(V.quad + (size_t)i * 8 + 4);
@@ -144,8 +157,8 @@ __device__ int gen_candidate(int i, const View& V, const Affine& M, const CarCon
         return 4;
     }
     i -= V.Q;
-    if (i < 12 * V.A) {                             // Car.draw for every car, mcr:559-564
-        const int c = i / 12, part = i % 12, car = V.env * V.A + c, N = V.N;
+    if (i < CAR_PARTS * V.A) {                      // Car.draw for every car, mcr:559-564
+        const int c = i / CAR_PARTS, part = i % CAR_PARTS, car = V.env * V.A + c, N = V.N;
         if (part < 8) {
             const int wl = part >> 1;
             const float* bp = V.body + (size_t)((1 + wl) * BODY_FIELDS) * N + car;
@@ -153,6 +166,7 @@ __device__ int gen_candidate(int i, const View& V, const Affine& M, const CarCon
             const float qs = bp[(size_t)BF_QS * N], qc = bp[(size_t)BF_QC * N];
             float lx[4], ly[4];
             if ((part & 1) == 0) {
+#pragma unroll
                 for (int k = 0; k < 4; ++k) { lx[k] = cc.wheel_poly.x[k]; ly[k] = cc.wheel_poly.y[k]; }
                 col = PAL_BLACK;
             } else {
@@ -160,11 +174,12 @@ __device__ int gen_candidate(int i, const View& V, const Affine& M, const CarCon
                 // (Car.draw: a1 = phase, a2 = phase + 1.2 ...); NaN = "not drawn this frame"
                 const float sy1 = V.stripe[(size_t)(wl * 2 + 0) * N + car], sy2 = V.stripe[(size_t)(wl * 2 + 1) * N + car];
                 if (sy1 != sy1) return 0;
-                const float hw = cc.wheel_poly.x[0] < 0 ? -cc.wheel_poly.x[0] : cc.wheel_poly.x[0];   // (float)(WHEEL_W*SIZE)
+                const float hw = fabsf(cc.wheel_poly.x[0]);            // (float)(WHEEL_W*SIZE)
                 lx[0] = -hw; ly[0] = sy1; lx[1] = +hw; ly[1] = sy1;
                 lx[2] = +hw; ly[2] = sy2; lx[3] = -hw; ly[3] = sy2;
                 col = PAL_WHEEL_WHITE;
             }
+#pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float wx = (qc * lx[k] - qs * ly[k]) + bx, wy = (qs * lx[k] + qc * ly[k]) + by;
                 xf_pt(M, wx, wy, px[k], py[k]);
@@ -176,16 +191,19 @@ __device__ int gen_candidate(int i, const View& V, const Affine& M, const CarCon
             const float bx = bp[(size_t)BF_PX * N], by = bp[(size_t)BF_PY * N];
             const float qs = bp[(size_t)BF_QS * N], qc = bp[(size_t)BF_QC * N];
             const Poly8& P = cc.hull_poly[f];
-            for (int k = 0; k < P.n; ++k) {
-                const float wx = (qc * P.x[k] - qs * P.y[k]) + bx, wy = (qs * P.x[k] + qc * P.y[k]) + by;
-                xf_pt(M, wx, wy, px[k], py[k]);
+#pragma unroll
+            for (int k = 0; k < MCR_MAXV; ++k) {
+                if (k < P.n) {
+                    const float wx = (qc * P.x[k] - qs * P.y[k]) + bx, wy = (qs * P.x[k] + qc * P.y[k]) + by;
+                    xf_pt(M, wx, wy, px[k], py[k]);
+                }
             }
             if (V.use_ego_color) col = (c == V.agent) ? PAL_CAR0 + 0 : PAL_CAR0 + 1;   // mcr:560-563
             else col = PAL_CAR0 + (c % 8);                                              // mcr:402
             return P.n;
         }
     }
-    i -= 12 * V.A;
+    i -= CAR_PARTS * V.A;
     {                                               // render_indicators, mcr:634-674
         const double Wd = 1000, Hd = 800, s = Wd / 40.0, h = Hd / 40.0;
         const int car = V.env * V.A + V.agent, N = V.N;
@@ -218,10 +236,12 @@ __device__ int gen_candidate(int i, const View& V, const Affine& M, const CarCon
             wx[2] = (place + val) * s; wy[2] = 2 * h; wx[3] = (place + 0) * s;   wy[3] = 2 * h;
         } else {
             if (!V.backward_flag_on) return 0;
-            wx[0] = Wd - 100; wy[0] = 30; wx[1] = Wd - 75; wy[1] = 70; wx[2] = Wd - 50; wy[2] = 30; n = 3;
+            wx[0] = Wd - 100; wy[0] = 30; wx[1] = Wd - 75; wy[1] = 70; wx[2] = Wd - 50; wy[2] = 30;
+            wx[3] = 0; wy[3] = 0; n = 3;
             col = PAL_FLAG_BLUE;
         }
-        for (int k = 0; k < n; ++k) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
             px[k] = (float)wx[k] * (float)(96.0 / 1000.0);
             py[k] = (float)wy[k] * (float)(96.0 / 800.0);
         }
@@ -229,60 +249,75 @@ __device__ int gen_candidate(int i, const View& V, const Affine& M, const CarCon
     }
 }
 
+// Evaluate one canonical edge on the row through yc; identical arithmetic to the CPU
+// restatement: x = ax + (yc - ay) * ((bx - ax) / (by - ay)), edge taken lower -> upper.
+__device__ __forceinline__ void edge_row(const RasterSmem& S, int e, int p, float yc, float& xl, float& xr) {
+    const float ay = S.e_ay[e][p];
+    if (yc >= ay && yc < S.e_by[e][p]) {
+        const float x = S.e_ax[e][p] + (yc - ay) * S.e_sl[e][p];
+        xl = fminf(xl, x); xr = fmaxf(xr, x);
+    }
+}
+
 __device__ void flush_list(RasterSmem& S, int tid) {
-    const int warp = tid >> 5, lane = tid & 31;
     __syncthreads();
-    const int n = S.list_count;
-    // ---- span generation: warp per polygon, lane per row ---------------------------------
-    for (int p = warp; p < n; p += RS_WARPS) {
-        const int nv = S.n[p], y0 = S.y0[p], y1 = S.y1[p], off = S.off[p];
-        for (int y = y0 + lane; y < y1; y += 32) {
-            const float yc = (float)y + 0.5f;
-            float xl = 3.402823466e+38f, xr = -3.402823466e+38f;
-            for (int i = 0; i < nv; ++i) {
-                const int k = i + 1 < nv ? i + 1 : 0;
-                float ax = S.vx[i][p], ay = S.vy[i][p], bx = S.vx[k][p], by = S.vy[k][p];
-                if (ay == by) continue;
-                if (ay > by) { float t = ax; ax = bx; bx = t; t = ay; ay = by; by = t; }
-                if (!(yc >= ay && yc < by)) continue;
-                const float x = ax + (yc - ay) * ((bx - ax) / (by - ay));
-                xl = fminf(xl, x); xr = fmaxf(xr, x);
-            }
-            int x0 = 0, x1 = 0;
-            if (xl < xr) {
-                xl = fminf(fmaxf(xl, -1.0f), (float)SW + 1.0f);
-                xr = fminf(fmaxf(xr, -1.0f), (float)SW + 1.0f);
-                x0 = (int)ceilf(xl - 0.5f); if (x0 < 0) x0 = 0;
-                x1 = (int)ceilf(xr - 0.5f); if (x1 > SW) x1 = SW;
-            }
-            S.span[off + (y - y0)] = make_uchar2((unsigned char)x0, (unsigned char)x1);
-            if (x0 < x1) atomicOr(&S.rowmask[y][p >> 5], 1u << (p & 31));
+    const int n = S.list_count, nslots = S.pool_count;
+    // ---- spans: one thread per (polygon,row) slot ---------------------------------------------
+    for (int s = tid; s < nslots; s += RS_THREADS) {
+        int lo = 0, hi = n - 1;                    // last p with off[p] <= s
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((int)S.off[mid] <= s) lo = mid; else hi = mid - 1;
         }
+        const int p = lo;
+        const int row = s - S.base[p];
+        const float yc = (float)row + 0.5f;
+        float xl = 3.402823466e+38f, xr = -3.402823466e+38f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) edge_row(S, e, p, yc, xl, xr);
+        if (S.ne[p] == 8) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) edge_row(S, e, p + 1, yc, xl, xr);
+        }
+        int x0 = 0, x1 = 0;
+        if (xl < xr) {
+            xl = fminf(fmaxf(xl, -1.0f), (float)SW + 1.0f);
+            xr = fminf(fmaxf(xr, -1.0f), (float)SW + 1.0f);
+            x0 = (int)ceilf(xl - 0.5f); if (x0 < 0) x0 = 0;
+            x1 = (int)ceilf(xr - 0.5f); if (x1 > SW) x1 = SW;
+        }
+        S.span[s] = make_uchar2((unsigned char)x0, (unsigned char)x1);
+        if (x0 < x1) atomicOr(&S.rowmask[row][p >> 5], 1u << (p & 31));
     }
     __syncthreads();
-    // ---- fill: warp per row, top-most polygon first, early exit when the row is resolved ----
-    for (int y = warp; y < SH; y += RS_WARPS) {
-        int c0 = -1, c1 = -1, c2 = -1;
-        const int xb = lane * 3;
-        bool row_done = false;
-        for (int wd = MASK_WORDS - 1; wd >= 0 && !row_done; --wd) {
+    // ---- fill: one thread per (row, 32-pixel segment), top-most polygon first ------------------
+    {
+        const int y = tid / 3, seg = tid - 3 * y;
+        const int xs = 32 * seg;
+        uint32_t uncovered = 0xffffffffu;
+        uint8_t* out = S.img + (SH - 1 - y) * IMG_STRIDE + xs;   // GL row y -> observation row 95 - y, mcr:602
+        for (int wd = MASK_WORDS - 1; wd >= 0 && uncovered; --wd) {
             uint32_t m = S.rowmask[y][wd];
-            while (m) {
+            while (m && uncovered) {
                 const int bit = 31 - __clz(m);
                 m &= ~(1u << bit);
                 const int p = wd * 32 + bit;
-                const uchar2 sp = S.span[S.off[p] + (y - S.y0[p])];
-                const int col = S.col[p];
-                if (c0 < 0 && xb + 0 >= sp.x && xb + 0 < sp.y) c0 = col;
-                if (c1 < 0 && xb + 1 >= sp.x && xb + 1 < sp.y) c1 = col;
-                if (c2 < 0 && xb + 2 >= sp.x && xb + 2 < sp.y) c2 = col;
-                if (__all_sync(0xffffffffu, (c0 | c1 | c2) >= 0)) { row_done = true; break; }
+                const uchar2 sp = S.span[S.base[p] + y];
+                int lo = (int)sp.x - xs, hi = (int)sp.y - xs;
+                lo = lo < 0 ? 0 : lo; hi = hi > 32 ? 32 : hi;
+                if (hi > lo) {
+                    const uint32_t cover = (uint32_t)((1ull << hi) - (1ull << lo));
+                    uint32_t fresh = cover & uncovered;
+                    uncovered &= ~cover;
+                    const uint8_t c = S.col[p];
+                    while (fresh) {
+                        const int i = __ffs(fresh) - 1;
+                        fresh &= fresh - 1;
+                        out[i] = c;
+                    }
+                }
             }
         }
-        uint8_t* row = S.img + (SH - 1 - y) * SW + xb;   // GL row y -> observation row 95 - y, mcr:602
-        if (c0 >= 0) row[0] = (uint8_t)c0;
-        if (c1 >= 0) row[1] = (uint8_t)c1;
-        if (c2 >= 0) row[2] = (uint8_t)c2;
     }
     __syncthreads();
     for (int i = tid; i < SH * MASK_WORDS; i += RS_THREADS) (&S.rowmask[0][0])[i] = 0;
@@ -306,29 +341,60 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
 
     // ---- camera (mcr:540-556) was evaluated by the physics kernel for this car ---------------
     if (tid < 6) (&S.M.m00)[tid] = b.camera[(size_t)tid * N + car];
-    if (tid < PAL_COUNT) S.pal32[tid] = (uint32_t)c_palette[tid][0] | ((uint32_t)c_palette[tid][1] << 8) | ((uint32_t)c_palette[tid][2] << 16);
-    if (tid == 0) {
+    if (tid >= 32 && tid < 32 + PAL_COUNT) {
+        const int i = tid - 32;
+        S.pal32[i] = (uint32_t)c_palette[i][0] | ((uint32_t)c_palette[i][1] << 8) | ((uint32_t)c_palette[i][2] << 16);
+    }
+    if (tid == 64) {
         S.list_count = 0; S.pool_count = 0;
         // score label "%04i" % reward  (mcr:665; drawn before reward -= 0.1)
         const double rw = b.reward[car];
         int val = (int)rw;
         const bool neg = rw < 0 && val != 0;
         int mag = val < 0 ? -val : val;
-        char digs[12]; int nd = 0;
-        do { digs[nd++] = (char)(mag % 10); mag /= 10; } while (mag > 0);
-        char buf[16]; int len = 0;
+        signed char digs[12]; int nd = 0;
+        do { digs[nd++] = (signed char)(mag % 10); mag /= 10; } while (mag > 0);
+        signed char buf[16]; int len = 0;
         const int width = nd + (neg ? 1 : 0), pad = width < 4 ? 4 - width : 0;
         if (neg) buf[len++] = 10;
         for (int i = 0; i < pad; ++i) buf[len++] = 0;
         for (int i = nd - 1; i >= 0; --i) buf[len++] = digs[i];
-        for (int i = 0; i < 4; ++i) S.glyph[i] = i < len ? buf[i] : (char)-1;
+        for (int i = 0; i < 4; ++i) S.glyph[i] = i < len ? buf[i] : (signed char)-1;
     }
-    for (int i = tid; i < SH * SW / 4; i += RS_THREADS) ((uint32_t*)S.img)[i] = 0;   // glClear -> black
+    if (tid == 96) {
+        // Checker squares the camera can see: invert the affine for the four viewport corners
+        // (+ a one-unit margin, far above fp32 error) and keep the index ranges that overlap.
+        const double m00 = b.camera[(size_t)0 * N + car], m01 = b.camera[(size_t)1 * N + car], m02 = b.camera[(size_t)2 * N + car];
+        const double m10 = b.camera[(size_t)3 * N + car], m11 = b.camera[(size_t)4 * N + car], m12 = b.camera[(size_t)5 * N + car];
+        const double det = m00 * m11 - m01 * m10;
+        int j0x = 0, j1x = N_CHECKER_AXIS - 1, j0y = 0, j1y = N_CHECKER_AXIS - 1;
+        if (fabs(det) > 1e-12) {
+            double wxmin = 1e300, wxmax = -1e300, wymin = 1e300, wymax = -1e300;
+            for (int cnr = 0; cnr < 4; ++cnr) {
+                const double u = ((cnr & 1) ? (double)SW : 0.0) - m02, v = ((cnr & 2) ? (double)SH : 0.0) - m12;
+                const double wx = (m11 * u - m01 * v) / det, wy = (-m10 * u + m00 * v) / det;
+                wxmin = fmin(wxmin, wx); wxmax = fmax(wxmax, wx); wymin = fmin(wymin, wy); wymax = fmax(wymax, wy);
+            }
+            const double k = (2000 / 6.0) / 20.0, margin = 1.0;
+            // square j spans k*(2j-20) .. k*(2j-19) on its axis
+            const double a0 = floor(((wxmin - margin) / k + 19.0) / 2.0 - 1e-9), a1 = ceil(((wxmax + margin) / k + 20.0) / 2.0 + 1e-9);
+            const double c0 = floor(((wymin - margin) / k + 19.0) / 2.0 - 1e-9), c1 = ceil(((wymax + margin) / k + 20.0) / 2.0 + 1e-9);
+            if (a0 == a0 && a1 == a1 && c0 == c0 && c1 == c1) {
+                j0x = (int)fmax(0.0, fmin(a0, 20.0)); j1x = (int)fmin((double)(N_CHECKER_AXIS - 1), fmax(a1, -1.0));
+                j0y = (int)fmax(0.0, fmin(c0, 20.0)); j1y = (int)fmin((double)(N_CHECKER_AXIS - 1), fmax(c1, -1.0));
+            }
+        }
+        S.ck_j0x = j0x; S.ck_nx = j1x >= j0x ? j1x - j0x + 1 : 0;
+        S.ck_j0y = j0y; S.ck_ny = j1y >= j0y ? j1y - j0y + 1 : 0;
+    }
+    for (int i = tid; i < SH * IMG_STRIDE / 4; i += RS_THREADS) ((uint32_t*)S.img)[i] = 0;   // glClear -> black
     for (int i = tid; i < SH * MASK_WORDS; i += RS_THREADS) (&S.rowmask[0][0])[i] = 0;
     __syncthreads();
 
     View V;
-    V.env = env; V.agent = agent; V.A = d.A; V.N = N; V.Q = Q; V.slot = slot;
+    V.env = env; V.agent = agent; V.A = d.A; V.N = N; V.Q = Q;
+    V.ck_j0x = S.ck_j0x; V.ck_j0y = S.ck_j0y; V.ck_ny = S.ck_ny > 0 ? S.ck_ny : 1;
+    V.n_checker = S.ck_nx * S.ck_ny;
     V.body = b.body; V.wheel = b.wheel; V.stripe = b.stripe;
     V.quad = b.trk_quad + (size_t)slot * d.Qmax * 8;
     V.quad_col = b.trk_quad_col + (size_t)slot * d.Qmax;
@@ -339,7 +405,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     const Affine M = S.M;
 
     // ---- candidates -> ordered display list -> flush -----------------------------------------
-    const int NC = 1 + N_CHECKER + Q + 12 * d.A + 9;
+    const int NC = 1 + V.n_checker + Q + CAR_PARTS * d.A + 9;
     int base = 0;
     while (base < NC) {
         const int i = base + tid;
@@ -349,9 +415,12 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
         bool valid = nv >= 3;
         if (valid) {
             float ymin = py[0], ymax = py[0], xmin = px[0], xmax = px[0];
-            for (int k = 1; k < nv; ++k) {
-                ymin = fminf(ymin, py[k]); ymax = fmaxf(ymax, py[k]);
-                xmin = fminf(xmin, px[k]); xmax = fmaxf(xmax, px[k]);
+#pragma unroll
+            for (int k = 1; k < MCR_MAXV; ++k) {
+                if (k < nv) {
+                    ymin = fminf(ymin, py[k]); ymax = fmaxf(ymax, py[k]);
+                    xmin = fminf(xmin, px[k]); xmax = fmaxf(xmax, px[k]);
+                }
             }
             if (!(ymax > 0.0f) || !(ymin < (float)SH) || !(xmax > 0.0f) || !(xmin < (float)SW)) valid = false;
             else {
@@ -361,8 +430,9 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
             }
         }
         const int rows = valid ? y1 - y0 : 0;
-        // block-wide exclusive scan of (valid, rows)
-        int cnt_inc = valid ? 1 : 0, rows_inc = rows;
+        const int ents = valid ? (nv > 4 ? 2 : 1) : 0;
+        // block-wide exclusive scan of (entries, rows)
+        int cnt_inc = ents, rows_inc = rows;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int a = __shfl_up_sync(0xffffffffu, cnt_inc, o), r = __shfl_up_sync(0xffffffffu, rows_inc, o);
@@ -375,34 +445,47 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
 #pragma unroll
         for (int wq = 0; wq < RS_WARPS; ++wq)
             if (wq < warp) { cnt_before += S.warp_cnt[wq]; rows_before += S.warp_rows[wq]; }
-        const int slot_rel = cnt_before + cnt_inc - (valid ? 1 : 0);
+        const int slot_rel = cnt_before + cnt_inc - ents;
         const int row_rel = rows_before + rows_inc - rows;
         const int lc = S.list_count, pc = S.pool_count;
-        const bool fits = (lc + slot_rel < LIST_CAP) && (pc + row_rel + rows <= SPAN_POOL);
+        const bool fits = (lc + slot_rel + ents <= LIST_CAP) && (pc + row_rel + rows <= SPAN_POOL);
         if (valid && !fits) atomicMin(&S.first_bad, tid);
         __syncthreads();
         const int first_bad = S.first_bad;
         if (valid && tid < first_bad) {
             const int sl = lc + slot_rel;
-            for (int k = 0; k < nv; ++k) { S.vx[k][sl] = px[k]; S.vy[k][sl] = py[k]; }
-            S.n[sl] = (uint8_t)nv; S.col[sl] = (uint8_t)col; S.y0[sl] = (uint8_t)y0; S.y1[sl] = (uint8_t)y1;
-            S.off[sl] = (uint16_t)(pc + row_rel);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            // totals of the accepted prefix
-            int acc_cnt = 0, acc_rows = 0;
-            if (first_bad == RS_THREADS) {
-                for (int wq = 0; wq < RS_WARPS; ++wq) { acc_cnt += S.warp_cnt[wq]; acc_rows += S.warp_rows[wq]; }
-                S.list_count = lc + acc_cnt; S.pool_count = pc + acc_rows;
+            // canonical edges: lower endpoint first, slope hoisted out of the row loop
+#pragma unroll
+            for (int k = 0; k < MCR_MAXV; ++k) {
+                if (k < 4 || nv > 4) {
+                    const int k2 = (k + 1 < nv) ? k + 1 : 0;
+                    float ax = px[k], ay = py[k], bx = px[k2], by = py[k2];
+                    const int ent = sl + (k >> 2), e = k & 3;
+                    if (k >= nv || ay == by) {
+                        S.e_ay[e][ent] = 3.402823466e+38f; S.e_by[e][ent] = 3.402823466e+38f;
+                        S.e_ax[e][ent] = 0.0f; S.e_sl[e][ent] = 0.0f;
+                    } else {
+                        if (ay > by) { float t = ax; ax = bx; bx = t; t = ay; ay = by; by = t; }
+                        S.e_ax[e][ent] = ax; S.e_ay[e][ent] = ay; S.e_by[e][ent] = by;
+                        S.e_sl[e][ent] = (bx - ax) / (by - ay);
+                    }
+                }
+            }
+            S.ne[sl] = (uint8_t)(nv > 4 ? 8 : 4); S.col[sl] = (uint8_t)col;
+            S.off[sl] = (uint16_t)(pc + row_rel); S.base[sl] = pc + row_rel - y0;
+            if (nv > 4) {   // row-less continuation entry: shares the NEXT polygon's first slot
+                S.ne[sl + 1] = 0; S.col[sl + 1] = (uint8_t)col;
+                S.off[sl + 1] = (uint16_t)(pc + row_rel + rows); S.base[sl + 1] = 0;
             }
         }
+        __syncthreads();
         if (first_bad < RS_THREADS) {
-            // the thread that did not fit publishes the accepted totals (its exclusive prefix)
+            // the first thread that did not fit publishes the accepted totals (its exclusive prefix)
             if (tid == first_bad) { S.list_count = lc + slot_rel; S.pool_count = pc + row_rel; }
             base += first_bad;
             flush_list(S, tid);
         } else {
+            if (tid == RS_THREADS - 1) { S.list_count = lc + slot_rel + ents; S.pool_count = pc + row_rel + rows; }
             base += RS_THREADS;
             __syncthreads();
         }
@@ -413,7 +496,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     if (tid < 60) {
         const int ch = tid / 15, ry = (tid % 15) / 3, rx = tid % 3;
         const int g = S.glyph[ch];
-        if (g >= 0 && (c_font[g][ry] & (4 >> rx))) S.img[(87 + ry) * SW + (2 + 3 * ch + rx)] = PAL_WHITE;
+        if (g >= 0 && (c_font[g][ry] & (4 >> rx))) S.img[(87 + ry) * IMG_STRIDE + (2 + 3 * ch + rx)] = PAL_WHITE;
     }
     __syncthreads();
 
@@ -422,8 +505,10 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     {
         uint4* dst = reinterpret_cast<uint4*>(obs + (size_t)frame * MCR_OBS_BYTES);
         for (int g = tid; g < SH * SW / 16; g += RS_THREADS) {
-            const uint4 idx4 = reinterpret_cast<const uint4*>(S.img)[g];
-            const uint32_t iw[4] = {idx4.x, idx4.y, idx4.z, idx4.w};
+            const int row = g / 6, c16 = g - 6 * row;
+            const uint2* src = reinterpret_cast<const uint2*>(S.img + row * IMG_STRIDE + c16 * 16);
+            const uint2 ia = src[0], ib = src[1];
+            const uint32_t iw[4] = {ia.x, ia.y, ib.x, ib.y};
             uint32_t o[12];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -466,7 +551,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
         const double PI = 3.141592653589793, PLAYFIELD = 2000 / 6.0;
         double reward = b.reward[car] - 0.1;                     // mcr:436
         double step_reward = reward - b.prev_reward[car];        // mcr:443
-        const double car_angle = b.heading[car];              // mcr:449-456, evaluated in the physics kernel
+        const double car_angle = b.heading[car];                 // mcr:449-456, evaluated in the physics kernel
         double desired = node[(size_t)besti * 3 + 0];
         if (b.env_cw[env]) desired += PI;
         desired = py_mod(desired + 2 * PI, 2 * PI);
@@ -478,7 +563,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
         b.reward[car] = reward;
         b.prev_reward[car] = reward;
         // done: ANY agent finished all tiles or left the playfield (evaluated identically by
-        // every agent's CTA of this env, so the plain store below is race-free in value)
+        // every agent's CTA of this env; only agent 0 stores it)
         uint8_t done = 0;
         for (int c = 0; c < d.A; ++c) {
             const int oc = env * d.A + c;

@@ -1,0 +1,775 @@
+// sim.cu -- kernels 1+2 fused per env: FrictionDetector/Collide on one warp, Car.step +
+// world.Step on another, one CTA per environment.
+//
+// Replaces, for every env of the batch (reference: gym_multi_car_racing/multi_car_racing.py):
+//   mcr:84-123   FrictionDetector.BeginContact/EndContact/_contact; Box2D b2Contact::Update for
+//                sensor fixtures: touching = b2TestOverlap = (GJK distance < rA + rB = 0.02),
+//                evaluated at the START of world.Step on the poses the previous step left
+//   mcr:421-424  car.steer(-a0) / car.gas(a1) / car.brake(a2)      (gym car_dynamics.Car)
+//   mcr:426-427  car.step(1/FPS)            -- fp64 tyre model on fp32 body state
+//   mcr:428      world.Step(1/FPS, 180, 60) -- b2Island::Solve specialised to the fixed
+//                topology {hull + 4 wheels + 4 revolute joints (limit + motor)}; island joint
+//                order [j3, j2, j1, j0]; sleeping; SynchronizeTransform.
+// Numerics: IEEE fp32, no FMA contraction (-fmad=false), same operation order as Box2D;
+// b2Rot::Set is (float)sin((double)a).  The wheel's local centre of mass and localAnchorB are
+// exactly 0 so every rB term of b2RevoluteJoint is an exact +-0 and is dropped.
+//
+// Mapping.  One CTA of (1 + A) warps per env.  Warps 1..A ("physics"): one car each; the 180
+// Gauss-Seidel sweeps are a serial dependency chain through the hull velocity (latency bound), so
+// a car's warp runs straight-line code specialised to its joints' limit pattern and leaves the
+// sweep loop as soon as the car has reached an exact fixed point.
+// warp 0 ("contacts"): builds the world-space fixture polygons in shared memory, strides the
+// tiles (coalesced float4 AABB loads), AABB-rejects against per-car then per-fixture boxes,
+// queues the surviving (tile, fixture) pairs, runs the exact overlap predicate one pair per
+// lane, and replays new visits in the contact-list order of a fresh b2World (tile descending,
+// car descending) so the float64 reward sums are bit-reproducible -- no racing atomicAdds.
+// Both read the step's start poses; a __syncthreads() orders the contact reads before the
+// physics stores.
+#include "mcr_internal.h"
+#include <cuda_runtime.h>
+
+#define AABB_MARGIN 0.05f
+#define FIX_STRIDE 21   // 8 x + 8 y + 4 aabb + (n | active<<8), odd stride spreads banks
+#define PAIRS_PER_CAR 128
+#define CANDS_PER_CAR 64
+
+enum { ROLE_CONTACTS = 1, ROLE_PHYSICS = 2 };
+
+__device__ __forceinline__ void rot_set(float a, float& s, float& c) {
+    double ds, dc;
+    sincos((double)a, &ds, &dc);
+    s = (float)ds; c = (float)dc;
+}
+__device__ __forceinline__ float clampf(float a, float lo, float hi) { return fmaxf(lo, fminf(a, hi)); }
+__device__ __forceinline__ double sign_d(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : 0.0); }
+
+struct JointC {            // per-step constants of one revolute joint
+    float rAx, rAy;
+    float k11, k12, k22;   // K.ex.x, K.ey.x (= K.ex.y), K.ey.y
+    float ezx, ezy, ezz;   // K.ez
+    float det22;           // 1/det of the 2x2 block (0 if singular)
+    float cfx, cfy, cfz;   // cross(K.ey, K.ez): row-independent part of b2Mat33::Solve33
+    float det33;           // 1/det of K (0 if singular)
+    float motorMass, motorSpeed;
+    int limit;
+};
+
+__device__ __forceinline__ void solve22(const JointC& J, float bx, float by, float& ox, float& oy) {
+    ox = J.det22 * (J.k22 * bx - J.k12 * by);
+    oy = J.det22 * (J.k11 * by - J.k12 * bx);
+}
+
+// b2Mat33::Solve33 with ex=(k11,k12,ezx) ey=(k12,k22,ezy) ez=(ezx,ezy,ezz); cross(ey,ez) and the
+// determinant do not depend on the right-hand side and are evaluated once per step (same values).
+__device__ __forceinline__ void solve33_init(JointC& J) {
+    const float ex0 = J.k11, ex1 = J.k12, ex2 = J.ezx;
+    const float ey0 = J.k12, ey1 = J.k22, ey2 = J.ezy;
+    const float ez0 = J.ezx, ez1 = J.ezy, ez2 = J.ezz;
+    J.cfx = ey1 * ez2 - ey2 * ez1; J.cfy = ey2 * ez0 - ey0 * ez2; J.cfz = ey0 * ez1 - ey1 * ez0;
+    float det = ex0 * J.cfx + ex1 * J.cfy + ex2 * J.cfz;
+    if (det != 0.0f) det = 1.0f / det;
+    J.det33 = det;
+}
+__device__ __forceinline__ void solve33(const JointC& J, float b0, float b1, float b2, float& x0, float& x1, float& x2) {
+    const float ex0 = J.k11, ex1 = J.k12, ex2 = J.ezx;
+    const float ey0 = J.k12, ey1 = J.k22, ey2 = J.ezy;
+    const float ez0 = J.ezx, ez1 = J.ezy, ez2 = J.ezz;
+    const float det = J.det33;
+    x0 = det * (b0 * J.cfx + b1 * J.cfy + b2 * J.cfz);
+    float dx = b1 * ez2 - b2 * ez1, dy = b2 * ez0 - b0 * ez2, dz = b0 * ez1 - b1 * ez0;
+    x1 = det * (ex0 * dx + ex1 * dy + ex2 * dz);
+    float fx = ey1 * b2 - ey2 * b1, fy = ey2 * b0 - ey0 * b2, fz = ey0 * b1 - ey1 * b0;
+    x2 = det * (ex0 * fx + ex1 * fy + ex2 * fz);
+}
+
+struct Masses { float mA, iA, mB, iB, maxMotorImpulse; };
+
+// b2RevoluteJoint::SolveVelocityConstraints for one joint.  LIMIT_ACTIVE is the joint's limit
+// state (at lower / at upper), fixed for the whole step by InitVelocityConstraints, so the 180
+// sweeps run straight-line code; the "release" case of the limit complementarity is a select.
+// (e_equalLimits cannot occur: upper - lower = 0.8 rad, checked at mcr_create.)
+template <bool LIMIT_ACTIVE>
+__device__ __forceinline__ void joint_sweep(const JointC& j, const Masses& m, float& vAx, float& vAy, float& wA,
+                                            float& vBx, float& vBy, float& wB, float& jix, float& jiy, float& jiz,
+                                            float& jmot) {
+    {   // motor
+        float Cdot = wB - wA - j.motorSpeed;
+        float impulse = -j.motorMass * Cdot;
+        float oldImpulse = jmot;
+        jmot = clampf(jmot + impulse, -m.maxMotorImpulse, m.maxMotorImpulse);
+        impulse = jmot - oldImpulse;
+        wA -= m.iA * impulse;
+        wB += m.iB * impulse;
+    }
+    // Cdot1 = vB + cross(wB, rB) - vA - cross(wA, rA),  cross(s, r) = (-s*r.y, s*r.x),  rB = 0
+    const float C1x = vBx - vAx - (-wA * j.rAy);
+    const float C1y = vBy - vAy - (wA * j.rAx);
+    if (LIMIT_ACTIVE) {
+        const float Cdot2 = wB - wA;
+        float i0, i1, i2;
+        solve33(j, C1x, C1y, Cdot2, i0, i1, i2);
+        i0 = -i0; i1 = -i1; i2 = -i2;
+        const float newImpulse = jiz + i2;
+        const bool release = (j.limit == LIM_LOWER) ? (newImpulse < 0.0f) : (newImpulse > 0.0f);
+        const float rx = -C1x + jiz * j.ezx, ry = -C1y + jiz * j.ezy;
+        float redx, redy; solve22(j, rx, ry, redx, redy);
+        i0 = release ? redx : i0; i1 = release ? redy : i1; i2 = release ? -jiz : i2;
+        jix += i0; jiy += i1; jiz = release ? 0.0f : newImpulse;
+        vAx -= m.mA * i0; vAy -= m.mA * i1;
+        wA -= m.iA * ((j.rAx * i1 - j.rAy * i0) + i2);
+        vBx += m.mB * i0; vBy += m.mB * i1;
+        wB += m.iB * i2;
+    } else {
+        float ix, iy; solve22(j, -C1x, -C1y, ix, iy);
+        jix += ix; jiy += iy;
+        vAx -= m.mA * ix; vAy -= m.mA * iy;
+        wA -= m.iA * (j.rAx * iy - j.rAy * ix);
+        vBx += m.mB * ix; vBy += m.mB * iy;
+    }
+}
+
+struct VelState { float vx[5], vy[5], w[5], jix[4], jiy[4], jiz[4], jmot[4]; };
+
+// One Gauss-Seidel sweep over the island's joints in Box2D's order [j3, j2, j1, j0].
+// PAT bit k = joint k has an active limit.  PAT < 0: decide per joint at run time.
+template <int PAT>
+__device__ __forceinline__ void sweep(VelState& s, const JointC (&J)[4], const Masses& m) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        const int k = 3 - kk, bi = 1 + k;
+        const bool act = PAT >= 0 ? ((PAT >> k) & 1) != 0 : (J[k].limit != LIM_INACTIVE);
+        if (act) joint_sweep<true>(J[k], m, s.vx[0], s.vy[0], s.w[0], s.vx[bi], s.vy[bi], s.w[bi], s.jix[k], s.jiy[k], s.jiz[k], s.jmot[k]);
+        else joint_sweep<false>(J[k], m, s.vx[0], s.vy[0], s.w[0], s.vx[bi], s.vy[bi], s.w[bi], s.jix[k], s.jiy[k], s.jiz[k], s.jmot[k]);
+    }
+}
+
+__device__ __forceinline__ unsigned state_diff(const VelState& a, const VelState& b) {
+    unsigned d0 = 0u, d1 = 0u, d2 = 0u, d3 = 0u;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        d0 |= __float_as_uint(a.vx[i]) ^ __float_as_uint(b.vx[i]);
+        d1 |= __float_as_uint(a.vy[i]) ^ __float_as_uint(b.vy[i]);
+        d2 |= __float_as_uint(a.w[i]) ^ __float_as_uint(b.w[i]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        d0 |= __float_as_uint(a.jix[k]) ^ __float_as_uint(b.jix[k]);
+        d1 |= __float_as_uint(a.jiy[k]) ^ __float_as_uint(b.jiy[k]);
+        d2 |= __float_as_uint(a.jiz[k]) ^ __float_as_uint(b.jiz[k]);
+        d3 |= __float_as_uint(a.jmot[k]) ^ __float_as_uint(b.jmot[k]);
+    }
+    return (d0 | d1) | (d2 | d3);
+}
+
+// Box2D runs all 180 sweeps.  A sweep is a deterministic map of (velocities, accumulated
+// impulses): when four sweeps leave that state bit-identical (a fixed point, a 2-cycle or a
+// 4-cycle, checked at multiples of 4 so the phase matches sweep 180) the remaining sweeps
+// cannot change it, so stopping there is exact.
+template <int PAT>
+__device__ __forceinline__ void solve_velocity(VelState& s, const JointC (&J)[4], const Masses& m) {
+    // one sweep per loop trip keeps the loop body (~3 KB of SASS) inside the L0 instruction cache
+#pragma unroll 1
+    for (int it = 0; it < MCR_VEL_ITERS; it += 4) {
+        const VelState before = s;
+#pragma unroll 1
+        for (int r = 0; r < 4; ++r) sweep<PAT>(s, J, m);
+        if (state_diff(before, s) == 0u) break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// contacts
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float seg_dist2(float px, float py, float ax, float ay, float bx, float by) {
+    float ex = bx - ax, ey = by - ay, wx = px - ax, wy = py - ay;
+    float t = wx * ex + wy * ey;
+    if (t <= 0.0f) return wx * wx + wy * wy;
+    float l2 = ex * ex + ey * ey;
+    if (t >= l2) { float ux = px - bx, uy = py - by; return ux * ux + uy * uy; }
+    float cr = ex * wy - ey * wx;
+    return (cr * cr) / l2;
+}
+
+// a = tile quad (4 verts), b = fixture polygon (nb verts); both CCW, world space.
+// Same predicate as b2TestOverlap: distance(a, b) < 2 * b2_polygonRadius (+ 10 eps).
+__device__ bool poly_touch(const float* ax, const float* ay, const float* bx, const float* by, int nb) {
+    bool separated = false;
+    for (int i = 0; i < 4 && !separated; ++i) {
+        int i2 = i + 1 < 4 ? i + 1 : 0;
+        float px = ax[i], py = ay[i], ex = ax[i2] - px, ey = ay[i2] - py;
+        bool all_out = true;
+        for (int k = 0; k < nb; ++k) {
+            float c = ex * (by[k] - py) - ey * (bx[k] - px);
+            if (!(c < 0.0f)) { all_out = false; break; }
+        }
+        separated = all_out;
+    }
+    for (int i = 0; i < nb && !separated; ++i) {
+        int i2 = i + 1 < nb ? i + 1 : 0;
+        float px = bx[i], py = by[i], ex = bx[i2] - px, ey = by[i2] - py;
+        bool all_out = true;
+        for (int k = 0; k < 4; ++k) {
+            float c = ex * (ay[k] - py) - ey * (ax[k] - px);
+            if (!(c < 0.0f)) { all_out = false; break; }
+        }
+        separated = all_out;
+    }
+    if (!separated) return true;
+    float d2 = 3.402823466e+38f;
+    for (int i = 0; i < 4; ++i)
+        for (int k = 0; k < nb; ++k) {
+            int k2 = k + 1 < nb ? k + 1 : 0;
+            d2 = fminf(d2, seg_dist2(ax[i], ay[i], bx[k], by[k], bx[k2], by[k2]));
+        }
+    for (int k = 0; k < nb; ++k)
+        for (int i = 0; i < 4; ++i) {
+            int i2 = i + 1 < 4 ? i + 1 : 0;
+            d2 = fminf(d2, seg_dist2(bx[k], by[k], ax[i], ay[i], ax[i2], ay[i2]));
+        }
+    float dist = sqrtf(d2);
+    const float rr = B2_POLYGON_RADIUS + B2_POLYGON_RADIUS;
+    if (dist > rr && dist > B2_EPS) return (dist - rr) < 10.0f * B2_EPS;
+    return true;
+}
+
+struct ContactSmem {      // carved from dynamic shared memory, sizes depend on A
+    float* fixt;          // [A*8][FIX_STRIDE]
+    float* carbox;        // [A][4]
+    uint32_t* pairs;      // [PAIRS_PER_CAR*A]  tile << 8 | fixture
+    uint32_t* cands;      // [CANDS_PER_CAR*A]  tile << 8 | car  (new-visit candidates)
+    uint32_t* road_bits;  // [2]
+    int* counts;          // [2] pairs, cands
+};
+
+__device__ __forceinline__ ContactSmem carve(unsigned char* base, int A) {
+    ContactSmem S;
+    S.fixt = (float*)base; base += (size_t)A * 8 * FIX_STRIDE * 4;
+    S.carbox = (float*)base; base += (size_t)A * 4 * 4;
+    S.pairs = (uint32_t*)base; base += (size_t)A * PAIRS_PER_CAR * 4;
+    S.cands = (uint32_t*)base; base += (size_t)A * CANDS_PER_CAR * 4;
+    S.road_bits = (uint32_t*)base; base += 8;
+    S.counts = (int*)base;
+    return S;
+}
+
+static size_t sim_smem_bytes(int A) {
+    return (size_t)A * 8 * FIX_STRIDE * 4 + (size_t)A * 16 + (size_t)A * PAIRS_PER_CAR * 4 + (size_t)A * CANDS_PER_CAR * 4 + 16;
+}
+
+__device__ void contacts_warp(const Dims& d, const DevBuffers& b, const CarConst& cc, int env, int lane, unsigned char* smem) {
+    const int A = d.A, N = d.N, nfix = A * 8;
+    ContactSmem S = carve(smem, A);
+    if (lane < 2) { S.counts[lane] = 0; S.road_bits[lane] = 0u; }
+    // ---- phase 1: world-space fixture polygons + AABBs -----------------------------------------
+    for (int f = lane; f < nfix; f += 32) {
+        const int c = f >> 3, fi = f & 7, car = env * A + c;
+        const int body = fi < 4 ? 1 + fi : 0;
+        const Poly8& P = fi < 4 ? cc.wheel_poly : cc.hull_poly[fi - 4];
+        const float* bp = b.body + (size_t)(body * BODY_FIELDS) * N + car;
+        const float px = bp[(size_t)BF_PX * N], py = bp[(size_t)BF_PY * N];
+        const float qs = bp[(size_t)BF_QS * N], qc = bp[(size_t)BF_QC * N];
+        float* o = S.fixt + (size_t)f * FIX_STRIDE;
+        float lx = 3.402823466e+38f, ly = lx, hx = -lx, hy = -lx;
+        for (int i = 0; i < P.n; ++i) {
+            float x = (qc * P.x[i] - qs * P.y[i]) + px;
+            float y = (qs * P.x[i] + qc * P.y[i]) + py;
+            o[i] = x; o[8 + i] = y;
+            lx = fminf(lx, x); ly = fminf(ly, y); hx = fmaxf(hx, x); hy = fmaxf(hy, y);
+        }
+        o[16] = lx; o[17] = ly; o[18] = hx; o[19] = hy;
+        // wheels are always awake at Collide time (Car.step woke them); the hull may sleep
+        const int active = fi < 4 ? 1 : (b.awake[car] != 0);   // awake[0 * N + car]
+        o[20] = __int_as_float(P.n | (active << 8));
+    }
+    __syncwarp();
+    for (int c = lane; c < A; c += 32) {
+        float lx = 3.402823466e+38f, ly = lx, hx = -lx, hy = -lx;
+        for (int fi = 0; fi < 8; ++fi) {
+            const float* o = S.fixt + (size_t)(c * 8 + fi) * FIX_STRIDE;
+            lx = fminf(lx, o[16]); ly = fminf(ly, o[17]); hx = fmaxf(hx, o[18]); hy = fmaxf(hy, o[19]);
+        }
+        S.carbox[c * 4 + 0] = lx; S.carbox[c * 4 + 1] = ly; S.carbox[c * 4 + 2] = hx; S.carbox[c * 4 + 3] = hy;
+    }
+    __syncwarp();
+    // ---- phase 2: broad phase, tiles strided over lanes ------------------------------------------
+    const int slot = b.env_track[env];
+    const int T = b.trk_T[slot];
+    const float4* aabbs = (const float4*)(b.trk_tile_aabb + (size_t)slot * d.Tmax * 4);
+    const float* tiles = b.trk_tile + (size_t)slot * d.Tmax * 8;
+    const int pair_cap = PAIRS_PER_CAR * A, cand_cap = CANDS_PER_CAR * A;
+    for (int t = lane; t < T; t += 32) {
+        const float4 ta = aabbs[t];
+        for (int c = 0; c < A; ++c) {
+            const float* cb = S.carbox + c * 4;
+            if (cb[0] - ta.z > AABB_MARGIN || cb[1] - ta.w > AABB_MARGIN || ta.x - cb[2] > AABB_MARGIN || ta.y - cb[3] > AABB_MARGIN) continue;
+            for (int fi = 0; fi < 8; ++fi) {
+                const float* o = S.fixt + (size_t)(c * 8 + fi) * FIX_STRIDE;
+                if (o[16] - ta.z > AABB_MARGIN || o[17] - ta.w > AABB_MARGIN || ta.x - o[18] > AABB_MARGIN || ta.y - o[19] > AABB_MARGIN) continue;
+                const int slot_p = atomicAdd(&S.counts[0], 1);
+                if (slot_p < pair_cap) S.pairs[slot_p] = ((uint32_t)t << 8) | (uint32_t)(c * 8 + fi);
+                else atomicExch(&b.status[ST_EVENT_OVERFLOW], 1);
+            }
+        }
+    }
+    __syncwarp();
+    // ---- phase 3: exact predicate, one queued pair per lane ---------------------------------------
+    uint8_t* touched = b.touched + (size_t)env * d.Tmax;
+    int npairs = S.counts[0]; if (npairs > pair_cap) npairs = pair_cap;
+    for (int i = lane; i < npairs; i += 32) {
+        const uint32_t pr = S.pairs[i];
+        const int t = (int)(pr >> 8), f = (int)(pr & 0xffu), c = f >> 3, fi = f & 7;
+        const float4 v0 = *(const float4*)(tiles + (size_t)t * 8);
+        const float4 v1 = *(const float4*)(tiles + (size_t)t * 8 + 4);
+        const float tx[4] = {v0.x, v0.z, v1.x, v1.z}, ty[4] = {v0.y, v0.w, v1.y, v1.w};
+        const float* o = S.fixt + (size_t)f * FIX_STRIDE;
+        const int meta = __float_as_int(o[20]);
+        if (!poly_touch(tx, ty, o, o + 8, meta & 0xff)) continue;
+        if (fi < 4) atomicOr(&S.road_bits[(c * 4 + fi) >> 5], 1u << ((c * 4 + fi) & 31));   // len(wheel.tiles) > 0
+        if (!(meta >> 8)) continue;              // sleeping body: contact not updated
+        touched[t] = 1;                          // tile.color = ROAD_COLOR, mcr:102-104 (any body, idempotent)
+        if (fi >= 4) continue;                   // hull.userData is None, mcr:108
+        const int slot_c = atomicAdd(&S.counts[1], 1);
+        if (slot_c < cand_cap) S.cands[slot_c] = ((uint32_t)t << 8) | (uint32_t)c;
+        else atomicExch(&b.status[ST_EVENT_OVERFLOW], 1);
+    }
+    __syncwarp();
+    // ---- phase 4: flags for the next Car.step; replay visits in contact-list order ------------------
+    for (int i = lane; i < A * 4; i += 32) {
+        const int c = i >> 2, k = i & 3;
+        b.on_road_next[(size_t)k * N + env * A + c] = (uint8_t)((S.road_bits[i >> 5] >> (i & 31)) & 1u);
+    }
+    if (lane == 0) {
+        int n = S.counts[1]; if (n > cand_cap) n = cand_cap;
+        uint32_t* ev = S.cands;
+        for (int i = 1; i < n; ++i) {            // insertion sort, descending (tile, car); n is tiny
+            const uint32_t k = ev[i]; int j = i - 1;
+            while (j >= 0 && ev[j] < k) { ev[j + 1] = ev[j]; --j; }
+            ev[j + 1] = k;
+        }
+        uint32_t* visited = b.visited + (size_t)env * d.Tmax;
+        uint32_t prev = 0xffffffffu;
+        for (int i = 0; i < n; ++i) {
+            const uint32_t k = ev[i];
+            if (k == prev) continue;             // another wheel of the same car on the same tile
+            prev = k;
+            const int t = (int)(k >> 8), c = (int)(k & 0xffu);
+            uint32_t vis = visited[t];
+            if ((vis >> c) & 1u) continue;       // mcr:113
+            vis |= 1u << c;
+            visited[t] = vis;
+            const int car = env * A + c;
+            b.visit_count[car] += 1;             // mcr:115
+            const int past = __popc(vis) - 1;    // mcr:118-120
+            const double reward_factor = 1 - ((double)past / (double)A);
+            b.reward[car] += reward_factor * 1000.0 / (double)T;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// the fused kernel
+// ---------------------------------------------------------------------------------------
+template <typename ActT, int MAX_THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
+sim_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, const ActT* __restrict__ action,
+           double h_ratio, int roles) {
+    extern __shared__ __align__(16) unsigned char sim_smem[];
+    const int env = blockIdx.x;
+    if (mask && !mask[env]) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) {
+        if (roles & ROLE_CONTACTS) contacts_warp(d, b, cc, env, lane, sim_smem);
+        __syncthreads();
+        return;
+    }
+    if (!(roles & ROLE_PHYSICS)) { __syncthreads(); return; }
+    // one warp per car: every lane runs the same scalar arithmetic (loads broadcast), lane 0 stores.
+    // The solver is a serial chain, so lanes buy nothing here; what matters is that each car leaves
+    // the sweep loop at ITS OWN fixed point and runs code specialised to ITS limit pattern.
+    const int N = d.N;
+    const int car = env * d.A + (warp - 1);
+    const bool writer = lane == 0;
+
+    // ---- load state ----------------------------------------------------------------
+    float cx[5], cy[5], ang[5], vx[5], vy[5], w[5], qs[5], qc[5], slp[5];
+    bool awake[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const float* p = b.body + (size_t)(i * BODY_FIELDS) * N + car;
+        cx[i] = p[(size_t)BF_CX * N]; cy[i] = p[(size_t)BF_CY * N]; ang[i] = p[(size_t)BF_A * N];
+        vx[i] = p[(size_t)BF_VX * N]; vy[i] = p[(size_t)BF_VY * N]; w[i] = p[(size_t)BF_W * N];
+        qs[i] = p[(size_t)BF_QS * N]; qc[i] = p[(size_t)BF_QC * N];
+        slp[i] = b.sleep_time[(size_t)i * N + car];
+        awake[i] = b.awake[(size_t)i * N + car] != 0;
+    }
+    float jix[4], jiy[4], jiz[4], jmot[4];
+    int lim[4];
+    double omega[4], phase[4];
+    bool on_road[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float* p = b.joint + (size_t)(k * JOINT_FIELDS) * N + car;
+        jix[k] = p[(size_t)JF_IX * N]; jiy[k] = p[(size_t)JF_IY * N]; jiz[k] = p[(size_t)JF_IZ * N];
+        jmot[k] = p[(size_t)JF_MOTOR * N];
+        lim[k] = b.limit_state[(size_t)k * N + car];
+        omega[k] = b.wheel[(size_t)(k * WHEEL_FIELDS + WF_OMEGA) * N + car];
+        phase[k] = b.wheel[(size_t)(k * WHEEL_FIELDS + WF_PHASE) * N + car];
+        on_road[k] = b.on_road[(size_t)k * N + car] != 0;
+    }
+    double gas = b.ctrl[(size_t)CF_GAS * N + car];
+    double brake = b.ctrl[(size_t)CF_BRAKE * N + car];
+    double steer = b.ctrl[(size_t)CF_STEER * N + car];
+
+    // ---- controls, mcr:421-424 -------------------------------------------------------
+    if (action) {
+        double a0 = (double)action[(size_t)car * 3 + 0];
+        double a1 = (double)action[(size_t)car * 3 + 1];
+        double a2 = (double)action[(size_t)car * 3 + 2];
+        steer = -a0;
+        double g = a1 < 0 ? 0 : (a1 > 1 ? 1 : a1);
+        double diff = g - gas;
+        if (diff > 0.1) diff = 0.1;
+        gas += diff;
+        brake = a2;
+    }
+
+    // ---- Car.step(dt): tyre model (float64), per wheel ------------------------------------
+    const double SIZE = 0.02;
+    const double ENGINE_POWER = 100000000 * SIZE * SIZE;
+    const double WHEEL_MOI = 4000 * SIZE * SIZE;
+    const double FRICTION_LIMIT = 1000000 * SIZE * SIZE;
+    const double dt = 1.0 / 50;
+    float motorSpeed[4], Fx[4], Fy[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int bi = 1 + k;
+        const double steer_w = k < 2 ? steer : 0.0;
+        const double gas_w = k >= 2 ? gas : 0.0;
+        double jangle = (double)(ang[bi] - ang[0]);
+        double dir = sign_d(steer_w - jangle);
+        double val = fabs(steer_w - jangle);
+        motorSpeed[k] = (float)(dir * fmin(50.0 * val, 3.0));
+        double friction_limit = FRICTION_LIMIT * 0.6;
+        if (on_road[k]) friction_limit = fmax(friction_limit, FRICTION_LIMIT * 1.0);
+        // GetWorldVector((0,1)) = (-s, c); ((1,0)) = (c, s)   (fp32 products with exact 0/1)
+        float forw_x = qc[bi] * 0.0f - qs[bi] * 1.0f, forw_y = qs[bi] * 0.0f + qc[bi] * 1.0f;
+        float side_x = qc[bi] * 1.0f - qs[bi] * 0.0f, side_y = qs[bi] * 1.0f + qc[bi] * 0.0f;
+        double wvx = vx[bi], wvy = vy[bi];
+        double vf = (double)forw_x * wvx + (double)forw_y * wvy;
+        double vs = (double)side_x * wvx + (double)side_y * wvy;
+        omega[k] += dt * ENGINE_POWER * gas_w / WHEEL_MOI / (fabs(omega[k]) + 5.0);
+        if (brake >= 0.9) {
+            omega[k] = 0;
+        } else if (brake > 0) {
+            double bdir = -sign_d(omega[k]);
+            double bval = 15 * brake;
+            if (fabs(bval) > fabs(omega[k])) bval = fabs(omega[k]);
+            omega[k] += bdir * bval;
+        }
+        phase[k] += omega[k] * dt;
+        const double wheel_rad = 1.0 * 27 * SIZE;
+        double vr = omega[k] * wheel_rad;
+        double f_force = -vf + vr;
+        double p_force = -vs;
+        f_force *= 205000 * SIZE * SIZE;
+        p_force *= 205000 * SIZE * SIZE;
+        double force = sqrt(f_force * f_force + p_force * p_force);
+        if (fabs(force) > friction_limit) {
+            f_force /= force; p_force /= force;
+            force = friction_limit;
+            f_force *= force; p_force *= force;
+        }
+        omega[k] -= dt * f_force * wheel_rad / WHEEL_MOI;
+        Fx[k] = (float)(p_force * (double)side_x + f_force * (double)forw_x);
+        Fy[k] = (float)(p_force * (double)side_y + f_force * (double)forw_y);
+        if (!awake[bi]) { awake[bi] = true; slp[bi] = 0.0f; }   // ApplyForceToCenter(wake=True)
+    }
+
+    // ---- b2Island::Solve ---------------------------------------------------------------
+    const float h = (float)(1.0 / 50);
+    if (!awake[0]) { awake[0] = true; slp[0] = 0.0f; }           // island DFS wakes the hull
+    const float mA = cc.hull_invMass, iA = cc.hull_invI, mB = cc.wheel_invMass, iB = cc.wheel_invI;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        vx[1 + k] += h * (mB * Fx[k]);
+        vy[1 + k] += h * (mB * Fy[k]);
+    }
+    // InitVelocityConstraints, joints in island order 3,2,1,0
+    JointC J[4];
+    {
+        float sA, cA; rot_set(ang[0], sA, cA);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const int k = 3 - kk;
+            const int bi = 1 + k;
+            float lx = cc.anchor_x[k] - cc.hull_lcx, ly = cc.anchor_y[k] - cc.hull_lcy;
+            float rAx = cA * lx - sA * ly, rAy = sA * lx + cA * ly;
+            JointC& j = J[k];
+            j.rAx = rAx; j.rAy = rAy;
+            j.k11 = mA + mB + rAy * rAy * iA;
+            j.k12 = -rAy * rAx * iA;
+            j.ezx = -rAy * iA;
+            j.k22 = mA + mB + rAx * rAx * iA;
+            j.ezy = rAx * iA;
+            j.ezz = iA + iB;
+            float det = j.k11 * j.k22 - j.k12 * j.k12;
+            if (det != 0.0f) det = 1.0f / det;
+            j.det22 = det;
+            float mm = iA + iB;
+            if (mm > 0.0f) mm = 1.0f / mm;
+            j.motorMass = mm;
+            j.motorSpeed = motorSpeed[k];
+            solve33_init(j);
+            float jointAngle = ang[bi] - ang[0] - 0.0f;
+            if (jointAngle <= cc.lower) {              // e_equalLimits is excluded at mcr_create
+                if (lim[k] != LIM_LOWER) jiz[k] = 0.0f;
+                lim[k] = LIM_LOWER;
+            } else if (jointAngle >= cc.upper) {
+                if (lim[k] != LIM_UPPER) jiz[k] = 0.0f;
+                lim[k] = LIM_UPPER;
+            } else {
+                lim[k] = LIM_INACTIVE;
+                jiz[k] = 0.0f;
+            }
+            j.limit = lim[k];
+            // warm start (dtRatio == 1 exactly: 50.0f * 0.02f rounds to 1.0f; impulses are 0 on the first step)
+            float Px = jix[k], Py = jiy[k];
+            vx[0] -= mA * Px; vy[0] -= mA * Py;
+            w[0] -= iA * ((rAx * Py - rAy * Px) + jmot[k] + jiz[k]);
+            vx[bi] += mB * Px; vy[bi] += mB * Py;
+            w[bi] += iB * (jmot[k] + jiz[k]);
+        }
+    }
+    // SolveVelocityConstraints x 180, specialised on the front joints' limit pattern
+    {
+        Masses m; m.mA = mA; m.iA = iA; m.mB = mB; m.iB = iB; m.maxMotorImpulse = h * cc.max_motor_torque;
+        VelState s;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { s.vx[i] = vx[i]; s.vy[i] = vy[i]; s.w[i] = w[i]; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { s.jix[k] = jix[k]; s.jiy[k] = jiy[k]; s.jiz[k] = jiz[k]; s.jmot[k] = jmot[k]; }
+        int pat = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pat |= (lim[k] != LIM_INACTIVE ? 1 : 0) << k;
+        switch (pat) {
+            case 0: solve_velocity<0>(s, J, m); break;
+            case 1: solve_velocity<1>(s, J, m); break;
+            case 2: solve_velocity<2>(s, J, m); break;
+            case 3: solve_velocity<3>(s, J, m); break;
+            default: solve_velocity<-1>(s, J, m); break;   // a rear joint at its limit: rare
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { vx[i] = s.vx[i]; vy[i] = s.vy[i]; w[i] = s.w[i]; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { jix[k] = s.jix[k]; jiy[k] = s.jiy[k]; jiz[k] = s.jiz[k]; jmot[k] = s.jmot[k]; }
+    }
+    // integrate positions
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        float tx = h * vx[i], ty = h * vy[i];
+        if (tx * tx + ty * ty > B2_MAX_TRANSLATION * B2_MAX_TRANSLATION) {
+            float ratio = B2_MAX_TRANSLATION / sqrtf(tx * tx + ty * ty);
+            vx[i] = ratio * vx[i]; vy[i] = ratio * vy[i];
+        }
+        float rotn = h * w[i];
+        if (rotn * rotn > B2_MAX_ROTATION * B2_MAX_ROTATION) {
+            float ratio = B2_MAX_ROTATION / fabsf(rotn);
+            w[i] *= ratio;
+        }
+        cx[i] += h * vx[i]; cy[i] += h * vy[i];
+        ang[i] += h * w[i];
+    }
+    // SolvePositionConstraints, up to 60 iterations with Box2D's early exit
+    bool positionSolved = false;
+    for (int it = 0; it < MCR_POS_ITERS; ++it) {
+        bool jointsOkay = true;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const int k = 3 - kk;
+            const int bi = 1 + k;
+            float aA = ang[0], aB = ang[bi];
+            float angularError = 0.0f;
+            if (lim[k] != LIM_INACTIVE) {
+                float angle = aB - aA - 0.0f;
+                float limitImpulse = 0.0f;
+                if (lim[k] == LIM_EQUAL) {
+                    float C = clampf(angle - cc.lower, -B2_MAX_ANGULAR_CORRECTION, B2_MAX_ANGULAR_CORRECTION);
+                    limitImpulse = -J[k].motorMass * C;
+                    angularError = fabsf(C);
+                } else if (lim[k] == LIM_LOWER) {
+                    float C = angle - cc.lower;
+                    angularError = -C;
+                    C = clampf(C + B2_ANGULAR_SLOP, -B2_MAX_ANGULAR_CORRECTION, 0.0f);
+                    limitImpulse = -J[k].motorMass * C;
+                } else {
+                    float C = angle - cc.upper;
+                    angularError = C;
+                    C = clampf(C - B2_ANGULAR_SLOP, 0.0f, B2_MAX_ANGULAR_CORRECTION);
+                    limitImpulse = -J[k].motorMass * C;
+                }
+                aA -= iA * limitImpulse;
+                aB += iB * limitImpulse;
+            }
+            float sA, cA; rot_set(aA, sA, cA);
+            float lx = cc.anchor_x[k] - cc.hull_lcx, ly = cc.anchor_y[k] - cc.hull_lcy;
+            float rAx = cA * lx - sA * ly, rAy = sA * lx + cA * ly;
+            float Cx = cx[bi] - cx[0] - rAx, Cy = cy[bi] - cy[0] - rAy;
+            float positionError = sqrtf(Cx * Cx + Cy * Cy);
+            float K11 = mA + mB + iA * rAy * rAy;
+            float K12 = -iA * rAx * rAy;
+            float K22 = mA + mB + iA * rAx * rAx;
+            float det = K11 * K22 - K12 * K12;
+            if (det != 0.0f) det = 1.0f / det;
+            float ix = -(det * (K22 * Cx - K12 * Cy));
+            float iy = -(det * (K11 * Cy - K12 * Cx));
+            cx[0] -= mA * ix; cy[0] -= mA * iy;
+            aA -= iA * (rAx * iy - rAy * ix);
+            cx[bi] += mB * ix; cy[bi] += mB * iy;
+            ang[0] = aA; ang[bi] = aB;
+            bool ok = positionError <= B2_LINEAR_SLOP && angularError <= B2_ANGULAR_SLOP;
+            jointsOkay = jointsOkay && ok;
+        }
+        if (jointsOkay) { positionSolved = true; break; }
+    }
+    // SynchronizeTransform + sleep
+    float px[5], py[5];
+    float minSleepTime = 3.402823466e+38f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        rot_set(ang[i], qs[i], qc[i]);
+        float lx = i == 0 ? cc.hull_lcx : 0.0f, ly = i == 0 ? cc.hull_lcy : 0.0f;
+        px[i] = cx[i] - (qc[i] * lx - qs[i] * ly);
+        py[i] = cy[i] - (qs[i] * lx + qc[i] * ly);
+        if (w[i] * w[i] > B2_ANGULAR_SLEEP_TOL * B2_ANGULAR_SLEEP_TOL ||
+            vx[i] * vx[i] + vy[i] * vy[i] > B2_LINEAR_SLEEP_TOL * B2_LINEAR_SLEEP_TOL) {
+            slp[i] = 0.0f; minSleepTime = 0.0f;
+        } else {
+            slp[i] += h; minSleepTime = fminf(minSleepTime, slp[i]);
+        }
+    }
+    if (minSleepTime >= B2_TIME_TO_SLEEP && positionSolved) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { awake[i] = false; slp[i] = 0.0f; vx[i] = 0.0f; vy[i] = 0.0f; w[i] = 0.0f; }
+    }
+
+    __syncthreads();   // the contacts warp has finished reading this step's start poses
+    if (writer) {
+    // ---- store ---------------------------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        float* p = b.body + (size_t)(i * BODY_FIELDS) * N + car;
+        p[(size_t)BF_CX * N] = cx[i]; p[(size_t)BF_CY * N] = cy[i]; p[(size_t)BF_A * N] = ang[i];
+        p[(size_t)BF_VX * N] = vx[i]; p[(size_t)BF_VY * N] = vy[i]; p[(size_t)BF_W * N] = w[i];
+        p[(size_t)BF_PX * N] = px[i]; p[(size_t)BF_PY * N] = py[i];
+        p[(size_t)BF_QS * N] = qs[i]; p[(size_t)BF_QC * N] = qc[i];
+        b.sleep_time[(size_t)i * N + car] = slp[i];
+        b.awake[(size_t)i * N + car] = awake[i] ? 1 : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float* p = b.joint + (size_t)(k * JOINT_FIELDS) * N + car;
+        p[(size_t)JF_IX * N] = jix[k]; p[(size_t)JF_IY * N] = jiy[k]; p[(size_t)JF_IZ * N] = jiz[k];
+        p[(size_t)JF_MOTOR * N] = jmot[k];
+        b.limit_state[(size_t)k * N + car] = (uint8_t)lim[k];
+        b.wheel[(size_t)(k * WHEEL_FIELDS + WF_OMEGA) * N + car] = omega[k];
+        b.wheel[(size_t)(k * WHEEL_FIELDS + WF_PHASE) * N + car] = phase[k];
+        // the contact pass of THIS step (already run) decides the friction of the NEXT Car.step
+        b.on_road[(size_t)k * N + car] = b.on_road_next[(size_t)k * N + car];
+    }
+    b.ctrl[(size_t)CF_GAS * N + car] = gas;
+    b.ctrl[(size_t)CF_BRAKE * N + car] = brake;
+    b.ctrl[(size_t)CF_STEER * N + car] = steer;
+    // ---- per-view values the rasteriser needs, evaluated once here (fp64 trig is serial latency) --
+    const double t = b.time[car] + 1.0 / 50;                      // mcr:429
+    b.time[car] = t;
+    if (action) b.steps[car] += 1;                                // TimeLimit counts step() calls only
+    {   // camera, mcr:540-556 + Transform.enable + glViewport(0,0,96,96) under glOrtho(0,1000,0,800)
+        const double SCALE = 6.0, ZOOM = 2.7, WINDOW_W = 1000, WINDOW_H = 800;
+        const double zoom = 0.1 * SCALE * fmax(1 - t, 0.0) + ZOOM * SCALE * fmin(t, 1.0);
+        const double scroll_x = px[0], scroll_y = py[0];
+        double angle = -(double)ang[0];
+        const double hvx = vx[0], hvy = vy[0];
+        const bool fast = sqrt(hvx * hvx + hvy * hvy) > 0.5;
+        double at = 0.0;
+        if (fast) { at = atan2(hvx, hvy); angle = at; }
+        const double tx = WINDOW_W / 2 - (scroll_x * zoom * cos(angle) - scroll_y * zoom * sin(angle));
+        const double ty = WINDOW_H * h_ratio - (scroll_x * zoom * sin(angle) + scroll_y * zoom * cos(angle));
+        const float ftx = (float)tx, fty = (float)ty, fdeg = (float)(57.29577951308232 * angle), fzoom = (float)zoom;
+        const double rad = (double)fdeg * (3.14159265358979323846 / 180.0);
+        const double cs = cos(rad), sn = sin(rad);
+        const double SX = 96.0 / 1000.0, SY = 96.0 / 800.0;
+        b.camera[(size_t)0 * N + car] = (float)(cs * (double)fzoom * SX);
+        b.camera[(size_t)1 * N + car] = (float)(-sn * (double)fzoom * SX);
+        b.camera[(size_t)2 * N + car] = (float)((double)ftx * SX);
+        b.camera[(size_t)3 * N + car] = (float)(sn * (double)fzoom * SY);
+        b.camera[(size_t)4 * N + car] = (float)(cs * (double)fzoom * SY);
+        b.camera[(size_t)5 * N + car] = (float)((double)fty * SY);
+        // car_angle of the backward test, mcr:449-456
+        const double PI = 3.141592653589793;
+        double car_angle = fast ? -at : (double)ang[0];
+        car_angle = fmod(car_angle + 2 * PI, 2 * PI);
+        if (car_angle != 0 && car_angle < 0) car_angle += 2 * PI;
+        b.heading[car] = car_angle;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {   // Car.draw wheel stripe, evaluated once per wheel for all A views
+        const double a1 = phase[k], a2 = phase[k] + 1.2;
+        double s1 = sin(a1), s2 = sin(a2), c1 = cos(a1), c2 = cos(a2);
+        float y1 = __int_as_float(0x7fc00000), y2 = 0.0f;
+        if (!(s1 > 0 && s2 > 0)) {
+            if (s1 > 0) c1 = sign_d(c1);
+            if (s2 > 0) c2 = sign_d(c2);
+            y1 = (float)(+27 * c1 * SIZE); y2 = (float)(+27 * c2 * SIZE);
+        }
+        b.stripe[(size_t)(k * 2 + 0) * N + car] = y1;
+        b.stripe[(size_t)(k * 2 + 1) * N + car] = y2;
+    }
+    }
+}
+
+template <typename ActT, int MAX_THREADS, int MIN_BLOCKS>
+static int launch_sim_t(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
+                        const ActT* action, double h_ratio, int roles, size_t smem, cudaStream_t s) {
+    static int configured_for = -1;
+    if (smem > 48 * 1024 && configured_for != d.A) {
+        if (cudaFuncSetAttribute(sim_kernel<ActT, MAX_THREADS, MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        configured_for = d.A;
+    }
+    sim_kernel<ActT, MAX_THREADS, MIN_BLOCKS><<<d.B, 32 * (d.A + 1), smem, s>>>(d, b, cc, mask, action, h_ratio, roles);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// Register budget per CTA size: the solver wants ~130+ registers; capping it a little below that
+// keeps enough CTAs resident that the envs whose solve runs all 180 sweeps do not serialise.
+template <typename ActT>
+static int launch_sim_a(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
+                        const ActT* action, double h_ratio, int roles, size_t smem, cudaStream_t s) {
+    const int threads = 32 * (d.A + 1);
+    if (threads <= 64) return launch_sim_t<ActT, 64, 8>(d, b, cc, mask, action, h_ratio, roles, smem, s);
+    if (threads <= 96) return launch_sim_t<ActT, 96, 5>(d, b, cc, mask, action, h_ratio, roles, smem, s);
+    if (threads <= 160) return launch_sim_t<ActT, 160, 3>(d, b, cc, mask, action, h_ratio, roles, smem, s);
+    if (threads <= 288) return launch_sim_t<ActT, 288, 1>(d, b, cc, mask, action, h_ratio, roles, smem, s);
+    return launch_sim_t<ActT, 32 * (MCR_MAX_AGENTS + 1), 1>(d, b, cc, mask, action, h_ratio, roles, smem, s);
+}
+
+static int launch_sim(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
+                      const void* action, int action_dtype, double h_ratio, int roles, void* stream) {
+    const size_t smem = sim_smem_bytes(d.A);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (action_dtype == MCR_F64) return launch_sim_a<double>(d, b, cc, mask, (const double*)action, h_ratio, roles, smem, s);
+    return launch_sim_a<float>(d, b, cc, mask, (const float*)action, h_ratio, roles, smem, s);
+}
+
+int launch_contacts(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, void* stream) {
+    return launch_sim(d, b, cc, mask, nullptr, MCR_F32, 0.0, ROLE_CONTACTS, stream);
+}
+
+int launch_physics(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
+                   const void* action, int action_dtype, double h_ratio, void* stream) {
+    return launch_sim(d, b, cc, mask, action, action_dtype, h_ratio, ROLE_PHYSICS, stream);
+}
+
+int launch_simulate(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
+                    const void* action, int action_dtype, double h_ratio, void* stream) {
+    return launch_sim(d, b, cc, mask, action, action_dtype, h_ratio, ROLE_CONTACTS | ROLE_PHYSICS, stream);
+}

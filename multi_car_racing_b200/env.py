@@ -274,22 +274,27 @@ class BatchedMultiCarRacing:
             self._dev_action64 = torch.zeros((B, A, 3), dtype=torch.float64, device=self.device)
         return self._host
 
-    def step_split(self, action, events=None):
-        """mcr_step without auto reset, issued as its three kernels through the split entry
-        points; `events` (4 torch.cuda.Event) are recorded around them (bench.py's per-kernel
-        timing).  Identical results to step()."""
+    def step_split(self, action, events=None, fused=True):
+        """mcr_step without auto reset, issued through the split entry points; `events`
+        (torch.cuda.Event list) are recorded around the launches (bench.py's per-kernel timing):
+        fused=True  -> [simulate, render]            (3 events; what mcr_step launches)
+        fused=False -> [contacts, physics, render]   (4 events).  Identical results to step()."""
         torch = _torch()
         dt = _lib.MCR_F32 if action.dtype == torch.float32 else _lib.MCR_F64
         st = self._stream()
         cur = torch.cuda.current_stream(self.device)
-        if events: events[0].record(cur)
-        _lib.check(self.L.mcr_contacts(self._h, None, st), "mcr_contacts")
-        if events: events[1].record(cur)
-        _lib.check(self.L.mcr_physics(self._h, None, action.data_ptr(), dt, st), "mcr_physics")
-        if events: events[2].record(cur)
+        k = 0
+        if events: events[k].record(cur); k += 1
+        if fused:
+            _lib.check(self.L.mcr_simulate(self._h, None, action.data_ptr(), dt, st), "mcr_simulate")
+        else:
+            _lib.check(self.L.mcr_contacts(self._h, None, st), "mcr_contacts")
+            if events: events[k].record(cur); k += 1
+            _lib.check(self.L.mcr_physics(self._h, None, action.data_ptr(), dt, st), "mcr_physics")
+        if events: events[k].record(cur); k += 1
         _lib.check(self.L.mcr_render(self._h, None, self.obs.data_ptr(), self.reward_out.data_ptr(),
                                      self.done_out.data_ptr(), 1, st), "mcr_render")
-        if events: events[3].record(cur)
+        if events: events[k].record(cur)
         return self.obs, self.reward_out, self.done_out, {}
 
     def render(self, mode='state_pixels'):
