@@ -22,10 +22,11 @@
 //      half-open pixel span [x0,x1) into a shared pool and sets the polygon's bit in the row's
 //      bitmask;
 //   3. fill: one thread per (row, 32-pixel segment) walks the row's bitmask top-most polygon
-//      first with a 32-bit "still uncovered" mask, so every pixel is written exactly once and
-//      the walk stops as soon as the segment is resolved;
-//   4. the palette-index tile is expanded to RGB and stored with 16-byte vector stores
-//      (1728 uint4 per frame) -- the only HBM traffic that scales with the frame count.
+//      first with a 32-bit "still uncovered" mask; the segment's 32 palette indices live in 8
+//      registers and are updated with byte-select masks (no per-pixel loop, no image in shared
+//      memory), the walk stops as soon as the segment is resolved;
+//   4. each thread expands its 32 pixels to RGB and stores them as 6 x uint4 (1728 uint4 per
+//      frame) -- the only HBM traffic that scales with the frame count.
 #include "mcr_internal.h"
 #include <cuda_runtime.h>
 
@@ -38,7 +39,6 @@
 #define CAR_PARTS 12        // 4 x (wheel, stripe) + 4 hull fixtures
 #define SW MCR_STATE_W
 #define SH MCR_STATE_H
-#define IMG_STRIDE 104      // bytes per tile row: 26 words -> rows land in different banks
 
 // initial values are documentation; launch_render overwrites them with mcr_host_palette()
 __constant__ uint8_t c_palette[PAL_COUNT][4] = {
@@ -97,7 +97,6 @@ struct __align__(16) RasterSmem {
     uint8_t ne[LIST_CAP], col[LIST_CAP];
     uchar2 span[SPAN_POOL];
     uint32_t rowmask[SH][MASK_WORDS];
-    uint8_t img[SH * IMG_STRIDE];  // palette indices, row 0 = TOP row of the observation
     Affine M;
     int list_count, pool_count, first_bad;
     int ck_j0x, ck_nx, ck_j0y, ck_ny;   // visible checker index range
@@ -259,7 +258,7 @@ __device__ __forceinline__ void edge_row(const RasterSmem& S, int e, int p, floa
     }
 }
 
-__device__ void flush_list(RasterSmem& S, int tid) {
+__device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pix)[8]) {
     __syncthreads();
     const int n = S.list_count, nslots = S.pool_count;
     // ---- spans: one thread per (polygon,row) slot ---------------------------------------------
@@ -291,11 +290,12 @@ __device__ void flush_list(RasterSmem& S, int tid) {
     }
     __syncthreads();
     // ---- fill: one thread per (row, 32-pixel segment), top-most polygon first ------------------
+    // pix[k] holds the palette indices of pixels 4k..4k+3 of this thread's segment.  Polygons of a
+    // later flush are later in painter's order, so they overwrite what earlier flushes left.
     {
         const int y = tid / 3, seg = tid - 3 * y;
         const int xs = 32 * seg;
         uint32_t uncovered = 0xffffffffu;
-        uint8_t* out = S.img + (SH - 1 - y) * IMG_STRIDE + xs;   // GL row y -> observation row 95 - y, mcr:602
         for (int wd = MASK_WORDS - 1; wd >= 0 && uncovered; --wd) {
             uint32_t m = S.rowmask[y][wd];
             while (m && uncovered) {
@@ -307,13 +307,20 @@ __device__ void flush_list(RasterSmem& S, int tid) {
                 lo = lo < 0 ? 0 : lo; hi = hi > 32 ? 32 : hi;
                 if (hi > lo) {
                     const uint32_t cover = (uint32_t)((1ull << hi) - (1ull << lo));
-                    uint32_t fresh = cover & uncovered;
+                    const uint32_t fresh = cover & uncovered;
                     uncovered &= ~cover;
-                    const uint8_t c = S.col[p];
-                    while (fresh) {
-                        const int i = __ffs(fresh) - 1;
-                        fresh &= fresh - 1;
-                        out[i] = c;
+                    const uint32_t c4 = (uint32_t)S.col[p] * 0x01010101u;
+                    if (fresh == 0xffffffffu) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) pix[k] = c4;
+                    } else if (fresh) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const uint32_t nib = (fresh >> (4 * k)) & 0xFu;
+                            // nibble -> byte mask: bit i of nib selects byte i
+                            const uint32_t bm = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;
+                            pix[k] = (pix[k] & ~bm) | (c4 & bm);
+                        }
                     }
                 }
             }
@@ -363,31 +370,32 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     }
     if (tid == 96) {
         // Checker squares the camera can see: invert the affine for the four viewport corners
-        // (+ a one-unit margin, far above fp32 error) and keep the index ranges that overlap.
-        const double m00 = b.camera[(size_t)0 * N + car], m01 = b.camera[(size_t)1 * N + car], m02 = b.camera[(size_t)2 * N + car];
-        const double m10 = b.camera[(size_t)3 * N + car], m11 = b.camera[(size_t)4 * N + car], m12 = b.camera[(size_t)5 * N + car];
-        const double det = m00 * m11 - m01 * m10;
+        // (+ a two-unit margin, far above fp32 error) and keep the index ranges that overlap.
+        const float m00 = b.camera[(size_t)0 * N + car], m01 = b.camera[(size_t)1 * N + car], m02 = b.camera[(size_t)2 * N + car];
+        const float m10 = b.camera[(size_t)3 * N + car], m11 = b.camera[(size_t)4 * N + car], m12 = b.camera[(size_t)5 * N + car];
+        const float det = m00 * m11 - m01 * m10;
         int j0x = 0, j1x = N_CHECKER_AXIS - 1, j0y = 0, j1y = N_CHECKER_AXIS - 1;
-        if (fabs(det) > 1e-12) {
-            double wxmin = 1e300, wxmax = -1e300, wymin = 1e300, wymax = -1e300;
+        if (fabsf(det) > 1e-12f) {
+            const float inv = 1.0f / det;
+            float wxmin = 3.0e38f, wxmax = -3.0e38f, wymin = 3.0e38f, wymax = -3.0e38f;
+#pragma unroll
             for (int cnr = 0; cnr < 4; ++cnr) {
-                const double u = ((cnr & 1) ? (double)SW : 0.0) - m02, v = ((cnr & 2) ? (double)SH : 0.0) - m12;
-                const double wx = (m11 * u - m01 * v) / det, wy = (-m10 * u + m00 * v) / det;
-                wxmin = fmin(wxmin, wx); wxmax = fmax(wxmax, wx); wymin = fmin(wymin, wy); wymax = fmax(wymax, wy);
+                const float u = ((cnr & 1) ? (float)SW : 0.0f) - m02, v = ((cnr & 2) ? (float)SH : 0.0f) - m12;
+                const float wx = (m11 * u - m01 * v) * inv, wy = (-m10 * u + m00 * v) * inv;
+                wxmin = fminf(wxmin, wx); wxmax = fmaxf(wxmax, wx); wymin = fminf(wymin, wy); wymax = fmaxf(wymax, wy);
             }
-            const double k = (2000 / 6.0) / 20.0, margin = 1.0;
+            const float ik = 20.0f / (float)(2000 / 6.0), margin = 2.0f;
             // square j spans k*(2j-20) .. k*(2j-19) on its axis
-            const double a0 = floor(((wxmin - margin) / k + 19.0) / 2.0 - 1e-9), a1 = ceil(((wxmax + margin) / k + 20.0) / 2.0 + 1e-9);
-            const double c0 = floor(((wymin - margin) / k + 19.0) / 2.0 - 1e-9), c1 = ceil(((wymax + margin) / k + 20.0) / 2.0 + 1e-9);
+            const float a0 = floorf(((wxmin - margin) * ik + 19.0f) * 0.5f - 1e-3f), a1 = ceilf(((wxmax + margin) * ik + 20.0f) * 0.5f + 1e-3f);
+            const float c0 = floorf(((wymin - margin) * ik + 19.0f) * 0.5f - 1e-3f), c1 = ceilf(((wymax + margin) * ik + 20.0f) * 0.5f + 1e-3f);
             if (a0 == a0 && a1 == a1 && c0 == c0 && c1 == c1) {
-                j0x = (int)fmax(0.0, fmin(a0, 20.0)); j1x = (int)fmin((double)(N_CHECKER_AXIS - 1), fmax(a1, -1.0));
-                j0y = (int)fmax(0.0, fmin(c0, 20.0)); j1y = (int)fmin((double)(N_CHECKER_AXIS - 1), fmax(c1, -1.0));
+                j0x = (int)fmaxf(0.0f, fminf(a0, 20.0f)); j1x = (int)fminf((float)(N_CHECKER_AXIS - 1), fmaxf(a1, -1.0f));
+                j0y = (int)fmaxf(0.0f, fminf(c0, 20.0f)); j1y = (int)fminf((float)(N_CHECKER_AXIS - 1), fmaxf(c1, -1.0f));
             }
         }
         S.ck_j0x = j0x; S.ck_nx = j1x >= j0x ? j1x - j0x + 1 : 0;
         S.ck_j0y = j0y; S.ck_ny = j1y >= j0y ? j1y - j0y + 1 : 0;
     }
-    for (int i = tid; i < SH * IMG_STRIDE / 4; i += RS_THREADS) ((uint32_t*)S.img)[i] = 0;   // glClear -> black
     for (int i = tid; i < SH * MASK_WORDS; i += RS_THREADS) (&S.rowmask[0][0])[i] = 0;
     __syncthreads();
 
@@ -403,6 +411,10 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     V.use_ego_color = use_ego_color;
     V.backward_flag_on = (b.backward[car] != 0) && backwards_flag;
     const Affine M = S.M;
+
+    uint32_t pix[8];                       // this thread's 32 pixels (palette indices); glClear -> black
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pix[k] = PAL_BLACK * 0x01010101u;
 
     // ---- candidates -> ordered display list -> flush -----------------------------------------
     const int NC = 1 + V.n_checker + Q + CAR_PARTS * d.A + 9;
@@ -483,45 +495,46 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
             // the first thread that did not fit publishes the accepted totals (its exclusive prefix)
             if (tid == first_bad) { S.list_count = lc + slot_rel; S.pool_count = pc + row_rel; }
             base += first_bad;
-            flush_list(S, tid);
+            flush_list(S, tid, pix);
         } else {
             if (tid == RS_THREADS - 1) { S.list_count = lc + slot_rel + ents; S.pool_count = pc + row_rel + rows; }
             base += RS_THREADS;
             __syncthreads();
         }
     }
-    flush_list(S, tid);
+    flush_list(S, tid, pix);
 
-    // ---- score label glyphs (D3), rows 87..91, cols 2..13 ---------------------------------------
-    if (tid < 60) {
-        const int ch = tid / 15, ry = (tid % 15) / 3, rx = tid % 3;
-        const int g = S.glyph[ch];
-        if (g >= 0 && (c_font[g][ry] & (4 >> rx))) S.img[(87 + ry) * IMG_STRIDE + (2 + 3 * ch + rx)] = PAL_WHITE;
-    }
-    __syncthreads();
-
-    // ---- expand palette -> RGB and store the frame with 16-byte vector stores --------------------
-    // 16 pixels = 48 bytes = 3 x uint4; byte stream r0 g0 b0 r1 g1 b1 ... from packed 0x00BBGGRR
-    {
-        uint4* dst = reinterpret_cast<uint4*>(obs + (size_t)frame * MCR_OBS_BYTES);
-        for (int g = tid; g < SH * SW / 16; g += RS_THREADS) {
-            const int row = g / 6, c16 = g - 6 * row;
-            const uint2* src = reinterpret_cast<const uint2*>(S.img + row * IMG_STRIDE + c16 * 16);
-            const uint2 ia = src[0], ib = src[1];
-            const uint32_t iw[4] = {ia.x, ia.y, ib.x, ib.y};
-            uint32_t o[12];
+    const int my_y = tid / 3, my_seg = tid - 3 * my_y;
+    // ---- score label glyphs (D3): observation rows 87..91 (= GL rows 8..4), cols 2..13 -------------
+    if (my_seg == 0 && my_y >= 4 && my_y <= 8) {
+        const int ry = (SH - 1 - my_y) - 87;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t c0 = S.pal32[iw[q] & 0xff], c1 = S.pal32[(iw[q] >> 8) & 0xff];
-                const uint32_t c2 = S.pal32[(iw[q] >> 16) & 0xff], c3 = S.pal32[iw[q] >> 24];
-                o[3 * q + 0] = c0 | (c1 << 24);
-                o[3 * q + 1] = (c1 >> 8) | (c2 << 16);
-                o[3 * q + 2] = (c2 >> 16) | (c3 << 8);
+        for (int ch = 0; ch < 4; ++ch) {
+            const int g = S.glyph[ch];
+            const int bits = g >= 0 ? c_font[g][ry] : 0;
+#pragma unroll
+            for (int rx = 0; rx < 3; ++rx) {
+                const int x = 2 + 3 * ch + rx;
+                if (bits & (4 >> rx)) pix[x >> 2] = (pix[x >> 2] & ~(0xFFu << (8 * (x & 3)))) | ((uint32_t)PAL_WHITE << (8 * (x & 3)));
             }
-            dst[3 * g + 0] = make_uint4(o[0], o[1], o[2], o[3]);
-            dst[3 * g + 1] = make_uint4(o[4], o[5], o[6], o[7]);
-            dst[3 * g + 2] = make_uint4(o[8], o[9], o[10], o[11]);
         }
+    }
+
+    // ---- expand palette -> RGB and store this thread's 32 pixels as 6 x uint4 ------------------------
+    // 4 pixels = 12 bytes = 3 words; byte stream r0 g0 b0 r1 g1 b1 ... from packed 0x00BBGGRR
+    {
+        uint4* dst = reinterpret_cast<uint4*>(obs + (size_t)frame * MCR_OBS_BYTES + (size_t)(SH - 1 - my_y) * (SW * 3) + my_seg * 96);
+        uint32_t o[24];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t c0 = S.pal32[pix[k] & 0xff], c1 = S.pal32[(pix[k] >> 8) & 0xff];
+            const uint32_t c2 = S.pal32[(pix[k] >> 16) & 0xff], c3 = S.pal32[pix[k] >> 24];
+            o[3 * k + 0] = c0 | (c1 << 24);
+            o[3 * k + 1] = (c1 >> 8) | (c2 << 16);
+            o[3 * k + 2] = (c2 >> 16) | (c3 << 8);
+        }
+#pragma unroll
+        for (int v = 0; v < 6; ++v) dst[v] = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
     }
 
     // ---- post-step block, mcr:433-507 (skipped for reset()'s step(None)) -----------------------

@@ -27,13 +27,14 @@
 // physics stores.
 #include "mcr_internal.h"
 #include <cuda_runtime.h>
+#include <cstdlib>
 
 #define AABB_MARGIN 0.05f
 #define FIX_STRIDE 21   // 8 x + 8 y + 4 aabb + (n | active<<8), odd stride spreads banks
 #define PAIRS_PER_CAR 128
 #define CANDS_PER_CAR 64
 
-enum { ROLE_CONTACTS = 1, ROLE_PHYSICS = 2 };
+enum { ROLE_CONTACTS = 1, ROLE_PHYSICS = 2, ROLE_NO_EARLY_EXIT = 4 /* diagnostics: always run all 180 sweeps */ };
 
 __device__ __forceinline__ void rot_set(float a, float& s, float& c) {
     double ds, dc;
@@ -166,14 +167,14 @@ __device__ __forceinline__ unsigned state_diff(const VelState& a, const VelState
 // 4-cycle, checked at multiples of 4 so the phase matches sweep 180) the remaining sweeps
 // cannot change it, so stopping there is exact.
 template <int PAT>
-__device__ __forceinline__ void solve_velocity(VelState& s, const JointC (&J)[4], const Masses& m) {
+__device__ __forceinline__ void solve_velocity(VelState& s, const JointC (&J)[4], const Masses& m, bool early_exit) {
     // one sweep per loop trip keeps the loop body (~3 KB of SASS) inside the L0 instruction cache
 #pragma unroll 1
     for (int it = 0; it < MCR_VEL_ITERS; it += 4) {
         const VelState before = s;
 #pragma unroll 1
         for (int r = 0; r < 4; ++r) sweep<PAT>(s, J, m);
-        if (state_diff(before, s) == 0u) break;
+        if (early_exit && state_diff(before, s) == 0u) break;
     }
 }
 
@@ -552,11 +553,11 @@ sim_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, 
 #pragma unroll
         for (int k = 0; k < 4; ++k) pat |= (lim[k] != LIM_INACTIVE ? 1 : 0) << k;
         switch (pat) {
-            case 0: solve_velocity<0>(s, J, m); break;
-            case 1: solve_velocity<1>(s, J, m); break;
-            case 2: solve_velocity<2>(s, J, m); break;
-            case 3: solve_velocity<3>(s, J, m); break;
-            default: solve_velocity<-1>(s, J, m); break;   // a rear joint at its limit: rare
+            case 0: solve_velocity<0>(s, J, m, !(roles & ROLE_NO_EARLY_EXIT)); break;
+            case 1: solve_velocity<1>(s, J, m, !(roles & ROLE_NO_EARLY_EXIT)); break;
+            case 2: solve_velocity<2>(s, J, m, !(roles & ROLE_NO_EARLY_EXIT)); break;
+            case 3: solve_velocity<3>(s, J, m, !(roles & ROLE_NO_EARLY_EXIT)); break;
+            default: solve_velocity<-1>(s, J, m, !(roles & ROLE_NO_EARLY_EXIT)); break;   // a rear joint at its limit: rare
         }
 #pragma unroll
         for (int i = 0; i < 5; ++i) { vx[i] = s.vx[i]; vy[i] = s.vy[i]; w[i] = s.w[i]; }
@@ -771,5 +772,6 @@ int launch_physics(const Dims& d, const DevBuffers& b, const CarConst& cc, const
 
 int launch_simulate(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
                     const void* action, int action_dtype, double h_ratio, void* stream) {
-    return launch_sim(d, b, cc, mask, action, action_dtype, h_ratio, ROLE_CONTACTS | ROLE_PHYSICS, stream);
+    static const int extra = getenv("MCR_NO_EARLY_EXIT") ? ROLE_NO_EARLY_EXIT : 0;   // diagnostics only
+    return launch_sim(d, b, cc, mask, action, action_dtype, h_ratio, ROLE_CONTACTS | ROLE_PHYSICS | extra, stream);
 }
