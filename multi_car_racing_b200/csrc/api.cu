@@ -369,6 +369,9 @@ struct mcr_handle_t {
     int64_t launches;
     uint8_t palette[PAL_COUNT][4];
     bool palette_ready;
+    cudaStream_t side;           // contacts run here, beside the solver
+    cudaEvent_t ev_fork, ev_join;
+    bool side_ready;
 };
 
 
@@ -395,7 +398,7 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
     if (!build_car_const(h->cc)) { delete h; return fail(-2, "car geometry set-up failed"); }
     std::memset(&h->buf, 0, sizeof(h->buf));
     std::memset(h->ptr, 0, sizeof(h->ptr));
-    h->launches = 0; h->palette_ready = false;
+    h->launches = 0; h->palette_ready = false; h->side_ready = false;
     const int64_t N = h->d.N, B = h->d.B, A = h->d.A, T = h->d.Tmax, Q = h->d.Qmax, P = h->d.P;
     set_spec(h, BUF_BODY, "body", MCR_F32, {5, BODY_FIELDS, N});
     set_spec(h, BUF_SLEEP_TIME, "sleep_time", MCR_F32, {5, N});
@@ -422,6 +425,7 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
     set_spec(h, BUF_TOUCHED, "touched", MCR_U8, {B, T});
     set_spec(h, BUF_RESET_MASK, "reset_mask", MCR_U8, {B});
     set_spec(h, BUF_STATUS, "status", MCR_I32, {STATUS_WORDS});
+    set_spec(h, BUF_SCRATCH, "scratch", MCR_F32, {MCR_SCRATCH_FIELDS, N});
     set_spec(h, BUF_TRK_T, "trk_T", MCR_I32, {P});
     set_spec(h, BUF_TRK_Q, "trk_Q", MCR_I32, {P});
     set_spec(h, BUF_TRK_NODE, "trk_node", MCR_F64, {P, T, 3});
@@ -435,7 +439,13 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
     return 0;
 }
 
-extern "C" int mcr_destroy(mcr_handle h) { delete h; return 0; }
+extern "C" int mcr_destroy(mcr_handle h) {
+    if (h && h->side_ready) {
+        cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
+    }
+    delete h;
+    return 0;
+}
 
 extern "C" int mcr_buffer_count(mcr_handle h) { return h ? BUF_COUNT : fail(-1, "null handle"); }
 
@@ -480,6 +490,7 @@ extern "C" int mcr_bind_buffer(mcr_handle h, int i, void* p) {
         case BUF_TOUCHED: b.touched = (uint8_t*)p; break;
         case BUF_RESET_MASK: b.reset_mask = (uint8_t*)p; break;
         case BUF_STATUS: b.status = (int32_t*)p; break;
+        case BUF_SCRATCH: b.scratch = (float*)p; break;
         case BUF_TRK_T: b.trk_T = (int32_t*)p; break;
         case BUF_TRK_Q: b.trk_Q = (int32_t*)p; break;
         case BUF_TRK_NODE: b.trk_node = (double*)p; break;
@@ -591,6 +602,28 @@ extern "C" int mcr_load_track(mcr_handle h, int32_t slot, int32_t T, const doubl
 // ---------------------------------------------------------------------------------------
 #define LAUNCH(expr) do { int n_ = (expr); if (n_ < 0) return fail(-101, "kernel launch failed in %s: %s", #expr, cudaGetErrorString(cudaGetLastError())); h->launches += n_; } while (0)
 
+// contacts || (pre -> sweep), then post.  The contact pass only reads the step's start poses, so it
+// runs on the handle's side stream while the solver occupies the main one; post_kernel (which
+// overwrites the poses and consumes on_road_next) waits for both.
+static int simulate(mcr_handle h, const uint8_t* mask, const void* action, int32_t action_dtype, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!h->side_ready) {
+        CUDA_OK(cudaSetDevice(h->cfg.device));
+        CUDA_OK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        h->side_ready = true;
+    }
+    CUDA_OK(cudaEventRecord(h->ev_fork, s));
+    CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    LAUNCH(launch_contacts(h->d, h->buf, h->cc, mask, h->side));
+    CUDA_OK(cudaEventRecord(h->ev_join, h->side));
+    LAUNCH(launch_physics(h->d, h->buf, h->cc, mask, action, action_dtype, h->cfg.h_ratio, s));
+    CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));
+    LAUNCH(launch_physics_post(h->d, h->buf, h->cc, mask, action != nullptr, h->cfg.h_ratio, s));
+    return 0;
+}
+
 extern "C" int mcr_contacts(mcr_handle h, const uint8_t* mask, void* stream) {
     int rc = check_bound(h); if (rc) return rc;
     LAUNCH(launch_contacts(h->d, h->buf, h->cc, mask, stream));
@@ -601,14 +634,14 @@ extern "C" int mcr_physics(mcr_handle h, const uint8_t* mask, const void* action
     int rc = check_bound(h); if (rc) return rc;
     if (action && action_dtype != MCR_F32 && action_dtype != MCR_F64) return fail(-1, "action dtype must be MCR_F32 or MCR_F64");
     LAUNCH(launch_physics(h->d, h->buf, h->cc, mask, action, action_dtype, h->cfg.h_ratio, stream));
+    LAUNCH(launch_physics_post(h->d, h->buf, h->cc, mask, action != nullptr, h->cfg.h_ratio, stream));
     return 0;
 }
 
 extern "C" int mcr_simulate(mcr_handle h, const uint8_t* mask, const void* action, int32_t action_dtype, void* stream) {
     int rc = check_bound(h); if (rc) return rc;
     if (action && action_dtype != MCR_F32 && action_dtype != MCR_F64) return fail(-1, "action dtype must be MCR_F32 or MCR_F64");
-    LAUNCH(launch_simulate(h->d, h->buf, h->cc, mask, action, action_dtype, h->cfg.h_ratio, stream));
-    return 0;
+    return simulate(h, mask, action, action_dtype, stream);
 }
 
 extern "C" int mcr_render(mcr_handle h, const uint8_t* mask, uint8_t* obs, double* reward, uint8_t* done, int32_t post_step, void* stream) {
@@ -626,7 +659,7 @@ extern "C" int mcr_reset(mcr_handle h, const uint8_t* mask, const int32_t* track
     if (!track_slot || !cw || !spawn_pose || !obs) return fail(-1, "mcr_reset: null argument");
     LAUNCH(launch_spawn(h->d, h->buf, h->cc, mask, track_slot, cw, spawn_pose, stream));
     // the implicit step(None), mcr:408
-    LAUNCH(launch_simulate(h->d, h->buf, h->cc, mask, nullptr, MCR_F32, h->cfg.h_ratio, stream));
+    rc = simulate(h, mask, nullptr, MCR_F32, stream); if (rc) return rc;
     LAUNCH(launch_render(h->d, h->buf, h->cc, mask, obs, nullptr, nullptr, 0, h->cfg.backwards_flag,
                          h->cfg.use_ego_color, h->cfg.max_episode_steps, stream));
     return 0;
@@ -637,14 +670,14 @@ extern "C" int mcr_step(mcr_handle h, const void* action, int32_t action_dtype, 
     int rc = check_bound(h); if (rc) return rc;
     if (!action || !obs || !reward || !done) return fail(-1, "mcr_step: null argument");
     if (action_dtype != MCR_F32 && action_dtype != MCR_F64) return fail(-1, "action dtype must be MCR_F32 or MCR_F64");
-    LAUNCH(launch_simulate(h->d, h->buf, h->cc, nullptr, action, action_dtype, h->cfg.h_ratio, stream));
+    rc = simulate(h, nullptr, action, action_dtype, stream); if (rc) return rc;
     LAUNCH(launch_render(h->d, h->buf, h->cc, nullptr, obs, reward, done, 1, h->cfg.backwards_flag,
                          h->cfg.use_ego_color, h->cfg.max_episode_steps, stream));
     if (flags & 1) {
         AutoResetCfg ar{h->cfg.use_random_direction, h->cfg.direction_cw, (unsigned long long)h->cfg.seed};
         LAUNCH(launch_auto_reset(h->d, h->buf, h->cc, done, ar, stream));
         const uint8_t* m = h->buf.reset_mask;
-        LAUNCH(launch_simulate(h->d, h->buf, h->cc, m, nullptr, MCR_F32, h->cfg.h_ratio, stream));
+        rc = simulate(h, m, nullptr, MCR_F32, stream); if (rc) return rc;
         LAUNCH(launch_render(h->d, h->buf, h->cc, m, obs, nullptr, nullptr, 0, h->cfg.backwards_flag,
                              h->cfg.use_ego_color, h->cfg.max_episode_steps, stream));
     }

@@ -22,6 +22,7 @@
 #define MCR_VEL_ITERS 180   // world.Step(1/FPS, 6*30, 2*30), mcr:428
 #define MCR_POS_ITERS 60
 #define MCR_MAXV 8
+#define MCR_SCRATCH_FIELDS 91   // 31 velocity/impulse values + 4 joints x 15 constants
 
 // body SoA: body[(b * BODY_FIELDS + f) * N + car], b = 0 hull, 1..4 wheels
 enum { BF_CX = 0, BF_CY, BF_A, BF_VX, BF_VY, BF_W, BF_PX, BF_PY, BF_QS, BF_QC, BODY_FIELDS };
@@ -39,7 +40,7 @@ enum {
     BUF_ON_ROAD, BUF_ON_ROAD_NEXT, BUF_REWARD, BUF_PREV_REWARD, BUF_VISIT_COUNT, BUF_BACKWARD,
     BUF_TIME, BUF_STEPS, BUF_CAMERA, BUF_STRIPE, BUF_HEADING,
     BUF_ENV_TRACK, BUF_ENV_CW, BUF_ENV_EPISODE,
-    BUF_VISITED, BUF_TOUCHED, BUF_RESET_MASK, BUF_STATUS,
+    BUF_VISITED, BUF_TOUCHED, BUF_RESET_MASK, BUF_STATUS, BUF_SCRATCH,
     BUF_TRK_T, BUF_TRK_Q, BUF_TRK_NODE, BUF_TRK_TILE, BUF_TRK_TILE_AABB, BUF_TRK_QUAD, BUF_TRK_QUAD_COL,
     BUF_TRK_QUAD_TILE, BUF_TRK_SLOT_POSE,
     BUF_COUNT
@@ -79,6 +80,7 @@ struct DevBuffers {
     double* heading;                     // [N] car_angle of mcr:449-456
     int32_t* env_track; uint8_t* env_cw; uint32_t* env_episode;
     uint32_t* visited; uint8_t* touched; uint8_t* reset_mask; int32_t* status;
+    float* scratch;                      // [MCR_SCRATCH_FIELDS][N] solver hand-over between pre/sweep/post kernels
     int32_t* trk_T; int32_t* trk_Q; double* trk_node; float* trk_tile; float* trk_tile_aabb;
     float* trk_quad; uint8_t* trk_quad_col; int16_t* trk_quad_tile; double* trk_slot_pose;
 };
@@ -89,8 +91,8 @@ struct Dims { int B, A, N, Tmax, Qmax, P; };
 int launch_contacts(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, void* stream);
 int launch_physics(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
                    const void* action, int action_dtype, double h_ratio, void* stream);
-int launch_simulate(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
-                    const void* action, int action_dtype, double h_ratio, void* stream);
+int launch_physics_post(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
+                        int has_action, double h_ratio, void* stream);
 int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* obs,
                   double* reward, uint8_t* done, int post_step, int backwards_flag,
                   int use_ego_color, int max_episode_steps, void* stream);

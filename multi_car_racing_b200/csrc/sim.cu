@@ -1,5 +1,5 @@
-// sim.cu -- kernels 1+2 fused per env: FrictionDetector/Collide on one warp, Car.step +
-// world.Step on another, one CTA per environment.
+// sim.cu -- kernels 1+2: FrictionDetector/Collide (contacts_kernel) and Car.step + world.Step
+// (pre_kernel -> sweep_kernel -> post_kernel).
 //
 // Replaces, for every env of the batch (reference: gym_multi_car_racing/multi_car_racing.py):
 //   mcr:84-123   FrictionDetector.BeginContact/EndContact/_contact; Box2D b2Contact::Update for
@@ -14,17 +14,24 @@
 // b2Rot::Set is (float)sin((double)a).  The wheel's local centre of mass and localAnchorB are
 // exactly 0 so every rB term of b2RevoluteJoint is an exact +-0 and is dropped.
 //
-// Mapping.  One CTA of (1 + A) warps per env.  Warps 1..A ("physics"): one car each; the 180
-// Gauss-Seidel sweeps are a serial dependency chain through the hull velocity (latency bound), so
-// a car's warp runs straight-line code specialised to its joints' limit pattern and leaves the
-// sweep loop as soon as the car has reached an exact fixed point.
-// warp 0 ("contacts"): builds the world-space fixture polygons in shared memory, strides the
-// tiles (coalesced float4 AABB loads), AABB-rejects against per-car then per-fixture boxes,
-// queues the surviving (tile, fixture) pairs, runs the exact overlap predicate one pair per
-// lane, and replays new visits in the contact-list order of a fresh b2World (tile descending,
-// car descending) so the float64 reward sums are bit-reproducible -- no racing atomicAdds.
-// Both read the step's start poses; a __syncthreads() orders the contact reads before the
-// physics stores.
+// Mapping.
+//   contacts_kernel  one warp per env: world-space fixture polygons in shared memory, tiles strided
+//                    over lanes (coalesced float4 AABB loads), AABB reject against per-car then
+//                    per-fixture boxes, surviving (tile, fixture) pairs queued and tested one pair
+//                    per lane with the exact predicate; new visits replayed in the contact-list order
+//                    of a fresh b2World (tile descending, car descending) so the float64 reward sums
+//                    are bit-reproducible -- no racing atomicAdds.  Runs on a side stream beside the
+//                    solver; it only reads the step's start poses.
+//   pre_kernel       one THREAD per car, SoA-coalesced: controls, the float64 tyre model, velocity
+//                    integration, InitVelocityConstraints + warm start.  Everything lane-parallel
+//                    (fp64 division/sqrt/sincos) lives here and in post_kernel, at full lane use.
+//   sweep_kernel     one WARP per car: the 180 Gauss-Seidel sweeps are a serial dependency chain
+//                    through the hull velocity (latency bound, ~650 cycles per sweep), so a car's
+//                    warp runs straight-line code specialised to its joints' limit pattern and
+//                    leaves the loop as soon as the car has reached an exact fixed point.
+//   post_kernel      one THREAD per car: position integration, <= 60 position iterations,
+//                    SynchronizeTransform, sleeping, and the per-view values the rasteriser needs
+//                    (camera affine, heading, wheel-stripe extents).
 #include "mcr_internal.h"
 #include <cuda_runtime.h>
 #include <cstdlib>
@@ -34,7 +41,6 @@
 #define PAIRS_PER_CAR 128
 #define CANDS_PER_CAR 64
 
-enum { ROLE_CONTACTS = 1, ROLE_PHYSICS = 2, ROLE_NO_EARLY_EXIT = 4 /* diagnostics: always run all 180 sweeps */ };
 
 __device__ __forceinline__ void rot_set(float a, float& s, float& c) {
     double ds, dc;
@@ -368,28 +374,34 @@ __device__ void contacts_warp(const Dims& d, const DevBuffers& b, const CarConst
 }
 
 // ---------------------------------------------------------------------------------------
-// the fused kernel
+// kernels
 // ---------------------------------------------------------------------------------------
-template <typename ActT, int MAX_THREADS, int MIN_BLOCKS>
-__global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS)
-sim_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, const ActT* __restrict__ action,
-           double h_ratio, int roles) {
+#define CT_WARPS 4
+
+__global__ void __launch_bounds__(CT_WARPS * 32)
+contacts_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, size_t smem_per_warp) {
     extern __shared__ __align__(16) unsigned char sim_smem[];
-    const int env = blockIdx.x;
-    if (mask && !mask[env]) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp == 0) {
-        if (roles & ROLE_CONTACTS) contacts_warp(d, b, cc, env, lane, sim_smem);
-        __syncthreads();
-        return;
-    }
-    if (!(roles & ROLE_PHYSICS)) { __syncthreads(); return; }
-    // one warp per car: every lane runs the same scalar arithmetic (loads broadcast), lane 0 stores.
-    // The solver is a serial chain, so lanes buy nothing here; what matters is that each car leaves
-    // the sweep loop at ITS OWN fixed point and runs code specialised to ITS limit pattern.
+    const int env = blockIdx.x * CT_WARPS + warp;
+    if (env >= d.B) return;
+    if (mask && !mask[env]) return;
+    contacts_warp(d, b, cc, env, lane, sim_smem + (size_t)warp * smem_per_warp);
+}
+
+// scratch SoA between pre / sweep / post: scratch[f * N + car]
+enum { SC_VX = 0, SC_VY = 5, SC_W = 10, SC_JIX = 15, SC_JIY = 19, SC_JIZ = 23, SC_JMOT = 27, SC_JOINT = 31, SC_JOINT_FIELDS = 15,
+       SC_FIELDS = SC_JOINT + 4 * SC_JOINT_FIELDS };
+
+#define PRE_BLOCK 128
+
+template <typename ActT>
+__global__ void __launch_bounds__(PRE_BLOCK)
+pre_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, const ActT* __restrict__ action) {
+    const int car = blockIdx.x * PRE_BLOCK + threadIdx.x;
+    if (car >= d.N) return;
+    const int env = car / d.A;
+    if (mask && !mask[env]) return;
     const int N = d.N;
-    const int car = env * d.A + (warp - 1);
-    const bool writer = lane == 0;
 
     // ---- load state ----------------------------------------------------------------
     float cx[5], cy[5], ang[5], vx[5], vy[5], w[5], qs[5], qc[5], slp[5];
@@ -541,28 +553,114 @@ sim_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, 
             w[bi] += iB * (jmot[k] + jiz[k]);
         }
     }
-    // SolveVelocityConstraints x 180, specialised on the front joints' limit pattern
-    {
-        Masses m; m.mA = mA; m.iA = iA; m.mB = mB; m.iB = iB; m.maxMotorImpulse = h * cc.max_motor_torque;
-        VelState s;
+    // ---- hand over to sweep_kernel / post_kernel ---------------------------------------------------
+    float* sc = b.scratch + car;
 #pragma unroll
-        for (int i = 0; i < 5; ++i) { s.vx[i] = vx[i]; s.vy[i] = vy[i]; s.w[i] = w[i]; }
+    for (int i = 0; i < 5; ++i) {
+        sc[(size_t)(SC_VX + i) * N] = vx[i]; sc[(size_t)(SC_VY + i) * N] = vy[i]; sc[(size_t)(SC_W + i) * N] = w[i];
+        b.sleep_time[(size_t)i * N + car] = slp[i];
+        b.awake[(size_t)i * N + car] = awake[i] ? 1 : 0;
+    }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { s.jix[k] = jix[k]; s.jiy[k] = jiy[k]; s.jiz[k] = jiz[k]; s.jmot[k] = jmot[k]; }
-        int pat = 0;
+    for (int k = 0; k < 4; ++k) {
+        sc[(size_t)(SC_JIX + k) * N] = jix[k]; sc[(size_t)(SC_JIY + k) * N] = jiy[k];
+        sc[(size_t)(SC_JIZ + k) * N] = jiz[k]; sc[(size_t)(SC_JMOT + k) * N] = jmot[k];
+        const JointC& j = J[k];
+        float* q = sc + (size_t)(SC_JOINT + k * SC_JOINT_FIELDS) * N;
+        q[(size_t)0 * N] = j.rAx; q[(size_t)1 * N] = j.rAy; q[(size_t)2 * N] = j.k11; q[(size_t)3 * N] = j.k12;
+        q[(size_t)4 * N] = j.k22; q[(size_t)5 * N] = j.ezx; q[(size_t)6 * N] = j.ezy; q[(size_t)7 * N] = j.ezz;
+        q[(size_t)8 * N] = j.det22; q[(size_t)9 * N] = j.cfx; q[(size_t)10 * N] = j.cfy; q[(size_t)11 * N] = j.cfz;
+        q[(size_t)12 * N] = j.det33; q[(size_t)13 * N] = j.motorMass; q[(size_t)14 * N] = j.motorSpeed;
+        b.limit_state[(size_t)k * N + car] = (uint8_t)lim[k];
+        b.wheel[(size_t)(k * WHEEL_FIELDS + WF_OMEGA) * N + car] = omega[k];
+        b.wheel[(size_t)(k * WHEEL_FIELDS + WF_PHASE) * N + car] = phase[k];
+    }
+    b.ctrl[(size_t)CF_GAS * N + car] = gas;
+    b.ctrl[(size_t)CF_BRAKE * N + car] = brake;
+    b.ctrl[(size_t)CF_STEER * N + car] = steer;
+}
+
+#define SWEEP_WARPS 4
+
+__global__ void __launch_bounds__(SWEEP_WARPS * 32, 4)
+sweep_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, int early_exit) {
+    const int car = blockIdx.x * SWEEP_WARPS + (threadIdx.x >> 5);
+    if (car >= d.N) return;
+    if (mask && !mask[car / d.A]) return;
+    const int N = d.N;
+    // every lane runs the same scalar arithmetic (the loads broadcast); lane 0 stores
+    const float* sc = b.scratch + car;
+    VelState s;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) pat |= (lim[k] != LIM_INACTIVE ? 1 : 0) << k;
-        switch (pat) {
-            case 0: solve_velocity<0>(s, J, m, !(roles & ROLE_NO_EARLY_EXIT)); break;
-            case 1: solve_velocity<1>(s, J, m, !(roles & ROLE_NO_EARLY_EXIT)); break;
-            case 2: solve_velocity<2>(s, J, m, !(roles & ROLE_NO_EARLY_EXIT)); break;
-            case 3: solve_velocity<3>(s, J, m, !(roles & ROLE_NO_EARLY_EXIT)); break;
-            default: solve_velocity<-1>(s, J, m, !(roles & ROLE_NO_EARLY_EXIT)); break;   // a rear joint at its limit: rare
+    for (int i = 0; i < 5; ++i) { s.vx[i] = sc[(size_t)(SC_VX + i) * N]; s.vy[i] = sc[(size_t)(SC_VY + i) * N]; s.w[i] = sc[(size_t)(SC_W + i) * N]; }
+    JointC J[4];
+    int pat = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        s.jix[k] = sc[(size_t)(SC_JIX + k) * N]; s.jiy[k] = sc[(size_t)(SC_JIY + k) * N];
+        s.jiz[k] = sc[(size_t)(SC_JIZ + k) * N]; s.jmot[k] = sc[(size_t)(SC_JMOT + k) * N];
+        const float* q = sc + (size_t)(SC_JOINT + k * SC_JOINT_FIELDS) * N;
+        JointC& j = J[k];
+        j.rAx = q[(size_t)0 * N]; j.rAy = q[(size_t)1 * N]; j.k11 = q[(size_t)2 * N]; j.k12 = q[(size_t)3 * N];
+        j.k22 = q[(size_t)4 * N]; j.ezx = q[(size_t)5 * N]; j.ezy = q[(size_t)6 * N]; j.ezz = q[(size_t)7 * N];
+        j.det22 = q[(size_t)8 * N]; j.cfx = q[(size_t)9 * N]; j.cfy = q[(size_t)10 * N]; j.cfz = q[(size_t)11 * N];
+        j.det33 = q[(size_t)12 * N]; j.motorMass = q[(size_t)13 * N]; j.motorSpeed = q[(size_t)14 * N];
+        j.limit = b.limit_state[(size_t)k * N + car];
+        pat |= (j.limit != LIM_INACTIVE ? 1 : 0) << k;
+    }
+    const float h = (float)(1.0 / 50);
+    Masses m; m.mA = cc.hull_invMass; m.iA = cc.hull_invI; m.mB = cc.wheel_invMass; m.iB = cc.wheel_invI;
+    m.maxMotorImpulse = h * cc.max_motor_torque;
+    switch (pat) {
+        case 0: solve_velocity<0>(s, J, m, early_exit != 0); break;
+        case 1: solve_velocity<1>(s, J, m, early_exit != 0); break;
+        case 2: solve_velocity<2>(s, J, m, early_exit != 0); break;
+        case 3: solve_velocity<3>(s, J, m, early_exit != 0); break;
+        default: solve_velocity<-1>(s, J, m, early_exit != 0); break;   // a rear joint at its limit: rare
+    }
+    if ((threadIdx.x & 31) == 0) {
+        float* so = b.scratch + car;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { so[(size_t)(SC_VX + i) * N] = s.vx[i]; so[(size_t)(SC_VY + i) * N] = s.vy[i]; so[(size_t)(SC_W + i) * N] = s.w[i]; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            so[(size_t)(SC_JIX + k) * N] = s.jix[k]; so[(size_t)(SC_JIY + k) * N] = s.jiy[k];
+            so[(size_t)(SC_JIZ + k) * N] = s.jiz[k]; so[(size_t)(SC_JMOT + k) * N] = s.jmot[k];
         }
+    }
+}
+
+__global__ void __launch_bounds__(PRE_BLOCK)
+post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, int has_action, double h_ratio) {
+    const int car = blockIdx.x * PRE_BLOCK + threadIdx.x;
+    if (car >= d.N) return;
+    const int env = car / d.A;
+    if (mask && !mask[env]) return;
+    const int N = d.N;
+    const float h = (float)(1.0 / 50);
+    const float mA = cc.hull_invMass, iA = cc.hull_invI, mB = cc.wheel_invMass, iB = cc.wheel_invI;
+    const double SIZE = 0.02;
+    float cx[5], cy[5], ang[5], vx[5], vy[5], w[5], qs[5], qc[5], slp[5];
+    bool awake[5];
+    const float* sc = b.scratch + car;
 #pragma unroll
-        for (int i = 0; i < 5; ++i) { vx[i] = s.vx[i]; vy[i] = s.vy[i]; w[i] = s.w[i]; }
+    for (int i = 0; i < 5; ++i) {
+        const float* p = b.body + (size_t)(i * BODY_FIELDS) * N + car;
+        cx[i] = p[(size_t)BF_CX * N]; cy[i] = p[(size_t)BF_CY * N]; ang[i] = p[(size_t)BF_A * N];
+        vx[i] = sc[(size_t)(SC_VX + i) * N]; vy[i] = sc[(size_t)(SC_VY + i) * N]; w[i] = sc[(size_t)(SC_W + i) * N];
+        slp[i] = b.sleep_time[(size_t)i * N + car];
+        awake[i] = b.awake[(size_t)i * N + car] != 0;
+    }
+    float jix[4], jiy[4], jiz[4], jmot[4], motorMassK[4];
+    int lim[4];
+    double phase[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { jix[k] = s.jix[k]; jiy[k] = s.jiy[k]; jiz[k] = s.jiz[k]; jmot[k] = s.jmot[k]; }
+    for (int k = 0; k < 4; ++k) {
+        jix[k] = sc[(size_t)(SC_JIX + k) * N]; jiy[k] = sc[(size_t)(SC_JIY + k) * N];
+        jiz[k] = sc[(size_t)(SC_JIZ + k) * N]; jmot[k] = sc[(size_t)(SC_JMOT + k) * N];
+        motorMassK[k] = sc[(size_t)(SC_JOINT + k * SC_JOINT_FIELDS + 13) * N];
+        lim[k] = b.limit_state[(size_t)k * N + car];
+        phase[k] = b.wheel[(size_t)(k * WHEEL_FIELDS + WF_PHASE) * N + car];
     }
     // integrate positions
 #pragma unroll
@@ -584,6 +682,11 @@ sim_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, 
     bool positionSolved = false;
     for (int it = 0; it < MCR_POS_ITERS; ++it) {
         bool jointsOkay = true;
+        // an iteration that leaves every position bit-identical is a fixed point of the remaining
+        // ones (e.g. a limit error that sits exactly at the angular slop): stopping there is exact
+        float p_cx[5], p_cy[5], p_an[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { p_cx[i] = cx[i]; p_cy[i] = cy[i]; p_an[i] = ang[i]; }
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             const int k = 3 - kk;
@@ -595,18 +698,18 @@ sim_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, 
                 float limitImpulse = 0.0f;
                 if (lim[k] == LIM_EQUAL) {
                     float C = clampf(angle - cc.lower, -B2_MAX_ANGULAR_CORRECTION, B2_MAX_ANGULAR_CORRECTION);
-                    limitImpulse = -J[k].motorMass * C;
+                    limitImpulse = -motorMassK[k] * C;
                     angularError = fabsf(C);
                 } else if (lim[k] == LIM_LOWER) {
                     float C = angle - cc.lower;
                     angularError = -C;
                     C = clampf(C + B2_ANGULAR_SLOP, -B2_MAX_ANGULAR_CORRECTION, 0.0f);
-                    limitImpulse = -J[k].motorMass * C;
+                    limitImpulse = -motorMassK[k] * C;
                 } else {
                     float C = angle - cc.upper;
                     angularError = C;
                     C = clampf(C - B2_ANGULAR_SLOP, 0.0f, B2_MAX_ANGULAR_CORRECTION);
-                    limitImpulse = -J[k].motorMass * C;
+                    limitImpulse = -motorMassK[k] * C;
                 }
                 aA -= iA * limitImpulse;
                 aB += iB * limitImpulse;
@@ -631,6 +734,12 @@ sim_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, 
             jointsOkay = jointsOkay && ok;
         }
         if (jointsOkay) { positionSolved = true; break; }
+        unsigned moved = 0u;
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+            moved |= (__float_as_uint(p_cx[i]) ^ __float_as_uint(cx[i])) | (__float_as_uint(p_cy[i]) ^ __float_as_uint(cy[i])) |
+                     (__float_as_uint(p_an[i]) ^ __float_as_uint(ang[i]));
+        if (moved == 0u) break;
     }
     // SynchronizeTransform + sleep
     float px[5], py[5];
@@ -653,8 +762,6 @@ sim_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, 
         for (int i = 0; i < 5; ++i) { awake[i] = false; slp[i] = 0.0f; vx[i] = 0.0f; vy[i] = 0.0f; w[i] = 0.0f; }
     }
 
-    __syncthreads();   // the contacts warp has finished reading this step's start poses
-    if (writer) {
     // ---- store ---------------------------------------------------------------------------
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
@@ -671,19 +778,13 @@ sim_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, 
         float* p = b.joint + (size_t)(k * JOINT_FIELDS) * N + car;
         p[(size_t)JF_IX * N] = jix[k]; p[(size_t)JF_IY * N] = jiy[k]; p[(size_t)JF_IZ * N] = jiz[k];
         p[(size_t)JF_MOTOR * N] = jmot[k];
-        b.limit_state[(size_t)k * N + car] = (uint8_t)lim[k];
-        b.wheel[(size_t)(k * WHEEL_FIELDS + WF_OMEGA) * N + car] = omega[k];
-        b.wheel[(size_t)(k * WHEEL_FIELDS + WF_PHASE) * N + car] = phase[k];
-        // the contact pass of THIS step (already run) decides the friction of the NEXT Car.step
+        // the contact pass of THIS step decides the friction of the NEXT Car.step
         b.on_road[(size_t)k * N + car] = b.on_road_next[(size_t)k * N + car];
     }
-    b.ctrl[(size_t)CF_GAS * N + car] = gas;
-    b.ctrl[(size_t)CF_BRAKE * N + car] = brake;
-    b.ctrl[(size_t)CF_STEER * N + car] = steer;
     // ---- per-view values the rasteriser needs, evaluated once here (fp64 trig is serial latency) --
     const double t = b.time[car] + 1.0 / 50;                      // mcr:429
     b.time[car] = t;
-    if (action) b.steps[car] += 1;                                // TimeLimit counts step() calls only
+    if (has_action) b.steps[car] += 1;                                // TimeLimit counts step() calls only
     {   // camera, mcr:540-556 + Transform.enable + glViewport(0,0,96,96) under glOrtho(0,1000,0,800)
         const double SCALE = 6.0, ZOOM = 2.7, WINDOW_W = 1000, WINDOW_H = 800;
         const double zoom = 0.1 * SCALE * fmax(1 - t, 0.0) + ZOOM * SCALE * fmin(t, 1.0);
@@ -725,53 +826,39 @@ sim_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, 
         b.stripe[(size_t)(k * 2 + 0) * N + car] = y1;
         b.stripe[(size_t)(k * 2 + 1) * N + car] = y2;
     }
-    }
 }
 
-template <typename ActT, int MAX_THREADS, int MIN_BLOCKS>
-static int launch_sim_t(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
-                        const ActT* action, double h_ratio, int roles, size_t smem, cudaStream_t s) {
+// ---------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------
+int launch_contacts(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, void* stream) {
     static int configured_for = -1;
+    const size_t per_warp = (sim_smem_bytes(d.A) + 15) & ~(size_t)15;
+    const size_t smem = per_warp * CT_WARPS;
     if (smem > 48 * 1024 && configured_for != d.A) {
-        if (cudaFuncSetAttribute(sim_kernel<ActT, MAX_THREADS, MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(contacts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         configured_for = d.A;
     }
-    sim_kernel<ActT, MAX_THREADS, MIN_BLOCKS><<<d.B, 32 * (d.A + 1), smem, s>>>(d, b, cc, mask, action, h_ratio, roles);
+    contacts_kernel<<<(d.B + CT_WARPS - 1) / CT_WARPS, CT_WARPS * 32, smem, (cudaStream_t)stream>>>(d, b, cc, mask, per_warp);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
-}
-
-// Register budget per CTA size: the solver wants ~130+ registers; capping it a little below that
-// keeps enough CTAs resident that the envs whose solve runs all 180 sweeps do not serialise.
-template <typename ActT>
-static int launch_sim_a(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
-                        const ActT* action, double h_ratio, int roles, size_t smem, cudaStream_t s) {
-    const int threads = 32 * (d.A + 1);
-    if (threads <= 64) return launch_sim_t<ActT, 64, 8>(d, b, cc, mask, action, h_ratio, roles, smem, s);
-    if (threads <= 96) return launch_sim_t<ActT, 96, 5>(d, b, cc, mask, action, h_ratio, roles, smem, s);
-    if (threads <= 160) return launch_sim_t<ActT, 160, 3>(d, b, cc, mask, action, h_ratio, roles, smem, s);
-    if (threads <= 288) return launch_sim_t<ActT, 288, 1>(d, b, cc, mask, action, h_ratio, roles, smem, s);
-    return launch_sim_t<ActT, 32 * (MCR_MAX_AGENTS + 1), 1>(d, b, cc, mask, action, h_ratio, roles, smem, s);
-}
-
-static int launch_sim(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
-                      const void* action, int action_dtype, double h_ratio, int roles, void* stream) {
-    const size_t smem = sim_smem_bytes(d.A);
-    cudaStream_t s = (cudaStream_t)stream;
-    if (action_dtype == MCR_F64) return launch_sim_a<double>(d, b, cc, mask, (const double*)action, h_ratio, roles, smem, s);
-    return launch_sim_a<float>(d, b, cc, mask, (const float*)action, h_ratio, roles, smem, s);
-}
-
-int launch_contacts(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, void* stream) {
-    return launch_sim(d, b, cc, mask, nullptr, MCR_F32, 0.0, ROLE_CONTACTS, stream);
 }
 
 int launch_physics(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
                    const void* action, int action_dtype, double h_ratio, void* stream) {
-    return launch_sim(d, b, cc, mask, action, action_dtype, h_ratio, ROLE_PHYSICS, stream);
+    static const int early_exit = getenv("MCR_NO_EARLY_EXIT") ? 0 : 1;   // diagnostics only
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nb = (d.N + PRE_BLOCK - 1) / PRE_BLOCK;
+    if (action_dtype == MCR_F64) pre_kernel<double><<<nb, PRE_BLOCK, 0, s>>>(d, b, cc, mask, (const double*)action);
+    else pre_kernel<float><<<nb, PRE_BLOCK, 0, s>>>(d, b, cc, mask, (const float*)action);
+    sweep_kernel<<<(d.N + SWEEP_WARPS - 1) / SWEEP_WARPS, SWEEP_WARPS * 32, 0, s>>>(d, b, cc, mask, early_exit);
+    return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
 
-int launch_simulate(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
-                    const void* action, int action_dtype, double h_ratio, void* stream) {
-    static const int extra = getenv("MCR_NO_EARLY_EXIT") ? ROLE_NO_EARLY_EXIT : 0;   // diagnostics only
-    return launch_sim(d, b, cc, mask, action, action_dtype, h_ratio, ROLE_CONTACTS | ROLE_PHYSICS | extra, stream);
+// post_kernel must not start before the contacts pass of the same step has finished reading the
+// start poses and writing on_road_next (the API joins the side stream before calling this).
+int launch_physics_post(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
+                        int has_action, double h_ratio, void* stream) {
+    const int nb = (d.N + PRE_BLOCK - 1) / PRE_BLOCK;
+    post_kernel<<<nb, PRE_BLOCK, 0, (cudaStream_t)stream>>>(d, b, cc, mask, has_action, h_ratio);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
