@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -390,7 +391,8 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
     if (cfg->batch_envs < 1) return fail(-1, "batch_envs must be >= 1");
     if (cfg->num_agents < 1 || cfg->num_agents > MCR_MAX_AGENTS) return fail(-1, "num_agents must be in [1, %d]", MCR_MAX_AGENTS);
     if (cfg->max_tiles < 16 || cfg->max_tiles > 32768) return fail(-1, "max_tiles out of range");
-    if (cfg->max_quads < cfg->max_tiles || cfg->max_quads > 32767) return fail(-1, "max_quads must be in [max_tiles, 32767]");
+    if (cfg->max_quads < cfg->max_tiles || cfg->max_quads > 2048 || cfg->max_quads % MCR_QUAD_CHUNK)
+        return fail(-1, "max_quads must be a multiple of %d in [max_tiles, 2048]", MCR_QUAD_CHUNK);
     if (cfg->pool_tracks < 1) return fail(-1, "pool_tracks must be >= 1");
     mcr_handle_t* h = new mcr_handle_t();
     h->cfg = *cfg;
@@ -435,6 +437,7 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
     set_spec(h, BUF_TRK_QUAD_COL, "trk_quad_col", MCR_U8, {P, Q});
     set_spec(h, BUF_TRK_QUAD_TILE, "trk_quad_tile", MCR_I16, {P, Q});
     set_spec(h, BUF_TRK_SLOT_POSE, "trk_slot_pose", MCR_F64, {P, 2, A, 3});
+    set_spec(h, BUF_TRK_CHUNK, "trk_chunk", MCR_F32, {P, Q / MCR_QUAD_CHUNK, 4});
     *out = h;
     return 0;
 }
@@ -500,6 +503,7 @@ extern "C" int mcr_bind_buffer(mcr_handle h, int i, void* p) {
         case BUF_TRK_QUAD_COL: b.trk_quad_col = (uint8_t*)p; break;
         case BUF_TRK_QUAD_TILE: b.trk_quad_tile = (int16_t*)p; break;
         case BUF_TRK_SLOT_POSE: b.trk_slot_pose = (double*)p; break;
+        case BUF_TRK_CHUNK: b.trk_chunk = (float*)p; break;
     }
     return 0;
 }
@@ -572,6 +576,22 @@ extern "C" int mcr_load_track(mcr_handle h, int32_t slot, int32_t T, const doubl
         }
     }
     for (int t = 0; t < T; ++t) if (!seen[t]) return fail(-4, "mcr_load_track: tile %d has no quad", t);
+    // bounding circle of every MCR_QUAD_CHUNK consecutive road_poly quads (rasteriser culling)
+    const int nchunk = d.Qmax / MCR_QUAD_CHUNK;
+    std::vector<float> chunk((size_t)nchunk * 4, 0.0f);
+    for (int c = 0; c * MCR_QUAD_CHUNK < Q; ++c) {
+        const int q0 = c * MCR_QUAD_CHUNK, q1 = std::min(Q, q0 + MCR_QUAD_CHUNK);
+        double sx = 0, sy = 0; int nvert = 0;
+        for (int q = q0; q < q1; ++q) for (int k = 0; k < 4; ++k) { sx += quadf[(size_t)q * 8 + 2 * k]; sy += quadf[(size_t)q * 8 + 2 * k + 1]; ++nvert; }
+        const double mx = sx / nvert, my = sy / nvert;
+        double r2 = 0;
+        for (int q = q0; q < q1; ++q) for (int k = 0; k < 4; ++k) {
+            const double dx = quadf[(size_t)q * 8 + 2 * k] - (double)(float)mx, dy = quadf[(size_t)q * 8 + 2 * k + 1] - (double)(float)my;
+            r2 = std::max(r2, dx * dx + dy * dy);
+        }
+        chunk[(size_t)c * 4] = (float)mx; chunk[(size_t)c * 4 + 1] = (float)my;
+        chunk[(size_t)c * 4 + 2] = (float)(std::sqrt(r2) * 1.0001 + 1e-3);
+    }
     // spawn pose of every grid position for the device-side auto reset
     const int A = d.A;
     std::vector<double> slot_pose((size_t)2 * A * 3);
@@ -592,6 +612,7 @@ extern "C" int mcr_load_track(mcr_handle h, int32_t slot, int32_t T, const doubl
     CUDA_OK(cudaMemcpyAsync(b.trk_quad + (size_t)slot * d.Qmax * 8, quadf.data(), quadf.size() * 4, cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaMemcpyAsync(b.trk_quad_col + (size_t)slot * d.Qmax, qcol.data(), qcol.size(), cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaMemcpyAsync(b.trk_quad_tile + (size_t)slot * d.Qmax, qtile.data(), qtile.size() * 2, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(b.trk_chunk + (size_t)slot * nchunk * 4, chunk.data(), chunk.size() * 4, cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaMemcpyAsync(b.trk_slot_pose + (size_t)slot * 2 * A * 3, slot_pose.data(), slot_pose.size() * 8, cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaStreamSynchronize(s));   // the staging vectors die with this frame
     return 0;

@@ -22,6 +22,7 @@
 #define MCR_VEL_ITERS 180   // world.Step(1/FPS, 6*30, 2*30), mcr:428
 #define MCR_POS_ITERS 60
 #define MCR_MAXV 8
+#define MCR_QUAD_CHUNK 8        // road_poly quads per culling chunk (bounding circle)
 #define MCR_SCRATCH_FIELDS 91   // 31 velocity/impulse values + 4 joints x 15 constants
 
 // body SoA: body[(b * BODY_FIELDS + f) * N + car], b = 0 hull, 1..4 wheels
@@ -42,7 +43,7 @@ enum {
     BUF_ENV_TRACK, BUF_ENV_CW, BUF_ENV_EPISODE,
     BUF_VISITED, BUF_TOUCHED, BUF_RESET_MASK, BUF_STATUS, BUF_SCRATCH,
     BUF_TRK_T, BUF_TRK_Q, BUF_TRK_NODE, BUF_TRK_TILE, BUF_TRK_TILE_AABB, BUF_TRK_QUAD, BUF_TRK_QUAD_COL,
-    BUF_TRK_QUAD_TILE, BUF_TRK_SLOT_POSE,
+    BUF_TRK_QUAD_TILE, BUF_TRK_SLOT_POSE, BUF_TRK_CHUNK,
     BUF_COUNT
 };
 
@@ -83,6 +84,7 @@ struct DevBuffers {
     float* scratch;                      // [MCR_SCRATCH_FIELDS][N] solver hand-over between pre/sweep/post kernels
     int32_t* trk_T; int32_t* trk_Q; double* trk_node; float* trk_tile; float* trk_tile_aabb;
     float* trk_quad; uint8_t* trk_quad_col; int16_t* trk_quad_tile; double* trk_slot_pose;
+    float* trk_chunk;                    // [P][Qmax/8][4] bounding circle (cx, cy, r, 0) of 8 consecutive road_poly quads
 };
 
 struct Dims { int B, A, N, Tmax, Qmax, P; };

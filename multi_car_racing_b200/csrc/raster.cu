@@ -37,6 +37,7 @@
 #define SPAN_POOL 4096
 #define N_CHECKER_AXIS 20   // range(-20, 20, 2)
 #define CAR_PARTS 12        // 4 x (wheel, stripe) + 4 hull fixtures
+#define MAX_CHUNKS 256      // road_poly chunks of MCR_QUAD_CHUNK quads (Qmax <= 2048)
 #define SW MCR_STATE_W
 #define SH MCR_STATE_H
 
@@ -98,9 +99,13 @@ struct __align__(16) RasterSmem {
     uchar2 span[SPAN_POOL];
     uint32_t rowmask[SH][MASK_WORDS];
     Affine M;
-    int list_count, pool_count, first_bad;
+    int first_bad;
     int ck_j0x, ck_nx, ck_j0y, ck_ny;   // visible checker index range
-    int warp_cnt[RS_WARPS], warp_rows[RS_WARPS];
+    uint32_t chunk_ballot[RS_WARPS];
+    int n_vis_chunks;
+    uint8_t vis_chunk[MAX_CHUNKS];    // ids of the road_poly chunks whose bounding circle touches the viewport, ascending
+    int warp_cnt[2][RS_WARPS], warp_rows[2][RS_WARPS];
+    int bc_cnt, bc_rows;
     double red_d[RS_WARPS]; int red_i[RS_WARPS];
     signed char glyph[4];
     uint32_t pal32[32];
@@ -115,6 +120,8 @@ __device__ __forceinline__ double py_mod(double a, double m) {
 struct View {
     int env, agent, A, N, Q;
     int n_checker, ck_j0x, ck_j0y, ck_ny;
+    int n_road;                          // 8 * visible chunks
+    const uint8_t* vis_chunk;
     const float* body; const double* wheel; const float* stripe;
     const float* quad; const uint8_t* quad_col; const int16_t* quad_tile; const uint8_t* touched;
     int use_ego_color, backward_flag_on;
@@ -146,7 +153,9 @@ __device__ int gen_candidate(int i, const View& V, const Affine& M, const CarCon
         col = PAL_GRASS_LIGHT; return 4;
     }
     i -= V.n_checker;
-    if (i < V.Q) {                                  // road_poly, mcr:628-631
+    if (i < V.n_road) {                             // road_poly (visible chunks only), mcr:628-631
+        i = (int)V.vis_chunk[i >> 3] * MCR_QUAD_CHUNK + (i & (MCR_QUAD_CHUNK - 1));
+        if (i >= V.Q) return 0;
         const float4 a = *(const float4*)(V.quad + (size_t)i * 8);
         const float4 b = *(const float4*)(V.quad + (size_t)i * 8 + 4);
         xf_pt(M, a.x, a.y, px[0], py[0]); xf_pt(M, a.z, a.w, px[1], py[1]);
@@ -155,7 +164,7 @@ __device__ int gen_candidate(int i, const View& V, const Affine& M, const CarCon
         col = (tl >= 0 && V.touched[tl]) ? PAL_ROAD0 : V.quad_col[i];   // tile.color reset, mcr:102-104
         return 4;
     }
-    i -= V.Q;
+    i -= V.n_road;
     if (i < CAR_PARTS * V.A) {                      // Car.draw for every car, mcr:559-564
         const int c = i / CAR_PARTS, part = i % CAR_PARTS, car = V.env * V.A + c, N = V.N;
         if (part < 8) {
@@ -258,9 +267,8 @@ __device__ __forceinline__ void edge_row(const RasterSmem& S, int e, int p, floa
     }
 }
 
-__device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pix)[8]) {
+__device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pix)[8], int n, int nslots) {
     __syncthreads();
-    const int n = S.list_count, nslots = S.pool_count;
     // ---- spans: one thread per (polygon,row) slot ---------------------------------------------
     for (int s = tid; s < nslots; s += RS_THREADS) {
         int lo = 0, hi = n - 1;                    // last p with off[p] <= s
@@ -328,11 +336,10 @@ __device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pi
     }
     __syncthreads();
     for (int i = tid; i < SH * MASK_WORDS; i += RS_THREADS) (&S.rowmask[0][0])[i] = 0;
-    if (tid == 0) { S.list_count = 0; S.pool_count = 0; }
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 4)
 render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, uint8_t* __restrict__ obs,
               double* __restrict__ out_reward, uint8_t* __restrict__ out_done, int post_step,
               int backwards_flag, int use_ego_color, int max_episode_steps) {
@@ -353,7 +360,6 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
         S.pal32[i] = (uint32_t)c_palette[i][0] | ((uint32_t)c_palette[i][1] << 8) | ((uint32_t)c_palette[i][2] << 16);
     }
     if (tid == 64) {
-        S.list_count = 0; S.pool_count = 0;
         // score label "%04i" % reward  (mcr:665; drawn before reward -= 0.1)
         const double rw = b.reward[car];
         int val = (int)rw;
@@ -397,12 +403,41 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
         S.ck_j0y = j0y; S.ck_ny = j1y >= j0y ? j1y - j0y + 1 : 0;
     }
     for (int i = tid; i < SH * MASK_WORDS; i += RS_THREADS) (&S.rowmask[0][0])[i] = 0;
+    // ---- road_poly chunk culling: bounding circle of every 8 consecutive quads vs the viewport ------
+    const int nchunks = (Q + MCR_QUAD_CHUNK - 1) / MCR_QUAD_CHUNK;
+    {
+        bool vis = false;
+        if (tid < nchunks) {
+            const float4 cc4 = *(const float4*)(b.trk_chunk + ((size_t)slot * (d.Qmax / MCR_QUAD_CHUNK) + tid) * 4);
+            const float m00 = b.camera[(size_t)0 * N + car], m01 = b.camera[(size_t)1 * N + car], m02 = b.camera[(size_t)2 * N + car];
+            const float m10 = b.camera[(size_t)3 * N + car], m11 = b.camera[(size_t)4 * N + car], m12 = b.camera[(size_t)5 * N + car];
+            const float cxp = (m00 * cc4.x + m01 * cc4.y) + m02, cyp = (m10 * cc4.x + m11 * cc4.y) + m12;
+            // |M v| <= ||M||_F |v|: conservative pixel radius, plus a 2-pixel margin
+            const float rp = cc4.z * sqrtf(m00 * m00 + m01 * m01 + m10 * m10 + m11 * m11) * 1.001f + 2.0f;
+            vis = (cxp + rp >= 0.0f) && (cxp - rp <= (float)SW) && (cyp + rp >= 0.0f) && (cyp - rp <= (float)SH);
+            if (!(rp == rp) || !(cxp == cxp) || !(cyp == cyp)) vis = true;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, vis);
+        if (lane == 0) S.chunk_ballot[warp] = bal;
+        __syncthreads();
+        if (tid < nchunks && vis) {
+            int pos = __popc(bal & ((1u << lane) - 1u));
+            for (int wq = 0; wq < warp; ++wq) pos += __popc(S.chunk_ballot[wq]);
+            S.vis_chunk[pos] = (uint8_t)tid;
+        }
+        if (tid == 0) {
+            int n = 0;
+            for (int wq = 0; wq < RS_WARPS; ++wq) n += __popc(S.chunk_ballot[wq]);
+            S.n_vis_chunks = n;
+        }
+    }
     __syncthreads();
 
     View V;
     V.env = env; V.agent = agent; V.A = d.A; V.N = N; V.Q = Q;
     V.ck_j0x = S.ck_j0x; V.ck_j0y = S.ck_j0y; V.ck_ny = S.ck_ny > 0 ? S.ck_ny : 1;
     V.n_checker = S.ck_nx * S.ck_ny;
+    V.n_road = S.n_vis_chunks * MCR_QUAD_CHUNK; V.vis_chunk = S.vis_chunk;
     V.body = b.body; V.wheel = b.wheel; V.stripe = b.stripe;
     V.quad = b.trk_quad + (size_t)slot * d.Qmax * 8;
     V.quad_col = b.trk_quad_col + (size_t)slot * d.Qmax;
@@ -417,8 +452,8 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     for (int k = 0; k < 8; ++k) pix[k] = PAL_BLACK * 0x01010101u;
 
     // ---- candidates -> ordered display list -> flush -----------------------------------------
-    const int NC = 1 + V.n_checker + Q + CAR_PARTS * d.A + 9;
-    int base = 0;
+    const int NC = 1 + V.n_checker + V.n_road + CAR_PARTS * d.A + 9;
+    int base = 0, lc = 0, pc = 0, round = 0;   // display-list / span-pool fill (same in every thread)
     while (base < NC) {
         const int i = base + tid;
         float px[MCR_MAXV], py[MCR_MAXV];
@@ -450,20 +485,29 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
             const int a = __shfl_up_sync(0xffffffffu, cnt_inc, o), r = __shfl_up_sync(0xffffffffu, rows_inc, o);
             if (lane >= o) { cnt_inc += a; rows_inc += r; }
         }
-        if (lane == 31) { S.warp_cnt[warp] = cnt_inc; S.warp_rows[warp] = rows_inc; }
-        if (tid == 0) S.first_bad = RS_THREADS;
+        const int par = round & 1; ++round;             // double-buffered warp totals: one barrier per round
+        if (lane == 31) { S.warp_cnt[par][warp] = cnt_inc; S.warp_rows[par][warp] = rows_inc; }
         __syncthreads();
-        int cnt_before = 0, rows_before = 0;
+        int cnt_before = 0, rows_before = 0, cnt_total = 0, rows_total = 0;
 #pragma unroll
-        for (int wq = 0; wq < RS_WARPS; ++wq)
-            if (wq < warp) { cnt_before += S.warp_cnt[wq]; rows_before += S.warp_rows[wq]; }
+        for (int wq = 0; wq < RS_WARPS; ++wq) {
+            const int c = S.warp_cnt[par][wq], r = S.warp_rows[par][wq];
+            if (wq < warp) { cnt_before += c; rows_before += r; }
+            cnt_total += c; rows_total += r;
+        }
         const int slot_rel = cnt_before + cnt_inc - ents;
         const int row_rel = rows_before + rows_inc - rows;
-        const int lc = S.list_count, pc = S.pool_count;
-        const bool fits = (lc + slot_rel + ents <= LIST_CAP) && (pc + row_rel + rows <= SPAN_POOL);
-        if (valid && !fits) atomicMin(&S.first_bad, tid);
-        __syncthreads();
-        const int first_bad = S.first_bad;
+        // (lc, pc) are tracked in registers: every thread sees the same totals
+        const bool all_fit = (lc + cnt_total <= LIST_CAP) && (pc + rows_total <= SPAN_POOL);
+        int first_bad = RS_THREADS;
+        if (!all_fit) {                                 // rare (zoomed-out frames): find the first candidate that does not fit
+            if (tid == 0) S.first_bad = RS_THREADS;
+            __syncthreads();
+            const bool fits = (lc + slot_rel + ents <= LIST_CAP) && (pc + row_rel + rows <= SPAN_POOL);
+            if (valid && !fits) atomicMin(&S.first_bad, tid);
+            __syncthreads();
+            first_bad = S.first_bad;
+        }
         if (valid && tid < first_bad) {
             const int sl = lc + slot_rel;
             // canonical edges: lower endpoint first, slope hoisted out of the row loop
@@ -490,19 +534,20 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
                 S.off[sl + 1] = (uint16_t)(pc + row_rel + rows); S.base[sl + 1] = 0;
             }
         }
-        __syncthreads();
         if (first_bad < RS_THREADS) {
-            // the first thread that did not fit publishes the accepted totals (its exclusive prefix)
-            if (tid == first_bad) { S.list_count = lc + slot_rel; S.pool_count = pc + row_rel; }
-            base += first_bad;
-            flush_list(S, tid, pix);
-        } else {
-            if (tid == RS_THREADS - 1) { S.list_count = lc + slot_rel + ents; S.pool_count = pc + row_rel + rows; }
-            base += RS_THREADS;
+            // accepted prefix = everything before the first candidate that did not fit
+            if (tid == first_bad) { S.bc_cnt = lc + slot_rel; S.bc_rows = pc + row_rel; }
             __syncthreads();
+            lc = S.bc_cnt; pc = S.bc_rows;
+            base += first_bad;
+            flush_list(S, tid, pix, lc, pc);
+            lc = 0; pc = 0;
+        } else {
+            lc += cnt_total; pc += rows_total;
+            base += RS_THREADS;
         }
     }
-    flush_list(S, tid, pix);
+    flush_list(S, tid, pix, lc, pc);
 
     const int my_y = tid / 3, my_seg = tid - 3 * my_y;
     // ---- score label glyphs (D3): observation rows 87..91 (= GL rows 8..4), cols 2..13 -------------
@@ -539,28 +584,35 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
 
     // ---- post-step block, mcr:433-507 (skipped for reset()'s step(None)) -----------------------
     if (!post_step) return;
-    // nearest track node: argmin_i || pos - track[i].xy ||, first minimum wins (np.argmin)
+    // nearest track node: argmin_i || pos - track[i].xy ||, first minimum wins (np.argmin over
+    // sqrt(dx^2 + dy^2)).  sqrt is monotone, so pass 1 finds the minimal squared distance and pass 2
+    // takes the sqrt only for nodes within a few ulp of it (sqrt can merge distinct squares).
     const double posx = b.body[(size_t)BF_PX * N + car], posy = b.body[(size_t)BF_PY * N + car];
     const double* node = b.trk_node + (size_t)slot * d.Tmax * 3;
-    double bestd = 1.0e300; int besti = 0x7fffffff;
+    double best2 = 1.0e300;
     for (int i = tid; i < T; i += RS_THREADS) {
         const double dx = posx - node[(size_t)i * 3 + 1], dy = posy - node[(size_t)i * 3 + 2];
-        const double dd = sqrt(dx * dx + dy * dy);
-        if (dd < bestd || (dd == bestd && i < besti)) { bestd = dd; besti = i; }
+        best2 = fmin(best2, dx * dx + dy * dy);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double od = __shfl_down_sync(0xffffffffu, bestd, o);
-        const int oi = __shfl_down_sync(0xffffffffu, besti, o);
-        if (od < bestd || (od == bestd && oi < besti)) { bestd = od; besti = oi; }
+    for (int o = 16; o > 0; o >>= 1) best2 = fmin(best2, __shfl_xor_sync(0xffffffffu, best2, o));
+    if (lane == 0) S.red_d[warp] = best2;
+    __syncthreads();
+#pragma unroll
+    for (int wq = 0; wq < RS_WARPS; ++wq) best2 = fmin(best2, S.red_d[wq]);
+    const double thresh = best2 * (1.0 + 1.0e-14), smin = sqrt(best2);
+    int besti = 0x7fffffff;
+    for (int i = tid; i < T; i += RS_THREADS) {
+        const double dx = posx - node[(size_t)i * 3 + 1], dy = posy - node[(size_t)i * 3 + 2];
+        const double d2 = dx * dx + dy * dy;
+        if (d2 <= thresh && sqrt(d2) == smin && i < besti) besti = i;
     }
-    if (lane == 0) { S.red_d[warp] = bestd; S.red_i[warp] = besti; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) besti = min(besti, __shfl_xor_sync(0xffffffffu, besti, o));
+    if (lane == 0) S.red_i[warp] = besti;
     __syncthreads();
     if (tid == 0) {
-        for (int wq = 1; wq < RS_WARPS; ++wq) {
-            const double od = S.red_d[wq]; const int oi = S.red_i[wq];
-            if (od < bestd || (od == bestd && oi < besti)) { bestd = od; besti = oi; }
-        }
+        for (int wq = 0; wq < RS_WARPS; ++wq) besti = min(besti, S.red_i[wq]);
         const double PI = 3.141592653589793, PLAYFIELD = 2000 / 6.0;
         double reward = b.reward[car] - 0.1;                     // mcr:436
         double step_reward = reward - b.prev_reward[car];        // mcr:443
