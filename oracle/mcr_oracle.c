@@ -523,54 +523,70 @@ static void world_poly(const Body* b, const Poly* P, V2* out, float* aabb) {
 
 #define AABB_MARGIN 0.05f /* conservative pre-reject; exact predicate threshold is 0.02 */
 
-static void collide(OrcWorld* W) {
-    int A = W->A, T = W->T;
-    /* world-space fixture polygons of every car: 4 wheels + 4 hull fixtures */
+/* One touching (tile, fixture) pair as b2Contact::Update would report it. */
+typedef struct { int tile, car, fixture /* 0..3 wheels, 4..7 hull fixtures */, active; } Pair;
+#define MAX_PAIRS 4096
+
+/* All currently touching pairs in the contact-list order of a fresh world:
+ * tile descending, then car descending, then fixture descending (D1). */
+static int collect_pairs(OrcWorld* W, Pair* out, int max) {
+    int A = W->A, T = W->T, n = 0;
     V2 wv[MAX_AGENTS][8][MAXV]; float wa[MAX_AGENTS][8][4]; int wn[MAX_AGENTS][8];
     int active[MAX_AGENTS][8];
-    int touching_now[MAX_AGENTS][4];
     for (int c = 0; c < A; ++c) {
         Car* car = &W->car[c];
         for (int w = 0; w < 4; ++w) {
             world_poly(&car->b[1 + w], &W->wheel_poly, wv[c][w], wa[c][w]); wn[c][w] = W->wheel_poly.n;
             active[c][w] = car->b[1 + w].awake;
-            touching_now[c][w] = 0;
         }
         for (int f = 0; f < 4; ++f) {
             world_poly(&car->b[0], &W->hull_poly[f], wv[c][4 + f], wa[c][4 + f]); wn[c][4 + f] = W->hull_poly[f].n;
             active[c][4 + f] = car->b[0].awake;
         }
     }
-    /* contact-list order on a fresh world: tile descending, then car descending, wheel descending (D1) */
     for (int t = T - 1; t >= 0; --t) {
         const float* ta = &W->tile_aabb[4 * t]; const Poly* TP = &W->tile_poly[t];
         for (int c = A - 1; c >= 0; --c) {
-            Car* car = &W->car[c];
             for (int f = 7; f >= 0; --f) {
                 const float* fa = wa[c][f];
                 if (fa[0] - ta[2] > AABB_MARGIN || fa[1] - ta[3] > AABB_MARGIN ||
                     ta[0] - fa[2] > AABB_MARGIN || ta[1] - fa[3] > AABB_MARGIN) continue;
-                int touch = poly_touch(TP->v, TP->n, wv[c][f], wn[c][f]);
-                if (!touch) continue;
-                if (f < 4) touching_now[c][f] += 1;
-                /* A sleeping body's contacts are not updated (b2ContactManager::Collide) */
-                if (!active[c][f]) continue;
-                W->touched[t] = 1;                      /* mcr:102-104 */
-                if (f >= 4) continue;                   /* hull: userData None, mcr:108 */
-                if (!W->visited[(size_t)t * A + c]) {   /* mcr:113-120 */
-                    W->visited[(size_t)t * A + c] = 1;
-                    W->tile_visited_count[c] += 1;
-                    int past = -1;
-                    for (int k = 0; k < A; ++k) past += W->visited[(size_t)t * A + k];
-                    double reward_factor = 1 - ((double)past / (double)A);
-                    W->reward[c] += reward_factor * 1000.0 / (double)T;
-                }
+                if (!poly_touch(TP->v, TP->n, wv[c][f], wn[c][f])) continue;
+                if (n < max) { out[n].tile = t; out[n].car = c; out[n].fixture = f; out[n].active = active[c][f]; }
+                ++n;
             }
+        }
+    }
+    return n < max ? n : max;
+}
+
+/* b2ContactManager::Collide + FrictionDetector (mcr:88-123).  road_visited makes BeginContact
+ * idempotent and tile colour only ever moves to ROAD_COLOR, so no per-pair state is kept. */
+static void collide(OrcWorld* W) {
+    int A = W->A, T = W->T;
+    static __thread Pair pairs[MAX_PAIRS];
+    int n = collect_pairs(W, pairs, MAX_PAIRS);
+    int touching_now[MAX_AGENTS][4];
+    for (int c = 0; c < A; ++c) for (int w = 0; w < 4; ++w) touching_now[c][w] = 0;
+    for (int i = 0; i < n; ++i) {
+        int t = pairs[i].tile, c = pairs[i].car, f = pairs[i].fixture;
+        if (f < 4) touching_now[c][f] += 1;
+        /* A sleeping body's contacts are not updated (b2ContactManager::Collide) */
+        if (!pairs[i].active) continue;
+        W->touched[t] = 1;                      /* mcr:102-104 */
+        if (f >= 4) continue;                   /* hull: userData None, mcr:108 */
+        if (!W->visited[(size_t)t * A + c]) {   /* mcr:113-120 */
+            W->visited[(size_t)t * A + c] = 1;
+            W->tile_visited_count[c] += 1;
+            int past = -1;
+            for (int k = 0; k < A; ++k) past += W->visited[(size_t)t * A + k];
+            double reward_factor = 1 - ((double)past / (double)A);
+            W->reward[c] += reward_factor * 1000.0 / (double)T;
         }
     }
     for (int c = 0; c < A; ++c)
         for (int w = 0; w < 4; ++w)
-            if (active[c][w]) W->car[c].ntiles[w] = touching_now[c][w];
+            if (W->car[c].b[1 + w].awake) W->car[c].ntiles[w] = touching_now[c][w];
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -834,8 +850,7 @@ static void solve_car_island(OrcWorld* W, Car* car, float h, int velIters, int p
     }
 }
 
-static void world_step(OrcWorld* W, float dt, int velIters, int posIters) {
-    collide(W);
+static void world_solve(OrcWorld* W, float dt, int velIters, int posIters) {
     float inv_dt = dt > 0.0f ? 1.0f / dt : 0.0f;
     float dtRatio = W->inv_dt0 * dt;
     W->vel_iters_used = 0;
@@ -851,6 +866,11 @@ static void world_step(OrcWorld* W, float dt, int velIters, int posIters) {
     /* ClearForces */
     for (int c = 0; c < W->A; ++c)
         for (int i = 0; i < 5; ++i) { W->car[c].b[i].force = v2(0.0f, 0.0f); W->car[c].b[i].torque = 0.0f; }
+}
+
+static void world_step(OrcWorld* W, float dt, int velIters, int posIters) {
+    collide(W);
+    world_solve(W, dt, velIters, posIters);
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -923,6 +943,20 @@ static const uint8_t FONT3x5[11][5] = { /* rows top->bottom, 3 bits per row (msb
     {7, 4, 7, 1, 7}, {7, 4, 7, 5, 7}, {7, 1, 1, 1, 1}, {7, 5, 7, 5, 7}, {7, 5, 7, 1, 7},
     {0, 0, 7, 0, 0} /* '-' */
 };
+
+/* pyglet Label at x=20, y=50 (window) -> 3x5 glyphs at cols 2..13, rows 87..91 from the top (D3) */
+static void draw_label(uint8_t* img, const char* text) {
+    for (int ch = 0; ch < 4 && text[ch]; ++ch) {
+        int g = text[ch] == '-' ? 10 : (text[ch] >= '0' && text[ch] <= '9' ? text[ch] - '0' : -1);
+        if (g < 0) continue;
+        for (int ry = 0; ry < 5; ++ry)
+            for (int rx = 0; rx < 3; ++rx)
+                if (FONT3x5[g][ry] & (4 >> rx)) {
+                    uint8_t* p = img + ((size_t)(87 + ry) * STATE_W + (2 + 3 * ch + rx)) * 3;
+                    p[0] = 255; p[1] = 255; p[2] = 255;
+                }
+    }
+}
 
 static const float CAR_COLORS[8][3] = { {0.8f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.8f}, {0.0f, 0.8f, 0.0f}, {0.0f, 0.8f, 0.8f},
                                         {0.8f, 0.8f, 0.8f}, {0.0f, 0.0f, 0.0f}, {0.8f, 0.0f, 0.8f}, {0.8f, 0.8f, 0.0f} };
@@ -1041,15 +1075,8 @@ static void render_view(OrcWorld* W, int agent, uint8_t* img) {
             if (neg) buf[len++] = '-';
             for (int i = 0; i < pad; ++i) buf[len++] = '0';
             for (int i = nd - 1; i >= 0; --i) buf[len++] = digs[i];
-            for (int ch = 0; ch < len && ch < 4; ++ch) {
-                int g = buf[ch] == '-' ? 10 : buf[ch] - '0';
-                for (int ry = 0; ry < 5; ++ry)
-                    for (int rx = 0; rx < 3; ++rx)
-                        if (FONT3x5[g][ry] & (4 >> rx)) {
-                            uint8_t* p = img + ((size_t)(87 + ry) * STATE_W + (2 + 3 * ch + rx)) * 3;
-                            p[0] = 255; p[1] = 255; p[2] = 255;
-                        }
-            }
+            buf[len] = 0;
+            draw_label(img, buf);
         }
         if (W->driving_backward[agent] && W->backwards_flag) {
             double fx[3] = { Wd - 100, Wd - 75, Wd - 50 }, fy[3] = { 30, 70, 30 };
@@ -1171,3 +1198,38 @@ ORC_API int orc_get_tile_poly(const OrcWorld* W, int t, float* out_xy) {
 /* direct state injection (used by the stubbed-reference harness and by tests) */
 ORC_API void orc_set_backward(OrcWorld* W, const uint8_t* flags) { for (int c = 0; c < W->A; ++c) W->driving_backward[c] = flags[c]; }
 ORC_API void orc_set_hull_color(OrcWorld* W, int car, int palette_index) { W->car[car].hull_color = palette_index; }
+
+/* ------------------------------------------------------------------------------------ */
+/* Hooks for tests/golden/make_golden.py: the UNMODIFIED reference module runs on stub      */
+/* Box2D / gym / pyglet modules whose arithmetic is this file, so the reference's own      */
+/* Python (reward rule, spawn, draw lists, HUD geometry, RNG order) pins the restatement.   */
+/* ------------------------------------------------------------------------------------ */
+ORC_API void orc_ext_steer(OrcWorld* W, int c, double s) { W->car[c].steer[0] = s; W->car[c].steer[1] = s; }
+ORC_API void orc_ext_gas(OrcWorld* W, int c, double gas) {
+    double g = gas < 0 ? 0 : (gas > 1 ? 1 : gas);
+    for (int w = 2; w < 4; ++w) { double diff = g - W->car[c].gas[w]; if (diff > 0.1) diff = 0.1; W->car[c].gas[w] += diff; }
+}
+ORC_API void orc_ext_brake(OrcWorld* W, int c, double b) { for (int w = 0; w < 4; ++w) W->car[c].brake[w] = b; }
+/* Car.step(dt) with len(wheel.tiles) supplied by the caller (the reference's listener owns the sets) */
+ORC_API void orc_ext_car_step(OrcWorld* W, int c, const int* ntiles4, double dt) {
+    for (int w = 0; w < 4; ++w) W->car[c].ntiles[w] = ntiles4[w];
+    car_step(&W->car[c], dt);
+}
+/* touching pairs in contact-list order: out[i] = {tile, car, fixture, active} */
+ORC_API int orc_ext_collide_pairs(OrcWorld* W, int* out, int max) {
+    static __thread Pair pairs[MAX_PAIRS];
+    int n = collect_pairs(W, pairs, max < MAX_PAIRS ? max : MAX_PAIRS);
+    for (int i = 0; i < n; ++i) { out[4 * i] = pairs[i].tile; out[4 * i + 1] = pairs[i].car; out[4 * i + 2] = pairs[i].fixture; out[4 * i + 3] = pairs[i].active; }
+    return n;
+}
+ORC_API void orc_ext_solve(OrcWorld* W, double dt, int velIters, int posIters) { world_solve(W, (float)dt, velIters, posIters); }
+/* GL fixed-function polygon fill on a 96x96 RGB canvas (row 0 = top), viewport pixel coordinates */
+ORC_API void orc_raster_fill(uint8_t* img, const float* px, const float* py, int n, float r, float g, float b) {
+    Canvas cv; cv.img = img;
+    fill_poly(&cv, px, py, n, rgbf(r, g, b));
+}
+ORC_API void orc_raster_fill_u8(uint8_t* img, const float* px, const float* py, int n, int r, int g, int b) {
+    Canvas cv; cv.img = img; RGB c; c.r = (uint8_t)r; c.g = (uint8_t)g; c.b = (uint8_t)b;
+    fill_poly(&cv, px, py, n, c);
+}
+ORC_API void orc_raster_text(uint8_t* img, const char* text) { draw_label(img, text); }
