@@ -241,6 +241,17 @@ typedef struct { uint8_t r, g, b; } RGB;
 static inline uint8_t col_u8(float c) { return (uint8_t)(int)floorf(c * 255.0f + 0.5f); }
 static inline RGB rgbf(float r, float g, float b) { RGB c; c.r = col_u8(r); c.g = col_u8(g); c.b = col_u8(b); return c; }
 
+/* persistent car-car contact manifolds (b2Manifold + ids, for warm starting) */
+typedef struct { V2 localPoint; uint32_t id; float normalImpulse, tangentImpulse; } MPoint;
+typedef struct {
+    int carA, fixA, carB, fixB;   /* fixture A belongs to the lower car index (lower proxy id on a fresh world) */
+    int type;                     /* 0 = e_faceA, 1 = e_faceB */
+    int pointCount;
+    V2 localNormal, localPoint;
+    MPoint pt[2];
+} Manifold;
+#define MAX_MANIFOLDS 64
+
 typedef struct OrcWorld {
     int A;
     int T, Q;
@@ -264,7 +275,8 @@ typedef struct OrcWorld {
     float inv_dt0;
     /* config */
     double h_ratio; int backwards_flag, use_ego_color;
-    int collisions;      /* stage 2 switch */
+    int collisions;      /* car-car rigid contacts on/off */
+    Manifold manifolds[MAX_MANIFOLDS]; int n_manifolds; int manifold_overflow;
     int vel_iters_used;  /* diagnostics: last fixed-point iteration index */
 } OrcWorld;
 
@@ -379,6 +391,7 @@ ORC_API void orc_spawn(OrcWorld* W, const double* init) {
     memset(W->visited, 0, (size_t)W->T * W->A);
     memset(W->touched, 0, W->T);
     W->t = 0.0;
+    W->n_manifolds = 0;
     for (int c = 0; c < W->A; ++c) {
         Car* car = &W->car[c];
         memset(car, 0, sizeof(*car));
@@ -785,67 +798,448 @@ static int state_equal(const Car* a, const Car* b) {
     return 1;
 }
 
-static void solve_car_island(OrcWorld* W, Car* car, float h, int velIters, int posIters, float dtRatio) {
-    /* DFS wakes every body of the island */
-    for (int i = 0; i < 5; ++i) {
-        Body* b = &car->b[i];
-        if (!b->awake) { b->awake = 1; b->sleepTime = 0.0f; }
+/* ------------------------------------------------------------------------------------ */
+/* Car-car rigid contacts: b2CollidePolygons + b2ContactSolver (Box2D 2.3.x)              */
+/* Filtering (car_dynamics): hull cat 0x0001 mask 0xFFFF, wheel cat 0x0020 mask 0x0001 ->  */
+/* hull-hull and wheel-(other car's) hull collide, wheel-wheel does not.                    */
+/* ------------------------------------------------------------------------------------ */
+static const Poly* fixture_poly(const OrcWorld* W, int f) { return f < 4 ? &W->wheel_poly : &W->hull_poly[f - 4]; }
+static Body* fixture_body(OrcWorld* W, int car, int f) { return f < 4 ? &W->car[car].b[1 + f] : &W->car[car].b[0]; }
+
+typedef struct { V2 v; uint32_t id; } ClipVertex;
+static uint32_t cf_key(int indexA, int indexB, int typeA, int typeB) {
+    return (uint32_t)(indexA & 0xff) | ((uint32_t)(indexB & 0xff) << 8) | ((uint32_t)(typeA & 0xff) << 16) | ((uint32_t)(typeB & 0xff) << 24);
+}
+enum { CF_VERTEX = 0, CF_FACE = 1 };
+static inline V2 xmulT(V2 p, Rot q, V2 v) { /* b2MulT(b2Transform, v) */
+    float px = v.x - p.x, py = v.y - p.y;
+    return v2(q.c * px + q.s * py, -q.s * px + q.c * py);
+}
+
+/* b2FindMaxSeparation (brute-force version of Box2D 2.3.1+) */
+static float find_max_separation(int* edgeIndex, const Poly* poly1, V2 p1, Rot q1, const Poly* poly2, V2 p2, Rot q2) {
+    /* xf = b2MulT(xf2, xf1) */
+    Rot q; q.s = q2.c * q1.s - q2.s * q1.c; q.c = q2.c * q1.c + q2.s * q1.s;
+    V2 p = rmulT(q2, vsub(p1, p2));
+    int bestIndex = 0; float maxSeparation = -FLT_MAX;
+    for (int i = 0; i < poly1->n; ++i) {
+        V2 n = rmul(q, poly1->nrm[i]);
+        V2 v1 = xmul(p, q, poly1->v[i]);
+        float si = FLT_MAX;
+        for (int j = 0; j < poly2->n; ++j) {
+            float sij = vdot(n, vsub(poly2->v[j], v1));
+            if (sij < si) si = sij;
+        }
+        if (si > maxSeparation) { maxSeparation = si; bestIndex = i; }
     }
-    for (int i = 0; i < 5; ++i) {
-        Body* b = &car->b[i];
-        /* gravity (0,0), gravityScale 1, damping 0 */
-        b->v.x += h * (b->invMass * b->force.x);
-        b->v.y += h * (b->invMass * b->force.y);
-        b->w += h * b->invI * b->torque;
+    *edgeIndex = bestIndex;
+    return maxSeparation;
+}
+
+static void find_incident_edge(ClipVertex c[2], const Poly* poly1, Rot q1, int edge1, const Poly* poly2, V2 p2, Rot q2) {
+    V2 normal1 = rmulT(q2, rmul(q1, poly1->nrm[edge1]));
+    int index = 0; float minDot = FLT_MAX;
+    for (int i = 0; i < poly2->n; ++i) {
+        float d = vdot(normal1, poly2->nrm[i]);
+        if (d < minDot) { minDot = d; index = i; }
     }
-    for (int k = 0; k < 4; ++k) { int j = JOINT_ORDER[k]; joint_init(&car->j[j], &car->b[0], &car->b[1 + j], dtRatio); }
+    int i1 = index, i2 = i1 + 1 < poly2->n ? i1 + 1 : 0;
+    c[0].v = xmul(p2, q2, poly2->v[i1]); c[0].id = cf_key(edge1, i1, CF_FACE, CF_VERTEX);
+    c[1].v = xmul(p2, q2, poly2->v[i2]); c[1].id = cf_key(edge1, i2, CF_FACE, CF_VERTEX);
+}
+
+static int clip_segment_to_line(ClipVertex vOut[2], const ClipVertex vIn[2], V2 normal, float offset, int vertexIndexA) {
+    int numOut = 0;
+    float distance0 = vdot(normal, vIn[0].v) - offset;
+    float distance1 = vdot(normal, vIn[1].v) - offset;
+    if (distance0 <= 0.0f) vOut[numOut++] = vIn[0];
+    if (distance1 <= 0.0f) vOut[numOut++] = vIn[1];
+    if (distance0 * distance1 < 0.0f) {
+        float interp = distance0 / (distance0 - distance1);
+        vOut[numOut].v = vadd(vIn[0].v, vscale(interp, vsub(vIn[1].v, vIn[0].v)));
+        vOut[numOut].id = cf_key(vertexIndexA, (int)((vIn[0].id >> 8) & 0xff), CF_VERTEX, CF_FACE);
+        ++numOut;
+    }
+    return numOut;
+}
+
+
+static void collide_polygons(Manifold* m, const Poly* polyA, V2 pA, Rot qA, const Poly* polyB, V2 pB, Rot qB) {
+    m->pointCount = 0;
+    const float totalRadius = B2_POLYGON_RADIUS + B2_POLYGON_RADIUS;
+    int edgeA = 0; float separationA = find_max_separation(&edgeA, polyA, pA, qA, polyB, pB, qB);
+    if (separationA > totalRadius) return;
+    int edgeB = 0; float separationB = find_max_separation(&edgeB, polyB, pB, qB, polyA, pA, qA);
+    if (separationB > totalRadius) return;
+    const Poly *poly1, *poly2; V2 p1, p2; Rot q1, q2; int edge1, flip;
+    const float k_tol = 0.1f * B2_LINEAR_SLOP;
+    if (separationB > separationA + k_tol) { poly1 = polyB; poly2 = polyA; p1 = pB; q1 = qB; p2 = pA; q2 = qA; edge1 = edgeB; m->type = 1; flip = 1; }
+    else { poly1 = polyA; poly2 = polyB; p1 = pA; q1 = qA; p2 = pB; q2 = qB; edge1 = edgeA; m->type = 0; flip = 0; }
+    ClipVertex incidentEdge[2];
+    find_incident_edge(incidentEdge, poly1, q1, edge1, poly2, p2, q2);
+    int iv1 = edge1, iv2 = edge1 + 1 < poly1->n ? edge1 + 1 : 0;
+    V2 v11 = poly1->v[iv1], v12 = poly1->v[iv2];
+    V2 localTangent = vsub(v12, v11);
+    { float len = vlen(localTangent); if (len >= B2_EPSILON) { float inv = 1.0f / len; localTangent.x *= inv; localTangent.y *= inv; } }
+    V2 localNormal = cross_vs(localTangent, 1.0f);
+    V2 planePoint = vscale(0.5f, vadd(v11, v12));
+    V2 tangent = rmul(q1, localTangent);
+    V2 normal = cross_vs(tangent, 1.0f);
+    v11 = xmul(p1, q1, v11); v12 = xmul(p1, q1, v12);
+    float frontOffset = vdot(normal, v11);
+    float sideOffset1 = -vdot(tangent, v11) + totalRadius;
+    float sideOffset2 = vdot(tangent, v12) + totalRadius;
+    ClipVertex clipPoints1[2], clipPoints2[2];
+    int np = clip_segment_to_line(clipPoints1, incidentEdge, vneg(tangent), sideOffset1, iv1);
+    if (np < 2) return;
+    np = clip_segment_to_line(clipPoints2, clipPoints1, tangent, sideOffset2, iv2);
+    if (np < 2) return;
+    m->localNormal = localNormal; m->localPoint = planePoint;
+    int pointCount = 0;
+    for (int i = 0; i < 2; ++i) {
+        float separation = vdot(normal, clipPoints2[i].v) - frontOffset;
+        if (separation <= totalRadius) {
+            MPoint* cp = &m->pt[pointCount];
+            cp->localPoint = xmulT(p2, q2, clipPoints2[i].v);
+            uint32_t id = clipPoints2[i].id;
+            if (flip) id = cf_key((int)((id >> 8) & 0xff), (int)(id & 0xff), (int)((id >> 24) & 0xff), (int)((id >> 16) & 0xff));
+            cp->id = id;
+            ++pointCount;
+        }
+    }
+    m->pointCount = pointCount;
+}
+
+/* b2ContactManager::Collide for the solid car-car pairs (start-of-step poses).  Pair order =
+ * (car a < car b, fixture of a ascending, fixture of b ascending): deterministic stand-in for
+ * the history-dependent contact-list order of Box2D (D1). */
+static void collide_cars(OrcWorld* W) {
+    Manifold* old = W->manifolds; int nold = W->n_manifolds;
+    static __thread Manifold fresh[MAX_MANIFOLDS]; int nnew = 0;
+    const float r = B2_POLYGON_RADIUS;
+    for (int a = 0; a < W->A; ++a) for (int b = a + 1; b < W->A; ++b)
+        for (int fa = 0; fa < 8; ++fa) for (int fb = 0; fb < 8; ++fb) {
+            if (fa < 4 && fb < 4) continue;                    /* wheel-wheel filtered out */
+            Body* bA = fixture_body(W, a, fa); Body* bB = fixture_body(W, b, fb);
+            const Poly* PA = fixture_poly(W, fa); const Poly* PB = fixture_poly(W, fb);
+            const Manifold* prev = NULL;
+            for (int i = 0; i < nold; ++i) if (old[i].carA == a && old[i].carB == b && old[i].fixA == fa && old[i].fixB == fb) { prev = &old[i]; break; }
+            if (!bA->awake && !bB->awake) {                    /* neither body active: contact not updated */
+                if (prev && prev->pointCount > 0 && nnew < MAX_MANIFOLDS) fresh[nnew++] = *prev;
+                continue;
+            }
+            /* b2PolygonShape::ComputeAABB (+ radius) and b2TestOverlap(aabb, aabb): a non-overlap means
+             * a separation > 2 r, for which b2CollidePolygons returns no points */
+            V2 va[MAXV], vb[MAXV]; float aa[4], ab[4];
+            world_poly(bA, PA, va, aa); world_poly(bB, PB, vb, ab);
+            if ((ab[0] - r) - (aa[2] + r) > 0.0f || (ab[1] - r) - (aa[3] + r) > 0.0f ||
+                (aa[0] - r) - (ab[2] + r) > 0.0f || (aa[1] - r) - (ab[3] + r) > 0.0f) continue;
+            Manifold m; memset(&m, 0, sizeof(m));
+            m.carA = a; m.fixA = fa; m.carB = b; m.fixB = fb;
+            collide_polygons(&m, PA, bA->p, bA->q, PB, bB->p, bB->q);
+            int wasTouching = prev && prev->pointCount > 0;
+            for (int i = 0; i < m.pointCount; ++i) {           /* b2Contact::Update: carry impulses by feature id */
+                m.pt[i].normalImpulse = 0.0f; m.pt[i].tangentImpulse = 0.0f;
+                if (prev) for (int j = 0; j < prev->pointCount; ++j)
+                    if (prev->pt[j].id == m.pt[i].id) { m.pt[i].normalImpulse = prev->pt[j].normalImpulse; m.pt[i].tangentImpulse = prev->pt[j].tangentImpulse; break; }
+            }
+            if ((m.pointCount > 0) != wasTouching) {
+                if (!bA->awake) { bA->awake = 1; bA->sleepTime = 0.0f; }
+                if (!bB->awake) { bB->awake = 1; bB->sleepTime = 0.0f; }
+            }
+            if (m.pointCount > 0) { if (nnew < MAX_MANIFOLDS) fresh[nnew++] = m; else W->manifold_overflow = 1; }
+        }
+    memcpy(W->manifolds, fresh, sizeof(Manifold) * nnew);
+    W->n_manifolds = nnew;
+}
+
+typedef struct {
+    Body *A, *B; Manifold* m;
+    V2 normal; float friction;
+    int pointCount;               /* may drop to 1 when the block solver finds the points redundant */
+    V2 rA[2], rB[2]; float normalMass[2], tangentMass[2], velocityBias[2], normalImpulse[2], tangentImpulse[2];
+    float K[2][2], NM[2][2];      /* b2Mat22 as [col][row] */
+} VC;
+
+static void world_manifold(const Manifold* m, V2 pA, Rot qA, V2 pB, Rot qB, V2* normal, V2 points[2]) {
+    const float radiusA = B2_POLYGON_RADIUS, radiusB = B2_POLYGON_RADIUS;
+    if (m->type == 0) {
+        *normal = rmul(qA, m->localNormal);
+        V2 planePoint = xmul(pA, qA, m->localPoint);
+        for (int i = 0; i < m->pointCount; ++i) {
+            V2 clipPoint = xmul(pB, qB, m->pt[i].localPoint);
+            V2 cA = vadd(clipPoint, vscale(radiusA - vdot(vsub(clipPoint, planePoint), *normal), *normal));
+            V2 cB = vsub(clipPoint, vscale(radiusB, *normal));
+            points[i] = vscale(0.5f, vadd(cA, cB));
+        }
+    } else {
+        *normal = rmul(qB, m->localNormal);
+        V2 planePoint = xmul(pB, qB, m->localPoint);
+        for (int i = 0; i < m->pointCount; ++i) {
+            V2 clipPoint = xmul(pA, qA, m->pt[i].localPoint);
+            V2 cB = vadd(clipPoint, vscale(radiusB - vdot(vsub(clipPoint, planePoint), *normal), *normal));
+            V2 cA = vsub(clipPoint, vscale(radiusA, *normal));
+            points[i] = vscale(0.5f, vadd(cA, cB));
+        }
+        *normal = vneg(*normal);
+    }
+}
+
+static void contact_init(VC* vc) {
+    Body *A = vc->A, *B = vc->B; const Manifold* m = vc->m;
+    float mA = A->invMass, mB = B->invMass, iA = A->invI, iB = B->invI;
+    Rot qA = rot_set(A->a), qB = rot_set(B->a);
+    V2 pA = vsub(A->c, rmul(qA, A->localCenter)), pB = vsub(B->c, rmul(qB, B->localCenter));
+    V2 points[2];
+    world_manifold(m, pA, qA, pB, qB, &vc->normal, points);
+    vc->pointCount = m->pointCount;
+    vc->friction = sqrtf(0.2f * 0.2f);            /* b2MixFriction of the default fixture frictions */
+    for (int j = 0; j < vc->pointCount; ++j) {
+        vc->normalImpulse[j] = m->pt[j].normalImpulse;   /* dtRatio == 1 */
+        vc->tangentImpulse[j] = m->pt[j].tangentImpulse;
+        vc->rA[j] = vsub(points[j], A->c); vc->rB[j] = vsub(points[j], B->c);
+        float rnA = vcross(vc->rA[j], vc->normal), rnB = vcross(vc->rB[j], vc->normal);
+        float kNormal = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+        vc->normalMass[j] = kNormal > 0.0f ? 1.0f / kNormal : 0.0f;
+        V2 tangent = cross_vs(vc->normal, 1.0f);
+        float rtA = vcross(vc->rA[j], tangent), rtB = vcross(vc->rB[j], tangent);
+        float kTangent = mA + mB + iA * rtA * rtA + iB * rtB * rtB;
+        vc->tangentMass[j] = kTangent > 0.0f ? 1.0f / kTangent : 0.0f;
+        vc->velocityBias[j] = 0.0f;               /* restitution 0 */
+    }
+    if (vc->pointCount == 2) {
+        float rn1A = vcross(vc->rA[0], vc->normal), rn1B = vcross(vc->rB[0], vc->normal);
+        float rn2A = vcross(vc->rA[1], vc->normal), rn2B = vcross(vc->rB[1], vc->normal);
+        float k11 = mA + mB + iA * rn1A * rn1A + iB * rn1B * rn1B;
+        float k22 = mA + mB + iA * rn2A * rn2A + iB * rn2B * rn2B;
+        float k12 = mA + mB + iA * rn1A * rn2A + iB * rn1B * rn2B;
+        const float k_maxConditionNumber = 1000.0f;
+        if (k11 * k11 < k_maxConditionNumber * (k11 * k22 - k12 * k12)) {
+            vc->K[0][0] = k11; vc->K[0][1] = k12; vc->K[1][0] = k12; vc->K[1][1] = k22;
+            float a = k11, b = k12, c = k12, d = k22;
+            float det = a * d - b * c;
+            if (det != 0.0f) det = 1.0f / det;
+            vc->NM[0][0] = det * d; vc->NM[1][0] = -det * b; vc->NM[0][1] = -det * c; vc->NM[1][1] = det * a;
+        } else {
+            vc->pointCount = 1;
+        }
+    }
+}
+
+static void contact_warm_start(VC* vc) {
+    Body *A = vc->A, *B = vc->B;
+    float mA = A->invMass, mB = B->invMass, iA = A->invI, iB = B->invI;
+    V2 tangent = cross_vs(vc->normal, 1.0f);
+    for (int j = 0; j < vc->pointCount; ++j) {
+        V2 P = vadd(vscale(vc->normalImpulse[j], vc->normal), vscale(vc->tangentImpulse[j], tangent));
+        A->w -= iA * vcross(vc->rA[j], P); A->v = vsub(A->v, vscale(mA, P));
+        B->w += iB * vcross(vc->rB[j], P); B->v = vadd(B->v, vscale(mB, P));
+    }
+}
+
+static void contact_apply2(VC* vc, V2* vA, float* wA, V2* vB, float* wB, float dx, float dy) {
+    Body *A = vc->A, *B = vc->B;
+    float mA = A->invMass, mB = B->invMass, iA = A->invI, iB = B->invI;
+    V2 P1 = vscale(dx, vc->normal), P2 = vscale(dy, vc->normal);
+    *vA = vsub(*vA, vscale(mA, vadd(P1, P2)));
+    *wA -= iA * (vcross(vc->rA[0], P1) + vcross(vc->rA[1], P2));
+    *vB = vadd(*vB, vscale(mB, vadd(P1, P2)));
+    *wB += iB * (vcross(vc->rB[0], P1) + vcross(vc->rB[1], P2));
+}
+
+static void contact_solve_vel(VC* vc) {
+    Body *A = vc->A, *B = vc->B;
+    float mA = A->invMass, mB = B->invMass, iA = A->invI, iB = B->invI;
+    V2 vA = A->v, vB = B->v; float wA = A->w, wB = B->w;
+    V2 normal = vc->normal, tangent = cross_vs(normal, 1.0f);
+    for (int j = 0; j < vc->pointCount; ++j) {      /* friction first */
+        V2 dv = vsub(vsub(vadd(vB, cross_sv(wB, vc->rB[j])), vA), cross_sv(wA, vc->rA[j]));
+        float vt = vdot(dv, tangent) - 0.0f;
+        float lambda = vc->tangentMass[j] * (-vt);
+        float maxFriction = vc->friction * vc->normalImpulse[j];
+        float newImpulse = clampf(vc->tangentImpulse[j] + lambda, -maxFriction, maxFriction);
+        lambda = newImpulse - vc->tangentImpulse[j];
+        vc->tangentImpulse[j] = newImpulse;
+        V2 P = vscale(lambda, tangent);
+        vA = vsub(vA, vscale(mA, P)); wA -= iA * vcross(vc->rA[j], P);
+        vB = vadd(vB, vscale(mB, P)); wB += iB * vcross(vc->rB[j], P);
+    }
+    if (vc->pointCount == 1) {
+        V2 dv = vsub(vsub(vadd(vB, cross_sv(wB, vc->rB[0])), vA), cross_sv(wA, vc->rA[0]));
+        float vn = vdot(dv, normal);
+        float lambda = -vc->normalMass[0] * (vn - vc->velocityBias[0]);
+        float newImpulse = fmaxf(vc->normalImpulse[0] + lambda, 0.0f);
+        lambda = newImpulse - vc->normalImpulse[0];
+        vc->normalImpulse[0] = newImpulse;
+        V2 P = vscale(lambda, normal);
+        vA = vsub(vA, vscale(mA, P)); wA -= iA * vcross(vc->rA[0], P);
+        vB = vadd(vB, vscale(mB, P)); wB += iB * vcross(vc->rB[0], P);
+    } else {                                        /* block solver */
+        float ax = vc->normalImpulse[0], ay = vc->normalImpulse[1];
+        V2 dv1 = vsub(vsub(vadd(vB, cross_sv(wB, vc->rB[0])), vA), cross_sv(wA, vc->rA[0]));
+        V2 dv2 = vsub(vsub(vadd(vB, cross_sv(wB, vc->rB[1])), vA), cross_sv(wA, vc->rA[1]));
+        float vn1 = vdot(dv1, normal), vn2 = vdot(dv2, normal);
+        float bx = vn1 - vc->velocityBias[0], by = vn2 - vc->velocityBias[1];
+        bx -= vc->K[0][0] * ax + vc->K[1][0] * ay;
+        by -= vc->K[0][1] * ax + vc->K[1][1] * ay;
+        for (;;) {
+            float xx = -(vc->NM[0][0] * bx + vc->NM[1][0] * by), xy = -(vc->NM[0][1] * bx + vc->NM[1][1] * by);
+            if (xx >= 0.0f && xy >= 0.0f) {
+                contact_apply2(vc, &vA, &wA, &vB, &wB, xx - ax, xy - ay);
+                vc->normalImpulse[0] = xx; vc->normalImpulse[1] = xy; break;
+            }
+            xx = -vc->normalMass[0] * bx; xy = 0.0f;
+            vn1 = 0.0f; vn2 = vc->K[0][1] * xx + by;
+            if (xx >= 0.0f && vn2 >= 0.0f) {
+                contact_apply2(vc, &vA, &wA, &vB, &wB, xx - ax, xy - ay);
+                vc->normalImpulse[0] = xx; vc->normalImpulse[1] = xy; break;
+            }
+            xx = 0.0f; xy = -vc->normalMass[1] * by;
+            vn1 = vc->K[1][0] * xy + bx; vn2 = 0.0f;
+            if (xy >= 0.0f && vn1 >= 0.0f) {
+                contact_apply2(vc, &vA, &wA, &vB, &wB, xx - ax, xy - ay);
+                vc->normalImpulse[0] = xx; vc->normalImpulse[1] = xy; break;
+            }
+            xx = 0.0f; xy = 0.0f; vn1 = bx; vn2 = by;
+            if (vn1 >= 0.0f && vn2 >= 0.0f) {
+                contact_apply2(vc, &vA, &wA, &vB, &wB, xx - ax, xy - ay);
+                vc->normalImpulse[0] = xx; vc->normalImpulse[1] = xy; break;
+            }
+            break;   /* no solution, give up */
+        }
+    }
+    A->v = vA; A->w = wA; B->v = vB; B->w = wB;
+}
+
+/* b2ContactSolver::SolvePositionConstraints for one contact; updates *minSeparation */
+static void contact_solve_pos(VC* vc, float* minSeparation) {
+    Body *A = vc->A, *B = vc->B; const Manifold* m = vc->m;
+    float mA = A->invMass, mB = B->invMass, iA = A->invI, iB = B->invI;
+    V2 cA = A->c, cB = B->c; float aA = A->a, aB = B->a;
+    for (int j = 0; j < m->pointCount; ++j) {
+        Rot qA = rot_set(aA), qB = rot_set(aB);
+        V2 pA = vsub(cA, rmul(qA, A->localCenter)), pB = vsub(cB, rmul(qB, B->localCenter));
+        V2 normal, point; float separation;
+        if (m->type == 0) {
+            normal = rmul(qA, m->localNormal);
+            V2 planePoint = xmul(pA, qA, m->localPoint);
+            V2 clipPoint = xmul(pB, qB, m->pt[j].localPoint);
+            separation = vdot(vsub(clipPoint, planePoint), normal) - B2_POLYGON_RADIUS - B2_POLYGON_RADIUS;
+            point = clipPoint;
+        } else {
+            normal = rmul(qB, m->localNormal);
+            V2 planePoint = xmul(pB, qB, m->localPoint);
+            V2 clipPoint = xmul(pA, qA, m->pt[j].localPoint);
+            separation = vdot(vsub(clipPoint, planePoint), normal) - B2_POLYGON_RADIUS - B2_POLYGON_RADIUS;
+            point = clipPoint;
+            normal = vneg(normal);
+        }
+        V2 rA = vsub(point, cA), rB = vsub(point, cB);
+        *minSeparation = fminf(*minSeparation, separation);
+        float C = clampf(B2_BAUMGARTE * (separation + B2_LINEAR_SLOP), -B2_MAX_LINEAR_CORRECTION, 0.0f);
+        float rnA = vcross(rA, normal), rnB = vcross(rB, normal);
+        float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+        float impulse = K > 0.0f ? -C / K : 0.0f;
+        V2 P = vscale(impulse, normal);
+        cA = vsub(cA, vscale(mA, P)); aA -= iA * vcross(rA, P);
+        cB = vadd(cB, vscale(mB, P)); aB += iB * vcross(rB, P);
+    }
+    A->c = cA; A->a = aA; B->c = cB; B->a = aB;
+}
+
+/* b2Island::Solve for one island = the cars in `cars` plus the touching manifolds among them. */
+static void solve_island(OrcWorld* W, const int* cars, int ncars, Manifold** mans, int nmans, float h, int velIters,
+                         int posIters, float dtRatio) {
+    static __thread VC vcs[MAX_MANIFOLDS];
+    for (int ci = 0; ci < ncars; ++ci) {
+        Car* car = &W->car[cars[ci]];
+        for (int i = 0; i < 5; ++i) {                 /* DFS wakes every body of the island */
+            Body* b = &car->b[i];
+            if (!b->awake) { b->awake = 1; b->sleepTime = 0.0f; }
+        }
+        for (int i = 0; i < 5; ++i) {                 /* gravity (0,0), damping 0 */
+            Body* b = &car->b[i];
+            b->v.x += h * (b->invMass * b->force.x);
+            b->v.y += h * (b->invMass * b->force.y);
+            b->w += h * b->invI * b->torque;
+        }
+    }
+    for (int i = 0; i < nmans; ++i) {
+        vcs[i].m = mans[i];
+        vcs[i].A = fixture_body(W, mans[i]->carA, mans[i]->fixA);
+        vcs[i].B = fixture_body(W, mans[i]->carB, mans[i]->fixB);
+        contact_init(&vcs[i]);
+    }
+    for (int i = 0; i < nmans; ++i) contact_warm_start(&vcs[i]);
+    for (int ci = 0; ci < ncars; ++ci) {
+        Car* car = &W->car[cars[ci]];
+        for (int k = 0; k < 4; ++k) { int j = JOINT_ORDER[k]; joint_init(&car->j[j], &car->b[0], &car->b[1 + j], dtRatio); }
+    }
     int fixed_at = -1;
     for (int it = 0; it < velIters; ++it) {
-        Car before;
-        if (fixed_at < 0) before = *car;
-        for (int k = 0; k < 4; ++k) { int j = JOINT_ORDER[k]; joint_solve_vel(&car->j[j], &car->b[0], &car->b[1 + j], h); }
-        if (fixed_at < 0 && state_equal(&before, car)) fixed_at = it; /* diagnostics only: we keep iterating */
+        Car before; if (fixed_at < 0 && ncars == 1) before = W->car[cars[0]];
+        for (int ci = 0; ci < ncars; ++ci) {
+            Car* car = &W->car[cars[ci]];
+            for (int k = 0; k < 4; ++k) { int j = JOINT_ORDER[k]; joint_solve_vel(&car->j[j], &car->b[0], &car->b[1 + j], h); }
+        }
+        for (int i = 0; i < nmans; ++i) contact_solve_vel(&vcs[i]);
+        if (fixed_at < 0 && ncars == 1 && state_equal(&before, &W->car[cars[0]])) fixed_at = it; /* diagnostics only */
     }
     { int fa = fixed_at < 0 ? velIters : fixed_at; if (fa > W->vel_iters_used) W->vel_iters_used = fa; }
-    for (int i = 0; i < 5; ++i) {
-        Body* b = &car->b[i];
-        V2 tr = vscale(h, b->v);
-        if (vdot(tr, tr) > B2_MAX_TRANSLATION_SQ) { float ratio = B2_MAX_TRANSLATION / vlen(tr); b->v = vscale(ratio, b->v); }
-        float rotn = h * b->w;
-        if (rotn * rotn > B2_MAX_ROTATION_SQ) { float ratio = B2_MAX_ROTATION / fabsf(rotn); b->w *= ratio; }
-        b->c.x += h * b->v.x; b->c.y += h * b->v.y;
-        b->a += h * b->w;
+    for (int i = 0; i < nmans; ++i)                   /* StoreImpulses */
+        for (int j = 0; j < vcs[i].pointCount; ++j) {
+            vcs[i].m->pt[j].normalImpulse = vcs[i].normalImpulse[j];
+            vcs[i].m->pt[j].tangentImpulse = vcs[i].tangentImpulse[j];
+        }
+    for (int ci = 0; ci < ncars; ++ci) {
+        Car* car = &W->car[cars[ci]];
+        for (int i = 0; i < 5; ++i) {
+            Body* b = &car->b[i];
+            V2 tr = vscale(h, b->v);
+            if (vdot(tr, tr) > B2_MAX_TRANSLATION_SQ) { float ratio = B2_MAX_TRANSLATION / vlen(tr); b->v = vscale(ratio, b->v); }
+            float rotn = h * b->w;
+            if (rotn * rotn > B2_MAX_ROTATION_SQ) { float ratio = B2_MAX_ROTATION / fabsf(rotn); b->w *= ratio; }
+            b->c.x += h * b->v.x; b->c.y += h * b->v.y;
+            b->a += h * b->w;
+        }
     }
     int positionSolved = 0;
     for (int it = 0; it < posIters; ++it) {
+        float minSeparation = 0.0f;
+        for (int i = 0; i < nmans; ++i) contact_solve_pos(&vcs[i], &minSeparation);
+        int contactsOkay = minSeparation >= -3.0f * B2_LINEAR_SLOP;
         int jointsOkay = 1;
-        for (int k = 0; k < 4; ++k) {
-            int j = JOINT_ORDER[k];
-            int ok = joint_solve_pos(&car->j[j], &car->b[0], &car->b[1 + j]);
-            jointsOkay = jointsOkay && ok;
+        for (int ci = 0; ci < ncars; ++ci) {
+            Car* car = &W->car[cars[ci]];
+            for (int k = 0; k < 4; ++k) {
+                int j = JOINT_ORDER[k];
+                int ok = joint_solve_pos(&car->j[j], &car->b[0], &car->b[1 + j]);
+                jointsOkay = jointsOkay && ok;
+            }
         }
-        if (jointsOkay) { positionSolved = 1; break; }
+        if (contactsOkay && jointsOkay) { positionSolved = 1; break; }
     }
-    /* SynchronizeTransform */
-    for (int i = 0; i < 5; ++i) {
-        Body* b = &car->b[i];
-        b->q = rot_set(b->a);
-        V2 rc = rmul(b->q, b->localCenter);
-        b->p = vsub(b->c, rc);
-    }
-    /* sleep management */
     float minSleepTime = FLT_MAX;
     const float linTolSqr = B2_LINEAR_SLEEP_TOL * B2_LINEAR_SLEEP_TOL;
     const float angTolSqr = B2_ANGULAR_SLEEP_TOL * B2_ANGULAR_SLEEP_TOL;
-    for (int i = 0; i < 5; ++i) {
-        Body* b = &car->b[i];
-        if (b->w * b->w > angTolSqr || vdot(b->v, b->v) > linTolSqr) { b->sleepTime = 0.0f; minSleepTime = 0.0f; }
-        else { b->sleepTime += h; minSleepTime = fminf(minSleepTime, b->sleepTime); }
-    }
-    if (minSleepTime >= B2_TIME_TO_SLEEP && positionSolved) {
+    for (int ci = 0; ci < ncars; ++ci) {
+        Car* car = &W->car[cars[ci]];
         for (int i = 0; i < 5; ++i) {
             Body* b = &car->b[i];
-            b->awake = 0; b->sleepTime = 0.0f; b->v = v2(0.0f, 0.0f); b->w = 0.0f; b->force = v2(0.0f, 0.0f); b->torque = 0.0f;
+            b->q = rot_set(b->a);                     /* SynchronizeTransform */
+            V2 rc = rmul(b->q, b->localCenter);
+            b->p = vsub(b->c, rc);
+            if (b->w * b->w > angTolSqr || vdot(b->v, b->v) > linTolSqr) { b->sleepTime = 0.0f; minSleepTime = 0.0f; }
+            else { b->sleepTime += h; minSleepTime = fminf(minSleepTime, b->sleepTime); }
+        }
+    }
+    if (minSleepTime >= B2_TIME_TO_SLEEP && positionSolved) {
+        for (int ci = 0; ci < ncars; ++ci) {
+            Car* car = &W->car[cars[ci]];
+            for (int i = 0; i < 5; ++i) {
+                Body* b = &car->b[i];
+                b->awake = 0; b->sleepTime = 0.0f; b->v = v2(0.0f, 0.0f); b->w = 0.0f; b->force = v2(0.0f, 0.0f); b->torque = 0.0f;
+            }
         }
     }
 }
@@ -854,13 +1248,28 @@ static void world_solve(OrcWorld* W, float dt, int velIters, int posIters) {
     float inv_dt = dt > 0.0f ? 1.0f / dt : 0.0f;
     float dtRatio = W->inv_dt0 * dt;
     W->vel_iters_used = 0;
+    if (W->collisions) collide_cars(W); else W->n_manifolds = 0;
+    /* islands: cars linked by touching manifolds (union-find, root = lowest car index) */
+    int root[MAX_AGENTS];
+    for (int c = 0; c < W->A; ++c) root[c] = c;
+    for (int i = 0; i < W->n_manifolds; ++i) {
+        int a = W->manifolds[i].carA, b = W->manifolds[i].carB;
+        while (root[a] != a) a = root[a];
+        while (root[b] != b) b = root[b];
+        if (a != b) { if (a < b) root[b] = a; else root[a] = b; }
+    }
+    for (int c = 0; c < W->A; ++c) { int r = c; while (root[r] != r) r = root[r]; root[c] = r; }
     /* islands are seeded from awake bodies in reverse creation order: last car first */
+    int done[MAX_AGENTS] = {0};
     for (int c = W->A - 1; c >= 0; --c) {
-        Car* car = &W->car[c];
-        int any_awake = 0;
-        for (int i = 0; i < 5; ++i) any_awake |= car->b[i].awake;
+        if (done[c]) continue;
+        int cars[MAX_AGENTS], ncars = 0, any_awake = 0;
+        for (int k = W->A - 1; k >= 0; --k) if (root[k] == root[c]) { cars[ncars++] = k; done[k] = 1; }
+        Manifold* mans[MAX_MANIFOLDS]; int nmans = 0;
+        for (int i = 0; i < W->n_manifolds; ++i) if (root[W->manifolds[i].carA] == root[c]) mans[nmans++] = &W->manifolds[i];
+        for (int k = 0; k < ncars; ++k) for (int i = 0; i < 5; ++i) any_awake |= W->car[cars[k]].b[i].awake;
         if (!any_awake) continue;
-        solve_car_island(W, car, dt, velIters, posIters, dtRatio);
+        solve_island(W, cars, ncars, mans, nmans, dt, velIters, posIters, dtRatio);
     }
     W->inv_dt0 = inv_dt;
     /* ClearForces */
@@ -1233,3 +1642,20 @@ ORC_API void orc_raster_fill_u8(uint8_t* img, const float* px, const float* py, 
     fill_poly(&cv, px, py, n, c);
 }
 ORC_API void orc_raster_text(uint8_t* img, const char* text) { draw_label(img, text); }
+
+/* manifold readback for parity tests: out[i] = carA, fixA, carB, fixB, type, pointCount, then per point
+ * (id, localPoint.x, localPoint.y, normalImpulse, tangentImpulse) x 2, localNormal.xy, localPoint.xy -> 20 floats */
+ORC_API int orc_get_manifolds(const OrcWorld* W, float* out, int max) {
+    int n = W->n_manifolds < max ? W->n_manifolds : max;
+    for (int i = 0; i < n; ++i) {
+        const Manifold* m = &W->manifolds[i]; float* o = out + 20 * i;
+        o[0] = (float)m->carA; o[1] = (float)m->fixA; o[2] = (float)m->carB; o[3] = (float)m->fixB; o[4] = (float)m->type; o[5] = (float)m->pointCount;
+        for (int j = 0; j < 2; ++j) {
+            o[6 + 5 * j] = j < m->pointCount ? (float)(m->pt[j].id & 0xffff) : 0.0f;
+            o[7 + 5 * j] = j < m->pointCount ? m->pt[j].localPoint.x : 0.0f; o[8 + 5 * j] = j < m->pointCount ? m->pt[j].localPoint.y : 0.0f;
+            o[9 + 5 * j] = j < m->pointCount ? m->pt[j].normalImpulse : 0.0f; o[10 + 5 * j] = j < m->pointCount ? m->pt[j].tangentImpulse : 0.0f;
+        }
+        o[16] = m->localNormal.x; o[17] = m->localNormal.y; o[18] = m->localPoint.x; o[19] = m->localPoint.y;
+    }
+    return W->n_manifolds;
+}
