@@ -47,7 +47,7 @@ typedef struct mcr_config {
     int32_t device;            /* CUDA device ordinal                                     */
     int32_t use_random_direction; /* mcr:132; only used by the device-side auto reset     */
     int32_t direction_cw;      /* mcr:131 direction == 'CW'; auto reset when not random   */
-    int32_t reserved;
+    int32_t collisions;        /* 1: car-car rigid contacts (Box2D polygon contacts); 0: cars pass through each other */
     uint64_t seed;             /* stream id of the device-side auto-reset RNG             */
 } mcr_config;
 

@@ -29,7 +29,7 @@ class McrConfig(ctypes.Structure):
         ("use_ego_color", ctypes.c_int32), ("max_episode_steps", ctypes.c_int32),
         ("h_ratio", ctypes.c_double), ("device", ctypes.c_int32),
         ("use_random_direction", ctypes.c_int32), ("direction_cw", ctypes.c_int32),
-        ("reserved", ctypes.c_int32), ("seed", ctypes.c_uint64),
+        ("collisions", ctypes.c_int32), ("seed", ctypes.c_uint64),
     ]
 
 

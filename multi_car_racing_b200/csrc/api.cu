@@ -101,7 +101,16 @@ Mass b2_polygon_mass(const std::vector<P2>& v, float density) {
 
 void to_poly8(const std::vector<P2>& v, Poly8& out) {
     out.n = (int)v.size();
-    for (int i = 0; i < MCR_MAXV; ++i) { out.x[i] = i < out.n ? v[i].x : 0.0f; out.y[i] = i < out.n ? v[i].y : 0.0f; }
+    for (int i = 0; i < MCR_MAXV; ++i) { out.x[i] = i < out.n ? v[i].x : 0.0f; out.y[i] = i < out.n ? v[i].y : 0.0f; out.nx[i] = 0.0f; out.ny[i] = 0.0f; }
+    // b2PolygonShape::Set: m_normals[i] = b2Cross(edge, 1.0f), normalised
+    for (int i = 0; i < out.n; ++i) {
+        const int i2 = i + 1 < out.n ? i + 1 : 0;
+        const P2 e = v[i2] - v[i];
+        P2 nn{1.0f * e.y, -1.0f * e.x};
+        const float len = std::sqrt(nn.x * nn.x + nn.y * nn.y);
+        if (len >= B2_EPS) { const float inv = 1.0f / len; nn.x *= inv; nn.y *= inv; }
+        out.nx[i] = nn.x; out.ny[i] = nn.y;
+    }
 }
 
 // car_dynamics.py geometry (gym 0.17.2), units of SIZE
@@ -428,6 +437,8 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
     set_spec(h, BUF_RESET_MASK, "reset_mask", MCR_U8, {B});
     set_spec(h, BUF_STATUS, "status", MCR_I32, {STATUS_WORDS});
     set_spec(h, BUF_SCRATCH, "scratch", MCR_F32, {MCR_SCRATCH_FIELDS, N});
+    set_spec(h, BUF_MANIFOLD, "manifold", MCR_F32, {B, MCR_MAX_MANIFOLDS, MCR_MANIFOLD_WORDS});
+    set_spec(h, BUF_N_MANIFOLD, "n_manifold", MCR_I32, {B});
     set_spec(h, BUF_TRK_T, "trk_T", MCR_I32, {P});
     set_spec(h, BUF_TRK_Q, "trk_Q", MCR_I32, {P});
     set_spec(h, BUF_TRK_NODE, "trk_node", MCR_F64, {P, T, 3});
@@ -494,6 +505,8 @@ extern "C" int mcr_bind_buffer(mcr_handle h, int i, void* p) {
         case BUF_RESET_MASK: b.reset_mask = (uint8_t*)p; break;
         case BUF_STATUS: b.status = (int32_t*)p; break;
         case BUF_SCRATCH: b.scratch = (float*)p; break;
+        case BUF_MANIFOLD: b.manifold = (float*)p; break;
+        case BUF_N_MANIFOLD: b.n_manifold = (int32_t*)p; break;
         case BUF_TRK_T: b.trk_T = (int32_t*)p; break;
         case BUF_TRK_Q: b.trk_Q = (int32_t*)p; break;
         case BUF_TRK_NODE: b.trk_node = (double*)p; break;
@@ -639,7 +652,7 @@ static int simulate(mcr_handle h, const uint8_t* mask, const void* action, int32
     CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
     LAUNCH(launch_contacts(h->d, h->buf, h->cc, mask, h->side));
     CUDA_OK(cudaEventRecord(h->ev_join, h->side));
-    LAUNCH(launch_physics(h->d, h->buf, h->cc, mask, action, action_dtype, h->cfg.h_ratio, s));
+    LAUNCH(launch_physics(h->d, h->buf, h->cc, mask, action, action_dtype, h->cfg.h_ratio, h->cfg.collisions, s));
     CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));
     LAUNCH(launch_physics_post(h->d, h->buf, h->cc, mask, action != nullptr, h->cfg.h_ratio, s));
     return 0;
@@ -654,7 +667,7 @@ extern "C" int mcr_contacts(mcr_handle h, const uint8_t* mask, void* stream) {
 extern "C" int mcr_physics(mcr_handle h, const uint8_t* mask, const void* action, int32_t action_dtype, void* stream) {
     int rc = check_bound(h); if (rc) return rc;
     if (action && action_dtype != MCR_F32 && action_dtype != MCR_F64) return fail(-1, "action dtype must be MCR_F32 or MCR_F64");
-    LAUNCH(launch_physics(h->d, h->buf, h->cc, mask, action, action_dtype, h->cfg.h_ratio, stream));
+    LAUNCH(launch_physics(h->d, h->buf, h->cc, mask, action, action_dtype, h->cfg.h_ratio, h->cfg.collisions, stream));
     LAUNCH(launch_physics_post(h->d, h->buf, h->cc, mask, action != nullptr, h->cfg.h_ratio, stream));
     return 0;
 }

@@ -23,7 +23,9 @@
 #define MCR_POS_ITERS 60
 #define MCR_MAXV 8
 #define MCR_QUAD_CHUNK 8        // road_poly quads per culling chunk (bounding circle)
-#define MCR_SCRATCH_FIELDS 91   // 31 velocity/impulse values + 4 joints x 15 constants
+#define MCR_SCRATCH_FIELDS 101  // 31 velocity/impulse values + 4 joints x 15 constants + 10 sleep hand-over
+#define MCR_MAX_MANIFOLDS 32    // touching car-car fixture pairs per env
+#define MCR_MANIFOLD_WORDS 16
 
 // body SoA: body[(b * BODY_FIELDS + f) * N + car], b = 0 hull, 1..4 wheels
 enum { BF_CX = 0, BF_CY, BF_A, BF_VX, BF_VY, BF_W, BF_PX, BF_PY, BF_QS, BF_QC, BODY_FIELDS };
@@ -41,14 +43,14 @@ enum {
     BUF_ON_ROAD, BUF_ON_ROAD_NEXT, BUF_REWARD, BUF_PREV_REWARD, BUF_VISIT_COUNT, BUF_BACKWARD,
     BUF_TIME, BUF_STEPS, BUF_CAMERA, BUF_STRIPE, BUF_HEADING,
     BUF_ENV_TRACK, BUF_ENV_CW, BUF_ENV_EPISODE,
-    BUF_VISITED, BUF_TOUCHED, BUF_RESET_MASK, BUF_STATUS, BUF_SCRATCH,
+    BUF_VISITED, BUF_TOUCHED, BUF_RESET_MASK, BUF_STATUS, BUF_SCRATCH, BUF_MANIFOLD, BUF_N_MANIFOLD,
     BUF_TRK_T, BUF_TRK_Q, BUF_TRK_NODE, BUF_TRK_TILE, BUF_TRK_TILE_AABB, BUF_TRK_QUAD, BUF_TRK_QUAD_COL,
     BUF_TRK_QUAD_TILE, BUF_TRK_SLOT_POSE, BUF_TRK_CHUNK,
     BUF_COUNT
 };
 
 // status words
-enum { ST_EVENT_OVERFLOW = 0, ST_NAN = 1, ST_RASTER_OVERFLOW = 2, ST_RESERVED = 3, STATUS_WORDS = 4 };
+enum { ST_EVENT_OVERFLOW = 0, ST_NAN = 1, ST_RASTER_OVERFLOW = 2, ST_MANIFOLD_OVERFLOW = 3, STATUS_WORDS = 4 };
 
 // palette indices (rgb values in raster.cu)
 enum {
@@ -57,7 +59,7 @@ enum {
     PAL_IND_BLUE = PAL_CAR0 + 8, PAL_IND_BLUE2, PAL_IND_GREEN, PAL_FLAG_BLUE, PAL_COUNT
 };
 
-struct Poly8 { int n; float x[MCR_MAXV]; float y[MCR_MAXV]; };
+struct Poly8 { int n; float x[MCR_MAXV]; float y[MCR_MAXV]; float nx[MCR_MAXV]; float ny[MCR_MAXV]; };   // vertices + unit edge normals
 
 // car_dynamics.Car rigid-body constants, computed on the host at mcr_create (fp32, Box2D's
 // ComputeMass / ResetMassData) and passed to the kernels by value.
@@ -82,6 +84,8 @@ struct DevBuffers {
     int32_t* env_track; uint8_t* env_cw; uint32_t* env_episode;
     uint32_t* visited; uint8_t* touched; uint8_t* reset_mask; int32_t* status;
     float* scratch;                      // [MCR_SCRATCH_FIELDS][N] solver hand-over between pre/sweep/post kernels
+    float* manifold;                     // [B][MCR_MAX_MANIFOLDS][MCR_MANIFOLD_WORDS] persistent car-car contact manifolds
+    int32_t* n_manifold;                 // [B]
     int32_t* trk_T; int32_t* trk_Q; double* trk_node; float* trk_tile; float* trk_tile_aabb;
     float* trk_quad; uint8_t* trk_quad_col; int16_t* trk_quad_tile; double* trk_slot_pose;
     float* trk_chunk;                    // [P][Qmax/8][4] bounding circle (cx, cy, r, 0) of 8 consecutive road_poly quads
@@ -92,7 +96,9 @@ struct Dims { int B, A, N, Tmax, Qmax, P; };
 // kernel launchers (each returns the number of kernels it launched, or < 0 on error)
 int launch_contacts(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, void* stream);
 int launch_physics(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
-                   const void* action, int action_dtype, double h_ratio, void* stream);
+                   const void* action, int action_dtype, double h_ratio, int collisions, void* stream);
+int launch_carcontacts(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, void* stream);
+int launch_coupled(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, int early_exit, void* stream);
 int launch_physics_post(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
                         int has_action, double h_ratio, void* stream);
 int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* obs,

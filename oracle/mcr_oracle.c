@@ -35,7 +35,8 @@
  *   D2  b2TestOverlap (GJK distance < rA+rB) restated as SAT-intersect OR
  *       min vertex/edge distance <= 0.02 (same predicate, different fp32 rounding).
  *   D3  score label glyphs: baked 3x5 digit font (reference uses the platform font).
- *   D4  car-car rigid contacts: stage 2 (see orc_set_collisions).
+ *   D4  car-car rigid contacts (b2CollidePolygons + b2ContactSolver) follow Box2D 2.3.1+'s brute-force
+ *       b2FindMaxSeparation; manifold order = (car a < b, fixture a, fixture b) ascending.
  */
 #include <math.h>
 #include <stdint.h>
@@ -325,6 +326,7 @@ ORC_API OrcWorld* orc_create(int num_agents, double h_ratio, int backwards_flag,
     if (num_agents < 1 || num_agents > MAX_AGENTS) return NULL;
     OrcWorld* W = (OrcWorld*)calloc(1, sizeof(OrcWorld));
     W->A = num_agents; W->h_ratio = h_ratio; W->backwards_flag = backwards_flag; W->use_ego_color = use_ego_color;
+    W->collisions = 1;
     build_shapes(W);
     return W;
 }
@@ -917,6 +919,10 @@ static void collide_cars(OrcWorld* W) {
     Manifold* old = W->manifolds; int nold = W->n_manifolds;
     static __thread Manifold fresh[MAX_MANIFOLDS]; int nnew = 0;
     const float r = B2_POLYGON_RADIUS;
+    /* awake flags as they are when Collide() starts (a wake caused by one pair does not change how
+     * a later pair of the same pass is treated; deterministic stand-in, see D1) */
+    int awake0[MAX_AGENTS][8];
+    for (int a = 0; a < W->A; ++a) for (int f = 0; f < 8; ++f) awake0[a][f] = fixture_body(W, a, f)->awake;
     for (int a = 0; a < W->A; ++a) for (int b = a + 1; b < W->A; ++b)
         for (int fa = 0; fa < 8; ++fa) for (int fb = 0; fb < 8; ++fb) {
             if (fa < 4 && fb < 4) continue;                    /* wheel-wheel filtered out */
@@ -924,7 +930,7 @@ static void collide_cars(OrcWorld* W) {
             const Poly* PA = fixture_poly(W, fa); const Poly* PB = fixture_poly(W, fb);
             const Manifold* prev = NULL;
             for (int i = 0; i < nold; ++i) if (old[i].carA == a && old[i].carB == b && old[i].fixA == fa && old[i].fixB == fb) { prev = &old[i]; break; }
-            if (!bA->awake && !bB->awake) {                    /* neither body active: contact not updated */
+            if (!awake0[a][fa] && !awake0[b][fb]) {            /* neither body active: contact not updated */
                 if (prev && prev->pointCount > 0 && nnew < MAX_MANIFOLDS) fresh[nnew++] = *prev;
                 continue;
             }

@@ -55,7 +55,7 @@ def test_reset_matches_oracle(oracle, mcr):
     assert venv.status().tolist() == [0, 0, 0, 0]
 
 
-@pytest.mark.parametrize("A,B,seed", [(1, 2, 2), (2, 4, 3), (4, 2, 4)])
+@pytest.mark.parametrize("A,B,seed", [(1, 2, 2), (2, 4, 3), (4, 2, 4), (8, 1, 5), (16, 1, 6)])
 def test_step_parity_300(oracle, mcr, A, B, seed):
     import torch
     venv, worlds, tracks, obs0, oobs0 = _setup(oracle, mcr, B=B, A=A, seed=seed)
@@ -124,3 +124,53 @@ def test_single_env_dropin_matches_oracle_env(oracle, mcr):
         assert np.array_equal(gr, orr) and gd == od
         assert np.array_equal(go, oo), "pixels at step %d" % s
     assert env.tile_visited_count == [int(v) for v in ref.tile_visited_count]
+
+
+def test_car_car_collisions(oracle, mcr):
+    """Rear row drives into the braking front row: hull-hull and wheel-hull manifolds, block solver,
+    warm starting by contact id, merged islands -- state bit-exact against the oracle every step."""
+    import torch
+    B, A, steps = 2, 4, 260
+    venv, worlds, tracks, obs0, oobs0 = _setup(oracle, mcr, B=B, A=A, seed=21, directions=['CCW', 'CW'])
+    rs = np.random.RandomState(3)
+    saw_manifolds = 0
+    for s in range(steps):
+        a = np.zeros((B, A, 3), np.float32)
+        for e in range(B):
+            order = venv.car_order[e]
+            for c in range(A):
+                front = order[c] < 2
+                a[e, c] = (rs.uniform(-0.2, 0.2), 0.0, 1.0) if front else (rs.uniform(-0.2, 0.2), 1.0, 0.0)
+        obs, rew, done, _ = venv.step(torch.from_numpy(a).to(venv.device))
+        oo = [w.step(a[e].astype(np.float64)) for e, w in enumerate(worlds)]
+        assert np.array_equal(rew.cpu().numpy(), np.stack([x[1] for x in oo])), "step_reward, step %d" % s
+        nman = venv.buffers["n_manifold"].cpu().numpy()
+        assert list(nman) == [len(w.manifolds()) for w in worlds], "manifold count, step %d" % s
+        saw_manifolds = max(saw_manifolds, int(nman.max()))
+        if s % 5 == 0 or nman.max() > 0:
+            _compare_state(venv, worlds, tracks, s)
+        if s % 20 == 0:
+            assert np.array_equal(obs.cpu().numpy(), np.stack([x[0] for x in oo])), "pixels, step %d" % s
+    assert saw_manifolds >= 2, "the tape never produced a car-car contact"
+    assert venv.status().tolist() == [0, 0, 0, 0]
+
+
+def test_collisions_keep_cars_apart(mcr):
+    """Physical sanity of the solid contacts: with collisions the pushing car never overlaps the
+    pushed one; without them (collisions=False) it drives straight through."""
+    import torch
+    mins = {}
+    for coll in (True, False):
+        np.random.seed(0)
+        venv = mcr.BatchedMultiCarRacing(1, num_agents=4, auto_reset=False, max_episode_steps=0, seed=5,
+                                         use_random_direction=False, collisions=coll)
+        venv.reset(car_orders=[np.arange(4)])
+        a = torch.zeros((1, 4, 3), device=venv.device)
+        a[0, 0, 2] = 1.0; a[0, 1, 2] = 1.0; a[0, 2, 1] = 1.0; a[0, 3, 1] = 1.0
+        dmin = 1e9
+        for s in range(200):
+            venv.step(a)
+            p = venv.bodies()[0, :, 0, 6:8].cpu().numpy()
+            dmin = min(dmin, float(np.linalg.norm(p[2] - p[0])))
+        mins[coll] = dmin
+    assert mins[True] > 4.0 and mins[False] < 2.0, mins
