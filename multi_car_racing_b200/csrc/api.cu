@@ -439,6 +439,8 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
     set_spec(h, BUF_SCRATCH, "scratch", MCR_F32, {MCR_SCRATCH_FIELDS, N});
     set_spec(h, BUF_MANIFOLD, "manifold", MCR_F32, {B, MCR_MAX_MANIFOLDS, MCR_MANIFOLD_WORDS});
     set_spec(h, BUF_N_MANIFOLD, "n_manifold", MCR_I32, {B});
+    set_spec(h, BUF_SCORE_SNAP, "score_snap", MCR_F64, {N});
+    set_spec(h, BUF_BACKWARD_SNAP, "backward_snap", MCR_U8, {N});
     set_spec(h, BUF_TRK_T, "trk_T", MCR_I32, {P});
     set_spec(h, BUF_TRK_Q, "trk_Q", MCR_I32, {P});
     set_spec(h, BUF_TRK_NODE, "trk_node", MCR_F64, {P, T, 3});
@@ -507,6 +509,8 @@ extern "C" int mcr_bind_buffer(mcr_handle h, int i, void* p) {
         case BUF_SCRATCH: b.scratch = (float*)p; break;
         case BUF_MANIFOLD: b.manifold = (float*)p; break;
         case BUF_N_MANIFOLD: b.n_manifold = (int32_t*)p; break;
+        case BUF_SCORE_SNAP: b.score_snap = (double*)p; break;
+        case BUF_BACKWARD_SNAP: b.backward_snap = (uint8_t*)p; break;
         case BUF_TRK_T: b.trk_T = (int32_t*)p; break;
         case BUF_TRK_Q: b.trk_Q = (int32_t*)p; break;
         case BUF_TRK_NODE: b.trk_node = (double*)p; break;
@@ -636,11 +640,7 @@ extern "C" int mcr_load_track(mcr_handle h, int32_t slot, int32_t T, const doubl
 // ---------------------------------------------------------------------------------------
 #define LAUNCH(expr) do { int n_ = (expr); if (n_ < 0) return fail(-101, "kernel launch failed in %s: %s", #expr, cudaGetErrorString(cudaGetLastError())); h->launches += n_; } while (0)
 
-// contacts || (pre -> sweep), then post.  The contact pass only reads the step's start poses, so it
-// runs on the handle's side stream while the solver occupies the main one; post_kernel (which
-// overwrites the poses and consumes on_road_next) waits for both.
-static int simulate(mcr_handle h, const uint8_t* mask, const void* action, int32_t action_dtype, void* stream) {
-    cudaStream_t s = (cudaStream_t)stream;
+static int ensure_side(mcr_handle h) {
     if (!h->side_ready) {
         CUDA_OK(cudaSetDevice(h->cfg.device));
         CUDA_OK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
@@ -648,6 +648,15 @@ static int simulate(mcr_handle h, const uint8_t* mask, const void* action, int32
         CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
         h->side_ready = true;
     }
+    return 0;
+}
+
+// contacts || (pre -> sweep), then post.  The contact pass only reads the step's start poses, so it
+// runs on the handle's side stream while the solver occupies the main one; post_kernel (which
+// overwrites the poses and consumes on_road_next) waits for both.
+static int simulate(mcr_handle h, const uint8_t* mask, const void* action, int32_t action_dtype, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    { int rc_ = ensure_side(h); if (rc_) return rc_; }
     CUDA_OK(cudaEventRecord(h->ev_fork, s));
     CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
     LAUNCH(launch_contacts(h->d, h->buf, h->cc, mask, h->side));
@@ -678,13 +687,28 @@ extern "C" int mcr_simulate(mcr_handle h, const uint8_t* mask, const void* actio
     return simulate(h, mask, action, action_dtype, stream);
 }
 
+// render || score: the rasteriser only reads the snapshots post_kernel took, so the reward / done
+// block runs beside it on the side stream; the caller's stream waits for both.
+static int render_and_score(mcr_handle h, const uint8_t* mask, uint8_t* obs, double* reward, uint8_t* done,
+                            int post_step, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (post_step) {
+        int rc = ensure_side(h); if (rc) return rc;
+        CUDA_OK(cudaEventRecord(h->ev_fork, s));
+        CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+        LAUNCH(launch_score(h->d, h->buf, mask, reward, done, h->cfg.max_episode_steps, h->side));
+        CUDA_OK(cudaEventRecord(h->ev_join, h->side));
+    }
+    LAUNCH(launch_render(h->d, h->buf, h->cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, s));
+    if (post_step) CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));
+    return 0;
+}
+
 extern "C" int mcr_render(mcr_handle h, const uint8_t* mask, uint8_t* obs, double* reward, uint8_t* done, int32_t post_step, void* stream) {
     int rc = check_bound(h); if (rc) return rc;
     if (!obs) return fail(-1, "mcr_render: d_obs is null");
     if (post_step && (!reward || !done)) return fail(-1, "mcr_render: post_step needs d_reward and d_done");
-    LAUNCH(launch_render(h->d, h->buf, h->cc, mask, obs, reward, done, post_step, h->cfg.backwards_flag,
-                         h->cfg.use_ego_color, h->cfg.max_episode_steps, stream));
-    return 0;
+    return render_and_score(h, mask, obs, reward, done, post_step, stream);
 }
 
 extern "C" int mcr_reset(mcr_handle h, const uint8_t* mask, const int32_t* track_slot, const uint8_t* cw,
@@ -694,8 +718,7 @@ extern "C" int mcr_reset(mcr_handle h, const uint8_t* mask, const int32_t* track
     LAUNCH(launch_spawn(h->d, h->buf, h->cc, mask, track_slot, cw, spawn_pose, stream));
     // the implicit step(None), mcr:408
     rc = simulate(h, mask, nullptr, MCR_F32, stream); if (rc) return rc;
-    LAUNCH(launch_render(h->d, h->buf, h->cc, mask, obs, nullptr, nullptr, 0, h->cfg.backwards_flag,
-                         h->cfg.use_ego_color, h->cfg.max_episode_steps, stream));
+    rc = render_and_score(h, mask, obs, nullptr, nullptr, 0, stream); if (rc) return rc;
     return 0;
 }
 
@@ -705,15 +728,13 @@ extern "C" int mcr_step(mcr_handle h, const void* action, int32_t action_dtype, 
     if (!action || !obs || !reward || !done) return fail(-1, "mcr_step: null argument");
     if (action_dtype != MCR_F32 && action_dtype != MCR_F64) return fail(-1, "action dtype must be MCR_F32 or MCR_F64");
     rc = simulate(h, nullptr, action, action_dtype, stream); if (rc) return rc;
-    LAUNCH(launch_render(h->d, h->buf, h->cc, nullptr, obs, reward, done, 1, h->cfg.backwards_flag,
-                         h->cfg.use_ego_color, h->cfg.max_episode_steps, stream));
+    rc = render_and_score(h, nullptr, obs, reward, done, 1, stream); if (rc) return rc;
     if (flags & 1) {
         AutoResetCfg ar{h->cfg.use_random_direction, h->cfg.direction_cw, (unsigned long long)h->cfg.seed};
         LAUNCH(launch_auto_reset(h->d, h->buf, h->cc, done, ar, stream));
         const uint8_t* m = h->buf.reset_mask;
         rc = simulate(h, m, nullptr, MCR_F32, stream); if (rc) return rc;
-        LAUNCH(launch_render(h->d, h->buf, h->cc, m, obs, nullptr, nullptr, 0, h->cfg.backwards_flag,
-                             h->cfg.use_ego_color, h->cfg.max_episode_steps, stream));
+        rc = render_and_score(h, m, obs, nullptr, nullptr, 0, stream); if (rc) return rc;
     }
     return 0;
 }

@@ -43,7 +43,7 @@ enum {
     BUF_ON_ROAD, BUF_ON_ROAD_NEXT, BUF_REWARD, BUF_PREV_REWARD, BUF_VISIT_COUNT, BUF_BACKWARD,
     BUF_TIME, BUF_STEPS, BUF_CAMERA, BUF_STRIPE, BUF_HEADING,
     BUF_ENV_TRACK, BUF_ENV_CW, BUF_ENV_EPISODE,
-    BUF_VISITED, BUF_TOUCHED, BUF_RESET_MASK, BUF_STATUS, BUF_SCRATCH, BUF_MANIFOLD, BUF_N_MANIFOLD,
+    BUF_VISITED, BUF_TOUCHED, BUF_RESET_MASK, BUF_STATUS, BUF_SCRATCH, BUF_MANIFOLD, BUF_N_MANIFOLD, BUF_SCORE_SNAP, BUF_BACKWARD_SNAP,
     BUF_TRK_T, BUF_TRK_Q, BUF_TRK_NODE, BUF_TRK_TILE, BUF_TRK_TILE_AABB, BUF_TRK_QUAD, BUF_TRK_QUAD_COL,
     BUF_TRK_QUAD_TILE, BUF_TRK_SLOT_POSE, BUF_TRK_CHUNK,
     BUF_COUNT
@@ -86,6 +86,7 @@ struct DevBuffers {
     float* scratch;                      // [MCR_SCRATCH_FIELDS][N] solver hand-over between pre/sweep/post kernels
     float* manifold;                     // [B][MCR_MAX_MANIFOLDS][MCR_MANIFOLD_WORDS] persistent car-car contact manifolds
     int32_t* n_manifold;                 // [B]
+    double* score_snap; uint8_t* backward_snap;   // [N] env.reward / driving_backward as the render of this step sees them
     int32_t* trk_T; int32_t* trk_Q; double* trk_node; float* trk_tile; float* trk_tile_aabb;
     float* trk_quad; uint8_t* trk_quad_col; int16_t* trk_quad_tile; double* trk_slot_pose;
     float* trk_chunk;                    // [P][Qmax/8][4] bounding circle (cx, cy, r, 0) of 8 consecutive road_poly quads
@@ -102,8 +103,9 @@ int launch_coupled(const Dims& d, const DevBuffers& b, const CarConst& cc, const
 int launch_physics_post(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
                         int has_action, double h_ratio, void* stream);
 int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* obs,
-                  double* reward, uint8_t* done, int post_step, int backwards_flag,
-                  int use_ego_color, int max_episode_steps, void* stream);
+                  int backwards_flag, int use_ego_color, void* stream);
+int launch_score(const Dims& d, const DevBuffers& b, const uint8_t* mask, double* reward, uint8_t* done,
+                 int max_episode_steps, void* stream);
 const uint8_t (*mcr_host_palette())[4];
 int launch_spawn(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
                  const int32_t* track_slot, const uint8_t* cw, const double* spawn_pose, void* stream);

@@ -1,4 +1,5 @@
-// raster.cu -- kernel 3: software top-down rasteriser + the post-step reward/done block.
+// raster.cu -- kernel 3: software top-down rasteriser (render_kernel) and the post-step
+// reward/done block (score_kernel, runs beside the rasteriser on the side stream).
 //
 // Replaces, per agent view (reference: gym_multi_car_racing/multi_car_racing.py):
 //   mcr:511-604  render("state_pixels") / _render_window: camera from ego pose/velocity/t,
@@ -97,7 +98,7 @@ struct __align__(16) RasterSmem {
     uint16_t off[LIST_CAP];       // first span slot (continuations: the next polygon's)
     uint8_t ne[LIST_CAP], col[LIST_CAP];
     uchar2 span[SPAN_POOL];
-    uint32_t rowmask[SH][MASK_WORDS];
+    uint32_t rowmask[SH * 3][MASK_WORDS];   // per (row, 32-pixel segment): polygons whose span touches it
     Affine M;
     int first_bad;
     int ck_j0x, ck_nx, ck_j0y, ck_ny;   // visible checker index range
@@ -106,7 +107,7 @@ struct __align__(16) RasterSmem {
     uint8_t vis_chunk[MAX_CHUNKS];    // ids of the road_poly chunks whose bounding circle touches the viewport, ascending
     int warp_cnt[2][RS_WARPS], warp_rows[2][RS_WARPS];
     int bc_cnt, bc_rows;
-    double red_d[RS_WARPS]; int red_i[RS_WARPS];
+    float red_f[RS_WARPS]; int cand[32]; int n_cand;
     signed char glyph[4];
     uint32_t pal32[32];
 };
@@ -294,7 +295,11 @@ __device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pi
             x1 = (int)ceilf(xr - 0.5f); if (x1 > SW) x1 = SW;
         }
         S.span[s] = make_uchar2((unsigned char)x0, (unsigned char)x1);
-        if (x0 < x1) atomicOr(&S.rowmask[row][p >> 5], 1u << (p & 31));
+        if (x0 < x1) {
+            const uint32_t bit = 1u << (p & 31);
+            const int g0 = x0 >> 5, g1 = (x1 - 1) >> 5;
+            for (int g = g0; g <= g1; ++g) atomicOr(&S.rowmask[row * 3 + g][p >> 5], bit);
+        }
     }
     __syncthreads();
     // ---- fill: one thread per (row, 32-pixel segment), top-most polygon first ------------------
@@ -305,7 +310,7 @@ __device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pi
         const int xs = 32 * seg;
         uint32_t uncovered = 0xffffffffu;
         for (int wd = MASK_WORDS - 1; wd >= 0 && uncovered; --wd) {
-            uint32_t m = S.rowmask[y][wd];
+            uint32_t m = S.rowmask[tid][wd];               // tid == y * 3 + seg
             while (m && uncovered) {
                 const int bit = 31 - __clz(m);
                 m &= ~(1u << bit);
@@ -325,9 +330,12 @@ __device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pi
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const uint32_t nib = (fresh >> (4 * k)) & 0xFu;
-                            // nibble -> byte mask: bit i of nib selects byte i
-                            const uint32_t bm = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;
-                            pix[k] = (pix[k] & ~bm) | (c4 & bm);
+                            if (nib == 0xFu) pix[k] = c4;
+                            else if (nib) {
+                                // nibble -> byte mask: bit i of nib selects byte i
+                                const uint32_t bm = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;
+                                pix[k] = (pix[k] & ~bm) | (c4 & bm);
+                            }
                         }
                     }
                 }
@@ -335,14 +343,13 @@ __device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pi
         }
     }
     __syncthreads();
-    for (int i = tid; i < SH * MASK_WORDS; i += RS_THREADS) (&S.rowmask[0][0])[i] = 0;
+    for (int i = tid; i < SH * 3 * MASK_WORDS; i += RS_THREADS) (&S.rowmask[0][0])[i] = 0;
     __syncthreads();
 }
 
 __global__ void __launch_bounds__(RS_THREADS, 4)
 render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, uint8_t* __restrict__ obs,
-              double* __restrict__ out_reward, uint8_t* __restrict__ out_done, int post_step,
-              int backwards_flag, int use_ego_color, int max_episode_steps) {
+              int backwards_flag, int use_ego_color) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
     const int frame = blockIdx.x;
@@ -351,7 +358,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = d.N, car = frame;
     const int slot = b.env_track[env];
-    const int T = b.trk_T[slot], Q = b.trk_Q[slot];
+    const int Q = b.trk_Q[slot];
 
     // ---- camera (mcr:540-556) was evaluated by the physics kernel for this car ---------------
     if (tid < 6) (&S.M.m00)[tid] = b.camera[(size_t)tid * N + car];
@@ -361,7 +368,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     }
     if (tid == 64) {
         // score label "%04i" % reward  (mcr:665; drawn before reward -= 0.1)
-        const double rw = b.reward[car];
+        const double rw = b.score_snap[car];           // env.reward as it is when the reference draws the label
         int val = (int)rw;
         const bool neg = rw < 0 && val != 0;
         int mag = val < 0 ? -val : val;
@@ -402,7 +409,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
         S.ck_j0x = j0x; S.ck_nx = j1x >= j0x ? j1x - j0x + 1 : 0;
         S.ck_j0y = j0y; S.ck_ny = j1y >= j0y ? j1y - j0y + 1 : 0;
     }
-    for (int i = tid; i < SH * MASK_WORDS; i += RS_THREADS) (&S.rowmask[0][0])[i] = 0;
+    for (int i = tid; i < SH * 3 * MASK_WORDS; i += RS_THREADS) (&S.rowmask[0][0])[i] = 0;
     // ---- road_poly chunk culling: bounding circle of every 8 consecutive quads vs the viewport ------
     const int nchunks = (Q + MCR_QUAD_CHUNK - 1) / MCR_QUAD_CHUNK;
     {
@@ -444,7 +451,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     V.quad_tile = b.trk_quad_tile + (size_t)slot * d.Qmax;
     V.touched = b.touched + (size_t)env * d.Tmax;
     V.use_ego_color = use_ego_color;
-    V.backward_flag_on = (b.backward[car] != 0) && backwards_flag;
+    V.backward_flag_on = (b.backward_snap[car] != 0) && backwards_flag;   // flag of the PREVIOUS step (render precedes mcr:445-495)
     const Affine M = S.M;
 
     uint32_t pix[8];                       // this thread's 32 pixels (palette indices); glClear -> black
@@ -582,37 +589,67 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
         for (int v = 0; v < 6; ++v) dst[v] = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
     }
 
-    // ---- post-step block, mcr:433-507 (skipped for reset()'s step(None)) -----------------------
-    if (!post_step) return;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// score_kernel: mcr:433-507 for one car per warp.  Runs concurrently with render_kernel (which
+// reads the snapshots post_kernel took of env.reward / driving_backward, because the reference
+// renders BEFORE this block).
+// ---------------------------------------------------------------------------------------
+#define SCORE_WARPS 4
+
+__global__ void __launch_bounds__(SCORE_WARPS * 32)
+score_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, double* __restrict__ out_reward,
+             uint8_t* __restrict__ out_done, int max_episode_steps) {
+    __shared__ int s_cand[SCORE_WARPS][32];
+    __shared__ int s_ncand[SCORE_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int car = blockIdx.x * SCORE_WARPS + warp;
+    if (car >= d.N) return;
+    const int env = car / d.A, agent = car - env * d.A;
+    if (mask && !mask[env]) return;
+    const int N = d.N;
+    const int slot = b.env_track[env];
+    const int T = b.trk_T[slot];
     // nearest track node: argmin_i || pos - track[i].xy ||, first minimum wins (np.argmin over
-    // sqrt(dx^2 + dy^2)).  sqrt is monotone, so pass 1 finds the minimal squared distance and pass 2
-    // takes the sqrt only for nodes within a few ulp of it (sqrt can merge distinct squares).
-    const double posx = b.body[(size_t)BF_PX * N + car], posy = b.body[(size_t)BF_PY * N + car];
+    // sqrt(dx^2 + dy^2) in float64).  Pass 1 finds the minimal squared distance in fp32 (error
+    // < 1e-3 near the minimum); pass 2 queues every node within 0.05 of it; lane 0 then evaluates
+    // those few exactly as the reference does.
+    const float posxf = b.body[(size_t)BF_PX * N + car], posyf = b.body[(size_t)BF_PY * N + car];
     const double* node = b.trk_node + (size_t)slot * d.Tmax * 3;
-    double best2 = 1.0e300;
-    for (int i = tid; i < T; i += RS_THREADS) {
-        const double dx = posx - node[(size_t)i * 3 + 1], dy = posy - node[(size_t)i * 3 + 2];
-        best2 = fmin(best2, dx * dx + dy * dy);
+    float best2 = 3.0e38f;
+    for (int i = lane; i < T; i += 32) {
+        const float dx = posxf - (float)node[(size_t)i * 3 + 1], dy = posyf - (float)node[(size_t)i * 3 + 2];
+        best2 = fminf(best2, dx * dx + dy * dy);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) best2 = fmin(best2, __shfl_xor_sync(0xffffffffu, best2, o));
-    if (lane == 0) S.red_d[warp] = best2;
-    __syncthreads();
-#pragma unroll
-    for (int wq = 0; wq < RS_WARPS; ++wq) best2 = fmin(best2, S.red_d[wq]);
-    const double thresh = best2 * (1.0 + 1.0e-14), smin = sqrt(best2);
-    int besti = 0x7fffffff;
-    for (int i = tid; i < T; i += RS_THREADS) {
-        const double dx = posx - node[(size_t)i * 3 + 1], dy = posy - node[(size_t)i * 3 + 2];
-        const double d2 = dx * dx + dy * dy;
-        if (d2 <= thresh && sqrt(d2) == smin && i < besti) besti = i;
+    for (int o = 16; o > 0; o >>= 1) best2 = fminf(best2, __shfl_xor_sync(0xffffffffu, best2, o));
+    if (lane == 0) s_ncand[warp] = 0;
+    __syncwarp();
+    for (int i = lane; i < T; i += 32) {
+        const float dx = posxf - (float)node[(size_t)i * 3 + 1], dy = posyf - (float)node[(size_t)i * 3 + 2];
+        if (dx * dx + dy * dy <= best2 + 0.05f) { const int q = atomicAdd(&s_ncand[warp], 1); if (q < 32) s_cand[warp][q] = i; }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) besti = min(besti, __shfl_xor_sync(0xffffffffu, besti, o));
-    if (lane == 0) S.red_i[warp] = besti;
-    __syncthreads();
-    if (tid == 0) {
-        for (int wq = 0; wq < RS_WARPS; ++wq) besti = min(besti, S.red_i[wq]);
+    __syncwarp();
+    if (lane == 0) {
+        const double posx = posxf, posy = posyf;
+        double bestd = 1.0e300; int besti = 0x7fffffff;
+        const int nc = s_ncand[warp];
+        if (nc <= 32) {
+            for (int q = 0; q < nc; ++q) {
+                const int i = s_cand[warp][q];
+                const double dx = posx - node[(size_t)i * 3 + 1], dy = posy - node[(size_t)i * 3 + 2];
+                const double dd = sqrt(dx * dx + dy * dy);
+                if (dd < bestd || (dd == bestd && i < besti)) { bestd = dd; besti = i; }
+            }
+        } else {                                    // pathological (many equidistant nodes): exact scan
+            for (int i = 0; i < T; ++i) {
+                const double dx = posx - node[(size_t)i * 3 + 1], dy = posy - node[(size_t)i * 3 + 2];
+                const double dd = sqrt(dx * dx + dy * dy);
+                if (dd < bestd) { bestd = dd; besti = i; }
+            }
+        }
         const double PI = 3.141592653589793, PLAYFIELD = 2000 / 6.0;
         double reward = b.reward[car] - 0.1;                     // mcr:436
         double step_reward = reward - b.prev_reward[car];        // mcr:443
@@ -643,8 +680,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
 }
 
 int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* obs,
-                  double* reward, uint8_t* done, int post_step, int backwards_flag,
-                  int use_ego_color, int max_episode_steps, void* stream) {
+                  int backwards_flag, int use_ego_color, void* stream) {
     static bool configured = false;
     const size_t smem = sizeof(RasterSmem);
     if (!configured) {
@@ -652,7 +688,12 @@ int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const 
         if (cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         configured = true;
     }
-    render_kernel<<<d.N, RS_THREADS, smem, (cudaStream_t)stream>>>(d, b, cc, mask, obs, reward, done, post_step,
-                                                                  backwards_flag, use_ego_color, max_episode_steps);
+    render_kernel<<<d.N, RS_THREADS, smem, (cudaStream_t)stream>>>(d, b, cc, mask, obs, backwards_flag, use_ego_color);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_score(const Dims& d, const DevBuffers& b, const uint8_t* mask, double* reward, uint8_t* done,
+                 int max_episode_steps, void* stream) {
+    score_kernel<<<(d.N + SCORE_WARPS - 1) / SCORE_WARPS, SCORE_WARPS * 32, 0, (cudaStream_t)stream>>>(d, b, mask, reward, done, max_episode_steps);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

@@ -572,6 +572,10 @@ post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
         // the contact pass of THIS step decides the friction of the NEXT Car.step
         b.on_road[(size_t)k * N + car] = b.on_road_next[(size_t)k * N + car];
     }
+    // what the reference's render() of this step sees: env.reward before `reward -= 0.1` (score label)
+    // and the backward flag of the previous step (mcr:431 precedes mcr:436-495)
+    b.score_snap[car] = b.reward[car];
+    b.backward_snap[car] = b.backward[car];
     // ---- per-view values the rasteriser needs, evaluated once here (fp64 trig is serial latency) --
     const double t = b.time[car] + 1.0 / 50;                      // mcr:429
     b.time[car] = t;
