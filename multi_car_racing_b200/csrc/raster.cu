@@ -121,6 +121,7 @@ __device__ __forceinline__ double py_mod(double a, double m) {
 struct View {
     int env, agent, A, N, Q;
     int n_checker, ck_j0x, ck_j0y, ck_ny;
+    int c_road, c_cars, c_hud;           // first candidate index of each class (warp aligned)
     int n_road;                          // 8 * visible chunks
     const uint8_t* vis_chunk;
     const float* body; const double* wheel; const float* stripe;
@@ -137,24 +138,29 @@ __device__ __forceinline__ void xf_pt(const Affine& M, float x, float y, float& 
 __device__ int gen_candidate(int i, const View& V, const Affine& M, const CarConst& cc, float (&px)[MCR_MAXV],
                              float (&py)[MCR_MAXV], int& col) {
     const double PLAYFIELD = 2000 / 6.0;
-    if (i == 0) {                                   // playfield, mcr:615-619
-        const float pf = (float)PLAYFIELD;
-        xf_pt(M, -pf, +pf, px[0], py[0]); xf_pt(M, +pf, +pf, px[1], py[1]);
-        xf_pt(M, +pf, -pf, px[2], py[2]); xf_pt(M, -pf, -pf, px[3], py[3]);
-        col = PAL_GRASS; return 4;
+    // candidate classes start on warp boundaries so that a warp executes one kind of polygon
+    if (i < V.c_road) {
+        if (i == 0) {                               // playfield, mcr:615-619
+            const float pf = (float)PLAYFIELD;
+            xf_pt(M, -pf, +pf, px[0], py[0]); xf_pt(M, +pf, +pf, px[1], py[1]);
+            xf_pt(M, +pf, -pf, px[2], py[2]); xf_pt(M, -pf, -pf, px[3], py[3]);
+            col = PAL_GRASS; return 4;
+        }
+        i -= 1;
+        if (i >= V.n_checker) return 0;
+        {                                           // checker quads that can be in view, mcr:620-627
+            const double k = PLAYFIELD / 20.0;
+            const int x = -20 + 2 * (V.ck_j0x + i / V.ck_ny), y = -20 + 2 * (V.ck_j0y + i % V.ck_ny);
+            xf_pt(M, (float)(k * x + k), (float)(k * y + 0), px[0], py[0]);
+            xf_pt(M, (float)(k * x + 0), (float)(k * y + 0), px[1], py[1]);
+            xf_pt(M, (float)(k * x + 0), (float)(k * y + k), px[2], py[2]);
+            xf_pt(M, (float)(k * x + k), (float)(k * y + k), px[3], py[3]);
+            col = PAL_GRASS_LIGHT; return 4;
+        }
     }
-    i -= 1;
-    if (i < V.n_checker) {                          // checker quads that can be in view, mcr:620-627
-        const double k = PLAYFIELD / 20.0;
-        const int x = -20 + 2 * (V.ck_j0x + i / V.ck_ny), y = -20 + 2 * (V.ck_j0y + i % V.ck_ny);
-        xf_pt(M, (float)(k * x + k), (float)(k * y + 0), px[0], py[0]);
-        xf_pt(M, (float)(k * x + 0), (float)(k * y + 0), px[1], py[1]);
-        xf_pt(M, (float)(k * x + 0), (float)(k * y + k), px[2], py[2]);
-        xf_pt(M, (float)(k * x + k), (float)(k * y + k), px[3], py[3]);
-        col = PAL_GRASS_LIGHT; return 4;
-    }
-    i -= V.n_checker;
-    if (i < V.n_road) {                             // road_poly (visible chunks only), mcr:628-631
+    if (i < V.c_cars) {                             // road_poly (visible chunks only), mcr:628-631
+        i -= V.c_road;
+        if (i >= V.n_road) return 0;
         i = (int)V.vis_chunk[i >> 3] * MCR_QUAD_CHUNK + (i & (MCR_QUAD_CHUNK - 1));
         if (i >= V.Q) return 0;
         const float4 a = *(const float4*)(V.quad + (size_t)i * 8);
@@ -165,8 +171,9 @@ __device__ int gen_candidate(int i, const View& V, const Affine& M, const CarCon
         col = (tl >= 0 && V.touched[tl]) ? PAL_ROAD0 : V.quad_col[i];   // tile.color reset, mcr:102-104
         return 4;
     }
-    i -= V.n_road;
-    if (i < CAR_PARTS * V.A) {                      // Car.draw for every car, mcr:559-564
+    if (i < V.c_hud) {                              // Car.draw for every car, mcr:559-564
+        i -= V.c_cars;
+        if (i >= CAR_PARTS * V.A) return 0;
         const int c = i / CAR_PARTS, part = i % CAR_PARTS, car = V.env * V.A + c, N = V.N;
         if (part < 8) {
             const int wl = part >> 1;
@@ -212,7 +219,8 @@ __device__ int gen_candidate(int i, const View& V, const Affine& M, const CarCon
             return P.n;
         }
     }
-    i -= CAR_PARTS * V.A;
+    i -= V.c_hud;
+    if (i >= 9) return 0;
     {                                               // render_indicators, mcr:634-674
         const double Wd = 1000, Hd = 800, s = Wd / 40.0, h = Hd / 40.0;
         const int car = V.env * V.A + V.agent, N = V.N;
@@ -445,6 +453,9 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     V.ck_j0x = S.ck_j0x; V.ck_j0y = S.ck_j0y; V.ck_ny = S.ck_ny > 0 ? S.ck_ny : 1;
     V.n_checker = S.ck_nx * S.ck_ny;
     V.n_road = S.n_vis_chunks * MCR_QUAD_CHUNK; V.vis_chunk = S.vis_chunk;
+    V.c_road = (1 + V.n_checker + 31) & ~31;
+    V.c_cars = V.c_road + ((V.n_road + 31) & ~31);
+    V.c_hud = V.c_cars + ((CAR_PARTS * d.A + 31) & ~31);
     V.body = b.body; V.wheel = b.wheel; V.stripe = b.stripe;
     V.quad = b.trk_quad + (size_t)slot * d.Qmax * 8;
     V.quad_col = b.trk_quad_col + (size_t)slot * d.Qmax;
@@ -459,7 +470,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     for (int k = 0; k < 8; ++k) pix[k] = PAL_BLACK * 0x01010101u;
 
     // ---- candidates -> ordered display list -> flush -----------------------------------------
-    const int NC = 1 + V.n_checker + V.n_road + CAR_PARTS * d.A + 9;
+    const int NC = V.c_hud + 9;
     int base = 0, lc = 0, pc = 0, round = 0;   // display-list / span-pool fill (same in every thread)
     while (base < NC) {
         const int i = base + tid;
