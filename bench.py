@@ -40,7 +40,7 @@ BATCH_ENVS = 1024
 
 def workload_config(A, B, world):
     return {"workload": "MultiCarRacing-v0 step+render, num_agents=%d, batch=%d envs per GPU, random policy, "
-                        "use_random_direction=True, device-side auto reset at 1000 steps" % (A, B),
+                        "use_random_direction=True, device-side next-step auto reset (done or 1000 steps)" % (A, B),
             "batch_envs_per_gpu": B, "num_agents": A, "l2": "256 MiB flush between timed steps",
             "parallelism": "env-sharded x%d, no data-path collective" % world}
 
@@ -202,7 +202,7 @@ def run_ours(args):
     frames_per_step = B * A
 
     np.random.seed(1234 + rank)
-    venv = mcr.BatchedMultiCarRacing(B, num_agents=A, use_random_direction=True, device=dev, auto_reset=True,
+    venv = mcr.BatchedMultiCarRacing(B, num_agents=A, use_random_direction=True, device=dev, auto_reset='next_step',
                                      max_episode_steps=1000, seed=1234 + rank * B)
     venv.reset()
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)

@@ -103,9 +103,14 @@ int mcr_reset(mcr_handle h, const uint8_t* d_env_mask, const int32_t* d_track_sl
 /* ---- step (replaces MultiCarRacing.step, mcr:410-509) ---------------------------------- */
 /* d_action: [B][A][3] (steer, gas, brake), dtype f32 (action_dtype=MCR_F32) or f64.
  * d_obs: [B][A][96][96][3] u8.  d_reward: [B][A] f64.  d_done: [B] u8.
- * flags: bit0 = device-side auto reset of finished envs (done or max_episode_steps reached)
- * from the track pool before returning (their d_obs is the new episode's first frame, the
- * reward/done are the terminal ones; bit1 of d_done marks TimeLimit truncation). */
+ * flags: bit0 = same-step device-side auto reset of finished envs (done or max_episode_steps
+ * reached) from the track pool before returning: their d_obs is the new episode's first frame,
+ * reward/done are the terminal ones (a second, masked pass of the kernels).
+ * bit1 = next-step auto reset (EnvPool convention, exclusive with bit0): an env that reported
+ * done at step k keeps its terminal observation; the call for step k+1 ignores that env's action,
+ * respawns it and runs reset()'s implicit step(None) (mcr:408) inside the same single pass, and
+ * returns the new episode's first frame with reward 0, done 0.
+ * Bit1 of d_done[env] marks TimeLimit truncation. */
 int mcr_step(mcr_handle h, const void* d_action, int32_t action_dtype, uint8_t* d_obs, double* d_reward,
              uint8_t* d_done, int32_t flags, void* stream);
 

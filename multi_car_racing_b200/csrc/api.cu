@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -380,8 +381,16 @@ struct mcr_handle_t {
     uint8_t palette[PAL_COUNT][4];
     bool palette_ready;
     cudaStream_t side;           // contacts run here, beside the solver
+    cudaStream_t cap;            // capture origin for the step graph (the caller's stream may be the legacy default stream, which cannot be captured)
     cudaEvent_t ev_fork, ev_join;
+    cudaStream_t side2;          // the chain of envs with touching cars: coupled -> post -> score -> render
+    cudaEvent_t ev_pre, ev_contacts, ev_chain2, ev_score;
     bool side_ready;
+    // mcr_step replays a captured CUDA graph of its launches (one graph per argument tuple)
+    struct StepGraph { int32_t dtype, flags; uint8_t* obs; double* reward; uint8_t* done; cudaGraphExec_t exec; int64_t launches; };
+    std::vector<StepGraph> graphs;
+    int64_t eager_steps;
+    bool use_graphs;
 };
 
 
@@ -410,6 +419,7 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
     std::memset(&h->buf, 0, sizeof(h->buf));
     std::memset(h->ptr, 0, sizeof(h->ptr));
     h->launches = 0; h->palette_ready = false; h->side_ready = false;
+    h->eager_steps = 0; h->use_graphs = std::getenv("MCR_NO_GRAPH") == nullptr;
     const int64_t N = h->d.N, B = h->d.B, A = h->d.A, T = h->d.Tmax, Q = h->d.Qmax, P = h->d.P;
     set_spec(h, BUF_BODY, "body", MCR_F32, {5, BODY_FIELDS, N});
     set_spec(h, BUF_SLEEP_TIME, "sleep_time", MCR_F32, {5, N});
@@ -441,6 +451,8 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
     set_spec(h, BUF_N_MANIFOLD, "n_manifold", MCR_I32, {B});
     set_spec(h, BUF_SCORE_SNAP, "score_snap", MCR_F64, {N});
     set_spec(h, BUF_BACKWARD_SNAP, "backward_snap", MCR_U8, {N});
+    set_spec(h, BUF_PENDING, "pending_reset", MCR_U8, {B});
+    set_spec(h, BUF_ACTION_STAGE, "action_stage", MCR_F64, {N, 3});
     set_spec(h, BUF_TRK_T, "trk_T", MCR_I32, {P});
     set_spec(h, BUF_TRK_Q, "trk_Q", MCR_I32, {P});
     set_spec(h, BUF_TRK_NODE, "trk_node", MCR_F64, {P, T, 3});
@@ -456,8 +468,10 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
 }
 
 extern "C" int mcr_destroy(mcr_handle h) {
+    if (h) for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
     if (h && h->side_ready) {
-        cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
+        cudaStreamDestroy(h->side); cudaStreamDestroy(h->cap); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
+        cudaStreamDestroy(h->side2); cudaEventDestroy(h->ev_pre); cudaEventDestroy(h->ev_contacts); cudaEventDestroy(h->ev_chain2); cudaEventDestroy(h->ev_score);
     }
     delete h;
     return 0;
@@ -511,6 +525,8 @@ extern "C" int mcr_bind_buffer(mcr_handle h, int i, void* p) {
         case BUF_N_MANIFOLD: b.n_manifold = (int32_t*)p; break;
         case BUF_SCORE_SNAP: b.score_snap = (double*)p; break;
         case BUF_BACKWARD_SNAP: b.backward_snap = (uint8_t*)p; break;
+        case BUF_PENDING: b.pending = (uint8_t*)p; break;
+        case BUF_ACTION_STAGE: b.action_stage = (double*)p; break;
         case BUF_TRK_T: b.trk_T = (int32_t*)p; break;
         case BUF_TRK_Q: b.trk_Q = (int32_t*)p; break;
         case BUF_TRK_NODE: b.trk_node = (double*)p; break;
@@ -644,8 +660,14 @@ static int ensure_side(mcr_handle h) {
     if (!h->side_ready) {
         CUDA_OK(cudaSetDevice(h->cfg.device));
         CUDA_OK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+        CUDA_OK(cudaStreamCreateWithFlags(&h->cap, cudaStreamNonBlocking));
         CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        CUDA_OK(cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&h->ev_pre, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&h->ev_contacts, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&h->ev_chain2, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&h->ev_score, cudaEventDisableTiming));
         h->side_ready = true;
     }
     return 0;
@@ -654,16 +676,17 @@ static int ensure_side(mcr_handle h) {
 // contacts || (pre -> sweep), then post.  The contact pass only reads the step's start poses, so it
 // runs on the handle's side stream while the solver occupies the main one; post_kernel (which
 // overwrites the poses and consumes on_road_next) waits for both.
-static int simulate(mcr_handle h, const uint8_t* mask, const void* action, int32_t action_dtype, void* stream) {
+static int simulate(mcr_handle h, const uint8_t* mask, const void* action, int32_t action_dtype, void* stream,
+                    const uint8_t* noact = nullptr) {
     cudaStream_t s = (cudaStream_t)stream;
     { int rc_ = ensure_side(h); if (rc_) return rc_; }
     CUDA_OK(cudaEventRecord(h->ev_fork, s));
     CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
     LAUNCH(launch_contacts(h->d, h->buf, h->cc, mask, h->side));
     CUDA_OK(cudaEventRecord(h->ev_join, h->side));
-    LAUNCH(launch_physics(h->d, h->buf, h->cc, mask, action, action_dtype, h->cfg.h_ratio, h->cfg.collisions, s));
+    LAUNCH(launch_physics(h->d, h->buf, h->cc, mask, noact, action, action_dtype, h->cfg.h_ratio, h->cfg.collisions, s));
     CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));
-    LAUNCH(launch_physics_post(h->d, h->buf, h->cc, mask, action != nullptr, h->cfg.h_ratio, s));
+    LAUNCH(launch_physics_post(h->d, h->buf, h->cc, mask, noact, action != nullptr, h->cfg.h_ratio, 0, s));
     return 0;
 }
 
@@ -676,8 +699,8 @@ extern "C" int mcr_contacts(mcr_handle h, const uint8_t* mask, void* stream) {
 extern "C" int mcr_physics(mcr_handle h, const uint8_t* mask, const void* action, int32_t action_dtype, void* stream) {
     int rc = check_bound(h); if (rc) return rc;
     if (action && action_dtype != MCR_F32 && action_dtype != MCR_F64) return fail(-1, "action dtype must be MCR_F32 or MCR_F64");
-    LAUNCH(launch_physics(h->d, h->buf, h->cc, mask, action, action_dtype, h->cfg.h_ratio, h->cfg.collisions, stream));
-    LAUNCH(launch_physics_post(h->d, h->buf, h->cc, mask, action != nullptr, h->cfg.h_ratio, stream));
+    LAUNCH(launch_physics(h->d, h->buf, h->cc, mask, nullptr, action, action_dtype, h->cfg.h_ratio, h->cfg.collisions, stream));
+    LAUNCH(launch_physics_post(h->d, h->buf, h->cc, mask, nullptr, action != nullptr, h->cfg.h_ratio, 0, stream));
     return 0;
 }
 
@@ -690,16 +713,16 @@ extern "C" int mcr_simulate(mcr_handle h, const uint8_t* mask, const void* actio
 // render || score: the rasteriser only reads the snapshots post_kernel took, so the reward / done
 // block runs beside it on the side stream; the caller's stream waits for both.
 static int render_and_score(mcr_handle h, const uint8_t* mask, uint8_t* obs, double* reward, uint8_t* done,
-                            int post_step, void* stream) {
+                            int post_step, void* stream, const uint8_t* noact = nullptr) {
     cudaStream_t s = (cudaStream_t)stream;
     if (post_step) {
         int rc = ensure_side(h); if (rc) return rc;
         CUDA_OK(cudaEventRecord(h->ev_fork, s));
         CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-        LAUNCH(launch_score(h->d, h->buf, mask, reward, done, h->cfg.max_episode_steps, h->side));
+        LAUNCH(launch_score(h->d, h->buf, mask, noact, reward, done, h->cfg.max_episode_steps, 0, h->side));
         CUDA_OK(cudaEventRecord(h->ev_join, h->side));
     }
-    LAUNCH(launch_render(h->d, h->buf, h->cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, s));
+    LAUNCH(launch_render(h->d, h->buf, h->cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, 0, s));
     if (post_step) CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));
     return 0;
 }
@@ -711,30 +734,129 @@ extern "C" int mcr_render(mcr_handle h, const uint8_t* mask, uint8_t* obs, doubl
     return render_and_score(h, mask, obs, reward, done, post_step, stream);
 }
 
+static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, const void* action, int32_t action_dtype,
+                    uint8_t* obs, double* reward, uint8_t* done, int post_step, void* stream);
+
 extern "C" int mcr_reset(mcr_handle h, const uint8_t* mask, const int32_t* track_slot, const uint8_t* cw,
                          const double* spawn_pose, uint8_t* obs, void* stream) {
     int rc = check_bound(h); if (rc) return rc;
     if (!track_slot || !cw || !spawn_pose || !obs) return fail(-1, "mcr_reset: null argument");
     LAUNCH(launch_spawn(h->d, h->buf, h->cc, mask, track_slot, cw, spawn_pose, stream));
     // the implicit step(None), mcr:408
-    rc = simulate(h, mask, nullptr, MCR_F32, stream); if (rc) return rc;
-    rc = render_and_score(h, mask, obs, nullptr, nullptr, 0, stream); if (rc) return rc;
+    return pipeline(h, mask, nullptr, nullptr, MCR_F32, obs, nullptr, nullptr, 0, stream);
+}
+
+// One full pass (contacts, physics, post-step block, render) as two chains that only meet at the end:
+//   side   : contacts_kernel (reads the start poses)                          ............. score_kernel
+//   main   : carcontacts -> pre -> sweep ------------------> post(cls 1) -> render(cls 1)
+//   side2  :                   \-> coupled_kernel ---------> post(cls 2) -> score(cls 2) -> render(cls 2)
+// cls 1 = envs without car-car manifolds (per-car solver), cls 2 = envs with touching cars.  The
+// coupled solver (joints + contacts of a merged island in lock step, 100-250 us when any env of the
+// batch has touching cars) no longer stalls the other envs' post/render; the classes are disjoint
+// sets of envs, so the chains never touch the same state.
+static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, const void* action, int32_t action_dtype,
+                    uint8_t* obs, double* reward, uint8_t* done, int post_step, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    { int rc_ = ensure_side(h); if (rc_) return rc_; }
+    const Dims& d = h->d; const DevBuffers& b = h->buf; const CarConst& cc = h->cc;
+    const bool split = h->cfg.collisions && d.A > 1;
+    static const int early_exit = std::getenv("MCR_NO_EARLY_EXIT") ? 0 : 1;   // diagnostics only
+    CUDA_OK(cudaEventRecord(h->ev_fork, s));
+    CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    LAUNCH(launch_contacts(d, b, cc, mask, h->side));
+    CUDA_OK(cudaEventRecord(h->ev_contacts, h->side));
+    LAUNCH(launch_presweep(d, b, cc, mask, noact, action, action_dtype, h->cfg.collisions, 0, s));
+    if (split) {
+        CUDA_OK(cudaEventRecord(h->ev_pre, s));
+        CUDA_OK(cudaStreamWaitEvent(h->side2, h->ev_pre, 0));
+        LAUNCH(launch_coupled(d, b, cc, mask, early_exit, h->side2));
+        CUDA_OK(cudaStreamWaitEvent(h->side2, h->ev_contacts, 0));
+        LAUNCH(launch_physics_post(d, b, cc, mask, noact, action != nullptr, h->cfg.h_ratio, 2, h->side2));
+        if (post_step) LAUNCH(launch_score(d, b, mask, noact, reward, done, h->cfg.max_episode_steps, 2, h->side2));
+        LAUNCH(launch_render(d, b, cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, 2, h->side2));
+        CUDA_OK(cudaEventRecord(h->ev_chain2, h->side2));
+    }
+    LAUNCH(launch_presweep(d, b, cc, mask, noact, action, action_dtype, h->cfg.collisions, 1, s));
+    CUDA_OK(cudaStreamWaitEvent(s, h->ev_contacts, 0));
+    const int cls = split ? 1 : 0;
+    LAUNCH(launch_physics_post(d, b, cc, mask, noact, action != nullptr, h->cfg.h_ratio, cls, s));
+    if (post_step) {
+        CUDA_OK(cudaEventRecord(h->ev_join, s));
+        CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_join, 0));
+        LAUNCH(launch_score(d, b, mask, noact, reward, done, h->cfg.max_episode_steps, cls, h->side));
+        CUDA_OK(cudaEventRecord(h->ev_score, h->side));
+    }
+    LAUNCH(launch_render(d, b, cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, cls, s));
+    if (post_step) CUDA_OK(cudaStreamWaitEvent(s, h->ev_score, 0));
+    if (split) CUDA_OK(cudaStreamWaitEvent(s, h->ev_chain2, 0));
     return 0;
 }
 
+static int step_enqueue(mcr_handle h, const void* action, int32_t action_dtype, uint8_t* obs, double* reward,
+                        uint8_t* done, int32_t flags, void* stream) {
+    int rc;
+    if (flags & 2) {
+        // next-step auto reset: envs whose previous step ended the episode respawn now and take
+        // reset()'s step(None) inside this very pass -- one pass, no masked second pass
+        AutoResetCfg ar{h->cfg.use_random_direction, h->cfg.direction_cw, (unsigned long long)h->cfg.seed};
+        LAUNCH(launch_auto_reset(h->d, h->buf, h->cc, h->buf.pending, ar, stream));
+        return pipeline(h, nullptr, h->buf.reset_mask, action, action_dtype, obs, reward, done, 1, stream);
+    }
+    rc = pipeline(h, nullptr, nullptr, action, action_dtype, obs, reward, done, 1, stream); if (rc) return rc;
+    if (flags & 1) {
+        AutoResetCfg ar{h->cfg.use_random_direction, h->cfg.direction_cw, (unsigned long long)h->cfg.seed};
+        LAUNCH(launch_auto_reset(h->d, h->buf, h->cc, done, ar, stream));
+        rc = pipeline(h, h->buf.reset_mask, nullptr, nullptr, MCR_F32, obs, nullptr, nullptr, 0, stream); if (rc) return rc;
+    }
+    return 0;
+}
+
+// The step is 9 dependent launches on two streams; issued one by one they cost more host time than
+// the GPU needs to run them (launch bound at ~0.1 ms per step).  After two eager steps (one-time
+// kernel attributes and constant uploads are done by then) the launch sequence is captured once per
+// argument tuple into a CUDA graph that reads the action from the bound `action_stage` buffer; a
+// step is then one device-to-device copy of the action plus one cudaGraphLaunch.
 extern "C" int mcr_step(mcr_handle h, const void* action, int32_t action_dtype, uint8_t* obs, double* reward,
                         uint8_t* done, int32_t flags, void* stream) {
     int rc = check_bound(h); if (rc) return rc;
     if (!action || !obs || !reward || !done) return fail(-1, "mcr_step: null argument");
     if (action_dtype != MCR_F32 && action_dtype != MCR_F64) return fail(-1, "action dtype must be MCR_F32 or MCR_F64");
-    rc = simulate(h, nullptr, action, action_dtype, stream); if (rc) return rc;
-    rc = render_and_score(h, nullptr, obs, reward, done, 1, stream); if (rc) return rc;
-    if (flags & 1) {
-        AutoResetCfg ar{h->cfg.use_random_direction, h->cfg.direction_cw, (unsigned long long)h->cfg.seed};
-        LAUNCH(launch_auto_reset(h->d, h->buf, h->cc, done, ar, stream));
-        const uint8_t* m = h->buf.reset_mask;
-        rc = simulate(h, m, nullptr, MCR_F32, stream); if (rc) return rc;
-        rc = render_and_score(h, m, obs, nullptr, nullptr, 0, stream); if (rc) return rc;
+    if ((flags & 3) == 3) return fail(-1, "mcr_step: flags bit0 (same-step) and bit1 (next-step) auto reset are exclusive");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!h->use_graphs || h->eager_steps < 2) {
+        ++h->eager_steps;
+        return step_enqueue(h, action, action_dtype, obs, reward, done, flags, stream);
     }
+    mcr_handle_t::StepGraph* g = nullptr;
+    for (auto& c : h->graphs)
+        if (c.dtype == action_dtype && c.flags == flags && c.obs == obs && c.reward == reward && c.done == done) { g = &c; break; }
+    if (!g) {
+        if (h->graphs.size() >= 16) { cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
+        rc = ensure_side(h); if (rc) return rc;
+        const int64_t before = h->launches;
+        CUDA_OK(cudaStreamBeginCapture(h->cap, cudaStreamCaptureModeRelaxed));
+        rc = step_enqueue(h, h->buf.action_stage, action_dtype, obs, reward, done, flags, h->cap);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(h->cap, &graph);
+        const int64_t per_step = h->launches - before;
+        h->launches = before;
+        cudaGraphExec_t exec = nullptr;
+        cudaError_t ie = cudaErrorUnknown;
+        if (!rc && ce == cudaSuccess && graph) ie = cudaGraphInstantiate(&exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) {
+            // graphs are an optimisation of the launch path only: issue this and all later steps directly
+            (void)cudaGetLastError();
+            h->use_graphs = false;
+            return step_enqueue(h, action, action_dtype, obs, reward, done, flags, stream);
+        }
+        h->graphs.push_back(mcr_handle_t::StepGraph{action_dtype, flags, obs, reward, done, exec, per_step});
+        g = &h->graphs.back();
+    }
+    const size_t abytes = (size_t)h->d.N * 3 * (action_dtype == MCR_F64 ? 8 : 4);
+    if (action != (const void*)h->buf.action_stage)
+        CUDA_OK(cudaMemcpyAsync(h->buf.action_stage, action, abytes, cudaMemcpyDeviceToDevice, s));
+    CUDA_OK(cudaGraphLaunch(g->exec, s));
+    h->launches += g->launches;
     return 0;
 }

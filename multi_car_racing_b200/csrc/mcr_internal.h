@@ -43,7 +43,7 @@ enum {
     BUF_ON_ROAD, BUF_ON_ROAD_NEXT, BUF_REWARD, BUF_PREV_REWARD, BUF_VISIT_COUNT, BUF_BACKWARD,
     BUF_TIME, BUF_STEPS, BUF_CAMERA, BUF_STRIPE, BUF_HEADING,
     BUF_ENV_TRACK, BUF_ENV_CW, BUF_ENV_EPISODE,
-    BUF_VISITED, BUF_TOUCHED, BUF_RESET_MASK, BUF_STATUS, BUF_SCRATCH, BUF_MANIFOLD, BUF_N_MANIFOLD, BUF_SCORE_SNAP, BUF_BACKWARD_SNAP,
+    BUF_VISITED, BUF_TOUCHED, BUF_RESET_MASK, BUF_STATUS, BUF_SCRATCH, BUF_MANIFOLD, BUF_N_MANIFOLD, BUF_SCORE_SNAP, BUF_BACKWARD_SNAP, BUF_PENDING, BUF_ACTION_STAGE,
     BUF_TRK_T, BUF_TRK_Q, BUF_TRK_NODE, BUF_TRK_TILE, BUF_TRK_TILE_AABB, BUF_TRK_QUAD, BUF_TRK_QUAD_COL,
     BUF_TRK_QUAD_TILE, BUF_TRK_SLOT_POSE, BUF_TRK_CHUNK,
     BUF_COUNT
@@ -87,6 +87,8 @@ struct DevBuffers {
     float* manifold;                     // [B][MCR_MAX_MANIFOLDS][MCR_MANIFOLD_WORDS] persistent car-car contact manifolds
     int32_t* n_manifold;                 // [B]
     double* score_snap; uint8_t* backward_snap;   // [N] env.reward / driving_backward as the render of this step sees them
+    uint8_t* pending;                    // [B] done flags of the previous step (next-step auto reset)
+    double* action_stage;                // [N][3] f64-sized staging copy of the step's action (CUDA-graph replay reads it)
     int32_t* trk_T; int32_t* trk_Q; double* trk_node; float* trk_tile; float* trk_tile_aabb;
     float* trk_quad; uint8_t* trk_quad_col; int16_t* trk_quad_tile; double* trk_slot_pose;
     float* trk_chunk;                    // [P][Qmax/8][4] bounding circle (cx, cy, r, 0) of 8 consecutive road_poly quads
@@ -96,16 +98,22 @@ struct Dims { int B, A, N, Tmax, Qmax, P; };
 
 // kernel launchers (each returns the number of kernels it launched, or < 0 on error)
 int launch_contacts(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, void* stream);
-int launch_physics(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
+// noact[env] != 0: that env takes the action=None path of mcr:421 this step (next-step auto reset)
+int launch_physics(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* noact,
                    const void* action, int action_dtype, double h_ratio, int collisions, void* stream);
 int launch_carcontacts(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, void* stream);
 int launch_coupled(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, int early_exit, void* stream);
-int launch_physics_post(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
-                        int has_action, double h_ratio, void* stream);
+// cls selects envs by their car-car contact state this step: 0 = all, 1 = only envs without
+// manifolds (per-car solver), 2 = only envs with manifolds (coupled_kernel) -- the two classes
+// flow through post / score / render on separate streams
+int launch_physics_post(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* noact,
+                        int has_action, double h_ratio, int cls, void* stream);
+int launch_presweep(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* noact,
+                    const void* action, int action_dtype, int collisions, int with_sweep, void* stream);
 int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* obs,
-                  int backwards_flag, int use_ego_color, void* stream);
-int launch_score(const Dims& d, const DevBuffers& b, const uint8_t* mask, double* reward, uint8_t* done,
-                 int max_episode_steps, void* stream);
+                  int backwards_flag, int use_ego_color, int cls, void* stream);
+int launch_score(const Dims& d, const DevBuffers& b, const uint8_t* mask, const uint8_t* noact, double* reward, uint8_t* done,
+                 int max_episode_steps, int cls, void* stream);
 const uint8_t (*mcr_host_palette())[4];
 int launch_spawn(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
                  const int32_t* track_slot, const uint8_t* cw, const double* spawn_pose, void* stream);

@@ -357,12 +357,13 @@ __device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pi
 
 __global__ void __launch_bounds__(RS_THREADS, 4)
 render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, uint8_t* __restrict__ obs,
-              int backwards_flag, int use_ego_color) {
+              int backwards_flag, int use_ego_color, int cls) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
     const int frame = blockIdx.x;
     const int env = frame / d.A, agent = frame % d.A;
     if (mask && !mask[env]) return;
+    if (cls && (cls == 2) != (b.n_manifold[env] > 0)) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = d.N, car = frame;
     const int slot = b.env_track[env];
@@ -611,8 +612,8 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
 #define SCORE_WARPS 4
 
 __global__ void __launch_bounds__(SCORE_WARPS * 32)
-score_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, double* __restrict__ out_reward,
-             uint8_t* __restrict__ out_done, int max_episode_steps) {
+score_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ noact,
+             double* __restrict__ out_reward, uint8_t* __restrict__ out_done, int max_episode_steps, int cls) {
     __shared__ int s_cand[SCORE_WARPS][32];
     __shared__ int s_ncand[SCORE_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -620,6 +621,13 @@ score_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, double* __r
     if (car >= d.N) return;
     const int env = car / d.A, agent = car - env * d.A;
     if (mask && !mask[env]) return;
+    if (cls && (cls == 2) != (b.n_manifold[env] > 0)) return;
+    if (noact && noact[env]) {
+        // this env was respawned at the start of the step and took reset()'s step(None): the whole
+        // `if action is not None` block of mcr:433-507 is skipped, the caller sees reward 0, done 0
+        if (lane == 0) { out_reward[car] = 0.0; if (agent == 0) { out_done[env] = 0; b.pending[env] = 0; } }
+        return;
+    }
     const int N = d.N;
     const int slot = b.env_track[env];
     const int T = b.trk_T[slot];
@@ -686,12 +694,12 @@ score_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, double* __r
         }
         if (max_episode_steps > 0 && b.steps[car] >= max_episode_steps) done |= 2;   // TimeLimit
         out_reward[car] = step_reward;
-        if (agent == 0) out_done[env] = done;
+        if (agent == 0) { out_done[env] = done; b.pending[env] = done; }
     }
 }
 
 int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* obs,
-                  int backwards_flag, int use_ego_color, void* stream) {
+                  int backwards_flag, int use_ego_color, int cls, void* stream) {
     static bool configured = false;
     const size_t smem = sizeof(RasterSmem);
     if (!configured) {
@@ -699,12 +707,12 @@ int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const 
         if (cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         configured = true;
     }
-    render_kernel<<<d.N, RS_THREADS, smem, (cudaStream_t)stream>>>(d, b, cc, mask, obs, backwards_flag, use_ego_color);
+    render_kernel<<<d.N, RS_THREADS, smem, (cudaStream_t)stream>>>(d, b, cc, mask, obs, backwards_flag, use_ego_color, cls);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-int launch_score(const Dims& d, const DevBuffers& b, const uint8_t* mask, double* reward, uint8_t* done,
-                 int max_episode_steps, void* stream) {
-    score_kernel<<<(d.N + SCORE_WARPS - 1) / SCORE_WARPS, SCORE_WARPS * 32, 0, (cudaStream_t)stream>>>(d, b, mask, reward, done, max_episode_steps);
+int launch_score(const Dims& d, const DevBuffers& b, const uint8_t* mask, const uint8_t* noact, double* reward, uint8_t* done,
+                 int max_episode_steps, int cls, void* stream) {
+    score_kernel<<<(d.N + SCORE_WARPS - 1) / SCORE_WARPS, SCORE_WARPS * 32, 0, (cudaStream_t)stream>>>(d, b, mask, noact, reward, done, max_episode_steps, cls);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

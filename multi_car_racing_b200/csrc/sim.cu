@@ -252,7 +252,8 @@ contacts_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ m
 
 template <typename ActT>
 __global__ void __launch_bounds__(PRE_BLOCK)
-pre_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, const ActT* __restrict__ action) {
+pre_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ noact,
+           const ActT* __restrict__ action) {
     const int car = blockIdx.x * PRE_BLOCK + threadIdx.x;
     if (car >= d.N) return;
     const int env = car / d.A;
@@ -290,7 +291,7 @@ pre_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, 
     double steer = b.ctrl[(size_t)CF_STEER * N + car];
 
     // ---- controls, mcr:421-424 -------------------------------------------------------
-    if (action) {
+    if (action && !(noact && noact[env])) {
         double a0 = (double)action[(size_t)car * 3 + 0];
         double a1 = (double)action[(size_t)car * 3 + 1];
         double a2 = (double)action[(size_t)car * 3 + 2];
@@ -401,22 +402,12 @@ pre_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, 
     b.ctrl[(size_t)CF_STEER * N + car] = steer;
 }
 
-#define SWEEP_WARPS 4
+#define SWEEP_BLOCK 128
 
-__global__ void __launch_bounds__(SWEEP_WARPS * 32, 4)
-sweep_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, int early_exit) {
-    const int car = blockIdx.x * SWEEP_WARPS + (threadIdx.x >> 5);
-    if (car >= d.N) return;
-    if (mask && !mask[car / d.A]) return;
-    if (b.n_manifold[car / d.A] > 0) return;      // solved by coupled_kernel
-    const int N = d.N;
-    // every lane runs the same scalar arithmetic (the loads broadcast); lane 0 stores
+__device__ __forceinline__ void sweep_load(const DevBuffers& b, int car, int N, VelState& s, JointC (&J)[4]) {
     const float* sc = b.scratch + car;
-    VelState s;
 #pragma unroll
     for (int i = 0; i < 5; ++i) { s.vx[i] = sc[(size_t)(SC_VX + i) * N]; s.vy[i] = sc[(size_t)(SC_VY + i) * N]; s.w[i] = sc[(size_t)(SC_W + i) * N]; }
-    JointC J[4];
-    int pat = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         s.jix[k] = sc[(size_t)(SC_JIX + k) * N]; s.jiy[k] = sc[(size_t)(SC_JIY + k) * N];
@@ -428,36 +419,81 @@ sweep_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask
         j.det22 = q[(size_t)8 * N]; j.cfx = q[(size_t)9 * N]; j.cfy = q[(size_t)10 * N]; j.cfz = q[(size_t)11 * N];
         j.det33 = q[(size_t)12 * N]; j.motorMass = q[(size_t)13 * N]; j.motorSpeed = q[(size_t)14 * N];
         j.limit = b.limit_state[(size_t)k * N + car];
-        pat |= (j.limit != LIM_INACTIVE ? 1 : 0) << k;
     }
+}
+
+__device__ __forceinline__ void sweep_store(const DevBuffers& b, int car, int N, const VelState& s) {
+    float* so = b.scratch + car;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { so[(size_t)(SC_VX + i) * N] = s.vx[i]; so[(size_t)(SC_VY + i) * N] = s.vy[i]; so[(size_t)(SC_W + i) * N] = s.w[i]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        so[(size_t)(SC_JIX + k) * N] = s.jix[k]; so[(size_t)(SC_JIY + k) * N] = s.jiy[k];
+        so[(size_t)(SC_JIZ + k) * N] = s.jiz[k]; so[(size_t)(SC_JMOT + k) * N] = s.jmot[k];
+    }
+}
+
+// The 180 Gauss-Seidel sweeps are a serial chain (349 cycles per sweep for one warp alone on a
+// scheduler, scripts/micro/chain_latency.cu); what a car costs is latency, what a WARP costs is issue
+// slots.  One warp per car made every scheduler issue ~170 instructions per sweep for each of its
+// ~3.5 resident warps (570-800 cycles per sweep measured), so the grid has two parts:
+//   CTAs [0, packed)      one THREAD per car for the cars whose four limits are inactive (99 %):
+//                         32 cars per warp, straight-line code, N/32 warps spread one per scheduler.
+//                         A warp leaves when ALL its cars sit on an exact fixed point / 2-cycle /
+//                         4-cycle (more multiples of four sweeps leave such a car bit-identical).
+//   CTAs [packed, ...)    one WARP per car for the few cars with an active limit: code specialised
+//                         to the limit pattern, no divergence inside the sweep, own early exit.
+__global__ void __launch_bounds__(SWEEP_BLOCK)
+sweep_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, int early_exit, int packed_ctas) {
+    const int N = d.N;
     const float h = (float)(1.0 / 50);
     Masses m; m.mA = cc.hull_invMass; m.iA = cc.hull_invI; m.mB = cc.wheel_invMass; m.iB = cc.wheel_invI;
     m.maxMotorImpulse = h * cc.max_motor_torque;
-    switch (pat) {
-        case 0: solve_velocity<0>(s, J, m, early_exit != 0); break;
-        case 1: solve_velocity<1>(s, J, m, early_exit != 0); break;
-        case 2: solve_velocity<2>(s, J, m, early_exit != 0); break;
-        case 3: solve_velocity<3>(s, J, m, early_exit != 0); break;
-        default: solve_velocity<-1>(s, J, m, early_exit != 0); break;   // a rear joint at its limit: rare
-    }
-    if ((threadIdx.x & 31) == 0) {
-        float* so = b.scratch + car;
+    const bool packed = (int)blockIdx.x < packed_ctas;
+    const int car = packed ? blockIdx.x * SWEEP_BLOCK + threadIdx.x
+                           : (blockIdx.x - packed_ctas) * (SWEEP_BLOCK / 32) + (threadIdx.x >> 5);
+    bool mine = car < N;
+    int pat = 0;
+    if (mine) {
+        const int env = car / d.A;
+        if (mask && !mask[env]) mine = false;
+        else if (b.n_manifold[env] > 0) mine = false;      // solved by coupled_kernel
+        else {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) { so[(size_t)(SC_VX + i) * N] = s.vx[i]; so[(size_t)(SC_VY + i) * N] = s.vy[i]; so[(size_t)(SC_W + i) * N] = s.w[i]; }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            so[(size_t)(SC_JIX + k) * N] = s.jix[k]; so[(size_t)(SC_JIY + k) * N] = s.jiy[k];
-            so[(size_t)(SC_JIZ + k) * N] = s.jiz[k]; so[(size_t)(SC_JMOT + k) * N] = s.jmot[k];
+            for (int k = 0; k < 4; ++k) pat |= (b.limit_state[(size_t)k * N + car] != LIM_INACTIVE ? 1 : 0) << k;
         }
+    }
+    if (packed) {
+        mine = mine && pat == 0;
+        const unsigned peers = __ballot_sync(0xffffffffu, mine);
+        if (!mine) return;
+        VelState s; JointC J[4];
+        sweep_load(b, car, N, s, J);
+        solve_velocity<0>(s, J, m, early_exit != 0, peers);
+        sweep_store(b, car, N, s);
+    } else {
+        if (!mine || pat == 0) return;
+        // every lane runs the same scalar arithmetic (the loads broadcast); lane 0 stores
+        VelState s; JointC J[4];
+        sweep_load(b, car, N, s, J);
+        switch (pat) {
+            case 1: solve_velocity<1>(s, J, m, early_exit != 0); break;
+            case 2: solve_velocity<2>(s, J, m, early_exit != 0); break;
+            case 3: solve_velocity<3>(s, J, m, early_exit != 0); break;
+            default: solve_velocity<-1>(s, J, m, early_exit != 0); break;   // a rear joint at its limit: rare
+        }
+        if ((threadIdx.x & 31) == 0) sweep_store(b, car, N, s);
     }
 }
 
 __global__ void __launch_bounds__(PRE_BLOCK)
-post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, int has_action, double h_ratio) {
+post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ noact, int has_action,
+            double h_ratio, int cls) {
     const int car = blockIdx.x * PRE_BLOCK + threadIdx.x;
     if (car >= d.N) return;
     const int env = car / d.A;
     if (mask && !mask[env]) return;
+    if (cls && (cls == 2) != (b.n_manifold[env] > 0)) return;
     const int N = d.N;
     const float h = (float)(1.0 / 50);
     const float mA = cc.hull_invMass, iA = cc.hull_invI, mB = cc.wheel_invMass, iB = cc.wheel_invI;
@@ -579,7 +615,7 @@ post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
     // ---- per-view values the rasteriser needs, evaluated once here (fp64 trig is serial latency) --
     const double t = b.time[car] + 1.0 / 50;                      // mcr:429
     b.time[car] = t;
-    if (has_action) b.steps[car] += 1;                                // TimeLimit counts step() calls only
+    if (has_action && !(noact && noact[env])) b.steps[car] += 1;                                // TimeLimit counts step() calls only
     {   // camera, mcr:540-556 + Transform.enable + glViewport(0,0,96,96) under glOrtho(0,1000,0,800)
         const double SCALE = 6.0, ZOOM = 2.7, WINDOW_W = 1000, WINDOW_H = 800;
         const double zoom = 0.1 * SCALE * fmax(1 - t, 0.0) + ZOOM * SCALE * fmin(t, 1.0);
@@ -638,26 +674,48 @@ int launch_contacts(const Dims& d, const DevBuffers& b, const CarConst& cc, cons
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-int launch_physics(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
+int launch_physics(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* noact,
                    const void* action, int action_dtype, double h_ratio, int collisions, void* stream) {
     static const int early_exit = getenv("MCR_NO_EARLY_EXIT") ? 0 : 1;   // diagnostics only
     cudaStream_t s = (cudaStream_t)stream;
     int launched = 0;
     if (collisions && d.A > 1) { if (launch_carcontacts(d, b, cc, mask, stream) < 0) return -1; ++launched; }
     const int nb = (d.N + PRE_BLOCK - 1) / PRE_BLOCK;
-    if (action_dtype == MCR_F64) pre_kernel<double><<<nb, PRE_BLOCK, 0, s>>>(d, b, cc, mask, (const double*)action);
-    else pre_kernel<float><<<nb, PRE_BLOCK, 0, s>>>(d, b, cc, mask, (const float*)action);
-    sweep_kernel<<<(d.N + SWEEP_WARPS - 1) / SWEEP_WARPS, SWEEP_WARPS * 32, 0, s>>>(d, b, cc, mask, early_exit);
+    if (action_dtype == MCR_F64) pre_kernel<double><<<nb, PRE_BLOCK, 0, s>>>(d, b, cc, mask, noact, (const double*)action);
+    else pre_kernel<float><<<nb, PRE_BLOCK, 0, s>>>(d, b, cc, mask, noact, (const float*)action);
+    const int packed_ctas = (d.N + SWEEP_BLOCK - 1) / SWEEP_BLOCK, percar_ctas = (d.N + SWEEP_BLOCK / 32 - 1) / (SWEEP_BLOCK / 32);
+    sweep_kernel<<<packed_ctas + percar_ctas, SWEEP_BLOCK, 0, s>>>(d, b, cc, mask, early_exit, packed_ctas);
     launched += 2;
     if (collisions && d.A > 1) { if (launch_coupled(d, b, cc, mask, early_exit, stream) < 0) return -1; ++launched; }
     return cudaGetLastError() == cudaSuccess ? launched : -1;
 }
 
+// carcontacts -> pre (with_sweep = 0) or the sweep alone (with_sweep = 1): the pieces mcr_step's
+// two-chain pipeline issues itself (coupled_kernel goes to its own stream there).
+int launch_presweep(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* noact,
+                    const void* action, int action_dtype, int collisions, int with_sweep, void* stream) {
+    static const int early_exit = getenv("MCR_NO_EARLY_EXIT") ? 0 : 1;   // diagnostics only
+    cudaStream_t s = (cudaStream_t)stream;
+    int launched = 0;
+    if (!with_sweep) {
+        if (collisions && d.A > 1) { if (launch_carcontacts(d, b, cc, mask, stream) < 0) return -1; ++launched; }
+        const int nb = (d.N + PRE_BLOCK - 1) / PRE_BLOCK;
+        if (action_dtype == MCR_F64) pre_kernel<double><<<nb, PRE_BLOCK, 0, s>>>(d, b, cc, mask, noact, (const double*)action);
+        else pre_kernel<float><<<nb, PRE_BLOCK, 0, s>>>(d, b, cc, mask, noact, (const float*)action);
+        ++launched;
+    } else {
+        const int packed_ctas = (d.N + SWEEP_BLOCK - 1) / SWEEP_BLOCK, percar_ctas = (d.N + SWEEP_BLOCK / 32 - 1) / (SWEEP_BLOCK / 32);
+        sweep_kernel<<<packed_ctas + percar_ctas, SWEEP_BLOCK, 0, s>>>(d, b, cc, mask, early_exit, packed_ctas);
+        ++launched;
+    }
+    return cudaGetLastError() == cudaSuccess ? launched : -1;
+}
+
 // post_kernel must not start before the contacts pass of the same step has finished reading the
 // start poses and writing on_road_next (the API joins the side stream before calling this).
-int launch_physics_post(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
-                        int has_action, double h_ratio, void* stream) {
+int launch_physics_post(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* noact,
+                        int has_action, double h_ratio, int cls, void* stream) {
     const int nb = (d.N + PRE_BLOCK - 1) / PRE_BLOCK;
-    post_kernel<<<nb, PRE_BLOCK, 0, (cudaStream_t)stream>>>(d, b, cc, mask, has_action, h_ratio);
+    post_kernel<<<nb, PRE_BLOCK, 0, (cudaStream_t)stream>>>(d, b, cc, mask, noact, has_action, h_ratio, cls);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

@@ -136,14 +136,17 @@ __device__ __forceinline__ unsigned state_diff(const VelState& a, const VelState
 // 4-cycle, checked at multiples of 4 so the phase matches sweep 180) the remaining sweeps
 // cannot change it, so stopping there is exact.
 template <int PAT>
-__device__ __forceinline__ void solve_velocity(VelState& s, const JointC (&J)[4], const Masses& m, bool early_exit) {
+__device__ __forceinline__ void solve_velocity(VelState& s, const JointC (&J)[4], const Masses& m, bool early_exit,
+                                               unsigned peers = 0u) {
     // one sweep per loop trip keeps the loop body (~3 KB of SASS) inside the L0 instruction cache
 #pragma unroll 1
     for (int it = 0; it < MCR_VEL_ITERS; it += 4) {
         const VelState before = s;
 #pragma unroll 1
         for (int r = 0; r < 4; ++r) sweep<PAT>(s, J, m);
-        if (early_exit && state_diff(before, s) == 0u) break;
+        // peers != 0: the lanes of `peers` hold one car each and leave together
+        const bool settled = state_diff(before, s) == 0u;
+        if (early_exit && (peers ? __all_sync(peers, settled) : settled)) break;
     }
 }
 

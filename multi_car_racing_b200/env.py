@@ -97,7 +97,14 @@ class BatchedMultiCarRacing:
         self.direction, self.use_random_direction = direction, use_random_direction
         self.backwards_flag, self.h_ratio, self.use_ego_color = backwards_flag, h_ratio, use_ego_color
         self.max_episode_steps = int(max_episode_steps or 0)
-        self.auto_reset = bool(auto_reset)
+        # auto_reset: False | True / 'same_step' (the finished env's obs is replaced by its next
+        # episode's first frame before step() returns) | 'next_step' (EnvPool convention: the terminal
+        # obs is returned; the NEXT step() ignores that env's action and returns the reset frame with
+        # reward 0 -- one kernel pass per step, the fast path bench.py measures)
+        if auto_reset not in (False, True, 'same_step', 'next_step', 0, 1, None):
+            raise ValueError("auto_reset must be False, True, 'same_step' or 'next_step'")
+        self.auto_reset = auto_reset if isinstance(auto_reset, str) else bool(auto_reset)
+        self._step_flags = 2 if self.auto_reset == 'next_step' else (1 if self.auto_reset else 0)
         self.pool_tracks = int(pool_tracks) if pool_tracks else self.batch_envs
         if self.pool_tracks < self.batch_envs:
             raise ValueError("pool_tracks must be >= batch_envs")
@@ -230,7 +237,7 @@ class BatchedMultiCarRacing:
         dt = _lib.MCR_F32 if action.dtype == torch.float32 else _lib.MCR_F64
         with torch.cuda.device(self.device):
             _lib.check(self.L.mcr_step(self._h, action.data_ptr(), dt, self.obs.data_ptr(), self.reward_out.data_ptr(),
-                                       self.done_out.data_ptr(), 1 if self.auto_reset else 0, self._stream()), "mcr_step")
+                                       self.done_out.data_ptr(), self._step_flags, self._stream()), "mcr_step")
         return self.obs, self.reward_out, self.done_out, {}
 
     def step_host(self, action):
@@ -270,8 +277,11 @@ class BatchedMultiCarRacing:
                 obs=torch.zeros((B, A, STATE_H, STATE_W, 3), dtype=torch.uint8).pin_memory(),
                 reward=torch.zeros((B, A), dtype=torch.float64).pin_memory(),
                 done=torch.zeros((B,), dtype=torch.uint8).pin_memory())
-            self._dev_action = torch.zeros((B, A, 3), dtype=torch.float32, device=self.device)
-            self._dev_action64 = torch.zeros((B, A, 3), dtype=torch.float64, device=self.device)
+            # the library's own action staging buffer (what its CUDA graph reads): copying the host
+            # action straight into it saves mcr_step's device-to-device copy
+            stage = self.buffers["action_stage"]
+            self._dev_action64 = stage.view(B, A, 3)
+            self._dev_action = stage.view(torch.float32).reshape(-1)[:B * A * 3].view(B, A, 3)
         return self._host
 
     def step_split(self, action, events=None, fused=True):

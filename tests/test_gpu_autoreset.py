@@ -1,0 +1,105 @@
+"""Device-side auto reset (both conventions) against the CPU oracle.
+
+The device picks the next track slot, direction and car order itself (counter-based RNG); the
+test reads that choice back (env_track / env_cw, car order recovered from the spawn positions),
+builds a fresh oracle world for it and demands bit-exact state, rewards and pixels afterwards.
+Reference behaviour being reproduced: reset() = respawn + step(None) (mcr:340-408), TimeLimit at
+max_episode_steps (reference __init__.py:5-10)."""
+import itertools
+
+import numpy as np
+import pytest
+
+from helpers import action_tape, make_oracle_worlds, gpu_state, oracle_state
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_for_reset(oracle, venv, env, A):
+    """Oracle world matching what the device respawned in `env` (after its step(None))."""
+    slot = int(venv.buffers["env_track"][env].item())
+    cw = bool(venv.buffers["env_cw"][env].item())
+    tr = venv.tracks[slot]
+    d = 'CW' if cw else 'CCW'
+    g = gpu_state(venv)
+    for order in itertools.permutations(range(A)):
+        w = make_oracle_worlds(oracle, [tr], [np.array(order)], [d], A)[0]
+        obs = w.step(None)[0]
+        if np.array_equal(w.bodies(), g["bodies"][env]):
+            return w, obs
+    raise AssertionError("no car order reproduces the respawned env %d (slot %d, %s)" % (env, slot, d))
+
+
+@pytest.mark.parametrize("mode", ["same_step", "next_step"])
+def test_auto_reset_matches_oracle(oracle, mcr, mode):
+    import torch
+    B, A, LIMIT = 3, 2, 6
+    np.random.seed(3)
+    venv = mcr.BatchedMultiCarRacing(B, num_agents=A, auto_reset=mode, max_episode_steps=LIMIT, seed=11, pool_tracks=5)
+    venv.reset()
+    tape = action_tape(21, 3 * LIMIT + 4, B, A)
+    worlds = [None] * B
+    steps_in_episode = 0
+    for s in range(len(tape)):
+        obs, rew, done, _ = venv.step(torch.from_numpy(tape[s]).to(venv.device))
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        steps_in_episode += 1
+        if mode == "same_step":
+            if steps_in_episode == LIMIT:
+                assert np.all(done & 2), "TimeLimit bit at step %d" % s
+                for e in range(B):
+                    worlds[e], oobs = _oracle_for_reset(oracle, venv, e, A)
+                    assert np.array_equal(obs[e], oobs), "reset frame, env %d" % e
+                steps_in_episode = 0
+                continue
+        else:
+            if steps_in_episode == LIMIT:
+                assert np.all(done & 2), "TimeLimit bit at step %d" % s
+                if worlds[0] is not None:      # terminal observation stays the stepped one
+                    oo = [w.step(tape[s, e].astype(np.float64)) for e, w in enumerate(worlds)]
+                    assert np.array_equal(obs, np.stack([x[0] for x in oo]))
+                    assert np.array_equal(rew, np.stack([x[1] for x in oo]))
+                continue
+            if steps_in_episode == LIMIT + 1:  # the reset step: action ignored, reward 0, done 0
+                assert np.all(done == 0) and np.all(rew == 0.0)
+                for e in range(B):
+                    worlds[e], oobs = _oracle_for_reset(oracle, venv, e, A)
+                    assert np.array_equal(obs[e], oobs), "reset frame, env %d" % e
+                steps_in_episode = 0
+                continue
+        assert np.all(done == 0)
+        if worlds[0] is None:
+            continue
+        oo = [w.step(tape[s, e].astype(np.float64)) for e, w in enumerate(worlds)]
+        assert np.array_equal(rew, np.stack([x[1] for x in oo])), "reward, step %d" % s
+        assert np.array_equal(obs, np.stack([x[0] for x in oo])), "pixels, step %d" % s
+        g, o = gpu_state(venv), oracle_state(worlds)
+        for k in ("bodies", "wheels", "joints", "reward", "counts"):
+            assert np.array_equal(g[k], o[k]), "%s, step %d" % (k, s)
+    assert venv.status().tolist() == [0, 0, 0, 0]
+
+
+def test_out_of_field_done_then_next_step_reset(mcr):
+    """done without TimeLimit: drive one env off the playfield by teleporting its hull."""
+    import torch
+    B, A = 2, 2
+    np.random.seed(4)
+    venv = mcr.BatchedMultiCarRacing(B, num_agents=A, auto_reset="next_step", max_episode_steps=0, seed=5)
+    venv.reset()
+    act = torch.zeros((B, A, 3), device=venv.device)
+    venv.step(act)
+    body = venv.buffers["body"]            # (5, 10, N): push every body of env 1 / car 0 far out in x
+    car = 1 * A + 0
+    for i in range(5):
+        body[i, 0, car] += 1000.0
+        body[i, 6, car] += 1000.0
+    obs, rew, done, _ = venv.step(act)
+    done = done.cpu().numpy(); rew = rew.cpu().numpy()
+    assert done[1] & 1 and not done[0]
+    assert rew[1, 0] == -100.0
+    obs, rew, done, _ = venv.step(act)
+    done = done.cpu().numpy(); rew = rew.cpu().numpy()
+    assert done[1] == 0 and np.all(rew[1] == 0.0)
+    x = venv.buffers["body"][0, 6, car].item()
+    assert abs(x) < 400.0, "env 1 was respawned inside the playfield"
+    assert int(venv.buffers["steps"][car].item()) == 0 and int(venv.buffers["steps"][0].item()) == 3
