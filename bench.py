@@ -38,9 +38,10 @@ NUM_AGENTS = 2
 BATCH_ENVS = 1024
 
 
-def workload_config(A, B, world):
+def workload_config(A, B, world, obs_format="rgb"):
     return {"workload": "MultiCarRacing-v0 step+render, num_agents=%d, batch=%d envs per GPU, random policy, "
-                        "use_random_direction=True, device-side next-step auto reset (done or 1000 steps)" % (A, B),
+                        "use_random_direction=True, device-side next-step auto reset (done or 1000 steps)%s" % (
+                            A, B, "" if obs_format == "rgb" else ", obs_format=%s (NOT the reference's layout)" % obs_format),
             "batch_envs_per_gpu": B, "num_agents": A, "l2": "256 MiB flush between timed steps",
             "parallelism": "env-sharded x%d, no data-path collective" % world}
 
@@ -203,7 +204,8 @@ def run_ours(args):
 
     np.random.seed(1234 + rank)
     venv = mcr.BatchedMultiCarRacing(B, num_agents=A, use_random_direction=True, device=dev, auto_reset='next_step',
-                                     max_episode_steps=1000, seed=1234 + rank * B)
+                                     max_episode_steps=1000, seed=1234 + rank * B, obs_format=args.obs_format)
+    obs_bytes = int(np.prod(venv.obs_shape))
     venv.reset()
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
     TAPE = 128
@@ -279,7 +281,7 @@ def run_ours(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         render_ms = k_ms[1]
-        achieved = frames_per_step * OBS_BYTES / (render_ms * 1e-3) / 1e9
+        achieved = frames_per_step * obs_bytes / (render_ms * 1e-3) / 1e9
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "render_traffic.json"))).get("dram_bytes_per_launch")
@@ -295,14 +297,14 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 rigid bodies + f64 tyre/reward (u8 frames)", "data": "synthetic",
-            "config": workload_config(A, B, world),
+            "config": workload_config(A, B, world, args.obs_format),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * A * 3 * 4,
-                    "d2h_bytes_per_step": B * A * OBS_BYTES + B * A * 8 + B, "steps": KE},
+                    "d2h_bytes_per_step": B * A * obs_bytes + B * A * 8 + B, "steps": KE},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "render_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
-                         "algorithmic_bytes_per_launch": frames_per_step * OBS_BYTES,
+                         "algorithmic_bytes_per_launch": frames_per_step * obs_bytes,
                          "kernel_ms": {"simulate": k_ms[0], "render": k_ms[1]}},
             "cpu_baseline": cpu,
             "status_words": status,
@@ -323,6 +325,8 @@ def main():
     ap.add_argument("--batch-envs", dest="batch_envs", type=int, default=BATCH_ENVS)
     ap.add_argument("--num-agents", dest="num_agents", type=int, default=NUM_AGENTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--obs-format", dest="obs_format", default="rgb", choices=["rgb", "gray", "rgb_chw"],
+                    help="rasteriser store layout; only 'rgb' is the reference's observation (the headline config)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -51,6 +51,14 @@ typedef struct mcr_config {
     uint64_t seed;             /* stream id of the device-side auto-reset RNG             */
 } mcr_config;
 
+/* Observation layouts the rasteriser can store (mcr_set_obs_format).  The reference returns
+ * MCR_OBS_RGB_HWC (mcr:599-604); the others are the usual first stage of a learner's
+ * pre-processing fused into the store, so the frame never makes an extra HBM round trip:
+ *   MCR_OBS_RGB_HWC  [96][96][3] u8   (27 648 B per agent-frame, the default)
+ *   MCR_OBS_GRAY     [96][96]    u8   ( 9 216 B) ITU-R 601 luma, (299 R + 587 G + 114 B + 500) / 1000
+ *   MCR_OBS_RGB_CHW  [3][96][96] u8   (27 648 B) planar, what a convolution stack wants */
+enum { MCR_OBS_RGB_HWC = 0, MCR_OBS_GRAY = 1, MCR_OBS_RGB_CHW = 2 };
+
 /* dtype codes used by mcr_buffer_spec */
 enum { MCR_U8 = 0, MCR_I32 = 1, MCR_U32 = 2, MCR_F32 = 3, MCR_F64 = 4, MCR_I16 = 5 };
 
@@ -123,6 +131,11 @@ int mcr_physics(mcr_handle h, const uint8_t* d_env_mask, const void* d_action, i
                 void* stream);                                                       /* Car.step + world.Step, mcr:421-428 */
 int mcr_render(mcr_handle h, const uint8_t* d_env_mask, uint8_t* d_obs, double* d_reward, uint8_t* d_done,
                int32_t post_step, void* stream);                                     /* render + mcr:433-507 */
+
+/* Select the layout every later mcr_reset / mcr_step / mcr_render call writes into d_obs (one of
+ * MCR_OBS_*).  mcr_obs_bytes() = bytes per agent-frame of the current layout. */
+int mcr_set_obs_format(mcr_handle h, int32_t format);
+int64_t mcr_obs_bytes(mcr_handle h);
 
 /* Car-constant readback for parity tests: 12 floats hull(mass,invMass,I,invI,lc.x,lc.y),
  * wheel(same). */

@@ -17,8 +17,9 @@ EXPORTS = [
     "mcr_create", "mcr_destroy", "mcr_last_error", "mcr_abi_version", "mcr_buffer_count",
     "mcr_buffer_spec", "mcr_bind_buffer", "mcr_track_generate", "mcr_mt_seed", "mcr_spawn_poses",
     "mcr_load_track", "mcr_reset", "mcr_step", "mcr_simulate", "mcr_contacts", "mcr_physics", "mcr_render",
-    "mcr_get_mass", "mcr_get_shape", "mcr_launch_count",
+    "mcr_get_mass", "mcr_get_shape", "mcr_launch_count", "mcr_set_obs_format", "mcr_obs_bytes",
 ]
+OBS_FORMATS = {"rgb": 0, "gray": 1, "rgb_chw": 2}     # MCR_OBS_RGB_HWC / MCR_OBS_GRAY / MCR_OBS_RGB_CHW
 
 
 class McrConfig(ctypes.Structure):
@@ -91,6 +92,10 @@ def load():
     L.mcr_get_shape.argtypes = [vp, i32, vp]
     L.mcr_launch_count.restype = i64
     L.mcr_launch_count.argtypes = [vp]
+    L.mcr_set_obs_format.restype = i32
+    L.mcr_set_obs_format.argtypes = [vp, i32]
+    L.mcr_obs_bytes.restype = i64
+    L.mcr_obs_bytes.argtypes = [vp]
     if L.mcr_abi_version() != 1:
         raise McrError("libmcr.so ABI version mismatch")
     _lib = L

@@ -391,6 +391,7 @@ struct mcr_handle_t {
     std::vector<StepGraph> graphs;
     int64_t eager_steps;
     bool use_graphs;
+    int obs_format;              // MCR_OBS_*
 };
 
 
@@ -419,6 +420,7 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
     std::memset(&h->buf, 0, sizeof(h->buf));
     std::memset(h->ptr, 0, sizeof(h->ptr));
     h->launches = 0; h->palette_ready = false; h->side_ready = false;
+    h->obs_format = MCR_OBS_RGB_HWC;
     h->eager_steps = 0; h->use_graphs = std::getenv("MCR_NO_GRAPH") == nullptr;
     const int64_t N = h->d.N, B = h->d.B, A = h->d.A, T = h->d.Tmax, Q = h->d.Qmax, P = h->d.P;
     set_spec(h, BUF_BODY, "body", MCR_F32, {5, BODY_FIELDS, N});
@@ -564,6 +566,24 @@ extern "C" int mcr_get_shape(mcr_handle h, int32_t which, float* o) {
 }
 
 extern "C" int64_t mcr_launch_count(mcr_handle h) { return h ? h->launches : -1; }
+
+extern "C" int mcr_set_obs_format(mcr_handle h, int32_t format) {
+    if (!h) return fail(-1, "null handle");
+    if (format != MCR_OBS_RGB_HWC && format != MCR_OBS_GRAY && format != MCR_OBS_RGB_CHW)
+        return fail(-1, "mcr_set_obs_format: unknown format %d", format);
+    if (format != h->obs_format) {
+        // captured step graphs bake the layout in
+        for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+        h->graphs.clear();
+        h->obs_format = format;
+    }
+    return 0;
+}
+
+extern "C" int64_t mcr_obs_bytes(mcr_handle h) {
+    if (!h) return -1;
+    return h->obs_format == MCR_OBS_GRAY ? MCR_STATE_W * MCR_STATE_H : MCR_OBS_BYTES;
+}
 
 // ---------------------------------------------------------------------------------------
 // tracks
@@ -722,7 +742,7 @@ static int render_and_score(mcr_handle h, const uint8_t* mask, uint8_t* obs, dou
         LAUNCH(launch_score(h->d, h->buf, mask, noact, reward, done, h->cfg.max_episode_steps, 0, h->side));
         CUDA_OK(cudaEventRecord(h->ev_join, h->side));
     }
-    LAUNCH(launch_render(h->d, h->buf, h->cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, 0, s));
+    LAUNCH(launch_render(h->d, h->buf, h->cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, 0, h->obs_format, s));
     if (post_step) CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));
     return 0;
 }
@@ -773,7 +793,7 @@ static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, con
         CUDA_OK(cudaStreamWaitEvent(h->side2, h->ev_contacts, 0));
         LAUNCH(launch_physics_post(d, b, cc, mask, noact, action != nullptr, h->cfg.h_ratio, 2, h->side2));
         if (post_step) LAUNCH(launch_score(d, b, mask, noact, reward, done, h->cfg.max_episode_steps, 2, h->side2));
-        LAUNCH(launch_render(d, b, cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, 2, h->side2));
+        LAUNCH(launch_render(d, b, cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, 2, h->obs_format, h->side2));
         CUDA_OK(cudaEventRecord(h->ev_chain2, h->side2));
     }
     LAUNCH(launch_presweep(d, b, cc, mask, noact, action, action_dtype, h->cfg.collisions, 1, s));
@@ -786,7 +806,7 @@ static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, con
         LAUNCH(launch_score(d, b, mask, noact, reward, done, h->cfg.max_episode_steps, cls, h->side));
         CUDA_OK(cudaEventRecord(h->ev_score, h->side));
     }
-    LAUNCH(launch_render(d, b, cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, cls, s));
+    LAUNCH(launch_render(d, b, cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, cls, h->obs_format, s));
     if (post_step) CUDA_OK(cudaStreamWaitEvent(s, h->ev_score, 0));
     if (split) CUDA_OK(cudaStreamWaitEvent(s, h->ev_chain2, 0));
     return 0;

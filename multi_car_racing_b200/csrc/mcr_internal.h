@@ -111,7 +111,7 @@ int launch_physics_post(const Dims& d, const DevBuffers& b, const CarConst& cc, 
 int launch_presweep(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* noact,
                     const void* action, int action_dtype, int collisions, int with_sweep, void* stream);
 int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* obs,
-                  int backwards_flag, int use_ego_color, int cls, void* stream);
+                  int backwards_flag, int use_ego_color, int cls, int obs_format, void* stream);
 int launch_score(const Dims& d, const DevBuffers& b, const uint8_t* mask, const uint8_t* noact, double* reward, uint8_t* done,
                  int max_episode_steps, int cls, void* stream);
 const uint8_t (*mcr_host_palette())[4];

@@ -74,7 +74,8 @@ const uint8_t (*mcr_host_palette())[4] {
     static uint8_t pal[PAL_COUNT][4];
     for (int i = 0; i < PAL_COUNT; ++i) {
         for (int c = 0; c < 3; ++c) pal[i][c] = (uint8_t)(int)floorf(h_palette_f[i][c] * 255.0f + 0.5f);
-        pal[i][3] = 0;
+        // ITU-R 601 luma in integers (MCR_OBS_GRAY): exact, so tests can restate it with numpy
+        pal[i][3] = (uint8_t)((299 * pal[i][0] + 587 * pal[i][1] + 114 * pal[i][2] + 500) / 1000);
     }
     return pal;
 }
@@ -109,7 +110,8 @@ struct __align__(16) RasterSmem {
     int bc_cnt, bc_rows;
     float red_f[RS_WARPS]; int cand[32]; int n_cand;
     signed char glyph[4];
-    uint32_t pal32[32];
+    uint32_t pal32[32];      // r | g << 8 | b << 16
+    uint32_t palY[32];       // luma (MCR_OBS_GRAY)
 };
 
 __device__ __forceinline__ double py_mod(double a, double m) {
@@ -357,7 +359,7 @@ __device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pi
 
 __global__ void __launch_bounds__(RS_THREADS, 4)
 render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, uint8_t* __restrict__ obs,
-              int backwards_flag, int use_ego_color, int cls) {
+              int backwards_flag, int use_ego_color, int cls, int obs_format) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
     const int frame = blockIdx.x;
@@ -374,6 +376,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     if (tid >= 32 && tid < 32 + PAL_COUNT) {
         const int i = tid - 32;
         S.pal32[i] = (uint32_t)c_palette[i][0] | ((uint32_t)c_palette[i][1] << 8) | ((uint32_t)c_palette[i][2] << 16);
+        S.palY[i] = (uint32_t)c_palette[i][3];
     }
     if (tid == 64) {
         // score label "%04i" % reward  (mcr:665; drawn before reward -= 0.1)
@@ -586,8 +589,9 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
 
     // ---- expand palette -> RGB and store this thread's 32 pixels as 6 x uint4 ------------------------
     // 4 pixels = 12 bytes = 3 words; byte stream r0 g0 b0 r1 g1 b1 ... from packed 0x00BBGGRR
-    {
-        uint4* dst = reinterpret_cast<uint4*>(obs + (size_t)frame * MCR_OBS_BYTES + (size_t)(SH - 1 - my_y) * (SW * 3) + my_seg * 96);
+    const int out_row = SH - 1 - my_y;
+    if (obs_format == MCR_OBS_RGB_HWC) {
+        uint4* dst = reinterpret_cast<uint4*>(obs + (size_t)frame * MCR_OBS_BYTES + (size_t)out_row * (SW * 3) + my_seg * 96);
         uint32_t o[24];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -599,8 +603,25 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
         }
 #pragma unroll
         for (int v = 0; v < 6; ++v) dst[v] = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+    } else {
+        // planar layouts: one byte per pixel and plane, 32 pixels = 2 x uint4 per plane
+        const int planes = obs_format == MCR_OBS_GRAY ? 1 : 3;
+        const size_t frame_bytes = (size_t)planes * SW * SH;
+        for (int c = 0; c < planes; ++c) {
+            const uint32_t* tab = obs_format == MCR_OBS_GRAY ? S.palY : S.pal32;
+            const int sh = 8 * c;
+            uint32_t o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t c0 = (tab[pix[k] & 0xff] >> sh) & 0xffu, c1 = (tab[(pix[k] >> 8) & 0xff] >> sh) & 0xffu;
+                const uint32_t c2 = (tab[(pix[k] >> 16) & 0xff] >> sh) & 0xffu, c3 = (tab[pix[k] >> 24] >> sh) & 0xffu;
+                o[k] = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(obs + (size_t)frame * frame_bytes + (size_t)c * (SW * SH) + (size_t)out_row * SW + my_seg * 32);
+            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
     }
-
 }
 
 
@@ -699,7 +720,7 @@ score_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, const uint8
 }
 
 int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* obs,
-                  int backwards_flag, int use_ego_color, int cls, void* stream) {
+                  int backwards_flag, int use_ego_color, int cls, int obs_format, void* stream) {
     static bool configured = false;
     const size_t smem = sizeof(RasterSmem);
     if (!configured) {
@@ -707,7 +728,7 @@ int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const 
         if (cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         configured = true;
     }
-    render_kernel<<<d.N, RS_THREADS, smem, (cudaStream_t)stream>>>(d, b, cc, mask, obs, backwards_flag, use_ego_color, cls);
+    render_kernel<<<d.N, RS_THREADS, smem, (cudaStream_t)stream>>>(d, b, cc, mask, obs, backwards_flag, use_ego_color, cls, obs_format);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -78,13 +78,15 @@ class BatchedMultiCarRacing:
 
     Constructor kwargs mirror MultiCarRacing.__init__ (reference :131-133); `batch_envs`,
     `device`, the pool/capacity knobs and `max_episode_steps` (the gym registration's TimeLimit,
-    reference __init__.py:8) are additions.
+    reference __init__.py:8) are additions.  `obs_format` selects what the rasteriser stores:
+    'rgb' (B,A,96,96,3) as the reference returns it, 'gray' (B,A,96,96) ITU-R 601 luma, or
+    'rgb_chw' (B,A,3,96,96) -- the learner's first pre-processing stage fused into the store.
     """
 
     def __init__(self, batch_envs, num_agents=2, verbose=0, direction='CCW', use_random_direction=True,
                  backwards_flag=True, h_ratio=0.25, use_ego_color=False, device=None,
                  max_tiles=MAX_TILES_DEFAULT, max_quads=MAX_QUADS_DEFAULT, pool_tracks=None,
-                 max_episode_steps=1000, auto_reset=True, seed=None, collisions=True):
+                 max_episode_steps=1000, auto_reset=True, seed=None, collisions=True, obs_format='rgb'):
         torch = _torch()
         if not torch.cuda.is_available():
             raise _lib.McrError("multi_car_racing_b200 needs a CUDA device (B200, sm_100a); none is visible")
@@ -130,7 +132,13 @@ class BatchedMultiCarRacing:
                 self.buffers[name.value.decode()] = t
                 _lib.check(self.L.mcr_bind_buffer(self._h, i, t.data_ptr()), "mcr_bind_buffer")
             B, A = self.batch_envs, self.num_agents
-            self.obs = torch.zeros((B, A, STATE_H, STATE_W, 3), dtype=torch.uint8, device=self.device)
+            if obs_format not in _lib.OBS_FORMATS:
+                raise ValueError("obs_format must be one of %s" % sorted(_lib.OBS_FORMATS))
+            self.obs_format = obs_format
+            _lib.check(self.L.mcr_set_obs_format(self._h, _lib.OBS_FORMATS[obs_format]), "mcr_set_obs_format")
+            self.obs_shape = {"rgb": (STATE_H, STATE_W, 3), "gray": (STATE_H, STATE_W), "rgb_chw": (3, STATE_H, STATE_W)}[obs_format]
+            assert int(np.prod(self.obs_shape)) == int(self.L.mcr_obs_bytes(self._h))
+            self.obs = torch.zeros((B, A) + self.obs_shape, dtype=torch.uint8, device=self.device)
             self.reward_out = torch.zeros((B, A), dtype=torch.float64, device=self.device)
             self.done_out = torch.zeros((B,), dtype=torch.uint8, device=self.device)
             self._slot = torch.zeros((B,), dtype=torch.int32, device=self.device)
@@ -141,7 +149,7 @@ class BatchedMultiCarRacing:
         self.episode_direction = [direction] * self.batch_envs
         self.car_order = [None] * self.batch_envs
         self.action_space = _make_box(np.array([-1, 0, 0]), np.array([+1, +1, +1]), dtype=np.float32)
-        self.observation_space = _make_box(0, 255, shape=(STATE_H, STATE_W, 3), dtype=np.uint8)
+        self.observation_space = _make_box(0, 255, shape=self.obs_shape, dtype=np.uint8)
         self.seed(seed)
 
     # ---- plumbing ---------------------------------------------------------------------------
@@ -274,7 +282,7 @@ class BatchedMultiCarRacing:
             self._host = dict(
                 action=torch.zeros((B, A, 3), dtype=torch.float32).pin_memory(),
                 action64=torch.zeros((B, A, 3), dtype=torch.float64).pin_memory(),
-                obs=torch.zeros((B, A, STATE_H, STATE_W, 3), dtype=torch.uint8).pin_memory(),
+                obs=torch.zeros((B, A) + self.obs_shape, dtype=torch.uint8).pin_memory(),
                 reward=torch.zeros((B, A), dtype=torch.float64).pin_memory(),
                 done=torch.zeros((B,), dtype=torch.uint8).pin_memory())
             # the library's own action staging buffer (what its CUDA graph reads): copying the host

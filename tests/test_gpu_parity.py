@@ -101,6 +101,35 @@ def test_render_options(oracle, mcr, kw):
             assert np.array_equal(obs.cpu().numpy(), np.stack([x[0] for x in oo])), "pixels, step %d" % s
 
 
+def _reformat(rgb, fmt):
+    """numpy restatement of the fused store layouts (include/mcr.h MCR_OBS_*) applied to oracle frames."""
+    if fmt == "gray":
+        c = rgb.astype(np.int64)
+        return ((299 * c[..., 0] + 587 * c[..., 1] + 114 * c[..., 2] + 500) // 1000).astype(np.uint8)
+    if fmt == "rgb_chw":
+        return np.ascontiguousarray(np.moveaxis(rgb, -1, -3))
+    return rgb
+
+
+@pytest.mark.parametrize("fmt", ["gray", "rgb_chw"])
+def test_fused_observation_formats(oracle, mcr, fmt):
+    """grayscale / planar layouts written straight from the rasteriser's registers;
+    bit-exact against the oracle's RGB frame pushed through the same integer formula.  Covers the
+    reset frame, eager steps and CUDA-graph replayed steps (the graph bakes the layout in)."""
+    import torch
+    venv, worlds, tracks, obs0, oobs0 = _setup(oracle, mcr, B=2, A=2, seed=21, obs_format=fmt)
+    assert obs0.shape == oobs0.shape[:2] + ({"gray": (96, 96), "rgb_chw": (3, 96, 96)}[fmt])
+    assert np.array_equal(obs0, _reformat(oobs0, fmt))
+    tape = action_tape(21, 40, 2, 2)
+    for s in range(40):
+        obs, _, _, _ = venv.step(torch.from_numpy(tape[s]).to(venv.device))
+        oo = np.stack([w.step(tape[s, e].astype(np.float64))[0] for e, w in enumerate(worlds)])
+        if s % 5 == 0 or s < 4:
+            assert np.array_equal(obs.cpu().numpy(), _reformat(oo, fmt)), "%s pixels, step %d" % (fmt, s)
+    hobs, _, _, _ = venv.step_host(tape[0])
+    assert hobs.shape == obs.shape
+
+
 def test_single_env_dropin_matches_oracle_env(oracle, mcr):
     """The reference-shaped API end to end: same seeds -> same tracks, spawn, rewards, frames."""
     np.random.seed(5)

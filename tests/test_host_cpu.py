@@ -115,6 +115,21 @@ def test_spawn_grid_matches_oracle(mcr, oracle):
             assert np.array_equal(p1, p2)
 
 
+def test_obs_format_abi(mcr):
+    """mcr_set_obs_format / mcr_obs_bytes are host-only calls: exercised without a GPU."""
+    import ctypes
+    from multi_car_racing_b200 import _lib
+    L = _lib.load()
+    cfg = _lib.McrConfig(2, 2, 512, 1024, 2, 1, 0, 1000, 0.25, 0, 1, 0, 1, 0)
+    h = ctypes.c_void_p()
+    assert L.mcr_create(ctypes.byref(cfg), ctypes.byref(h)) == 0
+    assert L.mcr_obs_bytes(h) == 96 * 96 * 3
+    assert L.mcr_set_obs_format(h, _lib.OBS_FORMATS["gray"]) == 0 and L.mcr_obs_bytes(h) == 96 * 96
+    assert L.mcr_set_obs_format(h, _lib.OBS_FORMATS["rgb_chw"]) == 0 and L.mcr_obs_bytes(h) == 96 * 96 * 3
+    assert L.mcr_set_obs_format(h, 7) < 0 and b"unknown format" in L.mcr_last_error()
+    L.mcr_destroy(h)
+
+
 def test_python_surface_without_gpu(mcr):
     import torch
     if torch.cuda.is_available():
