@@ -100,6 +100,20 @@ int mcr_spawn_poses(const double* h_nodes, int32_t T, const int32_t* car_order, 
 int mcr_load_track(mcr_handle h, int32_t slot, int32_t T, const double* h_nodes, int32_t Q,
                    const double* h_quads, const float* h_quad_rgb, const int32_t* h_quad_tile, void* stream);
 
+/* On-device batched generation (replaces the `while True: success = self._create_track()` loop of
+ * reset(), mcr:359-364, for n tracks at once, one GPU thread per track): track i consumes the
+ * MT19937 stream d_mt_state[i][625] (in/out, same layout as mcr_track_generate's) exactly like the
+ * host generator -- same uniforms, same float64 operation order -- and is written straight into
+ * pool slot d_slot[i] (tiles, AABBs, road_poly quads, palette, culling chunks, spawn grid).  CUDA's
+ * fp64 sin/cos/atan2 differ from glibc's by <= 1-2 ulp, so node coordinates agree with the host
+ * generator to ~1e-12 rather than bit for bit; the host generator remains the bit-exact path.
+ * d_scratch: n * mcr_trackgen_scratch_bytes() bytes; afterwards track i's path nodes
+ * (alpha, beta, x, y) f64 are rows [i1, i1 + T) of its scratch block.
+ * d_result[i][4] = { T (> 0) or an error code (< 0), attempts, i1, i2 }. */
+int mcr_tracks_generate_device(mcr_handle h, int32_t n, uint32_t* d_mt_state, const int32_t* d_slot,
+                               void* d_scratch, int32_t* d_result, void* stream);
+int64_t mcr_trackgen_scratch_bytes(void);
+
 /* ---- reset (replaces MultiCarRacing.reset, mcr:340-408) -------------------------------- */
 /* For every env with d_env_mask[env] != 0 (NULL = all): bind track slot d_track_slot[env],
  * direction d_cw[env], create the cars at d_spawn_pose[env][A][3] (f64: angle,x,y), zero the

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmcr.so")
-SOURCES = ["api.cu", "sim.cu", "carcontacts.cu", "raster.cu", "reset.cu"]
+SOURCES = ["api.cu", "sim.cu", "carcontacts.cu", "raster.cu", "reset.cu", "trackgen.cu"]
 HEADERS = [os.path.join(CSRC, "mcr_internal.h"), os.path.join(CSRC, "solver.cuh"), os.path.join(HERE, "..", "include", "mcr.h")]
 
 NVCC_FLAGS = [

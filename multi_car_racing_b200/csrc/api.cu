@@ -676,6 +676,15 @@ extern "C" int mcr_load_track(mcr_handle h, int32_t slot, int32_t T, const doubl
 // ---------------------------------------------------------------------------------------
 #define LAUNCH(expr) do { int n_ = (expr); if (n_ < 0) return fail(-101, "kernel launch failed in %s: %s", #expr, cudaGetErrorString(cudaGetLastError())); h->launches += n_; } while (0)
 
+extern "C" int mcr_tracks_generate_device(mcr_handle h, int32_t n, uint32_t* d_mt_state, const int32_t* d_slot,
+                                          void* d_scratch, int32_t* d_result, void* stream) {
+    int rc = check_bound(h); if (rc) return rc;
+    if (n < 1 || !d_mt_state || !d_slot || !d_scratch || !d_result) return fail(-1, "mcr_tracks_generate_device: bad arguments");
+    CUDA_OK(cudaSetDevice(h->cfg.device));
+    LAUNCH(launch_trackgen(h->d, h->buf, n, d_mt_state, d_slot, d_scratch, d_result, 64, stream));
+    return 0;
+}
+
 static int ensure_side(mcr_handle h) {
     if (!h->side_ready) {
         CUDA_OK(cudaSetDevice(h->cfg.device));

@@ -115,6 +115,8 @@ int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const 
 int launch_score(const Dims& d, const DevBuffers& b, const uint8_t* mask, const uint8_t* noact, double* reward, uint8_t* done,
                  int max_episode_steps, int cls, void* stream);
 const uint8_t (*mcr_host_palette())[4];
+int launch_trackgen(const Dims& d, const DevBuffers& b, int n, uint32_t* mt_state, const int32_t* slots, void* scratch,
+                    int32_t* result, int max_attempts, void* stream);
 int launch_spawn(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
                  const int32_t* track_slot, const uint8_t* cw, const double* spawn_pose, void* stream);
 struct AutoResetCfg { int use_random_direction, direction_cw; unsigned long long seed; };

@@ -99,7 +99,7 @@ struct __align__(16) RasterSmem {
     uint16_t off[LIST_CAP];       // first span slot (continuations: the next polygon's)
     uint8_t ne[LIST_CAP], col[LIST_CAP];
     uchar2 span[SPAN_POOL];
-    uint32_t rowmask[SH * 3][MASK_WORDS];   // per (row, 32-pixel segment): polygons whose span touches it
+    uint32_t rowmask[MASK_WORDS][SH * 3];   // per (32-pixel segment, row) = fill thread: polygons whose span touches it (word-major: conflict-free)
     Affine M;
     int first_bad;
     int ck_j0x, ck_nx, ck_j0y, ck_ny;   // visible checker index range
@@ -278,7 +278,7 @@ __device__ __forceinline__ void edge_row(const RasterSmem& S, int e, int p, floa
     }
 }
 
-__device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pix)[8], int n, int nslots) {
+__device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pix)[8], int n, int nslots, bool last) {
     __syncthreads();
     // ---- spans: one thread per (polygon,row) slot ---------------------------------------------
     for (int s = tid; s < nslots; s += RS_THREADS) {
@@ -308,7 +308,7 @@ __device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pi
         if (x0 < x1) {
             const uint32_t bit = 1u << (p & 31);
             const int g0 = x0 >> 5, g1 = (x1 - 1) >> 5;
-            for (int g = g0; g <= g1; ++g) atomicOr(&S.rowmask[row * 3 + g][p >> 5], bit);
+            for (int g = g0; g <= g1; ++g) atomicOr(&S.rowmask[p >> 5][g * SH + row], bit);
         }
     }
     __syncthreads();
@@ -316,11 +316,13 @@ __device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pi
     // pix[k] holds the palette indices of pixels 4k..4k+3 of this thread's segment.  Polygons of a
     // later flush are later in painter's order, so they overwrite what earlier flushes left.
     {
-        const int y = tid / 3, seg = tid - 3 * y;
+        // thread = (segment, row) with the row fastest: a warp walks 32 consecutive rows of one segment
+        // column, whose polygon lists are nearly the same (little divergence in the loop below)
+        const int seg = tid / SH, y = tid - SH * seg;
         const int xs = 32 * seg;
         uint32_t uncovered = 0xffffffffu;
-        for (int wd = MASK_WORDS - 1; wd >= 0 && uncovered; --wd) {
-            uint32_t m = S.rowmask[tid][wd];               // tid == y * 3 + seg
+        for (int wd = (n - 1) >> 5; wd >= 0 && uncovered; --wd) {
+            uint32_t m = S.rowmask[wd][tid];               // tid == seg * SH + y
             while (m && uncovered) {
                 const int bit = 31 - __clz(m);
                 m &= ~(1u << bit);
@@ -352,6 +354,7 @@ __device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pi
             }
         }
     }
+    if (last) return;                                  // nothing reads the list or the masks again
     __syncthreads();
     for (int i = tid; i < SH * 3 * MASK_WORDS; i += RS_THREADS) (&S.rowmask[0][0])[i] = 0;
     __syncthreads();
@@ -562,16 +565,16 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
             __syncthreads();
             lc = S.bc_cnt; pc = S.bc_rows;
             base += first_bad;
-            flush_list(S, tid, pix, lc, pc);
+            flush_list(S, tid, pix, lc, pc, false);
             lc = 0; pc = 0;
         } else {
             lc += cnt_total; pc += rows_total;
             base += RS_THREADS;
         }
     }
-    flush_list(S, tid, pix, lc, pc);
+    flush_list(S, tid, pix, lc, pc, true);
 
-    const int my_y = tid / 3, my_seg = tid - 3 * my_y;
+    const int my_seg = tid / SH, my_y = tid - SH * my_seg;
     // ---- score label glyphs (D3): observation rows 87..91 (= GL rows 8..4), cols 2..13 -------------
     if (my_seg == 0 && my_y >= 4 && my_y <= 8) {
         const int ry = (SH - 1 - my_y) - 87;

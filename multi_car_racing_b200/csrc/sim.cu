@@ -248,13 +248,16 @@ contacts_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ m
     contacts_warp(d, b, cc, env, lane, sim_smem + (size_t)warp * smem_per_warp);
 }
 
+// pre/post are per-thread latency chains (fp64 division / sqrt / sincos); block size 32..128 measured equal
+
 #define PRE_BLOCK 128
+static int pre_block() { const char* e = getenv("MCR_PRE_BLOCK"); const int v = e ? atoi(e) : PRE_BLOCK; return (v == 32 || v == 64 || v == 128) ? v : PRE_BLOCK; }   // tuning knob
 
 template <typename ActT>
-__global__ void __launch_bounds__(PRE_BLOCK)
+__global__ void __launch_bounds__(128)
 pre_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ noact,
            const ActT* __restrict__ action) {
-    const int car = blockIdx.x * PRE_BLOCK + threadIdx.x;
+    const int car = blockIdx.x * blockDim.x + threadIdx.x;
     if (car >= d.N) return;
     const int env = car / d.A;
     if (mask && !mask[env]) return;
@@ -486,10 +489,10 @@ sweep_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask
     }
 }
 
-__global__ void __launch_bounds__(PRE_BLOCK)
+__global__ void __launch_bounds__(128)
 post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ noact, int has_action,
             double h_ratio, int cls) {
-    const int car = blockIdx.x * PRE_BLOCK + threadIdx.x;
+    const int car = blockIdx.x * blockDim.x + threadIdx.x;
     if (car >= d.N) return;
     const int env = car / d.A;
     if (mask && !mask[env]) return;
@@ -680,9 +683,9 @@ int launch_physics(const Dims& d, const DevBuffers& b, const CarConst& cc, const
     cudaStream_t s = (cudaStream_t)stream;
     int launched = 0;
     if (collisions && d.A > 1) { if (launch_carcontacts(d, b, cc, mask, stream) < 0) return -1; ++launched; }
-    const int nb = (d.N + PRE_BLOCK - 1) / PRE_BLOCK;
-    if (action_dtype == MCR_F64) pre_kernel<double><<<nb, PRE_BLOCK, 0, s>>>(d, b, cc, mask, noact, (const double*)action);
-    else pre_kernel<float><<<nb, PRE_BLOCK, 0, s>>>(d, b, cc, mask, noact, (const float*)action);
+    const int pb = pre_block(), nb = (d.N + pb - 1) / pb;
+    if (action_dtype == MCR_F64) pre_kernel<double><<<nb, pb, 0, s>>>(d, b, cc, mask, noact, (const double*)action);
+    else pre_kernel<float><<<nb, pb, 0, s>>>(d, b, cc, mask, noact, (const float*)action);
     const int packed_ctas = (d.N + SWEEP_BLOCK - 1) / SWEEP_BLOCK, percar_ctas = (d.N + SWEEP_BLOCK / 32 - 1) / (SWEEP_BLOCK / 32);
     sweep_kernel<<<packed_ctas + percar_ctas, SWEEP_BLOCK, 0, s>>>(d, b, cc, mask, early_exit, packed_ctas);
     launched += 2;
@@ -699,9 +702,9 @@ int launch_presweep(const Dims& d, const DevBuffers& b, const CarConst& cc, cons
     int launched = 0;
     if (!with_sweep) {
         if (collisions && d.A > 1) { if (launch_carcontacts(d, b, cc, mask, stream) < 0) return -1; ++launched; }
-        const int nb = (d.N + PRE_BLOCK - 1) / PRE_BLOCK;
-        if (action_dtype == MCR_F64) pre_kernel<double><<<nb, PRE_BLOCK, 0, s>>>(d, b, cc, mask, noact, (const double*)action);
-        else pre_kernel<float><<<nb, PRE_BLOCK, 0, s>>>(d, b, cc, mask, noact, (const float*)action);
+        const int pb = pre_block(), nb = (d.N + pb - 1) / pb;
+        if (action_dtype == MCR_F64) pre_kernel<double><<<nb, pb, 0, s>>>(d, b, cc, mask, noact, (const double*)action);
+        else pre_kernel<float><<<nb, pb, 0, s>>>(d, b, cc, mask, noact, (const float*)action);
         ++launched;
     } else {
         const int packed_ctas = (d.N + SWEEP_BLOCK - 1) / SWEEP_BLOCK, percar_ctas = (d.N + SWEEP_BLOCK / 32 - 1) / (SWEEP_BLOCK / 32);
@@ -715,7 +718,7 @@ int launch_presweep(const Dims& d, const DevBuffers& b, const CarConst& cc, cons
 // start poses and writing on_road_next (the API joins the side stream before calling this).
 int launch_physics_post(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* noact,
                         int has_action, double h_ratio, int cls, void* stream) {
-    const int nb = (d.N + PRE_BLOCK - 1) / PRE_BLOCK;
-    post_kernel<<<nb, PRE_BLOCK, 0, (cudaStream_t)stream>>>(d, b, cc, mask, noact, has_action, h_ratio, cls);
+    const int pb = pre_block(), nb = (d.N + pb - 1) / pb;
+    post_kernel<<<nb, pb, 0, (cudaStream_t)stream>>>(d, b, cc, mask, noact, has_action, h_ratio, cls);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

@@ -193,14 +193,20 @@ class BatchedMultiCarRacing:
         self.tracks[slot] = track
 
     # ---- reset, reference :340-408 ---------------------------------------------------------------
-    def reset(self, tracks=None, car_orders=None, directions=None):
+    def reset(self, tracks=None, car_orders=None, directions=None, device_tracks=False):
         """Reset every env.  RNG usage per env follows the reference: direction and car order from
         the GLOBAL numpy RNG (:351-357), the track from the env's own RandomState (:359-364).
-        `tracks` / `car_orders` / `directions` inject host-made values (parity tests)."""
+        `tracks` / `car_orders` / `directions` inject host-made values (parity tests).
+        device_tracks=True generates all tracks on the GPU (mcr_tracks_generate_device, one thread
+        per track on the env's own MT19937 stream) instead of one by one on the host -- same draws,
+        same arithmetic, CUDA libm instead of glibc (coordinates agree to ~1e-12, not bit for bit)."""
         torch = _torch()
         B, A = self.batch_envs, self.num_agents
         poses = np.empty((B, A, 3), np.float64)
         cws = np.empty((B,), np.uint8)
+        orders = np.empty((B, A), np.int64)
+        if device_tracks and tracks is not None:
+            raise ValueError("device_tracks=True generates the tracks itself; do not pass `tracks`")
         for e in range(B):
             if directions is not None:
                 self.episode_direction[e] = directions[e]
@@ -211,21 +217,80 @@ class BatchedMultiCarRacing:
             else:
                 order = np.random.choice([i for i in range(A)], size=A, replace=False)
             self.car_order[e] = {i: order[i] for i in range(A)}
-            tr = tracks[e] if tracks is not None else self._gen.generate(self.np_randoms[e], self.verbose)
-            self.load_track(e, tr)
+            orders[e] = order
             cws[e] = self.episode_direction[e] == 'CW'
-            poses[e] = self._gen.spawn_poses(tr.nodes, order, cws[e])
-        # extra pool slots (device-side auto reset draws from the whole pool)
-        for s in range(B, self.pool_tracks):
-            if self.tracks[s] is None:
-                self.load_track(s, self._gen.generate(self.np_randoms[s % B], 0))
+            if not device_tracks:
+                tr = tracks[e] if tracks is not None else self._gen.generate(self.np_randoms[e], self.verbose)
+                self.load_track(e, tr)
+                poses[e] = self._gen.spawn_poses(tr.nodes, order, cws[e])
+        if device_tracks:
+            # every pool slot in rounds of B: slot s draws from env (s % B)'s stream, like the host path
+            for s0 in range(0, self.pool_tracks, B):
+                slots = list(range(s0, min(s0 + B, self.pool_tracks)))
+                if s0 == 0 or any(self.tracks[s] is None for s in slots):
+                    self.generate_tracks_device(slots, [self.np_randoms[s % B] for s in slots])
+        else:
+            # extra pool slots (device-side auto reset draws from the whole pool)
+            for s in range(B, self.pool_tracks):
+                if self.tracks[s] is None:
+                    self.load_track(s, self._gen.generate(self.np_randoms[s % B], 0))
         with torch.cuda.device(self.device):
             self._slot.copy_(torch.arange(B, dtype=torch.int32))
             self._cw.copy_(torch.from_numpy(cws))
-            self._pose.copy_(torch.from_numpy(poses))
+            if device_tracks:
+                # spawn grid poses were evaluated per slot / direction / grid position by the generator
+                sp = self.buffers["trk_slot_pose"]                     # (P, 2, A, 3)
+                e_idx = torch.arange(B, device=self.device).view(B, 1).expand(B, A)
+                cw_idx = torch.from_numpy(cws.astype(np.int64)).to(self.device).view(B, 1).expand(B, A)
+                self._pose.copy_(sp[e_idx, cw_idx, torch.from_numpy(orders).to(self.device)])
+            else:
+                self._pose.copy_(torch.from_numpy(poses))
             _lib.check(self.L.mcr_reset(self._h, None, self._slot.data_ptr(), self._cw.data_ptr(),
                                         self._pose.data_ptr(), self.obs.data_ptr(), self._stream()), "mcr_reset")
         return self.obs
+
+    def generate_tracks_device(self, slots, rngs):
+        """Generate len(slots) tracks on the GPU into the given pool slots, each on its own numpy
+        RandomState (MT19937) stream, which is advanced exactly as the host generator would.
+        Fills self.tracks[slot] with DeviceTrack views.  Returns the (n, 4) int32 result rows
+        (T, attempts, i1, i2)."""
+        torch = _torch()
+        n = len(slots)
+        mt = np.empty((n, 625), np.uint32)
+        states = []
+        for i, rng in enumerate(rngs):
+            st = rng.get_state()
+            assert st[0] == "MT19937"
+            mt[i, :624] = st[1]
+            mt[i, 624] = st[2]
+            states.append(st)
+        stride = int(self.L.mcr_trackgen_scratch_bytes())
+        with torch.cuda.device(self.device):
+            d_mt = torch.from_numpy(mt.view(np.int32)).to(self.device)
+            d_slot = torch.tensor(list(slots), dtype=torch.int32, device=self.device)
+            d_scratch = torch.empty((n, stride), dtype=torch.uint8, device=self.device)
+            d_res = torch.zeros((n, 4), dtype=torch.int32, device=self.device)
+            _lib.check(self.L.mcr_tracks_generate_device(self._h, n, d_mt.data_ptr(), d_slot.data_ptr(), d_scratch.data_ptr(),
+                                                         d_res.data_ptr(), self._stream()), "mcr_tracks_generate_device")
+            res = d_res.cpu().numpy()
+            if (res[:, 0] <= 0).any():
+                bad = int(np.argmax(res[:, 0] <= 0))
+                raise _lib.McrError("device track generation failed for slot %d: code %d (-3: more tiles than max_tiles, "
+                                    "-4: more quads than max_quads, -5: no valid track in 64 attempts)" % (slots[bad], res[bad, 0]))
+            mt_out = d_mt.cpu().numpy().view(np.uint32)
+            # path nodes (alpha, beta, x, y) of every track: rows [i1, i1 + T) of its scratch block
+            path = d_scratch[:, :2600 * 32].view(torch.float64).view(n, 2600, 4)
+            rows = (d_res[:, 2].long().view(n, 1) + torch.arange(self.max_tiles, device=self.device).view(1, -1)).clamp_(max=2599)
+            nodes = torch.gather(path, 1, rows.view(n, -1, 1).expand(n, self.max_tiles, 4)).cpu().numpy()
+        for i, rng in enumerate(rngs):
+            st = states[i]
+            rng.set_state((st[0], mt_out[i, :624].copy(), int(mt_out[i, 624]), st[3], st[4]))
+            T = int(res[i, 0])
+            self.tracks[slots[i]] = DeviceTrack(self, slots[i], nodes[i, :T].copy(), (int(res[i, 2]), int(res[i, 3])), int(res[i, 1]))
+        if self.verbose == 1:
+            for i in range(n):
+                print("Track generation: %i..%i -> %i-tiles track" % (res[i, 2], res[i, 3], res[i, 3] - res[i, 2]))
+        return res
 
     # ---- step, reference :410-509 ------------------------------------------------------------------
     def step(self, action):
@@ -352,6 +417,41 @@ class BatchedMultiCarRacing:
         out = np.empty(16, np.float32)
         n = _lib.check(self.L.mcr_get_shape(self._h, which, out.ctypes.data), "mcr_get_shape")
         return out[:2 * n].reshape(n, 2).copy()
+
+
+class DeviceTrack:
+    """A track generated on the GPU: nodes (alpha, beta, x, y) float64 on the host; the road_poly
+    quads are read back from the pool on demand (fp32 -- what GL and Box2D see of them)."""
+
+    def __init__(self, venv, slot, nodes, idx_range, attempts):
+        self._venv, self.slot, self.nodes, self.idx_range, self.attempts = venv, slot, nodes, idx_range, attempts
+
+    @property
+    def T(self):
+        return len(self.nodes)
+
+    @property
+    def Q(self):
+        return int(self._venv.buffers["trk_Q"][self.slot].item())
+
+    @property
+    def quads(self):
+        return self._venv.buffers["trk_quad"][self.slot, :self.Q].cpu().numpy().astype(np.float64).reshape(-1, 4, 2)
+
+    @property
+    def quad_tile(self):
+        return self._venv.buffers["trk_quad_tile"][self.slot, :self.Q].cpu().numpy().astype(np.int32)
+
+    @property
+    def quad_pal(self):
+        return self._venv.buffers["trk_quad_col"][self.slot, :self.Q].cpu().numpy()
+
+    @property
+    def quad_rgb(self):
+        """road_poly colours as _create_track leaves them (reference :316-317, :331-332), float32."""
+        c = [np.float32(0.4 + 0.01 * i) for i in range(3)]
+        table = {3: (c[0],) * 3, 4: (c[1],) * 3, 5: (c[2],) * 3, 6: (1.0, 1.0, 1.0), 7: (1.0, 0.0, 0.0)}
+        return np.array([table[int(p)] for p in self.quad_pal], np.float32)
 
 
 class _Vec2(tuple):
