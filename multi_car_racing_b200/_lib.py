@@ -18,7 +18,7 @@ EXPORTS = [
     "mcr_buffer_spec", "mcr_bind_buffer", "mcr_track_generate", "mcr_mt_seed", "mcr_spawn_poses",
     "mcr_load_track", "mcr_reset", "mcr_step", "mcr_simulate", "mcr_contacts", "mcr_physics", "mcr_render",
     "mcr_get_mass", "mcr_get_shape", "mcr_launch_count", "mcr_set_obs_format", "mcr_obs_bytes",
-    "mcr_tracks_generate_device", "mcr_trackgen_scratch_bytes",
+    "mcr_tracks_generate_device", "mcr_trackgen_scratch_bytes", "mcr_render_viewport",
 ]
 OBS_FORMATS = {"rgb": 0, "gray": 1, "rgb_chw": 2}     # MCR_OBS_RGB_HWC / MCR_OBS_GRAY / MCR_OBS_RGB_CHW
 
@@ -101,6 +101,8 @@ def load():
     L.mcr_tracks_generate_device.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.mcr_trackgen_scratch_bytes.restype = i64
     L.mcr_trackgen_scratch_bytes.argtypes = []
+    L.mcr_render_viewport.restype = i32
+    L.mcr_render_viewport.argtypes = [vp, vp, i32, i32, vp, vp]
     if L.mcr_abi_version() != 1:
         raise McrError("libmcr.so ABI version mismatch")
     _lib = L

@@ -455,6 +455,7 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
     set_spec(h, BUF_BACKWARD_SNAP, "backward_snap", MCR_U8, {N});
     set_spec(h, BUF_PENDING, "pending_reset", MCR_U8, {B});
     set_spec(h, BUF_ACTION_STAGE, "action_stage", MCR_F64, {N, 3});
+    set_spec(h, BUF_CAMERA_VP, "camera_vp", MCR_F32, {6, N});
     set_spec(h, BUF_TRK_T, "trk_T", MCR_I32, {P});
     set_spec(h, BUF_TRK_Q, "trk_Q", MCR_I32, {P});
     set_spec(h, BUF_TRK_NODE, "trk_node", MCR_F64, {P, T, 3});
@@ -529,6 +530,7 @@ extern "C" int mcr_bind_buffer(mcr_handle h, int i, void* p) {
         case BUF_BACKWARD_SNAP: b.backward_snap = (uint8_t*)p; break;
         case BUF_PENDING: b.pending = (uint8_t*)p; break;
         case BUF_ACTION_STAGE: b.action_stage = (double*)p; break;
+        case BUF_CAMERA_VP: b.camera_vp = (float*)p; break;
         case BUF_TRK_T: b.trk_T = (int32_t*)p; break;
         case BUF_TRK_Q: b.trk_Q = (int32_t*)p; break;
         case BUF_TRK_NODE: b.trk_node = (double*)p; break;
@@ -761,6 +763,15 @@ extern "C" int mcr_render(mcr_handle h, const uint8_t* mask, uint8_t* obs, doubl
     if (!obs) return fail(-1, "mcr_render: d_obs is null");
     if (post_step && (!reward || !done)) return fail(-1, "mcr_render: post_step needs d_reward and d_done");
     return render_and_score(h, mask, obs, reward, done, post_step, stream);
+}
+
+extern "C" int mcr_render_viewport(mcr_handle h, const uint8_t* mask, int32_t vw, int32_t vh, uint8_t* out, void* stream) {
+    int rc = check_bound(h); if (rc) return rc;
+    if (!out) return fail(-1, "mcr_render_viewport: d_out is null");
+    if (vw < 8 || vh < 8 || vw > 4096 || vh > 4096 || (vw & 3)) return fail(-1, "mcr_render_viewport: viewport must be 8..4096 pixels, width a multiple of 4");
+    LAUNCH(launch_render_viewport(h->d, h->buf, h->cc, mask, out, h->buf.camera_vp, vw, vh, h->cfg.h_ratio,
+                                  h->cfg.backwards_flag, h->cfg.use_ego_color, stream));
+    return 0;
 }
 
 static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, const void* action, int32_t action_dtype,

@@ -43,7 +43,7 @@ enum {
     BUF_ON_ROAD, BUF_ON_ROAD_NEXT, BUF_REWARD, BUF_PREV_REWARD, BUF_VISIT_COUNT, BUF_BACKWARD,
     BUF_TIME, BUF_STEPS, BUF_CAMERA, BUF_STRIPE, BUF_HEADING,
     BUF_ENV_TRACK, BUF_ENV_CW, BUF_ENV_EPISODE,
-    BUF_VISITED, BUF_TOUCHED, BUF_RESET_MASK, BUF_STATUS, BUF_SCRATCH, BUF_MANIFOLD, BUF_N_MANIFOLD, BUF_SCORE_SNAP, BUF_BACKWARD_SNAP, BUF_PENDING, BUF_ACTION_STAGE,
+    BUF_VISITED, BUF_TOUCHED, BUF_RESET_MASK, BUF_STATUS, BUF_SCRATCH, BUF_MANIFOLD, BUF_N_MANIFOLD, BUF_SCORE_SNAP, BUF_BACKWARD_SNAP, BUF_PENDING, BUF_ACTION_STAGE, BUF_CAMERA_VP,
     BUF_TRK_T, BUF_TRK_Q, BUF_TRK_NODE, BUF_TRK_TILE, BUF_TRK_TILE_AABB, BUF_TRK_QUAD, BUF_TRK_QUAD_COL,
     BUF_TRK_QUAD_TILE, BUF_TRK_SLOT_POSE, BUF_TRK_CHUNK,
     BUF_COUNT
@@ -89,6 +89,7 @@ struct DevBuffers {
     double* score_snap; uint8_t* backward_snap;   // [N] env.reward / driving_backward as the render of this step sees them
     uint8_t* pending;                    // [B] done flags of the previous step (next-step auto reset)
     double* action_stage;                // [N][3] f64-sized staging copy of the step's action (CUDA-graph replay reads it)
+    float* camera_vp;                    // [6][N] camera affine of the last mcr_render_viewport call
     int32_t* trk_T; int32_t* trk_Q; double* trk_node; float* trk_tile; float* trk_tile_aabb;
     float* trk_quad; uint8_t* trk_quad_col; int16_t* trk_quad_tile; double* trk_slot_pose;
     float* trk_chunk;                    // [P][Qmax/8][4] bounding circle (cx, cy, r, 0) of 8 consecutive road_poly quads
@@ -114,6 +115,9 @@ int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const 
                   int backwards_flag, int use_ego_color, int cls, int obs_format, void* stream);
 int launch_score(const Dims& d, const DevBuffers& b, const uint8_t* mask, const uint8_t* noact, double* reward, uint8_t* done,
                  int max_episode_steps, int cls, void* stream);
+// render(mode) for a vw x vh viewport (rgb_array: 600 x 400): camera_kernel + tiled render_kernel<true>
+int launch_render_viewport(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* out, float* cam,
+                           int vw, int vh, double h_ratio, int backwards_flag, int use_ego_color, void* stream);
 const uint8_t (*mcr_host_palette())[4];
 int launch_trackgen(const Dims& d, const DevBuffers& b, int n, uint32_t* mt_state, const int32_t* slots, void* scratch,
                     int32_t* result, int max_attempts, void* stream);

@@ -129,6 +129,7 @@ struct View {
     const float* body; const double* wheel; const float* stripe;
     const float* quad; const uint8_t* quad_col; const int16_t* quad_tile; const uint8_t* touched;
     int use_ego_color, backward_flag_on;
+    float hud_sx, hud_sy;                // window (1000 x 800) -> viewport pixels: (float)(vw / 1000.0), (float)(vh / 800.0)
 };
 
 __device__ __forceinline__ void xf_pt(const Affine& M, float x, float y, float& ox, float& oy) {
@@ -261,8 +262,8 @@ __device__ int gen_candidate(int i, const View& V, const Affine& M, const CarCon
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            px[k] = (float)wx[k] * (float)(96.0 / 1000.0);
-            py[k] = (float)wy[k] * (float)(96.0 / 800.0);
+            px[k] = (float)wx[k] * V.hud_sx;
+            py[k] = (float)wy[k] * V.hud_sy;
         }
         return n;
     }
@@ -278,7 +279,12 @@ __device__ __forceinline__ void edge_row(const RasterSmem& S, int e, int p, floa
     }
 }
 
-__device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pix)[8], int n, int nslots, bool last) {
+// (ox, oy) = viewport pixel of the tile's lower-left corner, vw = viewport width: every edge is
+// evaluated in VIEWPORT coordinates (identical arithmetic for any tiling), only the resulting
+// integer span is moved into the tile.  The 96 x 96 state frame is the single tile (0, 0).
+template <bool VP>
+__device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pix)[8], int n, int nslots, bool last,
+                                           int ox, int oy, int vw) {
     __syncthreads();
     // ---- spans: one thread per (polygon,row) slot ---------------------------------------------
     for (int s = tid; s < nslots; s += RS_THREADS) {
@@ -289,7 +295,7 @@ __device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pi
         }
         const int p = lo;
         const int row = s - S.base[p];
-        const float yc = (float)row + 0.5f;
+        const float yc = (float)(VP ? row + oy : row) + 0.5f;
         float xl = 3.402823466e+38f, xr = -3.402823466e+38f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) edge_row(S, e, p, yc, xl, xr);
@@ -299,10 +305,16 @@ __device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pi
         }
         int x0 = 0, x1 = 0;
         if (xl < xr) {
-            xl = fminf(fmaxf(xl, -1.0f), (float)SW + 1.0f);
-            xr = fminf(fmaxf(xr, -1.0f), (float)SW + 1.0f);
+            const int VW = VP ? vw : SW;
+            xl = fminf(fmaxf(xl, -1.0f), (float)VW + 1.0f);
+            xr = fminf(fmaxf(xr, -1.0f), (float)VW + 1.0f);
             x0 = (int)ceilf(xl - 0.5f); if (x0 < 0) x0 = 0;
-            x1 = (int)ceilf(xr - 0.5f); if (x1 > SW) x1 = SW;
+            x1 = (int)ceilf(xr - 0.5f); if (x1 > VW) x1 = VW;
+            if (VP) {   // viewport span -> tile columns
+                x0 -= ox; x1 -= ox;
+                x0 = x0 < 0 ? 0 : (x0 > SW ? SW : x0);
+                x1 = x1 < 0 ? 0 : (x1 > SW ? SW : x1);
+            }
         }
         S.span[s] = make_uchar2((unsigned char)x0, (unsigned char)x1);
         if (x0 < x1) {
@@ -360,12 +372,24 @@ __device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pi
     __syncthreads();
 }
 
+// VP = false: the 96 x 96 observation of step() (one CTA per agent-frame, camera and score snapshots
+// taken by post_kernel).  VP = true: render(mode) for any viewport (rgb_array 600 x 400, mcr:566-575)
+// as a grid of 96 x 96 tiles, blockIdx.y = tile; camera from vp.camera, live score / backward flag
+// (what a render() call outside step() shows), RGB rows of vp.vw pixels.
+struct VpParams { int vw, vh, tiles_x; float hud_sx, hud_sy; const float* camera; };
+
+template <bool VP>
 __global__ void __launch_bounds__(RS_THREADS, 4)
 render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, uint8_t* __restrict__ obs,
-              int backwards_flag, int use_ego_color, int cls, int obs_format) {
+              int backwards_flag, int use_ego_color, int cls, int obs_format, VpParams vp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
     const int frame = blockIdx.x;
+    const int ox = VP ? (int)(blockIdx.y % vp.tiles_x) * SW : 0, oy = VP ? (int)(blockIdx.y / vp.tiles_x) * SH : 0;
+    const int VW = VP ? vp.vw : SW, VH = VP ? vp.vh : SH;
+    const float* __restrict__ camera = VP ? vp.camera : b.camera;
+    // this tile's rectangle in viewport pixels (partial tiles at the right / top edge)
+    const float tx0 = (float)ox, ty0 = (float)oy, tx1 = (float)min(ox + SW, VW), ty1 = (float)min(oy + SH, VH);
     const int env = frame / d.A, agent = frame % d.A;
     if (mask && !mask[env]) return;
     if (cls && (cls == 2) != (b.n_manifold[env] > 0)) return;
@@ -375,7 +399,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     const int Q = b.trk_Q[slot];
 
     // ---- camera (mcr:540-556) was evaluated by the physics kernel for this car ---------------
-    if (tid < 6) (&S.M.m00)[tid] = b.camera[(size_t)tid * N + car];
+    if (tid < 6) (&S.M.m00)[tid] = camera[(size_t)tid * N + car];
     if (tid >= 32 && tid < 32 + PAL_COUNT) {
         const int i = tid - 32;
         S.pal32[i] = (uint32_t)c_palette[i][0] | ((uint32_t)c_palette[i][1] << 8) | ((uint32_t)c_palette[i][2] << 16);
@@ -383,7 +407,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     }
     if (tid == 64) {
         // score label "%04i" % reward  (mcr:665; drawn before reward -= 0.1)
-        const double rw = b.score_snap[car];           // env.reward as it is when the reference draws the label
+        const double rw = VP ? b.reward[car] : b.score_snap[car];   // env.reward as it is when the reference draws the label
         int val = (int)rw;
         const bool neg = rw < 0 && val != 0;
         int mag = val < 0 ? -val : val;
@@ -399,8 +423,8 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     if (tid == 96) {
         // Checker squares the camera can see: invert the affine for the four viewport corners
         // (+ a two-unit margin, far above fp32 error) and keep the index ranges that overlap.
-        const float m00 = b.camera[(size_t)0 * N + car], m01 = b.camera[(size_t)1 * N + car], m02 = b.camera[(size_t)2 * N + car];
-        const float m10 = b.camera[(size_t)3 * N + car], m11 = b.camera[(size_t)4 * N + car], m12 = b.camera[(size_t)5 * N + car];
+        const float m00 = camera[(size_t)0 * N + car], m01 = camera[(size_t)1 * N + car], m02 = camera[(size_t)2 * N + car];
+        const float m10 = camera[(size_t)3 * N + car], m11 = camera[(size_t)4 * N + car], m12 = camera[(size_t)5 * N + car];
         const float det = m00 * m11 - m01 * m10;
         int j0x = 0, j1x = N_CHECKER_AXIS - 1, j0y = 0, j1y = N_CHECKER_AXIS - 1;
         if (fabsf(det) > 1e-12f) {
@@ -408,7 +432,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
             float wxmin = 3.0e38f, wxmax = -3.0e38f, wymin = 3.0e38f, wymax = -3.0e38f;
 #pragma unroll
             for (int cnr = 0; cnr < 4; ++cnr) {
-                const float u = ((cnr & 1) ? (float)SW : 0.0f) - m02, v = ((cnr & 2) ? (float)SH : 0.0f) - m12;
+                const float u = ((cnr & 1) ? tx1 : tx0) - m02, v = ((cnr & 2) ? ty1 : ty0) - m12;
                 const float wx = (m11 * u - m01 * v) * inv, wy = (-m10 * u + m00 * v) * inv;
                 wxmin = fminf(wxmin, wx); wxmax = fmaxf(wxmax, wx); wymin = fminf(wymin, wy); wymax = fmaxf(wymax, wy);
             }
@@ -431,12 +455,12 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
         bool vis = false;
         if (tid < nchunks) {
             const float4 cc4 = *(const float4*)(b.trk_chunk + ((size_t)slot * (d.Qmax / MCR_QUAD_CHUNK) + tid) * 4);
-            const float m00 = b.camera[(size_t)0 * N + car], m01 = b.camera[(size_t)1 * N + car], m02 = b.camera[(size_t)2 * N + car];
-            const float m10 = b.camera[(size_t)3 * N + car], m11 = b.camera[(size_t)4 * N + car], m12 = b.camera[(size_t)5 * N + car];
+            const float m00 = camera[(size_t)0 * N + car], m01 = camera[(size_t)1 * N + car], m02 = camera[(size_t)2 * N + car];
+            const float m10 = camera[(size_t)3 * N + car], m11 = camera[(size_t)4 * N + car], m12 = camera[(size_t)5 * N + car];
             const float cxp = (m00 * cc4.x + m01 * cc4.y) + m02, cyp = (m10 * cc4.x + m11 * cc4.y) + m12;
             // |M v| <= ||M||_F |v|: conservative pixel radius, plus a 2-pixel margin
             const float rp = cc4.z * sqrtf(m00 * m00 + m01 * m01 + m10 * m10 + m11 * m11) * 1.001f + 2.0f;
-            vis = (cxp + rp >= 0.0f) && (cxp - rp <= (float)SW) && (cyp + rp >= 0.0f) && (cyp - rp <= (float)SH);
+            vis = (cxp + rp >= tx0) && (cxp - rp <= tx1) && (cyp + rp >= ty0) && (cyp - rp <= ty1);
             if (!(rp == rp) || !(cxp == cxp) || !(cyp == cyp)) vis = true;
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, vis);
@@ -469,7 +493,8 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     V.quad_tile = b.trk_quad_tile + (size_t)slot * d.Qmax;
     V.touched = b.touched + (size_t)env * d.Tmax;
     V.use_ego_color = use_ego_color;
-    V.backward_flag_on = (b.backward_snap[car] != 0) && backwards_flag;   // flag of the PREVIOUS step (render precedes mcr:445-495)
+    V.backward_flag_on = ((VP ? b.backward[car] : b.backward_snap[car]) != 0) && backwards_flag;   // step(): flag of the PREVIOUS step (render precedes mcr:445-495)
+    V.hud_sx = VP ? vp.hud_sx : (float)(96.0 / 1000.0); V.hud_sy = VP ? vp.hud_sy : (float)(96.0 / 800.0);
     const Affine M = S.M;
 
     uint32_t pix[8];                       // this thread's 32 pixels (palette indices); glClear -> black
@@ -494,10 +519,12 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
                     xmin = fminf(xmin, px[k]); xmax = fmaxf(xmax, px[k]);
                 }
             }
-            if (!(ymax > 0.0f) || !(ymin < (float)SH) || !(xmax > 0.0f) || !(xmin < (float)SW)) valid = false;
+            if (!(ymax > ty0) || !(ymin < ty1) || !(xmax > tx0) || !(xmin < tx1)) valid = false;
             else {
+                // rows of the VIEWPORT the polygon covers (as the full-frame fill takes them), then this tile's share
                 y0 = (int)ceilf(fmaxf(ymin, 0.0f) - 0.5f); if (y0 < 0) y0 = 0;
-                y1 = (int)ceilf(fminf(ymax, (float)SH) - 0.5f); if (y1 > SH) y1 = SH;
+                y1 = (int)ceilf(fminf(ymax, (float)VH) - 0.5f); if (y1 > VH) y1 = VH;
+                if (VP) { y0 = max(y0, oy) - oy; y1 = min(y1, min(oy + SH, VH)) - oy; }
                 if (y1 <= y0) valid = false;
             }
         }
@@ -565,18 +592,33 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
             __syncthreads();
             lc = S.bc_cnt; pc = S.bc_rows;
             base += first_bad;
-            flush_list(S, tid, pix, lc, pc, false);
+            flush_list<VP>(S, tid, pix, lc, pc, false, ox, oy, VW);
             lc = 0; pc = 0;
         } else {
             lc += cnt_total; pc += rows_total;
             base += RS_THREADS;
         }
     }
-    flush_list(S, tid, pix, lc, pc, true);
+    flush_list<VP>(S, tid, pix, lc, pc, true, ox, oy, VW);
 
     const int my_seg = tid / SH, my_y = tid - SH * my_seg;
     // ---- score label glyphs (D3): observation rows 87..91 (= GL rows 8..4), cols 2..13 -------------
-    if (my_seg == 0 && my_y >= 4 && my_y <= 8) {
+    if (VP) {
+        // the same glyph cells, scaled: viewport pixel -> state cell by nearest neighbour (oracle draw_label_vp)
+        const int Y = VH - 1 - (oy + my_y);                       // image row from the top
+        const int sy = (int)floor(((double)Y + 0.5) * 96.0 / (double)VH) - 87;
+        if (sy >= 0 && sy < 5 && oy + my_y < VH) {
+#pragma unroll 1
+            for (int i = 0; i < 32; ++i) {
+                const int X = ox + 32 * my_seg + i;
+                const int sx = (int)floor(((double)X + 0.5) * 96.0 / (double)VW) - 2;
+                if (sx < 0 || sx >= 12 || X >= VW) continue;
+                const int g = S.glyph[sx / 3];
+                const int bits = g >= 0 ? c_font[g][sy] : 0;
+                if (bits & (4 >> (sx % 3))) pix[i >> 2] = (pix[i >> 2] & ~(0xFFu << (8 * (i & 3)))) | ((uint32_t)PAL_WHITE << (8 * (i & 3)));
+            }
+        }
+    } else if (my_seg == 0 && my_y >= 4 && my_y <= 8) {
         const int ry = (SH - 1 - my_y) - 87;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
@@ -593,7 +635,21 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     // ---- expand palette -> RGB and store this thread's 32 pixels as 6 x uint4 ------------------------
     // 4 pixels = 12 bytes = 3 words; byte stream r0 g0 b0 r1 g1 b1 ... from packed 0x00BBGGRR
     const int out_row = SH - 1 - my_y;
-    if (obs_format == MCR_OBS_RGB_HWC) {
+    if (VP) {
+        // RGB rows of VW pixels; the row stride VW * 3 is only 4-byte aligned in general -> word stores
+        const int gy = oy + my_y, gx = ox + 32 * my_seg;
+        if (gy < VH && gx < VW) {
+            const int npx = min(32, VW - gx);                     // multiple of 4 (vw % 4 == 0 is checked by the API)
+            uint32_t* dst = reinterpret_cast<uint32_t*>(obs + ((size_t)frame * VH + (size_t)(VH - 1 - gy)) * ((size_t)VW * 3) + (size_t)gx * 3);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t c0 = S.pal32[pix[k] & 0xff], c1 = S.pal32[(pix[k] >> 8) & 0xff];
+                const uint32_t c2 = S.pal32[(pix[k] >> 16) & 0xff], c3 = S.pal32[pix[k] >> 24];
+                const uint32_t w0 = c0 | (c1 << 24), w1 = (c1 >> 8) | (c2 << 16), w2 = (c2 >> 16) | (c3 << 8);
+                if (4 * k < npx) { dst[3 * k] = w0; dst[3 * k + 1] = w1; dst[3 * k + 2] = w2; }   // 4 pixels = 12 bytes
+            }
+        }
+    } else if (obs_format == MCR_OBS_RGB_HWC) {
         uint4* dst = reinterpret_cast<uint4*>(obs + (size_t)frame * MCR_OBS_BYTES + (size_t)out_row * (SW * 3) + my_seg * 96);
         uint32_t o[24];
 #pragma unroll
@@ -722,17 +778,64 @@ score_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, const uint8
     }
 }
 
-int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* obs,
-                  int backwards_flag, int use_ego_color, int cls, int obs_format, void* stream) {
+static bool configure_render() {
     static bool configured = false;
-    const size_t smem = sizeof(RasterSmem);
     if (!configured) {
-        if (cudaMemcpyToSymbol(c_palette, mcr_host_palette(), sizeof(uint8_t) * PAL_COUNT * 4) != cudaSuccess) return -1;
-        if (cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        const size_t smem = sizeof(RasterSmem);
+        if (cudaMemcpyToSymbol(c_palette, mcr_host_palette(), sizeof(uint8_t) * PAL_COUNT * 4) != cudaSuccess) return false;
+        if (cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+        if (cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
         configured = true;
     }
-    render_kernel<<<d.N, RS_THREADS, smem, (cudaStream_t)stream>>>(d, b, cc, mask, obs, backwards_flag, use_ego_color, cls, obs_format);
+    return true;
+}
+
+int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* obs,
+                  int backwards_flag, int use_ego_color, int cls, int obs_format, void* stream) {
+    if (!configure_render()) return -1;
+    render_kernel<false><<<d.N, RS_THREADS, sizeof(RasterSmem), (cudaStream_t)stream>>>(d, b, cc, mask, obs, backwards_flag, use_ego_color, cls, obs_format, VpParams{});
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// camera of mcr:540-556 for a viewport of vw x vh pixels (post_kernel evaluates the 96 x 96 one); same
+// float64 expression order, time and poses as they are when render() is called
+__global__ void camera_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, float* __restrict__ cam, double h_ratio, int vw, int vh) {
+    const int car = blockIdx.x * blockDim.x + threadIdx.x;
+    if (car >= d.N) return;
+    if (mask && !mask[car / d.A]) return;
+    const int N = d.N;
+    const double SCALE = 6.0, ZOOM = 2.7, WINDOW_W = 1000, WINDOW_H = 800;
+    const double t = b.time[car];
+    const double zoom = 0.1 * SCALE * fmax(1 - t, 0.0) + ZOOM * SCALE * fmin(t, 1.0);
+    const double scroll_x = b.body[(size_t)BF_PX * N + car], scroll_y = b.body[(size_t)BF_PY * N + car];
+    double angle = -(double)b.body[(size_t)BF_A * N + car];
+    const double hvx = b.body[(size_t)BF_VX * N + car], hvy = b.body[(size_t)BF_VY * N + car];
+    if (sqrt(hvx * hvx + hvy * hvy) > 0.5) angle = atan2(hvx, hvy);
+    const double tx = WINDOW_W / 2 - (scroll_x * zoom * cos(angle) - scroll_y * zoom * sin(angle));
+    const double ty = WINDOW_H * h_ratio - (scroll_x * zoom * sin(angle) + scroll_y * zoom * cos(angle));
+    const float ftx = (float)tx, fty = (float)ty, fdeg = (float)(57.29577951308232 * angle), fzoom = (float)zoom;
+    const double rad = (double)fdeg * (3.14159265358979323846 / 180.0);
+    const double cs = cos(rad), sn = sin(rad);
+    const double SX = (double)vw / 1000.0, SY = (double)vh / 800.0;
+    cam[(size_t)0 * N + car] = (float)(cs * (double)fzoom * SX);
+    cam[(size_t)1 * N + car] = (float)(-sn * (double)fzoom * SX);
+    cam[(size_t)2 * N + car] = (float)((double)ftx * SX);
+    cam[(size_t)3 * N + car] = (float)(sn * (double)fzoom * SY);
+    cam[(size_t)4 * N + car] = (float)(cs * (double)fzoom * SY);
+    cam[(size_t)5 * N + car] = (float)((double)fty * SY);
+}
+
+int launch_render_viewport(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* out, float* cam,
+                           int vw, int vh, double h_ratio, int backwards_flag, int use_ego_color, void* stream) {
+    if (!configure_render()) return -1;
+    camera_kernel<<<(d.N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d, b, mask, cam, h_ratio, vw, vh);
+    VpParams vp;
+    vp.vw = vw; vp.vh = vh; vp.tiles_x = (vw + SW - 1) / SW;
+    vp.hud_sx = (float)((double)vw / 1000.0); vp.hud_sy = (float)((double)vh / 800.0); vp.camera = cam;
+    const int tiles = vp.tiles_x * ((vh + SH - 1) / SH);
+    render_kernel<true><<<dim3(d.N, tiles), RS_THREADS, sizeof(RasterSmem), (cudaStream_t)stream>>>(
+        d, b, cc, mask, out, backwards_flag, use_ego_color, 0, MCR_OBS_RGB_HWC, vp);
+    return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
 
 int launch_score(const Dims& d, const DevBuffers& b, const uint8_t* mask, const uint8_t* noact, double* reward, uint8_t* done,

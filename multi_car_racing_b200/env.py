@@ -20,6 +20,8 @@ from .track import TrackGenerator, np_random, MAX_TILES_DEFAULT, MAX_QUADS_DEFAU
 
 STATE_W = 96
 STATE_H = 96
+VIDEO_W = 600
+VIDEO_H = 400
 FPS = 50
 PLAYFIELD = 2000 / 6.0
 
@@ -381,12 +383,22 @@ class BatchedMultiCarRacing:
         return self.obs, self.reward_out, self.done_out, {}
 
     def render(self, mode='state_pixels'):
+        """render(mode) between steps, reference :511-604: 'state_pixels' -> (B, A, 96, 96, 3),
+        'rgb_array' -> (B, A, 400, 600, 3) uint8 on the device, showing the envs as they are now
+        (current score and backward flags).  Same rasteriser, tiled over the larger viewport; skid
+        particles are not drawn.  'human' opens windows in the reference; there is no display here."""
         assert mode in ['human', 'state_pixels', 'rgb_array']
-        if mode != 'state_pixels':
-            raise NotImplementedError("only the 'state_pixels' observation path is built (SURVEY.md §8: other modes are out of scope)")
-        with _torch().cuda.device(self.device):
-            _lib.check(self.L.mcr_render(self._h, None, self.obs.data_ptr(), None, None, 0, self._stream()), "mcr_render")
-        return self.obs
+        if mode == 'human':
+            raise NotImplementedError("mode='human' needs a display; use 'rgb_array' (same picture at 600x400)")
+        torch = _torch()
+        vw, vh = (STATE_W, STATE_H) if mode == 'state_pixels' else (VIDEO_W, VIDEO_H)
+        key = "_render_" + mode
+        if getattr(self, key, None) is None:
+            setattr(self, key, torch.zeros((self.batch_envs, self.num_agents, vh, vw, 3), dtype=torch.uint8, device=self.device))
+        out = getattr(self, key)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.mcr_render_viewport(self._h, None, vw, vh, out.data_ptr(), self._stream()), "mcr_render_viewport")
+        return out
 
     # ---- split entry points (bench / ncu / tests) ------------------------------------------------
     def contacts_only(self):
@@ -587,11 +599,9 @@ class MultiCarRacing:
 
     def render(self, mode='human'):
         assert mode in ['human', 'state_pixels', 'rgb_array']
-        if mode != 'state_pixels':
-            raise NotImplementedError("only mode='state_pixels' is built on the B200 path")
         if not self._has_reset:
-            return None
-        return self._batch.render('state_pixels')[0].cpu().numpy()
+            return None                                      # reference :538 ("reset() not called yet")
+        return self._batch.render(mode)[0].cpu().numpy()
 
     def close(self):
         pass

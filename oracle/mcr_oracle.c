@@ -1294,18 +1294,21 @@ static void world_step(OrcWorld* W, float dt, int velIters, int posIters) {
 #define STATE_W 96
 #define STATE_H 96
 
-typedef struct { uint8_t* img; } Canvas; /* img[(95 - y) * 96 * 3 + x * 3] (row flip, mcr:602) */
+/* img[(h - 1 - y) * w * 3 + x * 3] (row flip, mcr:602); w x h = the glViewport size of the render mode
+ * (state_pixels 96 x 96, rgb_array 600 x 400, mcr:566-575) */
+typedef struct { uint8_t* img; int w, h; } Canvas;
 
 /* Fill a convex polygon given in viewport pixel coordinates (origin bottom-left).  A pixel is
  * covered iff its centre lies in [xl, xr) on a row whose centre lies in [ylo, yhi) of two
  * edges; every edge is evaluated from its lower to its higher endpoint, so an edge shared
  * by two polygons yields bit-identical crossings (each pixel centre belongs to exactly one). */
 static void fill_poly(Canvas* cv, const float* px, const float* py, int n, RGB col) {
+    const int VW = cv->w, VH = cv->h;
     float ymin = py[0], ymax = py[0];
     for (int i = 1; i < n; ++i) { ymin = fminf(ymin, py[i]); ymax = fmaxf(ymax, py[i]); }
-    if (!(ymax > 0.0f) || !(ymin < (float)STATE_H)) return;
+    if (!(ymax > 0.0f) || !(ymin < (float)VH)) return;
     int y0 = (int)ceilf(fmaxf(ymin, 0.0f) - 0.5f); if (y0 < 0) y0 = 0;
-    int y1 = (int)ceilf(fminf(ymax, (float)STATE_H) - 0.5f); if (y1 > STATE_H) y1 = STATE_H;
+    int y1 = (int)ceilf(fminf(ymax, (float)VH) - 0.5f); if (y1 > VH) y1 = VH;
     for (int y = y0; y < y1; ++y) {
         float yc = (float)y + 0.5f;
         float xl = FLT_MAX, xr = -FLT_MAX;
@@ -1319,11 +1322,11 @@ static void fill_poly(Canvas* cv, const float* px, const float* py, int n, RGB c
             xl = fminf(xl, x); xr = fmaxf(xr, x);
         }
         if (!(xl < xr)) continue;
-        xl = fminf(fmaxf(xl, -1.0f), (float)STATE_W + 1.0f);
-        xr = fminf(fmaxf(xr, -1.0f), (float)STATE_W + 1.0f);
+        xl = fminf(fmaxf(xl, -1.0f), (float)VW + 1.0f);
+        xr = fminf(fmaxf(xr, -1.0f), (float)VW + 1.0f);
         int x0 = (int)ceilf(xl - 0.5f); if (x0 < 0) x0 = 0;
-        int x1 = (int)ceilf(xr - 0.5f); if (x1 > STATE_W) x1 = STATE_W;
-        uint8_t* row = cv->img + (size_t)(STATE_H - 1 - y) * STATE_W * 3;
+        int x1 = (int)ceilf(xr - 0.5f); if (x1 > VW) x1 = VW;
+        uint8_t* row = cv->img + (size_t)(VH - 1 - y) * VW * 3;
         for (int x = x0; x < x1; ++x) { row[3 * x] = col.r; row[3 * x + 1] = col.g; row[3 * x + 2] = col.b; }
     }
 }
@@ -1341,14 +1344,14 @@ static void fill_world_poly(Canvas* cv, const Affine* M, const V2* v, int n, RGB
     fill_poly(cv, px, py, n, col);
 }
 
-/* window (1000 x 800) coordinates -> viewport pixels: glViewport(0,0,96,96) under the
+/* window (1000 x 800) coordinates -> viewport pixels: glViewport(0,0,w,h) under the
  * unchanged glOrtho(0,1000,0,800) projection (mcr:576-586) */
 static void fill_window_poly(Canvas* cv, const double* wx, const double* wy, int n, RGB col) {
     float px[MAXV], py[MAXV];
     for (int i = 0; i < n; ++i) {
         float fx = (float)wx[i], fy = (float)wy[i]; /* glVertex3f */
-        px[i] = fx * (float)(96.0 / 1000.0);
-        py[i] = fy * (float)(96.0 / 800.0);
+        px[i] = fx * (float)((double)cv->w / 1000.0);
+        py[i] = fy * (float)((double)cv->h / 800.0);
     }
     fill_poly(cv, px, py, n, col);
 }
@@ -1359,26 +1362,44 @@ static const uint8_t FONT3x5[11][5] = { /* rows top->bottom, 3 bits per row (msb
     {0, 0, 7, 0, 0} /* '-' */
 };
 
-/* pyglet Label at x=20, y=50 (window) -> 3x5 glyphs at cols 2..13, rows 87..91 from the top (D3) */
-static void draw_label(uint8_t* img, const char* text) {
+/* pyglet Label at x=20, y=50 (window) -> 3x5 glyphs at cols 2..13, rows 87..91 from the top of the
+ * 96 x 96 state frame (D3); larger viewports show the same glyph cells scaled (nearest neighbour:
+ * viewport pixel (X, Y) takes state cell (floor((X + .5) * 96 / w), floor((Y + .5) * 96 / h))) */
+static void draw_label_vp(uint8_t* img, int vw, int vh, const char* text) {
+    uint8_t cell[5][12]; memset(cell, 0, sizeof(cell));
     for (int ch = 0; ch < 4 && text[ch]; ++ch) {
         int g = text[ch] == '-' ? 10 : (text[ch] >= '0' && text[ch] <= '9' ? text[ch] - '0' : -1);
         if (g < 0) continue;
         for (int ry = 0; ry < 5; ++ry)
             for (int rx = 0; rx < 3; ++rx)
-                if (FONT3x5[g][ry] & (4 >> rx)) {
-                    uint8_t* p = img + ((size_t)(87 + ry) * STATE_W + (2 + 3 * ch + rx)) * 3;
-                    p[0] = 255; p[1] = 255; p[2] = 255;
-                }
+                if (FONT3x5[g][ry] & (4 >> rx)) cell[ry][3 * ch + rx] = 1;
+    }
+    if (vw == STATE_W && vh == STATE_H) {
+        for (int ry = 0; ry < 5; ++ry) for (int cx = 0; cx < 12; ++cx) if (cell[ry][cx]) {
+            uint8_t* p = img + ((size_t)(87 + ry) * STATE_W + (2 + cx)) * 3;
+            p[0] = 255; p[1] = 255; p[2] = 255;
+        }
+        return;
+    }
+    for (int Y = 0; Y < vh; ++Y) {          /* Y, X: image row from the top, column */
+        int sy = (int)floor(((double)Y + 0.5) * 96.0 / (double)vh) - 87;
+        if (sy < 0 || sy >= 5) continue;
+        for (int X = 0; X < vw; ++X) {
+            int sx = (int)floor(((double)X + 0.5) * 96.0 / (double)vw) - 2;
+            if (sx < 0 || sx >= 12 || !cell[sy][sx]) continue;
+            uint8_t* p = img + ((size_t)Y * vw + X) * 3;
+            p[0] = 255; p[1] = 255; p[2] = 255;
+        }
     }
 }
+static void draw_label(uint8_t* img, const char* text) { draw_label_vp(img, STATE_W, STATE_H, text); }
 
 static const float CAR_COLORS[8][3] = { {0.8f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.8f}, {0.0f, 0.8f, 0.0f}, {0.0f, 0.8f, 0.8f},
                                         {0.8f, 0.8f, 0.8f}, {0.0f, 0.0f, 0.0f}, {0.8f, 0.0f, 0.8f}, {0.8f, 0.8f, 0.0f} };
 
-static void render_view(OrcWorld* W, int agent, uint8_t* img) {
-    Canvas cv; cv.img = img;
-    memset(img, 0, STATE_W * STATE_H * 3); /* glClear, default clear colour */
+static void render_view_vp(OrcWorld* W, int agent, uint8_t* img, int vw, int vh) {
+    Canvas cv; cv.img = img; cv.w = vw; cv.h = vh;
+    memset(img, 0, (size_t)vw * vh * 3); /* glClear, default clear colour */
     const double SCALE = 6.0, ZOOM = 2.7, WINDOW_W = 1000, WINDOW_H = 800;
     const double PLAYFIELD = 2000 / SCALE;
     /* camera, mcr:540-556 */
@@ -1395,7 +1416,7 @@ static void render_view(OrcWorld* W, int agent, uint8_t* img) {
     float ftx = (float)tx, fty = (float)ty, fdeg = (float)(57.29577951308232 * angle), fzoom = (float)zoom;
     double rad = (double)fdeg * (3.14159265358979323846 / 180.0);
     double cs = cos(rad), sn = sin(rad);
-    const double SX = 96.0 / 1000.0, SY = 96.0 / 800.0;
+    const double SX = (double)vw / 1000.0, SY = (double)vh / 800.0;
     Affine M;
     M.m00 = (float)(cs * (double)fzoom * SX); M.m01 = (float)(-sn * (double)fzoom * SX); M.m02 = (float)((double)ftx * SX);
     M.m10 = (float)(sn * (double)fzoom * SY); M.m11 = (float)(cs * (double)fzoom * SY);  M.m12 = (float)((double)fty * SY);
@@ -1491,7 +1512,7 @@ static void render_view(OrcWorld* W, int agent, uint8_t* img) {
             for (int i = 0; i < pad; ++i) buf[len++] = '0';
             for (int i = nd - 1; i >= 0; --i) buf[len++] = digs[i];
             buf[len] = 0;
-            draw_label(img, buf);
+            draw_label_vp(img, vw, vh, buf);
         }
         if (W->driving_backward[agent] && W->backwards_flag) {
             double fx[3] = { Wd - 100, Wd - 75, Wd - 50 }, fy[3] = { 30, 70, 30 };
@@ -1500,6 +1521,8 @@ static void render_view(OrcWorld* W, int agent, uint8_t* img) {
         }
     }
 }
+
+static void render_view(OrcWorld* W, int agent, uint8_t* img) { render_view_vp(W, agent, img, STATE_W, STATE_H); }
 
 /* ------------------------------------------------------------------------------------ */
 /* MultiCarRacing.step  (mcr:410-509).  action == NULL  <=>  step(None)                  */
@@ -1554,6 +1577,11 @@ ORC_API void orc_step(OrcWorld* W, const double* action, uint8_t* obs, double* s
 
 ORC_API void orc_render(OrcWorld* W, uint8_t* obs) {
     for (int c = 0; c < W->A; ++c) render_view(W, c, obs + (size_t)c * STATE_W * STATE_H * 3);
+}
+/* render(mode) for any viewport: state_pixels (96, 96), rgb_array (600, 400), mcr:566-575.  Skid
+ * particles (drawn in the non-state modes, mcr:564) are not restated (documented deviation D6). */
+ORC_API void orc_render_vp(OrcWorld* W, int vw, int vh, uint8_t* out) {
+    for (int c = 0; c < W->A; ++c) render_view_vp(W, c, out + (size_t)c * vw * vh * 3, vw, vh);
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -1640,11 +1668,11 @@ ORC_API int orc_ext_collide_pairs(OrcWorld* W, int* out, int max) {
 ORC_API void orc_ext_solve(OrcWorld* W, double dt, int velIters, int posIters) { world_solve(W, (float)dt, velIters, posIters); }
 /* GL fixed-function polygon fill on a 96x96 RGB canvas (row 0 = top), viewport pixel coordinates */
 ORC_API void orc_raster_fill(uint8_t* img, const float* px, const float* py, int n, float r, float g, float b) {
-    Canvas cv; cv.img = img;
+    Canvas cv; cv.img = img; cv.w = STATE_W; cv.h = STATE_H;
     fill_poly(&cv, px, py, n, rgbf(r, g, b));
 }
 ORC_API void orc_raster_fill_u8(uint8_t* img, const float* px, const float* py, int n, int r, int g, int b) {
-    Canvas cv; cv.img = img; RGB c; c.r = (uint8_t)r; c.g = (uint8_t)g; c.b = (uint8_t)b;
+    Canvas cv; cv.img = img; cv.w = STATE_W; cv.h = STATE_H; RGB c; c.r = (uint8_t)r; c.g = (uint8_t)g; c.b = (uint8_t)b;
     fill_poly(&cv, px, py, n, c);
 }
 ORC_API void orc_raster_text(uint8_t* img, const char* text) { draw_label(img, text); }

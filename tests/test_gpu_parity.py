@@ -130,6 +130,29 @@ def test_fused_observation_formats(oracle, mcr, fmt):
     assert hobs.shape == obs.shape
 
 
+def test_render_modes_between_steps(oracle, mcr):
+    """render('state_pixels') and render('rgb_array') (600 x 400) called between steps:
+    the tiled viewport rasteriser against the oracle's full-frame fill, bit-exact, zoomed-out first
+    frames and mid-episode ones, with the live score label / backward flag."""
+    import torch
+    venv, worlds, tracks, obs0, oobs0 = _setup(oracle, mcr, B=2, A=2, seed=31)
+    for mode in ("state_pixels", "rgb_array"):
+        got = venv.render(mode).cpu().numpy()
+        want = np.stack([w.render(mode) for w in worlds])
+        assert got.shape == want.shape and np.array_equal(got, want), "%s after reset" % mode
+    tape = action_tape(31, 90, 2, 2)
+    for s in range(90):
+        venv.step(torch.from_numpy(tape[s]).to(venv.device))
+        for e, w in enumerate(worlds):
+            w.step(tape[s, e].astype(np.float64), render=False)
+        if s in (0, 3, 20, 49, 50, 89):
+            for mode in ("state_pixels", "rgb_array"):
+                got = venv.render(mode).cpu().numpy()
+                want = np.stack([w.render(mode) for w in worlds])
+                bad = int((got != want).any(axis=-1).sum())
+                assert bad == 0, "%s, step %d: %d pixels differ" % (mode, s, bad)
+
+
 def test_single_env_dropin_matches_oracle_env(oracle, mcr):
     """The reference-shaped API end to end: same seeds -> same tracks, spawn, rewards, frames."""
     np.random.seed(5)
