@@ -9,15 +9,16 @@ Drop-in surface of igilitschenski/multi_car_racing (gym_multi_car_racing):
     obs, reward, done, info = env.step(action)      # action (num_agents, 3)
 
     venv = mcr.BatchedMultiCarRacing(batch_envs=1024, num_agents=2)   # torch tensors, on device
+    vec = mcr.MultiCarRacingVecEnv(1024, num_agents=2)                 # gym(nasium) VectorEnv protocol
 
 If a `gym` (or `gymnasium`) package is importable the id "MultiCarRacing-v0" is also registered
 there with the reference's max_episode_steps=1000 / reward_threshold=900
 (reference gym_multi_car_racing/__init__.py:5-10).
 """
 from ._lib import McrError, LIB_PATH  # noqa: F401
-from .env import BatchedMultiCarRacing, MultiCarRacing, TimeLimit, Box  # noqa: F401
+from .env import BatchedMultiCarRacing, MultiCarRacing, MultiCarRacingVecEnv, TimeLimit, Box  # noqa: F401
 
-__all__ = ["make", "MultiCarRacing", "BatchedMultiCarRacing", "TimeLimit", "Box", "McrError", "ENV_ID"]
+__all__ = ["make", "MultiCarRacing", "BatchedMultiCarRacing", "MultiCarRacingVecEnv", "TimeLimit", "Box", "McrError", "ENV_ID"]
 
 ENV_ID = "MultiCarRacing-v0"
 MAX_EPISODE_STEPS = 1000

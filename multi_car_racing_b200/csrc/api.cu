@@ -787,7 +787,7 @@ extern "C" int mcr_reset(mcr_handle h, const uint8_t* mask, const int32_t* track
 }
 
 // One full pass (contacts, physics, post-step block, render) as two chains that only meet at the end:
-//   side   : contacts_kernel (reads the start poses)                          ............. score_kernel
+//   side   : contacts_kernel (reads the start poses) -> stripe_kernel        ............. score_kernel
 //   main   : carcontacts -> pre -> sweep ------------------> post(cls 1) -> render(cls 1)
 //   side2  :                   \-> coupled_kernel ---------> post(cls 2) -> score(cls 2) -> render(cls 2)
 // cls 1 = envs without car-car manifolds (per-car solver), cls 2 = envs with touching cars.  The
@@ -804,10 +804,14 @@ static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, con
     CUDA_OK(cudaEventRecord(h->ev_fork, s));
     CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
     LAUNCH(launch_contacts(d, b, cc, mask, h->side));
-    CUDA_OK(cudaEventRecord(h->ev_contacts, h->side));
     LAUNCH(launch_presweep(d, b, cc, mask, noact, action, action_dtype, h->cfg.collisions, 0, s));
+    CUDA_OK(cudaEventRecord(h->ev_pre, s));
+    // wheel stripes for the rasteriser: they need pre_kernel's phase and nothing else, so they ride on
+    // the side stream behind the contact pass; ev_contacts (which every post_kernel waits for) covers both
+    CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_pre, 0));
+    LAUNCH(launch_stripes(d, b, mask, h->side));
+    CUDA_OK(cudaEventRecord(h->ev_contacts, h->side));
     if (split) {
-        CUDA_OK(cudaEventRecord(h->ev_pre, s));
         CUDA_OK(cudaStreamWaitEvent(h->side2, h->ev_pre, 0));
         LAUNCH(launch_coupled(d, b, cc, mask, early_exit, h->side2));
         CUDA_OK(cudaStreamWaitEvent(h->side2, h->ev_contacts, 0));

@@ -102,6 +102,8 @@ int launch_contacts(const Dims& d, const DevBuffers& b, const CarConst& cc, cons
 // noact[env] != 0: that env takes the action=None path of mcr:421 this step (next-step auto reset)
 int launch_physics(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* noact,
                    const void* action, int action_dtype, double h_ratio, int collisions, void* stream);
+// wheel-stripe extents for the rasteriser (needs pre_kernel's phase; launch_physics issues it itself)
+int launch_stripes(const Dims& d, const DevBuffers& b, const uint8_t* mask, void* stream);
 int launch_carcontacts(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, void* stream);
 int launch_coupled(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, int early_exit, void* stream);
 // cls selects envs by their car-car contact state this step: 0 = all, 1 = only envs without

@@ -112,6 +112,7 @@ struct __align__(16) RasterSmem {
     signed char glyph[4];
     uint32_t pal32[32];      // r | g << 8 | b << 16
     uint32_t palY[32];       // luma (MCR_OBS_GRAY)
+    uint32_t prmt_sel[16];   // nibble -> PRMT selector: byte i from operand b (4 + i) if bit i is set, else from a (i)
 };
 
 __device__ __forceinline__ double py_mod(double a, double m) {
@@ -353,13 +354,10 @@ __device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pi
                     } else if (fresh) {
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
+                            // bit i of the nibble selects byte i of c4 over byte i of pix[k]: one PRMT with a
+                            // selector from a 16-entry table instead of building a byte mask
                             const uint32_t nib = (fresh >> (4 * k)) & 0xFu;
-                            if (nib == 0xFu) pix[k] = c4;
-                            else if (nib) {
-                                // nibble -> byte mask: bit i of nib selects byte i
-                                const uint32_t bm = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;
-                                pix[k] = (pix[k] & ~bm) | (c4 & bm);
-                            }
+                            pix[k] = __byte_perm(pix[k], c4, S.prmt_sel[nib]);
                         }
                     }
                 }
@@ -404,6 +402,10 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
         const int i = tid - 32;
         S.pal32[i] = (uint32_t)c_palette[i][0] | ((uint32_t)c_palette[i][1] << 8) | ((uint32_t)c_palette[i][2] << 16);
         S.palY[i] = (uint32_t)c_palette[i][3];
+    }
+    if (tid >= 128 && tid < 144) {
+        const uint32_t nib = tid - 128;
+        S.prmt_sel[nib] = 0x3210u | ((nib & 1u) << 2) | ((nib & 2u) << 5) | ((nib & 4u) << 8) | ((nib & 8u) << 11);
     }
     if (tid == 64) {
         // score label "%04i" % reward  (mcr:665; drawn before reward -= 0.1)

@@ -500,7 +500,7 @@ post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
     const int N = d.N;
     const float h = (float)(1.0 / 50);
     const float mA = cc.hull_invMass, iA = cc.hull_invI, mB = cc.wheel_invMass, iB = cc.wheel_invI;
-    const double SIZE = 0.02;
+
     float cx[5], cy[5], ang[5], vx[5], vy[5], w[5], qs[5], qc[5], slp[5];
     bool awake[5];
     const float* sc = b.scratch + car;
@@ -514,14 +514,12 @@ post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
     }
     float jix[4], jiy[4], jiz[4], jmot[4], motorMassK[4];
     int lim[4];
-    double phase[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         jix[k] = sc[(size_t)(SC_JIX + k) * N]; jiy[k] = sc[(size_t)(SC_JIY + k) * N];
         jiz[k] = sc[(size_t)(SC_JIZ + k) * N]; jmot[k] = sc[(size_t)(SC_JMOT + k) * N];
         motorMassK[k] = sc[(size_t)(SC_JOINT + k * SC_JOINT_FIELDS + 13) * N];
         lim[k] = b.limit_state[(size_t)k * N + car];
-        phase[k] = b.wheel[(size_t)(k * WHEEL_FIELDS + WF_PHASE) * N + car];
     }
     const bool coupled = b.n_manifold[env] > 0;
     float px[5], py[5];
@@ -647,19 +645,36 @@ post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
         if (car_angle != 0 && car_angle < 0) car_angle += 2 * PI;
         b.heading[car] = car_angle;
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {   // Car.draw wheel stripe, evaluated once per wheel for all A views
-        const double a1 = phase[k], a2 = phase[k] + 1.2;
-        double s1 = sin(a1), s2 = sin(a2), c1 = cos(a1), c2 = cos(a2);
-        float y1 = __int_as_float(0x7fc00000), y2 = 0.0f;
-        if (!(s1 > 0 && s2 > 0)) {
-            if (s1 > 0) c1 = sign_d(c1);
-            if (s2 > 0) c2 = sign_d(c2);
-            y1 = (float)(+27 * c1 * SIZE); y2 = (float)(+27 * c2 * SIZE);
-        }
-        b.stripe[(size_t)(k * 2 + 0) * N + car] = y1;
-        b.stripe[(size_t)(k * 2 + 1) * N + car] = y2;
+}
+
+// Car.draw's wheel stripe (gym car_dynamics: a1 = phase, a2 = phase + 1.2, ...), evaluated once per
+// wheel for all A views: 4 fp64 sin/cos of a possibly large argument per wheel.  One THREAD per
+// (wheel, car) instead of a serial tail of post_kernel; phase is final once pre_kernel has run, so
+// mcr_step issues this beside the solver (side stream) and the rasteriser finds the result ready.
+__global__ void __launch_bounds__(128)
+stripe_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = d.N;
+    if (idx >= 4 * N) return;
+    const int k = idx / N, car = idx - k * N;
+    if (mask && !mask[car / d.A]) return;
+    const double SIZE = 0.02;
+    const double phase = b.wheel[(size_t)(k * WHEEL_FIELDS + WF_PHASE) * N + car];
+    const double a1 = phase, a2 = phase + 1.2;
+    double s1 = sin(a1), s2 = sin(a2), c1 = cos(a1), c2 = cos(a2);
+    float y1 = __int_as_float(0x7fc00000), y2 = 0.0f;
+    if (!(s1 > 0 && s2 > 0)) {
+        if (s1 > 0) c1 = sign_d(c1);
+        if (s2 > 0) c2 = sign_d(c2);
+        y1 = (float)(+27 * c1 * SIZE); y2 = (float)(+27 * c2 * SIZE);
     }
+    b.stripe[(size_t)(k * 2 + 0) * N + car] = y1;
+    b.stripe[(size_t)(k * 2 + 1) * N + car] = y2;
+}
+
+int launch_stripes(const Dims& d, const DevBuffers& b, const uint8_t* mask, void* stream) {
+    stripe_kernel<<<(4 * d.N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d, b, mask);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -687,8 +702,9 @@ int launch_physics(const Dims& d, const DevBuffers& b, const CarConst& cc, const
     if (action_dtype == MCR_F64) pre_kernel<double><<<nb, pb, 0, s>>>(d, b, cc, mask, noact, (const double*)action);
     else pre_kernel<float><<<nb, pb, 0, s>>>(d, b, cc, mask, noact, (const float*)action);
     const int packed_ctas = (d.N + SWEEP_BLOCK - 1) / SWEEP_BLOCK, percar_ctas = (d.N + SWEEP_BLOCK / 32 - 1) / (SWEEP_BLOCK / 32);
+    stripe_kernel<<<(4 * d.N + 127) / 128, 128, 0, s>>>(d, b, mask);
     sweep_kernel<<<packed_ctas + percar_ctas, SWEEP_BLOCK, 0, s>>>(d, b, cc, mask, early_exit, packed_ctas);
-    launched += 2;
+    launched += 3;
     if (collisions && d.A > 1) { if (launch_coupled(d, b, cc, mask, early_exit, stream) < 0) return -1; ++launched; }
     return cudaGetLastError() == cudaSuccess ? launched : -1;
 }

@@ -628,6 +628,59 @@ class MultiCarRacing:
         return float(self._batch.buffers["time"][0].item())
 
 
+class MultiCarRacingVecEnv:
+    """Vector-env adapter over BatchedMultiCarRacing for learners that speak the
+    gym(nasium) VectorEnv protocol: `num_envs`, `single_observation_space`, `single_action_space`,
+    `reset(seed=None) -> (obs, info)`, `step(actions) -> (obs, reward, terminated, truncated, info)`
+    and the older `step_async` / `step_wait` pair.  Tensors stay on the device; an env that ended
+    (terminated: mcr:497-507, truncated: the registration's TimeLimit) is reset by the NEXT step
+    (gymnasium's NEXT_STEP autoreset mode == mcr_step flag bit1).  One "env" of the vector is one
+    MultiCarRacing-v0 instance with `num_agents` cars: observations (num_envs, A, ...), actions
+    (num_envs, A, 3), rewards (num_envs, A)."""
+
+    def __init__(self, num_envs, num_agents=2, device=None, seed=None, **kwargs):
+        kwargs.setdefault("max_episode_steps", 1000)
+        self._device_tracks = kwargs.pop("device_tracks", False)
+        self.venv = BatchedMultiCarRacing(num_envs, num_agents=num_agents, device=device, auto_reset='next_step',
+                                          seed=seed, **kwargs)
+        self.num_envs, self.num_agents = int(num_envs), int(num_agents)
+        A = self.num_agents
+        self.single_action_space = _make_box(np.tile(np.array([-1, 0, 0], np.float32), (A, 1)),
+                                             np.tile(np.array([+1, +1, +1], np.float32), (A, 1)), dtype=np.float32)
+        self.single_observation_space = _make_box(0, 255, shape=(A,) + self.venv.obs_shape, dtype=np.uint8)
+        self.action_space = _make_box(np.tile(np.array([-1, 0, 0], np.float32), (self.num_envs, A, 1)),
+                                      np.tile(np.array([+1, +1, +1], np.float32), (self.num_envs, A, 1)), dtype=np.float32)
+        self.observation_space = _make_box(0, 255, shape=(self.num_envs, A) + self.venv.obs_shape, dtype=np.uint8)
+        self.metadata = {'render.modes': ['rgb_array', 'state_pixels'], 'video.frames_per_second': FPS,
+                         'autoreset_mode': 'next_step'}
+        self._pending_actions = None
+
+    def reset(self, seed=None, options=None):
+        if seed is not None:
+            self.venv.seed(seed)
+        return self.venv.reset(device_tracks=self._device_tracks), {}
+
+    def step(self, actions):
+        obs, reward, done, _ = self.venv.step(actions)
+        return obs, reward, (done & 1).bool(), (done & 2).bool(), {}
+
+    def step_async(self, actions):
+        self._pending_actions = actions
+
+    def step_wait(self):
+        if self._pending_actions is None:
+            raise RuntimeError("step_wait() without step_async()")
+        actions, self._pending_actions = self._pending_actions, None
+        obs, reward, terminated, truncated, info = self.step(actions)
+        return obs, reward, terminated | truncated, info      # gym 0.17 VectorEnv.step_wait -> (obs, rews, dones, infos)
+
+    def render(self, mode='rgb_array'):
+        return self.venv.render(mode)
+
+    def close(self):
+        self.venv.close()
+
+
 class TimeLimit:
     """gym.wrappers.TimeLimit semantics (gym 0.17.2) for make(): done at max_episode_steps with
     info['TimeLimit.truncated'] = not done (reference __init__.py:5-10)."""

@@ -103,3 +103,37 @@ def test_out_of_field_done_then_next_step_reset(mcr):
     x = venv.buffers["body"][0, 6, car].item()
     assert abs(x) < 400.0, "env 1 was respawned inside the playfield"
     assert int(venv.buffers["steps"][car].item()) == 0 and int(venv.buffers["steps"][0].item()) == 3
+
+
+def test_vector_env_adapter(mcr):
+    """gym(nasium) VectorEnv protocol over the batched env: shapes, dtypes, terminated / truncated
+    split, next-step autoreset, and the same numbers as BatchedMultiCarRacing driven directly."""
+    import torch
+    vec = mcr.MultiCarRacingVecEnv(6, num_agents=2, seed=40, max_episode_steps=25)
+    ref = mcr.BatchedMultiCarRacing(6, num_agents=2, seed=40, max_episode_steps=25, auto_reset='next_step')
+    np.random.seed(5)                      # reset() draws direction / car order from the global numpy RNG (mcr:351-357)
+    obs, info = vec.reset()
+    np.random.seed(5)
+    robs = ref.reset()
+    assert info == {} and obs.shape == (6, 2, 96, 96, 3) and obs.dtype == torch.uint8 and torch.equal(obs, robs)
+    assert vec.single_action_space.shape == (2, 3) and vec.single_observation_space.shape == (2, 96, 96, 3)
+    assert vec.action_space.shape == (6, 2, 3) and vec.num_envs == 6
+    tape = action_tape(12, 60, 6, 2)
+    n_trunc = 0
+    for s in range(60):
+        a = torch.from_numpy(tape[s]).to(obs.device)
+        if s % 2:
+            vec.step_async(a)
+            o, r, d, _ = vec.step_wait()
+            term = trunc = None
+        else:
+            o, r, term, trunc, _ = vec.step(a)
+            d = term | trunc
+            assert term.dtype == torch.bool and trunc.dtype == torch.bool and r.shape == (6, 2) and r.dtype == torch.float64
+            n_trunc += int(trunc.sum())
+        ro, rr, rd, _ = ref.step(a)
+        assert torch.equal(o, ro) and torch.equal(r, rr) and torch.equal(d, rd != 0)
+    assert n_trunc > 0
+    assert vec.render('rgb_array').shape == (6, 2, 400, 600, 3)
+    with pytest.raises(RuntimeError):
+        vec.step_wait()
