@@ -456,6 +456,7 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
     set_spec(h, BUF_PENDING, "pending_reset", MCR_U8, {B});
     set_spec(h, BUF_ACTION_STAGE, "action_stage", MCR_F64, {N, 3});
     set_spec(h, BUF_CAMERA_VP, "camera_vp", MCR_F32, {6, N});
+    set_spec(h, BUF_TIMELINE, "timeline", MCR_F64, {TL_COUNT});      // u64 nanosecond stamps (8-byte slots)
     set_spec(h, BUF_TRK_T, "trk_T", MCR_I32, {P});
     set_spec(h, BUF_TRK_Q, "trk_Q", MCR_I32, {P});
     set_spec(h, BUF_TRK_NODE, "trk_node", MCR_F64, {P, T, 3});
@@ -531,6 +532,7 @@ extern "C" int mcr_bind_buffer(mcr_handle h, int i, void* p) {
         case BUF_PENDING: b.pending = (uint8_t*)p; break;
         case BUF_ACTION_STAGE: b.action_stage = (double*)p; break;
         case BUF_CAMERA_VP: b.camera_vp = (float*)p; break;
+        case BUF_TIMELINE: b.timeline = (unsigned long long*)p; break;
         case BUF_TRK_T: b.trk_T = (int32_t*)p; break;
         case BUF_TRK_Q: b.trk_Q = (int32_t*)p; break;
         case BUF_TRK_NODE: b.trk_node = (double*)p; break;
@@ -775,7 +777,7 @@ extern "C" int mcr_render_viewport(mcr_handle h, const uint8_t* mask, int32_t vw
 }
 
 static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, const void* action, int32_t action_dtype,
-                    uint8_t* obs, double* reward, uint8_t* done, int post_step, void* stream);
+                    uint8_t* obs, double* reward, uint8_t* done, int post_step, void* stream, const uint8_t* reset_flags = nullptr);
 
 extern "C" int mcr_reset(mcr_handle h, const uint8_t* mask, const int32_t* track_slot, const uint8_t* cw,
                          const double* spawn_pose, uint8_t* obs, void* stream) {
@@ -788,23 +790,34 @@ extern "C" int mcr_reset(mcr_handle h, const uint8_t* mask, const int32_t* track
 
 // One full pass (contacts, physics, post-step block, render) as two chains that only meet at the end:
 //   side   : contacts_kernel (reads the start poses) -> stripe_kernel        ............. score_kernel
-//   main   : carcontacts -> pre -> sweep ------------------> post(cls 1) -> render(cls 1)
+//   main   : head (auto reset + carcontacts + pre) -> sweep -> post(cls 1) -> render(cls 1)
 //   side2  :                   \-> coupled_kernel ---------> post(cls 2) -> score(cls 2) -> render(cls 2)
 // cls 1 = envs without car-car manifolds (per-car solver), cls 2 = envs with touching cars.  The
 // coupled solver (joints + contacts of a merged island in lock step, 100-250 us when any env of the
 // batch has touching cars) no longer stalls the other envs' post/render; the classes are disjoint
 // sets of envs, so the chains never touch the same state.
 static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, const void* action, int32_t action_dtype,
-                    uint8_t* obs, double* reward, uint8_t* done, int post_step, void* stream) {
+                    uint8_t* obs, double* reward, uint8_t* done, int post_step, void* stream, const uint8_t* reset_flags) {
     cudaStream_t s = (cudaStream_t)stream;
     { int rc_ = ensure_side(h); if (rc_) return rc_; }
     const Dims& d = h->d; const DevBuffers& b = h->buf; const CarConst& cc = h->cc;
     const bool split = h->cfg.collisions && d.A > 1;
     static const int early_exit = std::getenv("MCR_NO_EARLY_EXIT") ? 0 : 1;   // diagnostics only
-    CUDA_OK(cudaEventRecord(h->ev_fork, s));
-    CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-    LAUNCH(launch_contacts(d, b, cc, mask, h->side));
-    LAUNCH(launch_presweep(d, b, cc, mask, noact, action, action_dtype, h->cfg.collisions, 0, s));
+    const AutoResetCfg ar{h->cfg.use_random_direction, h->cfg.direction_cw, (unsigned long long)h->cfg.seed};
+    if (reset_flags) {
+        // next-step auto reset: the head kernel respawns the flagged envs first, so the contact pass
+        // (which reads the start poses) has to follow it
+        LAUNCH(launch_head(d, b, cc, mask, reset_flags, ar, action, action_dtype, h->cfg.collisions, s));
+        CUDA_OK(cudaEventRecord(h->ev_fork, s));
+        CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+        LAUNCH(launch_contacts(d, b, cc, mask, h->side));
+    } else {
+        CUDA_OK(cudaEventRecord(h->ev_fork, s));
+        CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+        LAUNCH(launch_contacts(d, b, cc, mask, h->side));
+        if (noact) LAUNCH(launch_presweep(d, b, cc, mask, noact, action, action_dtype, h->cfg.collisions, 0, s));
+        else LAUNCH(launch_head(d, b, cc, mask, nullptr, ar, action, action_dtype, h->cfg.collisions, s));
+    }
     CUDA_OK(cudaEventRecord(h->ev_pre, s));
     // wheel stripes for the rasteriser: they need pre_kernel's phase and nothing else, so they ride on
     // the side stream behind the contact pass; ev_contacts (which every post_kernel waits for) covers both
@@ -842,9 +855,8 @@ static int step_enqueue(mcr_handle h, const void* action, int32_t action_dtype, 
     if (flags & 2) {
         // next-step auto reset: envs whose previous step ended the episode respawn now and take
         // reset()'s step(None) inside this very pass -- one pass, no masked second pass
-        AutoResetCfg ar{h->cfg.use_random_direction, h->cfg.direction_cw, (unsigned long long)h->cfg.seed};
-        LAUNCH(launch_auto_reset(h->d, h->buf, h->cc, h->buf.pending, ar, stream));
-        return pipeline(h, nullptr, h->buf.reset_mask, action, action_dtype, obs, reward, done, 1, stream);
+        // (the respawn itself is the first stage of the pipeline's head kernel; it writes reset_mask)
+        return pipeline(h, nullptr, h->buf.reset_mask, action, action_dtype, obs, reward, done, 1, stream, h->buf.pending);
     }
     rc = pipeline(h, nullptr, nullptr, action, action_dtype, obs, reward, done, 1, stream); if (rc) return rc;
     if (flags & 1) {

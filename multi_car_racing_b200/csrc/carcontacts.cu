@@ -20,6 +20,8 @@
 //                       decision through lane masks.  Envs without manifolds never enter here:
 //                       their cars take the per-car fast path of sim.cu.
 #include "solver.cuh"
+#include "pre.cuh"
+#include "reset.cuh"
 
 #define CC_WARPS 4
 #define MAXM MCR_MAX_MANIFOLDS
@@ -175,18 +177,14 @@ __device__ __forceinline__ XF body_xf(const DevBuffers& b, int N, int car, int b
     return x;
 }
 
-__global__ void __launch_bounds__(CC_WARPS * 32)
-carcontacts_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask) {
-    __shared__ float s_old[CC_WARPS][MAXM * MW];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * CC_WARPS + warp;
-    if (env >= d.B) return;
-    if (mask && !mask[env]) return;
+// Narrow phase of one env by one warp (lanes over the fixture pairs of every car pair); s_old = this
+// warp's MAXM * MW floats of shared memory.
+__device__ void carcontacts_warp(const Dims& d, const DevBuffers& b, const CarConst& cc, int env, int lane, float* s_old_w) {
     const int A = d.A, N = d.N;
     float* gman = b.manifold + (size_t)env * MAXM * MW;
     if (A < 2) { if (lane == 0) b.n_manifold[env] = 0; return; }
     const int nold = b.n_manifold[env];
-    for (int i = lane; i < nold * MW; i += 32) s_old[warp][i] = gman[i];
+    for (int i = lane; i < nold * MW; i += 32) s_old_w[i] = gman[i];
     __syncwarp();
     const float r = B2_POLYGON_RADIUS;
     const int ncp = A * (A - 1) / 2;
@@ -207,11 +205,11 @@ carcontacts_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict_
             const Poly8& PB = fb < 4 ? cc.wheel_poly : cc.hull_poly[fb - 4];
             const uint32_t key = (uint32_t)a | ((uint32_t)fa << 8) | ((uint32_t)bcar << 16) | ((uint32_t)fb << 24);
             int prev = -1;
-            for (int i = 0; i < nold; ++i) if (__float_as_uint(s_old[warp][i * MW]) == key) { prev = i; break; }
+            for (int i = 0; i < nold; ++i) if (__float_as_uint(s_old_w[i * MW]) == key) { prev = i; break; }
             // wheels are always awake at Collide time (Car.step woke them); hull flags are the start-of-step ones
             const bool awakeA = fa < 4 ? true : (b.awake[carA] != 0), awakeB = fb < 4 ? true : (b.awake[carB] != 0);
             if (!awakeA && !awakeB) {
-                if (prev >= 0) { manifold_load(&s_old[warp][prev * MW], m); emit = m.pointCount > 0; }
+                if (prev >= 0) { manifold_load(&s_old_w[prev * MW], m); emit = m.pointCount > 0; }
             } else {
                 const XF xfA = body_xf(b, N, carA, bodyA), xfB = body_xf(b, N, carB, bodyB);
                 float alx = 3.402823466e+38f, aly = alx, ahx = -alx, ahy = -alx, blx = alx, bly = alx, bhx = -alx, bhy = -alx;
@@ -231,7 +229,7 @@ carcontacts_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict_
                     for (int i = 0; i < m.pointCount; ++i) {          // b2Contact::Update: impulses follow the feature id
                         m.ni[i] = 0.0f; m.ti[i] = 0.0f;
                         if (prev >= 0) {
-                            Manifold o; manifold_load(&s_old[warp][prev * MW], o);
+                            Manifold o; manifold_load(&s_old_w[prev * MW], o);
                             for (int j = 0; j < o.pointCount; ++j) if (o.id[j] == m.id[i]) { m.ni[i] = o.ni[j]; m.ti[i] = o.ti[j]; break; }
                         }
                     }
@@ -250,6 +248,47 @@ carcontacts_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict_
         nnew += __popc(bal);
     }
     if (lane == 0) b.n_manifold[env] = nnew < MAXM ? nnew : MAXM;
+}
+
+__global__ void __launch_bounds__(CC_WARPS * 32)
+carcontacts_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask) {
+    __shared__ float s_old[CC_WARPS][MAXM * MW];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int env = blockIdx.x * CC_WARPS + warp;
+    if (env >= d.B) return;
+    if (mask && !mask[env]) return;
+    carcontacts_warp(d, b, cc, env, lane, s_old[warp]);
+}
+
+// The head of mcr_step's pipeline as ONE launch, one warp per env: the next-step auto reset of the
+// envs whose previous step ended the episode (reset.cuh), the car-car narrow phase (above), then the
+// per-car head of the step (pre.cuh) on lanes 0 .. A-1.  Three dependent latency-bound launches
+// (auto_reset -> carcontacts -> pre, 3 + 7 + 9 us plus two launch gaps) become one.
+template <typename ActT>
+__global__ void __launch_bounds__(CC_WARPS * 32)
+head_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ reset_flags,
+            AutoResetCfg ar, const ActT* __restrict__ action, int collisions) {
+    __shared__ float s_old[CC_WARPS][MAXM * MW];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int env = blockIdx.x * CC_WARPS + warp;
+    if (env >= d.B) return;
+    if (mask && !mask[env]) return;
+    bool respawned = false;
+    tl_stamp(b.timeline, TL_HEAD);
+    if (reset_flags) {
+        respawned = reset_flags[env] != 0;
+        if (lane == 0) b.reset_mask[env] = respawned ? 1 : 0;
+        if (respawned) {
+            const uint32_t episode = b.env_episode[env] + 1u;
+            __syncwarp();                              // every lane has read the counter before lane 0 bumps it
+            auto_reset_env(d, b, cc, ar, env, episode, lane, 32);
+        }
+        __syncwarp();                                  // the respawned poses are visible to every lane
+    }
+    if (collisions && d.A > 1) carcontacts_warp(d, b, cc, env, lane, s_old[warp]);
+    __syncwarp();                                      // n_manifold[env]
+    // a respawned env takes reset()'s implicit step(None) (mcr:408): its action is ignored
+    if (lane < d.A) pre_car<ActT>(d, b, cc, env * d.A + lane, env, action != nullptr && !respawned, action);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -456,6 +495,7 @@ coupled_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
     __shared__ int s_root[MCR_MAX_AGENTS];
     __shared__ float s_minsep[MCR_MAX_AGENTS];
     __shared__ int s_changed;
+    tl_stamp(b.timeline, TL_COUPLED);
     const int env = blockIdx.x, lane = threadIdx.x;
     if (mask && !mask[env]) return;
     const int nman = b.n_manifold[env];
@@ -667,6 +707,16 @@ coupled_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
 
 int launch_carcontacts(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, void* stream) {
     carcontacts_kernel<<<(d.B + CC_WARPS - 1) / CC_WARPS, CC_WARPS * 32, 0, (cudaStream_t)stream>>>(d, b, cc, mask);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_head(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* reset_flags,
+                const AutoResetCfg& ar, const void* action, int action_dtype, int collisions, void* stream) {
+    const int nb = (d.B + CC_WARPS - 1) / CC_WARPS;
+    if (action_dtype == MCR_F64)
+        head_kernel<double><<<nb, CC_WARPS * 32, 0, (cudaStream_t)stream>>>(d, b, cc, mask, reset_flags, ar, (const double*)action, collisions);
+    else
+        head_kernel<float><<<nb, CC_WARPS * 32, 0, (cudaStream_t)stream>>>(d, b, cc, mask, reset_flags, ar, (const float*)action, collisions);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -43,7 +43,7 @@ enum {
     BUF_ON_ROAD, BUF_ON_ROAD_NEXT, BUF_REWARD, BUF_PREV_REWARD, BUF_VISIT_COUNT, BUF_BACKWARD,
     BUF_TIME, BUF_STEPS, BUF_CAMERA, BUF_STRIPE, BUF_HEADING,
     BUF_ENV_TRACK, BUF_ENV_CW, BUF_ENV_EPISODE,
-    BUF_VISITED, BUF_TOUCHED, BUF_RESET_MASK, BUF_STATUS, BUF_SCRATCH, BUF_MANIFOLD, BUF_N_MANIFOLD, BUF_SCORE_SNAP, BUF_BACKWARD_SNAP, BUF_PENDING, BUF_ACTION_STAGE, BUF_CAMERA_VP,
+    BUF_VISITED, BUF_TOUCHED, BUF_RESET_MASK, BUF_STATUS, BUF_SCRATCH, BUF_MANIFOLD, BUF_N_MANIFOLD, BUF_SCORE_SNAP, BUF_BACKWARD_SNAP, BUF_PENDING, BUF_ACTION_STAGE, BUF_CAMERA_VP, BUF_TIMELINE,
     BUF_TRK_T, BUF_TRK_Q, BUF_TRK_NODE, BUF_TRK_TILE, BUF_TRK_TILE_AABB, BUF_TRK_QUAD, BUF_TRK_QUAD_COL,
     BUF_TRK_QUAD_TILE, BUF_TRK_SLOT_POSE, BUF_TRK_CHUNK,
     BUF_COUNT
@@ -90,12 +90,21 @@ struct DevBuffers {
     uint8_t* pending;                    // [B] done flags of the previous step (next-step auto reset)
     double* action_stage;                // [N][3] f64-sized staging copy of the step's action (CUDA-graph replay reads it)
     float* camera_vp;                    // [6][N] camera affine of the last mcr_render_viewport call
+    unsigned long long* timeline;        // [TL_COUNT] %globaltimer stamps (ns) of the last step's kernels, see TL_*
     int32_t* trk_T; int32_t* trk_Q; double* trk_node; float* trk_tile; float* trk_tile_aabb;
     float* trk_quad; uint8_t* trk_quad_col; int16_t* trk_quad_tile; double* trk_slot_pose;
     float* trk_chunk;                    // [P][Qmax/8][4] bounding circle (cx, cy, r, 0) of 8 consecutive road_poly quads
 };
 
 struct Dims { int B, A, N, Tmax, Qmax, P; };
+// timeline slots: kernel start stamps (block 0, thread 0) and the latest CTA end of the rasteriser
+enum { TL_HEAD = 0, TL_CONTACTS, TL_STRIPES, TL_SWEEP, TL_COUPLED, TL_POST, TL_SCORE, TL_RENDER, TL_RENDER_END, TL_POST2, TL_RENDER2, TL_SWEEP_END, TL_SWEEP_END_PACKED, TL_COUNT = 16 };
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long mcr_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void tl_stamp(const unsigned long long* tl_base, int slot) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) const_cast<unsigned long long*>(tl_base)[slot] = mcr_globaltimer();
+}
+#endif
 
 // kernel launchers (each returns the number of kernels it launched, or < 0 on error)
 int launch_contacts(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, void* stream);
@@ -126,5 +135,8 @@ int launch_trackgen(const Dims& d, const DevBuffers& b, int n, uint32_t* mt_stat
 int launch_spawn(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
                  const int32_t* track_slot, const uint8_t* cw, const double* spawn_pose, void* stream);
 struct AutoResetCfg { int use_random_direction, direction_cw; unsigned long long seed; };
+// auto reset (reset_flags != NULL: respawn the flagged envs, write reset_mask) + carcontacts + pre in one launch
+int launch_head(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* reset_flags,
+                const AutoResetCfg& ar, const void* action, int action_dtype, int collisions, void* stream);
 int launch_auto_reset(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* done,
                       const AutoResetCfg& cfg, void* stream);

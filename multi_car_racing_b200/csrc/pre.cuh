@@ -1,0 +1,154 @@
+// pre.cuh -- the per-car head of a step: controls (mcr:421-424), Car.step's float64 tyre model
+// (mcr:426-427, gym car_dynamics) and the start of b2Island::Solve (integrate forces,
+// InitVelocityConstraints + warm start), handed to the sweep kernels through `scratch`.
+// One THREAD per car.  Shared by pre_kernel (sim.cu) and the fused head_kernel (carcontacts.cu).
+#pragma once
+#include "solver.cuh"
+
+// take_action = false: the action=None path of mcr:421 (reset()'s implicit step, next-step auto reset)
+template <typename ActT>
+__device__ __forceinline__ void pre_car(const Dims& d, const DevBuffers& b, const CarConst& cc, int car, int env,
+                                        bool take_action, const ActT* __restrict__ action) {
+    const int N = d.N;
+
+    // ---- load state ----------------------------------------------------------------
+    float cx[5], cy[5], ang[5], vx[5], vy[5], w[5], qs[5], qc[5], slp[5];
+    bool awake[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const float* p = b.body + (size_t)(i * BODY_FIELDS) * N + car;
+        cx[i] = p[(size_t)BF_CX * N]; cy[i] = p[(size_t)BF_CY * N]; ang[i] = p[(size_t)BF_A * N];
+        vx[i] = p[(size_t)BF_VX * N]; vy[i] = p[(size_t)BF_VY * N]; w[i] = p[(size_t)BF_W * N];
+        qs[i] = p[(size_t)BF_QS * N]; qc[i] = p[(size_t)BF_QC * N];
+        slp[i] = b.sleep_time[(size_t)i * N + car];
+        awake[i] = b.awake[(size_t)i * N + car] != 0;
+    }
+    float jix[4], jiy[4], jiz[4], jmot[4];
+    int lim[4];
+    double omega[4], phase[4];
+    bool on_road[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float* p = b.joint + (size_t)(k * JOINT_FIELDS) * N + car;
+        jix[k] = p[(size_t)JF_IX * N]; jiy[k] = p[(size_t)JF_IY * N]; jiz[k] = p[(size_t)JF_IZ * N];
+        jmot[k] = p[(size_t)JF_MOTOR * N];
+        lim[k] = b.limit_state[(size_t)k * N + car];
+        omega[k] = b.wheel[(size_t)(k * WHEEL_FIELDS + WF_OMEGA) * N + car];
+        phase[k] = b.wheel[(size_t)(k * WHEEL_FIELDS + WF_PHASE) * N + car];
+        on_road[k] = b.on_road[(size_t)k * N + car] != 0;
+    }
+    double gas = b.ctrl[(size_t)CF_GAS * N + car];
+    double brake = b.ctrl[(size_t)CF_BRAKE * N + car];
+    double steer = b.ctrl[(size_t)CF_STEER * N + car];
+
+    // ---- controls, mcr:421-424 -------------------------------------------------------
+    if (take_action) {
+        double a0 = (double)action[(size_t)car * 3 + 0];
+        double a1 = (double)action[(size_t)car * 3 + 1];
+        double a2 = (double)action[(size_t)car * 3 + 2];
+        steer = -a0;
+        double g = a1 < 0 ? 0 : (a1 > 1 ? 1 : a1);
+        double diff = g - gas;
+        if (diff > 0.1) diff = 0.1;
+        gas += diff;
+        brake = a2;
+    }
+
+    // ---- Car.step(dt): tyre model (float64), per wheel ------------------------------------
+    const double SIZE = 0.02;
+    const double ENGINE_POWER = 100000000 * SIZE * SIZE;
+    const double WHEEL_MOI = 4000 * SIZE * SIZE;
+    const double FRICTION_LIMIT = 1000000 * SIZE * SIZE;
+    const double dt = 1.0 / 50;
+    float motorSpeed[4], Fx[4], Fy[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int bi = 1 + k;
+        const double steer_w = k < 2 ? steer : 0.0;
+        const double gas_w = k >= 2 ? gas : 0.0;
+        double jangle = (double)(ang[bi] - ang[0]);
+        double dir = sign_d(steer_w - jangle);
+        double val = fabs(steer_w - jangle);
+        motorSpeed[k] = (float)(dir * fmin(50.0 * val, 3.0));
+        double friction_limit = FRICTION_LIMIT * 0.6;
+        if (on_road[k]) friction_limit = fmax(friction_limit, FRICTION_LIMIT * 1.0);
+        // GetWorldVector((0,1)) = (-s, c); ((1,0)) = (c, s)   (fp32 products with exact 0/1)
+        float forw_x = qc[bi] * 0.0f - qs[bi] * 1.0f, forw_y = qs[bi] * 0.0f + qc[bi] * 1.0f;
+        float side_x = qc[bi] * 1.0f - qs[bi] * 0.0f, side_y = qs[bi] * 1.0f + qc[bi] * 0.0f;
+        double wvx = vx[bi], wvy = vy[bi];
+        double vf = (double)forw_x * wvx + (double)forw_y * wvy;
+        double vs = (double)side_x * wvx + (double)side_y * wvy;
+        omega[k] += dt * ENGINE_POWER * gas_w / WHEEL_MOI / (fabs(omega[k]) + 5.0);
+        if (brake >= 0.9) {
+            omega[k] = 0;
+        } else if (brake > 0) {
+            double bdir = -sign_d(omega[k]);
+            double bval = 15 * brake;
+            if (fabs(bval) > fabs(omega[k])) bval = fabs(omega[k]);
+            omega[k] += bdir * bval;
+        }
+        phase[k] += omega[k] * dt;
+        const double wheel_rad = 1.0 * 27 * SIZE;
+        double vr = omega[k] * wheel_rad;
+        double f_force = -vf + vr;
+        double p_force = -vs;
+        f_force *= 205000 * SIZE * SIZE;
+        p_force *= 205000 * SIZE * SIZE;
+        double force = sqrt(f_force * f_force + p_force * p_force);
+        if (fabs(force) > friction_limit) {
+            f_force /= force; p_force /= force;
+            force = friction_limit;
+            f_force *= force; p_force *= force;
+        }
+        omega[k] -= dt * f_force * wheel_rad / WHEEL_MOI;
+        Fx[k] = (float)(p_force * (double)side_x + f_force * (double)forw_x);
+        Fy[k] = (float)(p_force * (double)side_y + f_force * (double)forw_y);
+        if (!awake[bi]) { awake[bi] = true; slp[bi] = 0.0f; }   // ApplyForceToCenter(wake=True)
+    }
+
+    // ---- b2Island::Solve ---------------------------------------------------------------
+    const float h = (float)(1.0 / 50);
+    const float mA = cc.hull_invMass, iA = cc.hull_invI, mB = cc.wheel_invMass, iB = cc.wheel_invI;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        vx[1 + k] += h * (mB * Fx[k]);
+        vy[1 + k] += h * (mB * Fy[k]);
+    }
+    // InitVelocityConstraints, joints in island order 3,2,1,0 (coupled envs do it after the contact warm start)
+    // Cars of an env with car-car manifolds are solved together by coupled_kernel (contact warm start
+    // comes before the joints' in b2Island::Solve), so their joints are NOT initialised here.
+    const bool coupled = b.n_manifold[env] > 0;
+    JointC J[4];
+    if (!coupled) joints_init(cc, ang, motorSpeed, vx, vy, w, jix, jiy, jiz, jmot, lim, J);
+    else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { J[k] = JointC(); J[k].motorSpeed = motorSpeed[k]; }
+    }
+    // ---- hand over to sweep_kernel / post_kernel ---------------------------------------------------
+    float* sc = b.scratch + car;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        sc[(size_t)(SC_VX + i) * N] = vx[i]; sc[(size_t)(SC_VY + i) * N] = vy[i]; sc[(size_t)(SC_W + i) * N] = w[i];
+        if (i > 0) {   // wheels woken by ApplyForceToCenter; the hull's flag is read by contacts_kernel right now
+            b.sleep_time[(size_t)i * N + car] = slp[i];
+            b.awake[(size_t)i * N + car] = awake[i] ? 1 : 0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        sc[(size_t)(SC_JIX + k) * N] = jix[k]; sc[(size_t)(SC_JIY + k) * N] = jiy[k];
+        sc[(size_t)(SC_JIZ + k) * N] = jiz[k]; sc[(size_t)(SC_JMOT + k) * N] = jmot[k];
+        const JointC& j = J[k];
+        float* q = sc + (size_t)(SC_JOINT + k * SC_JOINT_FIELDS) * N;
+        q[(size_t)0 * N] = j.rAx; q[(size_t)1 * N] = j.rAy; q[(size_t)2 * N] = j.k11; q[(size_t)3 * N] = j.k12;
+        q[(size_t)4 * N] = j.k22; q[(size_t)5 * N] = j.ezx; q[(size_t)6 * N] = j.ezy; q[(size_t)7 * N] = j.ezz;
+        q[(size_t)8 * N] = j.det22; q[(size_t)9 * N] = j.cfx; q[(size_t)10 * N] = j.cfy; q[(size_t)11 * N] = j.cfz;
+        q[(size_t)12 * N] = j.det33; q[(size_t)13 * N] = j.motorMass; q[(size_t)14 * N] = j.motorSpeed;
+        b.limit_state[(size_t)k * N + car] = (uint8_t)lim[k];
+        b.wheel[(size_t)(k * WHEEL_FIELDS + WF_OMEGA) * N + car] = omega[k];
+        b.wheel[(size_t)(k * WHEEL_FIELDS + WF_PHASE) * N + car] = phase[k];
+    }
+    b.ctrl[(size_t)CF_GAS * N + car] = gas;
+    b.ctrl[(size_t)CF_BRAKE * N + car] = brake;
+    b.ctrl[(size_t)CF_STEER * N + car] = steer;
+}
