@@ -605,6 +605,7 @@ coupled_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
         }
         if (early_exit && !__any_sync(0xffffffffu, changed)) break;
     }
+    if (lane == 0) { atomicMax(b.timeline + TL_COUPLED_VEL_END, mcr_globaltimer()); }
     // StoreImpulses
     if (lane < nman) {
         float* w = gman + (size_t)lane * MW;
@@ -670,6 +671,7 @@ coupled_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
         }
         __syncwarp();
     }
+    if (lane == 0) { atomicMax(b.timeline + TL_COUPLED_POS_END, mcr_globaltimer()); }
     // ---- sleep, island-wide ------------------------------------------------------------------------------------
     float laneMin = 3.402823466e+38f;
 #pragma unroll

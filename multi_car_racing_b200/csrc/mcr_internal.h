@@ -98,7 +98,7 @@ struct DevBuffers {
 
 struct Dims { int B, A, N, Tmax, Qmax, P; };
 // timeline slots: kernel start stamps (block 0, thread 0) and the latest CTA end of the rasteriser
-enum { TL_HEAD = 0, TL_CONTACTS, TL_STRIPES, TL_SWEEP, TL_COUPLED, TL_POST, TL_SCORE, TL_RENDER, TL_RENDER_END, TL_POST2, TL_RENDER2, TL_SWEEP_END, TL_SWEEP_END_PACKED, TL_COUNT = 16 };
+enum { TL_HEAD = 0, TL_CONTACTS, TL_STRIPES, TL_SWEEP, TL_COUPLED, TL_POST, TL_SCORE, TL_RENDER, TL_RENDER_END, TL_POST2, TL_RENDER2, TL_SWEEP_END, TL_SWEEP_END_PACKED, TL_COUPLED_VEL_END, TL_COUPLED_POS_END, TL_COUNT = 16 };
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned long long mcr_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void tl_stamp(const unsigned long long* tl_base, int slot) {

@@ -529,6 +529,12 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
                 y1 = (int)ceilf(fminf(ymax, (float)VH) - 0.5f); if (y1 > VH) y1 = VH;
                 if (VP) { y0 = max(y0, oy) - oy; y1 = min(y1, min(oy + SH, VH)) - oy; }
                 if (y1 <= y0) valid = false;
+                // same test along x: a polygon whose bounding box holds no pixel-centre column fills nothing
+                // (every span lies inside [xmin, xmax]); most road quads of a zoomed-out frame go here
+                // (such a box is < 1 px wide, so |x| <= vw + 1 and the interpolated crossings stay within a few
+                // ulp(vw) ~ 1e-4 of [xmin, xmax]: the 1e-3 margin keeps the cull conservative, hence exact)
+                const float cx0 = ceilf((fmaxf(xmin, tx0) - 1e-3f) - 0.5f), cx1 = ceilf((fminf(xmax, tx1) + 1e-3f) - 0.5f);
+                if (!(cx1 > cx0)) valid = false;
             }
         }
         const int rows = valid ? y1 - y0 : 0;

@@ -1,26 +1,27 @@
 """Where one step's time goes INSIDE the CUDA graph: %globaltimer stamps written by the kernels
 themselves (start of each kernel, latest CTA end of sweep / render), averaged over steps.
-    python scripts/timeline.py [B] [steps]"""
+    python scripts/timeline.py [B] [steps] [warm steps]"""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 import numpy as np, torch
 import multi_car_racing_b200 as mcr
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 200
-names = ["head", "contacts", "stripes", "sweep", "coupled", "post", "score", "render", "render_end", "post2", "render2", "sweep_end_percar", "sweep_end_packed"]
+WARM = int(sys.argv[3]) if len(sys.argv) > 3 else 60      # e.g. 900: late-episode steps (cars collide more)
+names = ["head", "contacts", "stripes", "sweep", "coupled", "post", "score", "render", "render_end", "post2", "render2", "sweep_end_percar", "sweep_end_packed", "coupled_vel_end", "coupled_pos_end"]
 np.random.seed(1234)
 venv = mcr.BatchedMultiCarRacing(B, num_agents=2, auto_reset="next_step", max_episode_steps=1000, seed=1234)
 venv.reset()
 g = torch.Generator(device=venv.device); g.manual_seed(1234)
 tape = torch.rand((128, B, 2, 3), device=venv.device, generator=g); tape[..., 0] = tape[..., 0] * 2 - 1
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-for s in range(60): venv.step(tape[s % 128])
+for s in range(WARM): venv.step(tape[s % 128])
 tl = venv.buffers["timeline"].view(torch.int64)
 acc = np.zeros(len(names)); n = 0; tot = 0.0
 for s in range(STEPS):
     flush.zero_(); tl.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); venv.step(tape[(60 + s) % 128]); e1.record()
+    e0.record(); venv.step(tape[(WARM + s) % 128]); e1.record()
     torch.cuda.synchronize()
     t = tl.cpu().numpy()[:len(names)].astype(np.float64)
     acc += (t - t[0]) / 1e3; n += 1; tot += e0.elapsed_time(e1) * 1e3
