@@ -196,8 +196,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
     import multi_car_racing_b200 as mcr
+    from multi_car_racing_b200.dist import bind_to_gpu_numa_node
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa_node = bind_to_gpu_numa_node(local_rank)     # before any pinned allocation
     K, W = max(1, int(args.steps)), max(3, int(args.warmup))
     B, A = int(args.batch_envs), int(args.num_agents)
     frames_per_step = B * A
@@ -308,6 +310,7 @@ def run_ours(args):
                          "kernel_ms": {"simulate": k_ms[0], "render": k_ms[1]}},
             "cpu_baseline": cpu,
             "status_words": status,
+            "host": {"numa_node_rank0": numa_node, "cpus_rank0": len(os.sched_getaffinity(0))},
         }
         print(json.dumps(line))
     if world > 1:

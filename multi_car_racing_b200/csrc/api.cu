@@ -384,7 +384,8 @@ struct mcr_handle_t {
     cudaStream_t cap;            // capture origin for the step graph (the caller's stream may be the legacy default stream, which cannot be captured)
     cudaEvent_t ev_fork, ev_join;
     cudaStream_t side2;          // the chain of envs with touching cars: coupled -> post -> score -> render
-    cudaEvent_t ev_pre, ev_contacts, ev_chain2, ev_score;
+    cudaStream_t side3;          // score_kernel of the touching-car envs, beside their rasteriser
+    cudaEvent_t ev_pre, ev_contacts, ev_chain2, ev_score, ev_post2, ev_score2;
     bool side_ready;
     // mcr_step replays a captured CUDA graph of its launches (one graph per argument tuple)
     struct StepGraph { int32_t dtype, flags; uint8_t* obs; double* reward; uint8_t* done; cudaGraphExec_t exec; int64_t launches; };
@@ -475,6 +476,7 @@ extern "C" int mcr_destroy(mcr_handle h) {
     if (h) for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
     if (h && h->side_ready) {
         cudaStreamDestroy(h->side); cudaStreamDestroy(h->cap); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
+        cudaStreamDestroy(h->side3); cudaEventDestroy(h->ev_post2); cudaEventDestroy(h->ev_score2);
         cudaStreamDestroy(h->side2); cudaEventDestroy(h->ev_pre); cudaEventDestroy(h->ev_contacts); cudaEventDestroy(h->ev_chain2); cudaEventDestroy(h->ev_score);
     }
     delete h;
@@ -701,6 +703,9 @@ static int ensure_side(mcr_handle h) {
         CUDA_OK(cudaEventCreateWithFlags(&h->ev_contacts, cudaEventDisableTiming));
         CUDA_OK(cudaEventCreateWithFlags(&h->ev_chain2, cudaEventDisableTiming));
         CUDA_OK(cudaEventCreateWithFlags(&h->ev_score, cudaEventDisableTiming));
+        CUDA_OK(cudaStreamCreateWithFlags(&h->side3, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&h->ev_post2, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&h->ev_score2, cudaEventDisableTiming));
         h->side_ready = true;
     }
     return 0;
@@ -829,8 +834,17 @@ static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, con
         LAUNCH(launch_coupled(d, b, cc, mask, early_exit, h->side2));
         CUDA_OK(cudaStreamWaitEvent(h->side2, h->ev_contacts, 0));
         LAUNCH(launch_physics_post(d, b, cc, mask, noact, action != nullptr, h->cfg.h_ratio, 2, h->side2));
-        if (post_step) LAUNCH(launch_score(d, b, mask, noact, reward, done, h->cfg.max_episode_steps, 2, h->side2));
+        // this chain is the long pole whenever an env has touching cars (coupled_kernel: 220 us): render first,
+        // the reward / done block after it costs nothing on the main chain's clock only if it is short, so it
+        // goes on the third side stream beside the rasteriser
+        if (post_step) {
+            CUDA_OK(cudaEventRecord(h->ev_post2, h->side2));
+            CUDA_OK(cudaStreamWaitEvent(h->side3, h->ev_post2, 0));
+            LAUNCH(launch_score(d, b, mask, noact, reward, done, h->cfg.max_episode_steps, 2, h->side3));
+            CUDA_OK(cudaEventRecord(h->ev_score2, h->side3));
+        }
         LAUNCH(launch_render(d, b, cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, 2, h->obs_format, h->side2));
+        if (post_step) CUDA_OK(cudaStreamWaitEvent(h->side2, h->ev_score2, 0));
         CUDA_OK(cudaEventRecord(h->ev_chain2, h->side2));
     }
     LAUNCH(launch_presweep(d, b, cc, mask, noact, action, action_dtype, h->cfg.collisions, 1, s));

@@ -102,7 +102,7 @@ enum { TL_HEAD = 0, TL_CONTACTS, TL_STRIPES, TL_SWEEP, TL_COUPLED, TL_POST, TL_S
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned long long mcr_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void tl_stamp(const unsigned long long* tl_base, int slot) {
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) const_cast<unsigned long long*>(tl_base)[slot] = mcr_globaltimer();
+    if ((blockIdx.x | blockIdx.y | threadIdx.x) == 0) const_cast<unsigned long long*>(tl_base)[slot] = mcr_globaltimer();
 }
 #endif
 

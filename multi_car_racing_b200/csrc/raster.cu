@@ -383,13 +383,14 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
     if (!VP) tl_stamp(b.timeline, cls == 2 ? TL_RENDER2 : TL_RENDER);
-    const int frame = blockIdx.x;
+    // VP = false: grid (B, A) -- env and agent come from the block index, no integer division per thread
+    const int frame = VP ? (int)blockIdx.x : (int)(blockIdx.x * d.A + blockIdx.y);
     const int ox = VP ? (int)(blockIdx.y % vp.tiles_x) * SW : 0, oy = VP ? (int)(blockIdx.y / vp.tiles_x) * SH : 0;
     const int VW = VP ? vp.vw : SW, VH = VP ? vp.vh : SH;
     const float* __restrict__ camera = VP ? vp.camera : b.camera;
     // this tile's rectangle in viewport pixels (partial tiles at the right / top edge)
     const float tx0 = (float)ox, ty0 = (float)oy, tx1 = (float)min(ox + SW, VW), ty1 = (float)min(oy + SH, VH);
-    const int env = frame / d.A, agent = frame % d.A;
+    const int env = VP ? frame / d.A : (int)blockIdx.x, agent = VP ? frame % d.A : (int)blockIdx.y;
     if (mask && !mask[env]) return;
     if (cls && (cls == 2) != (b.n_manifold[env] > 0)) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -804,7 +805,7 @@ static bool configure_render() {
 int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* obs,
                   int backwards_flag, int use_ego_color, int cls, int obs_format, void* stream) {
     if (!configure_render()) return -1;
-    render_kernel<false><<<d.N, RS_THREADS, sizeof(RasterSmem), (cudaStream_t)stream>>>(d, b, cc, mask, obs, backwards_flag, use_ego_color, cls, obs_format, VpParams{});
+    render_kernel<false><<<dim3(d.B, d.A), RS_THREADS, sizeof(RasterSmem), (cudaStream_t)stream>>>(d, b, cc, mask, obs, backwards_flag, use_ego_color, cls, obs_format, VpParams{});
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -30,3 +30,40 @@ def reduce_throughput(frames, elapsed_ms, device=None):
     dist.all_reduce(t_sum, op=dist.ReduceOp.SUM)
     dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
     return float(t_sum.item()), float(t_max.item())
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index):
+    """One process per GPU: pin this process to the CPUs of the NUMA node its GPU hangs off, so that
+    the pinned staging buffers of step_host (allocated afterwards, first-touch local) and the copy
+    threads sit next to the GPU's PCIe root.  With 8 ranks copying 56.6 MB of observations per step
+    each, remote-node staging halves the aggregate device-to-host bandwidth.  Returns the node id,
+    or None when the topology cannot be read (nothing is changed then).  MCR_NUMA_BIND=0 disables."""
+    if os.environ.get("MCR_NUMA_BIND", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = _parse_cpulist(open("/sys/devices/system/node/node%d/cpulist" % node).read())
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None

@@ -24,8 +24,8 @@ for s in range(STEPS):
     e0.record(); venv.step(tape[(WARM + s) % 128]); e1.record()
     torch.cuda.synchronize()
     t = tl.cpu().numpy()[:len(names)].astype(np.float64)
-    acc += (t - t[0]) / 1e3; n += 1; tot += e0.elapsed_time(e1) * 1e3
+    acc += np.where(t > 0, (t - t[0]) / 1e3, np.nan); n += 1; tot += e0.elapsed_time(e1) * 1e3
 print("step (events) %.1f us; kernel start stamps relative to head_kernel start, us:" % (tot / n))
-for k, v in sorted(zip(names, acc / n), key=lambda kv: kv[1]):
-    print("  %-11s %8.1f" % (k, v))
+for k, v in sorted(zip(names, acc / n), key=lambda kv: (np.isnan(kv[1]), kv[1])):
+    print("  %-18s %8.1f" % (k, v) if not np.isnan(v) else "  %-18s  (did not run in every step)" % k)
 
