@@ -583,13 +583,19 @@ coupled_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
     joints_init(cc, ang, motorSpeed, s.vx, s.vy, s.w, s.jix, s.jiy, s.jiz, s.jmot, lim, J);
     Masses m; m.mA = cc.hull_invMass; m.iA = cc.hull_invI; m.mB = cc.wheel_invMass; m.iB = cc.wheel_invI;
     m.maxMotorImpulse = h * cc.max_motor_torque;
+    // joints_init fixed every joint's limit state for the step: when no car of the env has an active limit
+    // (the common case) the whole warp runs the straight-line sweep<0> instead of the branching sweep<-1>
+    // (696 -> 540 cycles per sweep, clock64 in situ).  The contact solve itself (~550 cycles for one two-point
+    // manifold) is a dependent chain too: moving it from lane 0 / shared memory to a redundant solve in
+    // registers fed by shuffles was measured and is not faster (809 cycles).
+    const bool no_limits = __all_sync(0xffffffffu, !mine || (lim[0] | lim[1] | lim[2] | lim[3]) == LIM_INACTIVE);
     for (int it = 0; it < MCR_VEL_ITERS; it += 4) {
         const VelState before = s;
         float ci_before[2][4];                         // contact impulses of "my" manifold (lane < nman)
         if (lane < nman) { ci_before[0][0] = s_vc[lane].ni[0]; ci_before[0][1] = s_vc[lane].ni[1]; ci_before[0][2] = s_vc[lane].ti[0]; ci_before[0][3] = s_vc[lane].ti[1]; }
 #pragma unroll 1
         for (int rep = 0; rep < 4; ++rep) {
-            sweep<-1>(s, J, m);
+            if (no_limits) sweep<0>(s, J, m); else sweep<-1>(s, J, m);
             push_vel();
             __syncwarp();
             if (lane == 0) for (int i = 0; i < nman; ++i) contact_solve_vel(s_vc[i], s_bm);

@@ -614,7 +614,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     const int my_seg = tid / SH, my_y = tid - SH * my_seg;
     // ---- score label glyphs (D3): observation rows 87..91 (= GL rows 8..4), cols 2..13 -------------
     if (VP) {
-        // the same glyph cells, scaled: viewport pixel -> state cell by nearest neighbour (oracle draw_label_vp)
+        // the same glyph cells, scaled: viewport pixel -> state cell by nearest neighbour (D3)
         const int Y = VH - 1 - (oy + my_y);                       // image row from the top
         const int sy = (int)floor(((double)Y + 0.5) * 96.0 / (double)VH) - 87;
         if (sy >= 0 && sy < 5 && oy + my_y < VH) {
