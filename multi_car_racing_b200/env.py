@@ -390,14 +390,18 @@ class BatchedMultiCarRacing:
         assert mode in ['human', 'state_pixels', 'rgb_array']
         if mode == 'human':
             raise NotImplementedError("mode='human' needs a display; use 'rgb_array' (same picture at 600x400)")
-        torch = _torch()
         vw, vh = (STATE_W, STATE_H) if mode == 'state_pixels' else (VIDEO_W, VIDEO_H)
-        key = "_render_" + mode
-        if getattr(self, key, None) is None:
-            setattr(self, key, torch.zeros((self.batch_envs, self.num_agents, vh, vw, 3), dtype=torch.uint8, device=self.device))
-        out = getattr(self, key)
+        return self.render_viewport(vw, vh)
+
+    def render_viewport(self, vw, vh):
+        """The render() picture for any glViewport size (width a multiple of 4): (B, A, vh, vw, 3) uint8."""
+        torch = _torch()
+        cache = self.__dict__.setdefault("_render_buffers", {})
+        out = cache.get((vw, vh))
+        if out is None:
+            out = cache[(vw, vh)] = torch.zeros((self.batch_envs, self.num_agents, vh, vw, 3), dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self.L.mcr_render_viewport(self._h, None, vw, vh, out.data_ptr(), self._stream()), "mcr_render_viewport")
+            _lib.check(self.L.mcr_render_viewport(self._h, None, int(vw), int(vh), out.data_ptr(), self._stream()), "mcr_render_viewport")
         return out
 
     # ---- split entry points (bench / ncu / tests) ------------------------------------------------

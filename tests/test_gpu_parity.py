@@ -153,6 +153,27 @@ def test_render_modes_between_steps(oracle, mcr):
                 assert bad == 0, "%s, step %d: %d pixels differ" % (mode, s, bad)
 
 
+def test_viewport_tiling_partial_tiles_ego_color(oracle, mcr):
+    """mcr_render_viewport on viewports that do not divide into 96 x 96 tiles (partial tiles on the right
+    and top edges, a single partial tile, a human-sized window), 3 agents with use_ego_color and a
+    non-default h_ratio: bit-exact against the oracle's full-frame fill."""
+    import torch
+    venv, worlds, tracks, obs0, oobs0 = _setup(oracle, mcr, B=2, A=3, seed=41, use_ego_color=True, h_ratio=0.4)
+    tape = action_tape(41, 70, 2, 3)
+    for s in range(70):
+        venv.step(torch.from_numpy(tape[s]).to(venv.device))
+        for e, w in enumerate(worlds):
+            w.step(tape[s, e].astype(np.float64), render=False)
+        if s in (1, 69):
+            for vw, vh in ((200, 120), (52, 40), (1000, 800)):
+                got = venv.render_viewport(vw, vh).cpu().numpy()
+                want = np.stack([w.render_viewport(vw, vh) for w in worlds])
+                bad = int((got != want).any(axis=-1).sum())
+                assert got.shape == want.shape and bad == 0, "%dx%d, step %d: %d pixels differ" % (vw, vh, s, bad)
+    with pytest.raises(mcr.McrError):
+        venv.render_viewport(50, 40)            # width must be a multiple of 4
+
+
 def test_single_env_dropin_matches_oracle_env(oracle, mcr):
     """The reference-shaped API end to end: same seeds -> same tracks, spawn, rewards, frames."""
     np.random.seed(5)

@@ -176,6 +176,15 @@ def test_box_and_timelimit_shims(mcr):
     assert tl.step(None)[3] == {'TimeLimit.truncated': True}
 
 
+def test_numa_binding_helper_is_safe_without_topology():
+    from multi_car_racing_b200.dist import _parse_cpulist, bind_to_gpu_numa_node
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa_node(0) is None or isinstance(bind_to_gpu_numa_node(0), int)   # no GPU / no sysfs entry: no-op
+    os.sched_setaffinity(0, before)
+
+
 def test_env_sharding():
     from multi_car_racing_b200.dist import shard_envs
     for total, world in ((8192, 8), (1000, 3), (5, 8)):
