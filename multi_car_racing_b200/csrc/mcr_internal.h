@@ -106,6 +106,25 @@ __device__ __forceinline__ void tl_stamp(const unsigned long long* tl_base, int 
 }
 #endif
 
+// Programmatic dependent launch for the kernels of the critical chain (head -> sweep -> post -> render): the
+// dependent kernel's CTAs are launched while its predecessor in the stream is still draining and wait in
+// cudaGridDependencySynchronize() (first statement of the kernel), which takes the launch latency of the big
+// grids off the chain.  MCR_NO_PDL=1 falls back to plain stream order.
+#ifdef __CUDACC__
+#include <cstdlib>
+template <typename... KArgs, typename... Args>
+static inline cudaError_t mcr_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    static const bool use_pdl = std::getenv("MCR_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 // kernel launchers (each returns the number of kernels it launched, or < 0 on error)
 int launch_contacts(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, void* stream);
 // noact[env] != 0: that env takes the action=None path of mcr:421 this step (next-step auto reset)

@@ -382,6 +382,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
               int backwards_flag, int use_ego_color, int cls, int obs_format, VpParams vp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
+    if (!VP) cudaGridDependencySynchronize();      // programmatic dependent launch behind post_kernel (mcr_launch_pdl)
     if (!VP) tl_stamp(b.timeline, cls == 2 ? TL_RENDER2 : TL_RENDER);
     // VP = false: grid (B, A) -- env and agent come from the block index, no integer division per thread
     const int frame = VP ? (int)blockIdx.x : (int)(blockIdx.x * d.A + blockIdx.y);
@@ -805,7 +806,8 @@ static bool configure_render() {
 int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* obs,
                   int backwards_flag, int use_ego_color, int cls, int obs_format, void* stream) {
     if (!configure_render()) return -1;
-    render_kernel<false><<<dim3(d.B, d.A), RS_THREADS, sizeof(RasterSmem), (cudaStream_t)stream>>>(d, b, cc, mask, obs, backwards_flag, use_ego_color, cls, obs_format, VpParams{});
+    mcr_launch_pdl(render_kernel<false>, dim3(d.B, d.A), dim3(RS_THREADS), sizeof(RasterSmem), (cudaStream_t)stream,
+                   d, b, cc, mask, obs, backwards_flag, use_ego_color, cls, obs_format, VpParams{});
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -856,7 +858,8 @@ int launch_score(const Dims& d, const DevBuffers& b, const uint8_t* mask, const 
     // idle, so score CTAs that were placed first (small carve-out) held render_kernel's CTAs back by ~7 us.
     // Asking for 12 KB of (unused) dynamic shared memory per CTA -- 16 resident CTAs x 12 KB lands in the same
     // carve-out class as the rasteriser's 4 x 37 KB -- makes both kernels want the same configuration
-    // (measured: render start 98.4 -> 91.3 us into the step; 0 and 9.5 KB do not).
+    // (measured: render start 98.4 -> 91.3 us into the step; 0 and 9.5 KB do not).  With the programmatic
+    // dependent launch of render_kernel the rasteriser's CTAs are placed first and score fills in as they retire.
     const size_t score_smem = 12288;
     score_kernel<<<(d.N + SCORE_WARPS - 1) / SCORE_WARPS, SCORE_WARPS * 32, score_smem, (cudaStream_t)stream>>>(d, b, mask, noact, reward, done, max_episode_steps, cls);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;

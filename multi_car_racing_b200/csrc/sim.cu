@@ -310,6 +310,7 @@ __device__ __forceinline__ void sweep_store(const DevBuffers& b, int car, int N,
 //                         to the limit pattern, no divergence inside the sweep, own early exit.
 __global__ void __launch_bounds__(SWEEP_BLOCK)
 sweep_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, int early_exit, int packed_ctas) {
+    cudaGridDependencySynchronize();               // programmatic dependent launch behind head_kernel
     const int N = d.N;
     tl_stamp(b.timeline, TL_SWEEP);
     const float h = (float)(1.0 / 50);
@@ -356,6 +357,7 @@ sweep_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask
 __global__ void __launch_bounds__(128)
 post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ noact, int has_action,
             double h_ratio, int cls) {
+    cudaGridDependencySynchronize();               // programmatic dependent launch behind the sweep / coupled kernel
     const int car = blockIdx.x * blockDim.x + threadIdx.x;
     tl_stamp(b.timeline, cls == 2 ? TL_POST2 : TL_POST);
     if (car >= d.N) return;
@@ -592,7 +594,7 @@ int launch_presweep(const Dims& d, const DevBuffers& b, const CarConst& cc, cons
     } else {
         const int sb = sweep_block();
         const int packed_ctas = (d.N + sb - 1) / sb, percar_ctas = (d.N + sb / 32 - 1) / (sb / 32);
-        sweep_kernel<<<packed_ctas + percar_ctas, sb, 0, s>>>(d, b, cc, mask, early_exit, packed_ctas);
+        mcr_launch_pdl(sweep_kernel, dim3(packed_ctas + percar_ctas), dim3(sb), 0, s, d, b, cc, mask, early_exit, packed_ctas);
         ++launched;
     }
     return cudaGetLastError() == cudaSuccess ? launched : -1;
@@ -603,6 +605,6 @@ int launch_presweep(const Dims& d, const DevBuffers& b, const CarConst& cc, cons
 int launch_physics_post(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* noact,
                         int has_action, double h_ratio, int cls, void* stream) {
     const int pb = pre_block(), nb = (d.N + pb - 1) / pb;
-    post_kernel<<<nb, pb, 0, (cudaStream_t)stream>>>(d, b, cc, mask, noact, has_action, h_ratio, cls);
+    mcr_launch_pdl(post_kernel, dim3(nb), dim3(pb), 0, (cudaStream_t)stream, d, b, cc, mask, noact, has_action, h_ratio, cls);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
