@@ -1,7 +1,8 @@
 """Where one step's time goes INSIDE the CUDA graph: %globaltimer stamps written by the kernels
 themselves (start of each kernel, latest CTA end of sweep / render), averaged over steps.
     python scripts/timeline.py [B] [steps] [warm steps]"""
-import os, sys
+import os, sys, signal
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)     # BrokenPipe-safe when piped into head
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 import numpy as np, torch
 import multi_car_racing_b200 as mcr
