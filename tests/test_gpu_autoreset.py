@@ -5,6 +5,7 @@ test reads that choice back (env_track / env_cw, car order recovered from the sp
 builds a fresh oracle world for it and demands bit-exact state, rewards and pixels afterwards.
 Reference behaviour being reproduced: reset() = respawn + step(None) (mcr:340-408), TimeLimit at
 max_episode_steps (reference __init__.py:5-10)."""
+import hashlib
 import itertools
 
 import numpy as np
@@ -137,3 +138,29 @@ def test_vector_env_adapter(mcr):
     assert vec.render('rgb_array').shape == (6, 2, 400, 600, 3)
     with pytest.raises(RuntimeError):
         vec.step_wait()
+
+
+def test_graph_replay_equals_direct_launches(mcr, monkeypatch):
+    """mcr_step replays a captured CUDA graph after two eager steps; MCR_NO_GRAPH=1 (read at mcr_create)
+    issues every step directly.  Same seeds -> bit-identical frames, rewards, dones and state over 80 steps
+    with the next-step auto reset firing (max_episode_steps=30)."""
+    import torch
+
+    def run(no_graph):
+        if no_graph:
+            monkeypatch.setenv("MCR_NO_GRAPH", "1")
+        else:
+            monkeypatch.delenv("MCR_NO_GRAPH", raising=False)
+        np.random.seed(8)
+        venv = mcr.BatchedMultiCarRacing(16, num_agents=2, seed=77, max_episode_steps=30, auto_reset='next_step')
+        venv.reset()
+        tape = action_tape(13, 80, 16, 2)
+        sha = hashlib.sha1()
+        for s in range(80):
+            obs, rew, done, _ = venv.step(torch.from_numpy(tape[s]).to(venv.device))
+            sha.update(obs.cpu().numpy().tobytes()); sha.update(rew.cpu().numpy().tobytes()); sha.update(done.cpu().numpy().tobytes())
+        sha.update(venv.buffers["body"].cpu().numpy().tobytes())
+        return sha.hexdigest(), venv.launch_count
+
+    (a, la), (b, lb) = run(False), run(True)
+    assert a == b and la == lb
