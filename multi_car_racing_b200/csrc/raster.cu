@@ -112,7 +112,8 @@ struct __align__(16) RasterSmem {
     signed char glyph[4];
     uint32_t pal32[32];      // r | g << 8 | b << 16
     uint32_t palY[32];       // luma (MCR_OBS_GRAY)
-    uint32_t prmt_sel[16];   // nibble -> PRMT selector: byte i from operand b (4 + i) if bit i is set, else from a (i)
+    uint32_t prmt_sel[256];  // coverage byte -> two PRMT selectors (low half: pixels 0-3, high half: pixels 4-7):
+                             // byte i comes from operand b (4 + i) if its bit is set, else from a (i)
 };
 
 __device__ __forceinline__ double py_mod(double a, double m) {
@@ -353,11 +354,12 @@ __device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pi
                         for (int k = 0; k < 8; ++k) pix[k] = c4;
                     } else if (fresh) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            // bit i of the nibble selects byte i of c4 over byte i of pix[k]: one PRMT with a
-                            // selector from a 16-entry table instead of building a byte mask
-                            const uint32_t nib = (fresh >> (4 * k)) & 0xFu;
-                            pix[k] = __byte_perm(pix[k], c4, S.prmt_sel[nib]);
+                        for (int k2 = 0; k2 < 4; ++k2) {
+                            // bit i of a coverage nibble selects byte i of c4 over byte i of pix[k]: one PRMT per
+                            // four pixels, the selectors of eight pixels from one table load
+                            const uint32_t sel = S.prmt_sel[(fresh >> (8 * k2)) & 0xFFu];
+                            pix[2 * k2] = __byte_perm(pix[2 * k2], c4, sel);
+                            pix[2 * k2 + 1] = __byte_perm(pix[2 * k2 + 1], c4, sel >> 16);
                         }
                     }
                 }
@@ -406,9 +408,11 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
         S.pal32[i] = (uint32_t)c_palette[i][0] | ((uint32_t)c_palette[i][1] << 8) | ((uint32_t)c_palette[i][2] << 16);
         S.palY[i] = (uint32_t)c_palette[i][3];
     }
-    if (tid >= 128 && tid < 144) {
-        const uint32_t nib = tid - 128;
-        S.prmt_sel[nib] = 0x3210u | ((nib & 1u) << 2) | ((nib & 2u) << 5) | ((nib & 4u) << 8) | ((nib & 8u) << 11);
+    if (tid < 256) {
+        const uint32_t lo = tid & 15u, hi = (uint32_t)tid >> 4;
+        const uint32_t slo = 0x3210u | ((lo & 1u) << 2) | ((lo & 2u) << 5) | ((lo & 4u) << 8) | ((lo & 8u) << 11);
+        const uint32_t shi = 0x3210u | ((hi & 1u) << 2) | ((hi & 2u) << 5) | ((hi & 4u) << 8) | ((hi & 8u) << 11);
+        S.prmt_sel[tid] = slo | (shi << 16);
     }
     if (tid == 64) {
         // score label "%04i" % reward  (mcr:665; drawn before reward -= 0.1)
@@ -663,6 +667,19 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     } else if (obs_format == MCR_OBS_RGB_HWC) {
         uint4* dst = reinterpret_cast<uint4*>(obs + (size_t)frame * MCR_OBS_BYTES + (size_t)out_row * (SW * 3) + my_seg * 96);
         uint32_t o[24];
+        const uint32_t p0 = pix[0];
+        const bool uniform = __byte_perm(p0, 0, 0x0000) == p0 &&
+                             ((p0 ^ pix[1]) | (p0 ^ pix[2]) | (p0 ^ pix[3]) | (p0 ^ pix[4]) | (p0 ^ pix[5]) | (p0 ^ pix[6]) | (p0 ^ pix[7])) == 0u;
+        if (uniform) {
+            // one colour across the 32 pixels (grass, road, HUD bar: about half of all segments): the 12-byte
+            // r g b pattern repeats, one palette lookup instead of 32
+            const uint32_t c = S.pal32[p0 & 0xff];
+            const uint32_t w0 = c | (c << 24), w1 = (c >> 8) | (c << 16), w2 = (c >> 16) | (c << 8);
+            const uint4 q0 = make_uint4(w0, w1, w2, w0), q1 = make_uint4(w1, w2, w0, w1), q2 = make_uint4(w2, w0, w1, w2);
+            dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q0; dst[4] = q1; dst[5] = q2;
+            if (cls != 2 && tid == 0) atomicMax(b.timeline + TL_RENDER_END, mcr_globaltimer());
+            return;
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const uint32_t c0 = S.pal32[pix[k] & 0xff], c1 = S.pal32[(pix[k] >> 8) & 0xff];
