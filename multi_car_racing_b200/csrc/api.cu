@@ -458,6 +458,7 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
     set_spec(h, BUF_ACTION_STAGE, "action_stage", MCR_F64, {N, 3});
     set_spec(h, BUF_CAMERA_VP, "camera_vp", MCR_F32, {6, N});
     set_spec(h, BUF_TIMELINE, "timeline", MCR_F64, {TL_COUNT});      // u64 nanosecond stamps (8-byte slots)
+    set_spec(h, BUF_ON_GRASS, "on_grass", MCR_U8, {N});
     set_spec(h, BUF_TRK_T, "trk_T", MCR_I32, {P});
     set_spec(h, BUF_TRK_Q, "trk_Q", MCR_I32, {P});
     set_spec(h, BUF_TRK_NODE, "trk_node", MCR_F64, {P, T, 3});
@@ -468,6 +469,7 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
     set_spec(h, BUF_TRK_QUAD_TILE, "trk_quad_tile", MCR_I16, {P, Q});
     set_spec(h, BUF_TRK_SLOT_POSE, "trk_slot_pose", MCR_F64, {P, 2, A, 3});
     set_spec(h, BUF_TRK_CHUNK, "trk_chunk", MCR_F32, {P, Q / MCR_QUAD_CHUNK, 4});
+    set_spec(h, BUF_TRK_QUAD64, "trk_quad64", MCR_F64, {P, Q, 8});
     *out = h;
     return 0;
 }
@@ -535,6 +537,8 @@ extern "C" int mcr_bind_buffer(mcr_handle h, int i, void* p) {
         case BUF_ACTION_STAGE: b.action_stage = (double*)p; break;
         case BUF_CAMERA_VP: b.camera_vp = (float*)p; break;
         case BUF_TIMELINE: b.timeline = (unsigned long long*)p; break;
+        case BUF_ON_GRASS: b.on_grass = (uint8_t*)p; break;
+        case BUF_TRK_QUAD64: b.trk_quad64 = (double*)p; break;
         case BUF_TRK_T: b.trk_T = (int32_t*)p; break;
         case BUF_TRK_Q: b.trk_Q = (int32_t*)p; break;
         case BUF_TRK_NODE: b.trk_node = (double*)p; break;
@@ -669,6 +673,7 @@ extern "C" int mcr_load_track(mcr_handle h, int32_t slot, int32_t T, const doubl
     CUDA_OK(cudaMemcpyAsync(b.trk_tile + (size_t)slot * d.Tmax * 8, tile.data(), tile.size() * 4, cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaMemcpyAsync(b.trk_tile_aabb + (size_t)slot * d.Tmax * 4, aabb.data(), aabb.size() * 4, cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaMemcpyAsync(b.trk_quad + (size_t)slot * d.Qmax * 8, quadf.data(), quadf.size() * 4, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(b.trk_quad64 + (size_t)slot * d.Qmax * 8, quads, (size_t)Q * 8 * 8, cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaMemcpyAsync(b.trk_quad_col + (size_t)slot * d.Qmax, qcol.data(), qcol.size(), cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaMemcpyAsync(b.trk_quad_tile + (size_t)slot * d.Qmax, qtile.data(), qtile.size() * 2, cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaMemcpyAsync(b.trk_chunk + (size_t)slot * nchunk * 4, chunk.data(), chunk.size() * 4, cudaMemcpyHostToDevice, s));

@@ -761,6 +761,36 @@ score_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, const uint8
         if (dx * dx + dy * dy <= best2 + 0.05f) { const int q = atomicAdd(&s_ncand[warp], 1); if (q < 32) s_cand[warp][q] = i; }
     }
     __syncwarp();
+    // driving_on_grass, mcr:469-472: the hull position is strictly inside none of the road_poly quads (shapely
+    // Point.within(Polygon), float64).  Lanes take the culling chunks (8 quads, fp32 bounding circle whose radius
+    // is padded far beyond the fp32 / float64 vertex difference) and test the quads of the chunks in reach exactly.
+    {
+        const double posx = posxf, posy = posyf;
+        const int Q = b.trk_Q[slot], nchunks = (Q + MCR_QUAD_CHUNK - 1) / MCR_QUAD_CHUNK;
+        const float4* chunk = (const float4*)(b.trk_chunk + (size_t)slot * (d.Qmax / MCR_QUAD_CHUNK) * 4);
+        const double* quad64 = b.trk_quad64 + (size_t)slot * d.Qmax * 8;
+        bool inside = false;
+        for (int c = lane; c < nchunks; c += 32) {
+            const float4 cc4 = chunk[c];
+            const float dx = posxf - cc4.x, dy = posyf - cc4.y;
+            if (dx * dx + dy * dy > cc4.z * cc4.z + 1.0f) continue;
+            const int q1 = min(Q, (c + 1) * MCR_QUAD_CHUNK);
+            for (int q = c * MCR_QUAD_CHUNK; q < q1 && !inside; ++q) {
+                const double* v = quad64 + (size_t)q * 8;
+                int pos = 0, neg = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int k2 = (k + 1) & 3;
+                    const double ex = v[2 * k2] - v[2 * k], ey = v[2 * k2 + 1] - v[2 * k + 1];
+                    const double cr = ex * (posy - v[2 * k + 1]) - ey * (posx - v[2 * k]);
+                    if (cr > 0) ++pos; else if (cr < 0) ++neg;
+                }
+                inside = pos == 4 || neg == 4;
+            }
+        }
+        const bool any_inside = __any_sync(0xffffffffu, inside);
+        if (lane == 0) b.on_grass[car] = any_inside ? 0 : 1;
+    }
     if (lane == 0) {
         const double posx = posxf, posy = posyf;
         double bestd = 1.0e300; int besti = 0x7fffffff;

@@ -167,6 +167,7 @@ __device__ int tg_attempt(DevMT& rng, const Dims& d, const DevBuffers& b, int sl
         for (int neg = 0; neg < BORDER_MIN_COUNT; ++neg) border[pyidx(k - neg, n)] |= border[k];
     // ---- pool slot ---------------------------------------------------------------------------
     float* quad = b.trk_quad + (size_t)slot * d.Qmax * 8;
+    double* quad64 = b.trk_quad64 + (size_t)slot * d.Qmax * 8;
     uint8_t* qcol = b.trk_quad_col + (size_t)slot * d.Qmax;
     int16_t* qtile = b.trk_quad_tile + (size_t)slot * d.Qmax;
     float* tile = b.trk_tile + (size_t)slot * d.Tmax * 8;
@@ -179,10 +180,12 @@ __device__ int tg_attempt(DevMT& rng, const Dims& d, const DevBuffers& b, int sl
         const double c1 = cos(b1), s1 = sin(b1), c2 = cos(b2), s2 = sin(b2);
         if (q >= d.Qmax) return -4;
         float* qv = quad + (size_t)q * 8;
-        qv[0] = (float)(x1 - TRACK_WIDTH * c1); qv[1] = (float)(y1 - TRACK_WIDTH * s1);
-        qv[2] = (float)(x1 + TRACK_WIDTH * c1); qv[3] = (float)(y1 + TRACK_WIDTH * s1);
-        qv[4] = (float)(x2 + TRACK_WIDTH * c2); qv[5] = (float)(y2 + TRACK_WIDTH * s2);
-        qv[6] = (float)(x2 - TRACK_WIDTH * c2); qv[7] = (float)(y2 - TRACK_WIDTH * s2);
+        double* qd = quad64 + (size_t)q * 8;
+        qd[0] = x1 - TRACK_WIDTH * c1; qd[1] = y1 - TRACK_WIDTH * s1;
+        qd[2] = x1 + TRACK_WIDTH * c1; qd[3] = y1 + TRACK_WIDTH * s1;
+        qd[4] = x2 + TRACK_WIDTH * c2; qd[5] = y2 + TRACK_WIDTH * s2;
+        qd[6] = x2 - TRACK_WIDTH * c2; qd[7] = y2 - TRACK_WIDTH * s2;
+        for (int v = 0; v < 8; ++v) qv[v] = (float)qd[v];
         qcol[q] = (uint8_t)(PAL_ROAD0 + k % 3);           // 0.4 + 0.01 * (k % 3), mcr:316-317
         qtile[q] = (int16_t)k;
         {   // fd_tile.shape.vertices = ..., mcr:318 -> Box2D polygon + AABB
@@ -201,10 +204,12 @@ __device__ int tg_attempt(DevMT& rng, const Dims& d, const DevBuffers& b, int sl
             const double side = npsign(b2 - b1);
             if (q >= d.Qmax) return -4;
             float* bv = quad + (size_t)q * 8;
-            bv[0] = (float)(x1 + side * TRACK_WIDTH * c1); bv[1] = (float)(y1 + side * TRACK_WIDTH * s1);
-            bv[2] = (float)(x1 + side * (TRACK_WIDTH + BORDER) * c1); bv[3] = (float)(y1 + side * (TRACK_WIDTH + BORDER) * s1);
-            bv[4] = (float)(x2 + side * (TRACK_WIDTH + BORDER) * c2); bv[5] = (float)(y2 + side * (TRACK_WIDTH + BORDER) * s2);
-            bv[6] = (float)(x2 + side * TRACK_WIDTH * c2); bv[7] = (float)(y2 + side * TRACK_WIDTH * s2);
+            double* bd = quad64 + (size_t)q * 8;
+            bd[0] = x1 + side * TRACK_WIDTH * c1; bd[1] = y1 + side * TRACK_WIDTH * s1;
+            bd[2] = x1 + side * (TRACK_WIDTH + BORDER) * c1; bd[3] = y1 + side * (TRACK_WIDTH + BORDER) * s1;
+            bd[4] = x2 + side * (TRACK_WIDTH + BORDER) * c2; bd[5] = y2 + side * (TRACK_WIDTH + BORDER) * s2;
+            bd[6] = x2 + side * TRACK_WIDTH * c2; bd[7] = y2 + side * TRACK_WIDTH * s2;
+            for (int v = 0; v < 8; ++v) bv[v] = (float)bd[v];
             qcol[q] = (uint8_t)(k % 2 == 0 ? PAL_WHITE : PAL_RED);
             qtile[q] = (int16_t)-1;
             ++q;

@@ -628,6 +628,11 @@ class MultiCarRacing:
         return self._batch.buffers["backward"].cpu().numpy().astype(bool)
 
     @property
+    def driving_on_grass(self):
+        """reference :153, :469-472: the hull position is inside none of the road_poly polygons"""
+        return self._batch.buffers["on_grass"].cpu().numpy().astype(bool)
+
+    @property
     def t(self):
         return float(self._batch.buffers["time"][0].item())
 

@@ -258,6 +258,7 @@ typedef struct OrcWorld {
     int T, Q;
     double* track;       /* T*4 alpha,beta,x,y */
     float* quad;         /* Q*8 fp32 render verts (as passed to glVertex3f) */
+    double* quad64;      /* Q*8 float64 road_poly verts (what shapely's Polygon holds, mcr:336-337) */
     float* quad_rgb;     /* Q*3 float colours */
     int* quad_tile;      /* Q: tile index or -1 */
     Poly* tile_poly;     /* T Box2D polygon of each tile */
@@ -272,6 +273,7 @@ typedef struct OrcWorld {
     double reward[MAX_AGENTS], prev_reward[MAX_AGENTS];
     int tile_visited_count[MAX_AGENTS];
     uint8_t driving_backward[MAX_AGENTS];
+    uint8_t driving_on_grass[MAX_AGENTS];   /* mcr:153, 350, 469-472 */
     double t;
     float inv_dt0;
     /* config */
@@ -332,9 +334,9 @@ ORC_API OrcWorld* orc_create(int num_agents, double h_ratio, int backwards_flag,
 }
 
 static void free_track(OrcWorld* W) {
-    free(W->track); free(W->quad); free(W->quad_rgb); free(W->quad_tile); free(W->tile_poly);
+    free(W->track); free(W->quad); free(W->quad64); free(W->quad_rgb); free(W->quad_tile); free(W->tile_poly);
     free(W->tile_aabb); free(W->visited); free(W->touched);
-    W->track = NULL; W->quad = NULL; W->quad_rgb = NULL; W->quad_tile = NULL; W->tile_poly = NULL;
+    W->track = NULL; W->quad = NULL; W->quad64 = NULL; W->quad_rgb = NULL; W->quad_tile = NULL; W->tile_poly = NULL;
     W->tile_aabb = NULL; W->visited = NULL; W->touched = NULL;
 }
 
@@ -352,6 +354,7 @@ ORC_API int orc_set_track(OrcWorld* W, int T, const double* track_abxy, int Q, c
     W->track = (double*)malloc(sizeof(double) * 4 * T); memcpy(W->track, track_abxy, sizeof(double) * 4 * T);
     W->quad = (float*)malloc(sizeof(float) * 8 * Q);
     for (int i = 0; i < 8 * Q; ++i) W->quad[i] = (float)quad_verts[i];
+    W->quad64 = (double*)malloc(sizeof(double) * 8 * Q); memcpy(W->quad64, quad_verts, sizeof(double) * 8 * Q);
     W->quad_rgb = (float*)malloc(sizeof(float) * 3 * Q); memcpy(W->quad_rgb, quad_rgb, sizeof(float) * 3 * Q);
     W->quad_tile = (int*)malloc(sizeof(int) * Q); memcpy(W->quad_tile, quad_tile, sizeof(int) * Q);
     W->tile_poly = (Poly*)calloc(T, sizeof(Poly));
@@ -412,7 +415,7 @@ ORC_API void orc_spawn(OrcWorld* W, const double* init) {
             J->limitState = LIM_INACTIVE;
         }
         car->hull_color = c % 8;
-        W->reward[c] = 0.0; W->prev_reward[c] = 0.0; W->tile_visited_count[c] = 0; W->driving_backward[c] = 0;
+        W->reward[c] = 0.0; W->prev_reward[c] = 0.0; W->tile_visited_count[c] = 0; W->driving_backward[c] = 0; W->driving_on_grass[c] = 0;
     }
 }
 
@@ -1557,6 +1560,23 @@ ORC_API void orc_step(OrcWorld* W, const double* action, uint8_t* obs, double* s
                 double d = sqrt(dx * dx + dy * dy);
                 if (i == 0 || d < bestd) { bestd = d; best = i; }
             }
+            /* on_grass = not any(Point(car_pos).within(Polygon(road_poly[i]))), mcr:469-472: strictly inside one
+             * of the (convex) road / border quads, float64 */
+            {
+                int inside_any = 0;
+                for (int q = 0; q < W->Q && !inside_any; ++q) {
+                    const double* v = &W->quad64[8 * q];
+                    int pos = 0, neg = 0;
+                    for (int k = 0; k < 4; ++k) {
+                        int k2 = (k + 1) & 3;
+                        double ex = v[2 * k2] - v[2 * k], ey = v[2 * k2 + 1] - v[2 * k + 1];
+                        double cr = ex * (py - v[2 * k + 1]) - ey * (px - v[2 * k]);
+                        if (cr > 0) ++pos; else if (cr < 0) ++neg;
+                    }
+                    if (pos == 4 || neg == 4) inside_any = 1;
+                }
+                W->driving_on_grass[c] = (uint8_t)!inside_any;
+            }
             double desired = W->track[4 * best + 1];
             if (W->cw) desired += PI;
             desired = py_mod(desired + 2 * PI, 2 * PI);
@@ -1620,6 +1640,7 @@ ORC_API void orc_get_visited(const OrcWorld* W, uint8_t* visited /*T*A*/, uint8_
 ORC_API void orc_get_scores(const OrcWorld* W, double* reward, int* counts, uint8_t* backward) {
     for (int c = 0; c < W->A; ++c) { reward[c] = W->reward[c]; counts[c] = W->tile_visited_count[c]; backward[c] = W->driving_backward[c]; }
 }
+ORC_API void orc_get_grass(const OrcWorld* W, uint8_t* grass) { for (int c = 0; c < W->A; ++c) grass[c] = W->driving_on_grass[c]; }
 ORC_API double orc_get_time(const OrcWorld* W) { return W->t; }
 ORC_API int orc_get_fixed_point_iter(const OrcWorld* W) { return W->vel_iters_used; }
 /* mass constants: hull mass, invMass, I, invI, lc.x, lc.y, wheel mass, invMass, I, invI, lc.x, lc.y */

@@ -59,6 +59,7 @@ def gpu_state(venv):
         reward=venv.buffers["reward"].cpu().numpy().reshape(B, A),
         counts=venv.buffers["visit_count"].cpu().numpy().reshape(B, A),
         backward=venv.buffers["backward"].cpu().numpy().reshape(B, A),
+        grass=venv.buffers["on_grass"].cpu().numpy().reshape(B, A),
         visited=venv.buffers["visited"].cpu().numpy(), touched=venv.buffers["touched"].cpu().numpy())
 
 
@@ -72,7 +73,7 @@ def oracle_state(worlds):
     vis = [w.visited() for w in worlds]
     return dict(bodies=bodies, wheels=wheels, joints=joints,
                 reward=np.stack([s[0] for s in sc]), counts=np.stack([s[1] for s in sc]),
-                backward=np.stack([s[2] for s in sc]),
+                backward=np.stack([s[2] for s in sc]), grass=np.stack([w.grass() for w in worlds]),
                 visited=[v[0] for v in vis], touched=[v[1] for v in vis])
 
 

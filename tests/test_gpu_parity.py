@@ -39,6 +39,7 @@ def _compare_state(venv, worlds, tracks, step, exact=True):
     assert np.array_equal(g["counts"], o["counts"]), "tile_visited_count, step %d" % step
     assert np.array_equal(g["reward"], o["reward"]), "reward (float64, bit-exact), step %d" % step
     assert np.array_equal(g["backward"], o["backward"]), "driving_backward, step %d" % step
+    assert np.array_equal(g["grass"], o["grass"]), "driving_on_grass, step %d" % step
     if exact:
         for k in ("bodies", "wheels", "joints"):
             assert np.array_equal(g[k], o[k]), "%s differ at step %d: max abs %g" % (k, step, np.abs(g[k].astype(np.float64) - o[k]).max())
