@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MCR_ABI_VERSION 1
+#define MCR_ABI_VERSION 2
 #define MCR_STATE_W 96
 #define MCR_STATE_H 96
 #define MCR_MAX_AGENTS 16
@@ -49,6 +49,8 @@ typedef struct mcr_config {
     int32_t direction_cw;      /* mcr:131 direction == 'CW'; auto reset when not random   */
     int32_t collisions;        /* 1: car-car rigid contacts (Box2D polygon contacts); 0: cars pass through each other */
     uint64_t seed;             /* stream id of the device-side auto-reset RNG             */
+    int32_t particles;         /* 1: keep the skid traces of gym car_dynamics.Car (Car.particles, "Skid trace" block of
+                                  Car.step) so that the non-state render modes draw them (mcr:564); 0: no bookkeeping */
 } mcr_config;
 
 /* Observation layouts the rasteriser can store (mcr_set_obs_format).  The reference returns

@@ -31,7 +31,7 @@ class McrConfig(ctypes.Structure):
         ("use_ego_color", ctypes.c_int32), ("max_episode_steps", ctypes.c_int32),
         ("h_ratio", ctypes.c_double), ("device", ctypes.c_int32),
         ("use_random_direction", ctypes.c_int32), ("direction_cw", ctypes.c_int32),
-        ("collisions", ctypes.c_int32), ("seed", ctypes.c_uint64),
+        ("collisions", ctypes.c_int32), ("seed", ctypes.c_uint64), ("particles", ctypes.c_int32),
     ]
 
 
@@ -103,7 +103,7 @@ def load():
     L.mcr_trackgen_scratch_bytes.argtypes = []
     L.mcr_render_viewport.restype = i32
     L.mcr_render_viewport.argtypes = [vp, vp, i32, i32, vp, vp]
-    if L.mcr_abi_version() != 1:
+    if L.mcr_abi_version() != 2:
         raise McrError("libmcr.so ABI version mismatch")
     _lib = L
     return L

@@ -416,7 +416,7 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
     if (cfg->pool_tracks < 1) return fail(-1, "pool_tracks must be >= 1");
     mcr_handle_t* h = new mcr_handle_t();
     h->cfg = *cfg;
-    h->d = Dims{cfg->batch_envs, cfg->num_agents, cfg->batch_envs * cfg->num_agents, cfg->max_tiles, cfg->max_quads, cfg->pool_tracks};
+    h->d = Dims{cfg->batch_envs, cfg->num_agents, cfg->batch_envs * cfg->num_agents, cfg->max_tiles, cfg->max_quads, cfg->pool_tracks, cfg->particles ? 1 : 0};
     if (!build_car_const(h->cc)) { delete h; return fail(-2, "car geometry set-up failed"); }
     std::memset(&h->buf, 0, sizeof(h->buf));
     std::memset(h->ptr, 0, sizeof(h->ptr));
@@ -459,6 +459,12 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
     set_spec(h, BUF_CAMERA_VP, "camera_vp", MCR_F32, {6, N});
     set_spec(h, BUF_TIMELINE, "timeline", MCR_F64, {TL_COUNT});      // u64 nanosecond stamps (8-byte slots)
     set_spec(h, BUF_ON_GRASS, "on_grass", MCR_U8, {N});
+    const int64_t Np = cfg->particles ? N : 1;                           // skid traces are only kept on request
+    set_spec(h, BUF_PRT_PTS, "prt_pts", MCR_F32, {PRT_MAX * PRT_PTS, 2, Np});
+    set_spec(h, BUF_PRT_META, "prt_meta", MCR_I32, {PRT_MAX, Np});
+    set_spec(h, BUF_PRT_HDR, "prt_hdr", MCR_I32, {2, Np});
+    set_spec(h, BUF_SKID_START, "skid_start", MCR_F32, {4, 2, Np});
+    set_spec(h, BUF_SKID_META, "skid_meta", MCR_I32, {4, Np});
     set_spec(h, BUF_TRK_T, "trk_T", MCR_I32, {P});
     set_spec(h, BUF_TRK_Q, "trk_Q", MCR_I32, {P});
     set_spec(h, BUF_TRK_NODE, "trk_node", MCR_F64, {P, T, 3});
@@ -538,6 +544,11 @@ extern "C" int mcr_bind_buffer(mcr_handle h, int i, void* p) {
         case BUF_CAMERA_VP: b.camera_vp = (float*)p; break;
         case BUF_TIMELINE: b.timeline = (unsigned long long*)p; break;
         case BUF_ON_GRASS: b.on_grass = (uint8_t*)p; break;
+        case BUF_PRT_PTS: b.prt_pts = (float*)p; break;
+        case BUF_PRT_META: b.prt_meta = (int32_t*)p; break;
+        case BUF_PRT_HDR: b.prt_hdr = (int32_t*)p; break;
+        case BUF_SKID_START: b.skid_start = (float*)p; break;
+        case BUF_SKID_META: b.skid_meta = (int32_t*)p; break;
         case BUF_TRK_QUAD64: b.trk_quad64 = (double*)p; break;
         case BUF_TRK_T: b.trk_T = (int32_t*)p; break;
         case BUF_TRK_Q: b.trk_Q = (int32_t*)p; break;

@@ -43,7 +43,7 @@ enum {
     BUF_ON_ROAD, BUF_ON_ROAD_NEXT, BUF_REWARD, BUF_PREV_REWARD, BUF_VISIT_COUNT, BUF_BACKWARD,
     BUF_TIME, BUF_STEPS, BUF_CAMERA, BUF_STRIPE, BUF_HEADING,
     BUF_ENV_TRACK, BUF_ENV_CW, BUF_ENV_EPISODE,
-    BUF_VISITED, BUF_TOUCHED, BUF_RESET_MASK, BUF_STATUS, BUF_SCRATCH, BUF_MANIFOLD, BUF_N_MANIFOLD, BUF_SCORE_SNAP, BUF_BACKWARD_SNAP, BUF_PENDING, BUF_ACTION_STAGE, BUF_CAMERA_VP, BUF_TIMELINE, BUF_ON_GRASS,
+    BUF_VISITED, BUF_TOUCHED, BUF_RESET_MASK, BUF_STATUS, BUF_SCRATCH, BUF_MANIFOLD, BUF_N_MANIFOLD, BUF_SCORE_SNAP, BUF_BACKWARD_SNAP, BUF_PENDING, BUF_ACTION_STAGE, BUF_CAMERA_VP, BUF_TIMELINE, BUF_ON_GRASS, BUF_PRT_PTS, BUF_PRT_META, BUF_PRT_HDR, BUF_SKID_START, BUF_SKID_META,
     BUF_TRK_T, BUF_TRK_Q, BUF_TRK_NODE, BUF_TRK_TILE, BUF_TRK_TILE_AABB, BUF_TRK_QUAD, BUF_TRK_QUAD_COL,
     BUF_TRK_QUAD_TILE, BUF_TRK_SLOT_POSE, BUF_TRK_CHUNK, BUF_TRK_QUAD64,
     BUF_COUNT
@@ -56,7 +56,7 @@ enum { ST_EVENT_OVERFLOW = 0, ST_NAN = 1, ST_RASTER_OVERFLOW = 2, ST_MANIFOLD_OV
 enum {
     PAL_BLACK = 0, PAL_GRASS, PAL_GRASS_LIGHT, PAL_ROAD0, PAL_ROAD1, PAL_ROAD2, PAL_WHITE, PAL_RED,
     PAL_WHEEL_WHITE, PAL_CAR0, /* 8 car colours: PAL_CAR0 .. PAL_CAR0+7 */
-    PAL_IND_BLUE = PAL_CAR0 + 8, PAL_IND_BLUE2, PAL_IND_GREEN, PAL_FLAG_BLUE, PAL_COUNT
+    PAL_IND_BLUE = PAL_CAR0 + 8, PAL_IND_BLUE2, PAL_IND_GREEN, PAL_FLAG_BLUE, PAL_MUD, PAL_COUNT
 };
 
 struct Poly8 { int n; float x[MCR_MAXV]; float y[MCR_MAXV]; float nx[MCR_MAXV]; float ny[MCR_MAXV]; };   // vertices + unit edge normals
@@ -91,6 +91,11 @@ struct DevBuffers {
     double* action_stage;                // [N][3] f64-sized staging copy of the step's action (CUDA-graph replay reads it)
     float* camera_vp;                    // [6][N] camera affine of the last mcr_render_viewport call
     uint8_t* on_grass;                   // [N] driving_on_grass, mcr:469-472
+    float* prt_pts;                      // [PRT_MAX][PRT_PTS][2][N] skid-trace points (ring slot, point, xy)
+    int32_t* prt_meta;                   // [PRT_MAX][N] length | grass << 8 of the particle in a ring slot
+    int32_t* prt_hdr;                    // [2][N] ring head (oldest particle), particle count
+    float* skid_start;                   // [4][2][N] wheel.skid_start
+    int32_t* skid_meta;                  // [4][N] see above
     unsigned long long* timeline;        // [TL_COUNT] %globaltimer stamps (ns) of the last step's kernels, see TL_*
     int32_t* trk_T; int32_t* trk_Q; double* trk_node; float* trk_tile; float* trk_tile_aabb;
     float* trk_quad; uint8_t* trk_quad_col; int16_t* trk_quad_tile; double* trk_slot_pose;
@@ -98,7 +103,11 @@ struct DevBuffers {
     double* trk_quad64;                  // [P][Qmax][8] road_poly vertices in float64 (what shapely's polygons hold, mcr:336-337)
 };
 
-struct Dims { int B, A, N, Tmax, Qmax, P; };
+struct Dims { int B, A, N, Tmax, Qmax, P; int particles; };
+// skid traces (gym car_dynamics Car.particles): per car a ring of PRT_MAX polylines of <= PRT_PTS wheel positions
+#define PRT_MAX 30
+#define PRT_PTS 30
+// skid_meta[wheel] bits: 0 skid_start valid, 1 skid_particle valid, 2 its grass flag, 8-15 its length, 16-23 its ring slot + 1 (0 = popped from Car.particles)
 // timeline slots: kernel start stamps (block 0, thread 0) and the latest CTA end of the rasteriser
 enum { TL_HEAD = 0, TL_CONTACTS, TL_STRIPES, TL_SWEEP, TL_COUPLED, TL_POST, TL_SCORE, TL_RENDER, TL_RENDER_END, TL_POST2, TL_RENDER2, TL_SWEEP_END, TL_SWEEP_END_PACKED, TL_COUPLED_VEL_END, TL_COUPLED_POS_END, TL_COUNT = 16 };
 #ifdef __CUDACC__

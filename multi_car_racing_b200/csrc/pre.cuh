@@ -95,6 +95,46 @@ __device__ __forceinline__ void pre_car(const Dims& d, const DevBuffers& b, cons
         f_force *= 205000 * SIZE * SIZE;
         p_force *= 205000 * SIZE * SIZE;
         double force = sqrt(f_force * f_force + p_force * p_force);
+        if (d.particles) {
+            // Skid trace (gym car_dynamics Car.step): wheel.position is the wheel body's origin = its centre
+            const bool grass = !on_road[k];
+            int meta = b.skid_meta[(size_t)k * N + car];
+            if (fabs(force) > 2.0 * friction_limit) {
+                const bool ref_valid = (meta & 2) != 0, ref_grass = (meta & 4) != 0;
+                const int ref_len = (meta >> 8) & 0xff, ref_slot = ((meta >> 16) & 0xff) - 1;
+                if (ref_valid && ref_grass == grass && ref_len < PRT_PTS) {
+                    if (ref_slot >= 0) {             // still in Car.particles: the drawn polyline grows
+                        float* pt = b.prt_pts + ((size_t)(ref_slot * PRT_PTS + ref_len) * 2) * N + car;
+                        pt[0] = cx[bi]; pt[N] = cy[bi];
+                        b.prt_meta[(size_t)ref_slot * N + car] = (ref_len + 1) | (ref_grass ? 256 : 0);
+                    }
+                    meta = (meta & ~0xff00) | ((ref_len + 1) << 8);
+                } else if (!(meta & 1)) {
+                    b.skid_start[(size_t)(k * 2 + 0) * N + car] = cx[bi]; b.skid_start[(size_t)(k * 2 + 1) * N + car] = cy[bi];
+                    meta |= 1;
+                } else {
+                    // _create_particle(skid_start, position, grass): append, pop(0) while more than PRT_MAX
+                    int head = b.prt_hdr[car], count = b.prt_hdr[(size_t)N + car], slot;
+                    if (count < PRT_MAX) { slot = head + count; if (slot >= PRT_MAX) slot -= PRT_MAX; ++count; }
+                    else {
+                        slot = head; head = head + 1 == PRT_MAX ? 0 : head + 1;
+                        for (int k2 = 0; k2 < 4; ++k2) {     // wheels still extending the popped particle keep doing so, unseen
+                            const size_t mi = (size_t)k2 * N + car;
+                            if (k2 != k) { const int m2 = b.skid_meta[mi]; if (((m2 >> 16) & 0xff) - 1 == slot) b.skid_meta[mi] = m2 & ~0xff0000; }
+                        }
+                    }
+                    b.prt_hdr[car] = head; b.prt_hdr[(size_t)N + car] = count;
+                    float* pt = b.prt_pts + ((size_t)(slot * PRT_PTS) * 2) * N + car;
+                    pt[0] = b.skid_start[(size_t)(k * 2 + 0) * N + car]; pt[N] = b.skid_start[(size_t)(k * 2 + 1) * N + car];
+                    pt[(size_t)2 * N] = cx[bi]; pt[(size_t)3 * N] = cy[bi];
+                    b.prt_meta[(size_t)slot * N + car] = 2 | (grass ? 256 : 0);
+                    meta = 2 | (grass ? 4 : 0) | (2 << 8) | ((slot + 1) << 16);      // skid_start = None
+                }
+            } else {
+                meta = 0;                             // skid_start = None, skid_particle = None
+            }
+            b.skid_meta[(size_t)k * N + car] = meta;
+        }
         if (fabs(force) > friction_limit) {
             f_force /= force; p_force /= force;
             force = friction_limit;

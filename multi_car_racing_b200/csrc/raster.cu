@@ -59,6 +59,7 @@ __constant__ uint8_t c_palette[PAL_COUNT][4] = {
     {51, 0, 255, 0},    // PAL_IND_BLUE2    (0.2, 0, 1)
     {0, 255, 0, 0},     // PAL_IND_GREEN
     {0, 0, 255, 0},     // PAL_FLAG_BLUE    c3B (0, 0, 255)
+    {102, 102, 0, 0},   // PAL_MUD          (0.4, 0.4, 0.0) skid traces on grass
 };
 
 // Host copy of the palette, derived from the reference's float colours with the GL rule
@@ -68,7 +69,7 @@ static const float h_palette_f[PAL_COUNT][3] = {
     {1, 1, 1}, {1, 0, 0}, {0.3f, 0.3f, 0.3f},
     {0.8f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.8f}, {0.0f, 0.8f, 0.0f}, {0.0f, 0.8f, 0.8f},
     {0.8f, 0.8f, 0.8f}, {0.0f, 0.0f, 0.0f}, {0.8f, 0.0f, 0.8f}, {0.8f, 0.8f, 0.0f},
-    {0, 0, 1}, {0.2f, 0, 1}, {0, 1, 0}, {0, 0, 1}};
+    {0, 0, 1}, {0.2f, 0, 1}, {0, 1, 0}, {0, 0, 1}, {0.4f, 0.4f, 0.0f}};
 
 const uint8_t (*mcr_host_palette())[4] {
     static uint8_t pal[PAL_COUNT][4];
@@ -131,6 +132,8 @@ struct View {
     const float* body; const double* wheel; const float* stripe;
     const float* quad; const uint8_t* quad_col; const int16_t* quad_tile; const uint8_t* touched;
     int use_ego_color, backward_flag_on;
+    int car_slots;                       // candidate slots per car: 12 parts (+ PRT_MAX * (PRT_PTS - 1) skid-trace segments before them)
+    const float* prt_pts; const int32_t* prt_meta; const int32_t* prt_hdr;
     float hud_sx, hud_sy;                // window (1000 x 800) -> viewport pixels: (float)(vw / 1000.0), (float)(vh / 800.0)
 };
 
@@ -178,8 +181,36 @@ __device__ int gen_candidate(int i, const View& V, const Affine& M, const CarCon
     }
     if (i < V.c_hud) {                              // Car.draw for every car, mcr:559-564
         i -= V.c_cars;
-        if (i >= CAR_PARTS * V.A) return 0;
-        const int c = i / CAR_PARTS, part = i % CAR_PARTS, car = V.env * V.A + c, N = V.N;
+        if (i >= V.car_slots * V.A) return 0;
+        const int c = i / V.car_slots, car = V.env * V.A + c, N = V.N;
+        int part = i - c * V.car_slots;
+        if (V.car_slots > CAR_PARTS) {
+            // Car.draw(viewer, draw_particles=True): the skid traces come first, one candidate per polyline segment.
+            // D6: a glLineWidth(5) line-strip segment is the parallelogram spanning +-2.5 viewport pixels along the
+            // minor axis (y for |dx| >= |dy|, else x), filled with the polygon rule.
+            const int nseg = PRT_MAX * (PRT_PTS - 1);
+            if (part < nseg) {
+                const int pi = part / (PRT_PTS - 1), seg = part - pi * (PRT_PTS - 1);
+                const int head = V.prt_hdr[car], count = V.prt_hdr[(size_t)N + car];
+                if (pi >= count) return 0;
+                int slot = head + pi; if (slot >= PRT_MAX) slot -= PRT_MAX;
+                const int meta = V.prt_meta[(size_t)slot * N + car];
+                if (seg + 1 >= (meta & 0xff)) return 0;
+                const float* pt = V.prt_pts + ((size_t)(slot * PRT_PTS + seg) * 2) * N + car;
+                float x0, y0, x1, y1;
+                xf_pt(M, pt[0], pt[N], x0, y0);
+                xf_pt(M, pt[(size_t)2 * N], pt[(size_t)3 * N], x1, y1);
+                const float hw = 2.5f;
+                if (fabsf(x1 - x0) >= fabsf(y1 - y0)) {
+                    px[0] = x0; py[0] = y0 - hw; px[1] = x1; py[1] = y1 - hw; px[2] = x1; py[2] = y1 + hw; px[3] = x0; py[3] = y0 + hw;
+                } else {
+                    px[0] = x0 - hw; py[0] = y0; px[1] = x1 - hw; py[1] = y1; px[2] = x1 + hw; py[2] = y1; px[3] = x0 + hw; py[3] = y0;
+                }
+                col = (meta & 256) ? PAL_MUD : PAL_BLACK;
+                return 4;
+            }
+            part -= nseg;
+        }
         if (part < 8) {
             const int wl = part >> 1;
             const float* bp = V.body + (size_t)((1 + wl) * BODY_FIELDS) * N + car;
@@ -495,7 +526,9 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     V.n_road = S.n_vis_chunks * MCR_QUAD_CHUNK; V.vis_chunk = S.vis_chunk;
     V.c_road = (1 + V.n_checker + 31) & ~31;
     V.c_cars = V.c_road + ((V.n_road + 31) & ~31);
-    V.c_hud = V.c_cars + ((CAR_PARTS * d.A + 31) & ~31);
+    V.car_slots = CAR_PARTS + ((VP && d.particles) ? PRT_MAX * (PRT_PTS - 1) : 0);
+    V.prt_pts = b.prt_pts; V.prt_meta = b.prt_meta; V.prt_hdr = b.prt_hdr;
+    V.c_hud = V.c_cars + ((V.car_slots * d.A + 31) & ~31);
     V.body = b.body; V.wheel = b.wheel; V.stripe = b.stripe;
     V.quad = b.trk_quad + (size_t)slot * d.Qmax * 8;
     V.quad_col = b.trk_quad_col + (size_t)slot * d.Qmax;

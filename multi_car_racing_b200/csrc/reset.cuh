@@ -45,6 +45,10 @@ __device__ __forceinline__ void spawn_car(const Dims& d, const DevBuffers& b, co
     }
     for (int f = 0; f < CTRL_FIELDS; ++f) b.ctrl[(size_t)f * N + car] = 0.0;
     b.reward[car] = 0.0; b.prev_reward[car] = 0.0; b.visit_count[car] = 0; b.backward[car] = 0; b.on_grass[car] = 0;
+    if (d.particles) {                       // Car.__init__: particles = [], skid_start = skid_particle = None
+        b.prt_hdr[car] = 0; b.prt_hdr[(size_t)N + car] = 0;
+        for (int k = 0; k < 4; ++k) b.skid_meta[(size_t)k * N + car] = 0;
+    }
     b.time[car] = 0.0; b.steps[car] = 0;
 }
 

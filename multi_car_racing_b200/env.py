@@ -83,12 +83,15 @@ class BatchedMultiCarRacing:
     reference __init__.py:8) are additions.  `obs_format` selects what the rasteriser stores:
     'rgb' (B,A,96,96,3) as the reference returns it, 'gray' (B,A,96,96) ITU-R 601 luma, or
     'rgb_chw' (B,A,3,96,96) -- the learner's first pre-processing stage fused into the store.
+    `particles=True` keeps the cars' skid traces (gym car_dynamics Car.particles) so that
+    render('rgb_array') draws them like the reference does in its non-state modes (:564).
     """
 
     def __init__(self, batch_envs, num_agents=2, verbose=0, direction='CCW', use_random_direction=True,
                  backwards_flag=True, h_ratio=0.25, use_ego_color=False, device=None,
                  max_tiles=MAX_TILES_DEFAULT, max_quads=MAX_QUADS_DEFAULT, pool_tracks=None,
-                 max_episode_steps=1000, auto_reset=True, seed=None, collisions=True, obs_format='rgb'):
+                 max_episode_steps=1000, auto_reset=True, seed=None, collisions=True, obs_format='rgb',
+                 particles=False):
         torch = _torch()
         if not torch.cuda.is_available():
             raise _lib.McrError("multi_car_racing_b200 needs a CUDA device (B200, sm_100a); none is visible")
@@ -116,7 +119,9 @@ class BatchedMultiCarRacing:
         cfg = _lib.McrConfig(self.batch_envs, self.num_agents, max_tiles, max_quads, self.pool_tracks,
                              int(bool(backwards_flag)), int(bool(use_ego_color)), self.max_episode_steps,
                              float(h_ratio), dev_index, int(bool(use_random_direction)),
-                             int(direction == 'CW'), int(bool(collisions)), int(seed if seed is not None else 0) & (2 ** 64 - 1))
+                             int(direction == 'CW'), int(bool(collisions)), int(seed if seed is not None else 0) & (2 ** 64 - 1),
+                             int(bool(particles)))
+        self.particles = bool(particles)
         self._h = ctypes.c_void_p()
         _lib.check(self.L.mcr_create(ctypes.byref(cfg), ctypes.byref(self._h)), "mcr_create")
         self.max_tiles, self.max_quads = max_tiles, max_quads
@@ -559,7 +564,7 @@ class MultiCarRacing:
                                             use_random_direction=use_random_direction, backwards_flag=backwards_flag,
                                             h_ratio=h_ratio, use_ego_color=use_ego_color, device=device,
                                             max_tiles=max_tiles, max_quads=max_quads, pool_tracks=1,
-                                            max_episode_steps=0, auto_reset=False, collisions=collisions)
+                                            max_episode_steps=0, auto_reset=False, collisions=collisions, particles=True)
         self.action_space = self._batch.action_space
         self.observation_space = self._batch.observation_space
         self.car_order = None

@@ -233,7 +233,17 @@ typedef struct {
     double gas[4], brake[4], steer[4], phase[4], omega[4];
     int ntiles[4];         /* len(wheel.tiles) */
     int hull_color;        /* palette index */
+    /* skid traces (gym car_dynamics Car.step "Skid trace" block, Car._create_particle, Car.particles): at most
+     * PRT_MAX particles per car in creation order, each a polyline of <= PRT_PTS wheel positions */
+    int n_prt; uint32_t prt_next_id;
+    struct { uint32_t id; int len; int grass; V2 pt[30]; } prt[30];
+    /* per wheel: skid_start (b2Vec2 snapshot or None), skid_particle (id of the particle the wheel extends, its
+     * length and grass flag are kept here too: a particle popped from Car.particles is still extended) */
+    int skid_start_valid[4]; V2 skid_start[4];
+    int skid_ref_valid[4]; uint32_t skid_ref_id[4]; int skid_ref_len[4], skid_ref_grass[4];
 } Car;
+#define PRT_MAX 30
+#define PRT_PTS 30
 
 #define MAX_AGENTS 16
 
@@ -274,6 +284,8 @@ typedef struct OrcWorld {
     int tile_visited_count[MAX_AGENTS];
     uint8_t driving_backward[MAX_AGENTS];
     uint8_t driving_on_grass[MAX_AGENTS];   /* mcr:153, 350, 469-472 */
+    int draw_particles;  /* 1: the non-state render modes draw the skid traces (the reference always does; the CUDA
+                            path keeps them on request only) */
     double t;
     float inv_dt0;
     /* config */
@@ -474,6 +486,30 @@ static void car_step(Car* car, double dt) {
         f_force *= 205000 * SIZE * SIZE;
         p_force *= 205000 * SIZE * SIZE;
         double force = sqrt(f_force * f_force + p_force * p_force);
+        /* Skid trace (gym car_dynamics.Car.step) */
+        {
+            const int grass = car->ntiles[w] == 0;
+            if (fabs(force) > 2.0 * friction_limit) {
+                if (car->skid_ref_valid[w] && car->skid_ref_grass[w] == grass && car->skid_ref_len[w] < PRT_PTS) {
+                    for (int i = 0; i < car->n_prt; ++i)          /* still in Car.particles: the drawn copy grows too */
+                        if (car->prt[i].id == car->skid_ref_id[w]) { car->prt[i].pt[car->prt[i].len++] = wb->p; break; }
+                    car->skid_ref_len[w] += 1;
+                } else if (!car->skid_start_valid[w]) {
+                    car->skid_start_valid[w] = 1; car->skid_start[w] = wb->p;
+                } else {
+                    /* _create_particle(skid_start, position, grass): append, then pop(0) while more than 30 */
+                    if (car->n_prt == PRT_MAX) { memmove(&car->prt[0], &car->prt[1], sizeof(car->prt[0]) * (PRT_MAX - 1)); car->n_prt = PRT_MAX - 1; }
+                    const int i = car->n_prt++;
+                    car->prt[i].id = car->prt_next_id++; car->prt[i].len = 2; car->prt[i].grass = grass;
+                    car->prt[i].pt[0] = car->skid_start[w]; car->prt[i].pt[1] = wb->p;
+                    car->skid_ref_valid[w] = 1; car->skid_ref_id[w] = car->prt[i].id; car->skid_ref_len[w] = 2; car->skid_ref_grass[w] = grass;
+                    car->skid_start_valid[w] = 0;
+                }
+            } else {
+                car->skid_start_valid[w] = 0;
+                car->skid_ref_valid[w] = 0;
+            }
+        }
         if (fabs(force) > friction_limit) {
             f_force /= force; p_force /= force;
             force = friction_limit;
@@ -1450,6 +1486,27 @@ static void render_view_vp(OrcWorld* W, int agent, uint8_t* img, int vw, int vh)
     /* cars: Car.draw(viewer, draw_particles=False), all cars in id order, mcr:559-564 */
     for (int c = 0; c < W->A; ++c) {
         const Car* car = &W->car[c];
+        /* Car.draw(viewer, draw_particles = mode != "state_pixels"), mcr:564: skid traces first.  D6: a
+         * glLineWidth(5) GL_LINE_STRIP segment is the parallelogram spanning +-2.5 viewport pixels along the
+         * minor axis (y for |dx| >= |dy|, else x), filled with the polygon rule. */
+        if (W->draw_particles && !(vw == STATE_W && vh == STATE_H)) {
+            for (int i = 0; i < car->n_prt; ++i) {
+                RGB pc = car->prt[i].grass ? rgbf(0.4f, 0.4f, 0.0f) : rgbf(0.0f, 0.0f, 0.0f);
+                for (int k = 0; k + 1 < car->prt[i].len; ++k) {
+                    float x0, y0, x1, y1;
+                    xf_pt(&M, car->prt[i].pt[k].x, car->prt[i].pt[k].y, &x0, &y0);
+                    xf_pt(&M, car->prt[i].pt[k + 1].x, car->prt[i].pt[k + 1].y, &x1, &y1);
+                    const float hw = 2.5f;
+                    float qx[4], qy[4];
+                    if (fabsf(x1 - x0) >= fabsf(y1 - y0)) {
+                        qx[0] = x0; qy[0] = y0 - hw; qx[1] = x1; qy[1] = y1 - hw; qx[2] = x1; qy[2] = y1 + hw; qx[3] = x0; qy[3] = y0 + hw;
+                    } else {
+                        qx[0] = x0 - hw; qy[0] = y0; qx[1] = x1 - hw; qy[1] = y1; qx[2] = x1 + hw; qy[2] = y1; qx[3] = x0 + hw; qy[3] = y0;
+                    }
+                    fill_poly(&cv, qx, qy, 4, pc);
+                }
+            }
+        }
         RGB hullcol;
         if (W->use_ego_color) hullcol = (c == agent) ? rgbf(0.8f, 0.0f, 0.0f) : rgbf(0.0f, 0.0f, 0.8f);
         else hullcol = rgbf(CAR_COLORS[car->hull_color][0], CAR_COLORS[car->hull_color][1], CAR_COLORS[car->hull_color][2]);
@@ -1640,7 +1697,17 @@ ORC_API void orc_get_visited(const OrcWorld* W, uint8_t* visited /*T*A*/, uint8_
 ORC_API void orc_get_scores(const OrcWorld* W, double* reward, int* counts, uint8_t* backward) {
     for (int c = 0; c < W->A; ++c) { reward[c] = W->reward[c]; counts[c] = W->tile_visited_count[c]; backward[c] = W->driving_backward[c]; }
 }
+ORC_API void orc_set_particles(OrcWorld* W, int on) { W->draw_particles = on; }
 ORC_API void orc_get_grass(const OrcWorld* W, uint8_t* grass) { for (int c = 0; c < W->A; ++c) grass[c] = W->driving_on_grass[c]; }
+/* skid traces of car c: out[i] = (len, grass, 30 x (x, y)) floats per particle, returns the particle count */
+ORC_API int orc_get_particles(const OrcWorld* W, int c, float* out) {
+    const Car* car = &W->car[c];
+    for (int i = 0; i < car->n_prt; ++i) {
+        float* o = out + (size_t)i * 62; o[0] = (float)car->prt[i].len; o[1] = (float)car->prt[i].grass;
+        for (int k = 0; k < PRT_PTS; ++k) { o[2 + 2 * k] = k < car->prt[i].len ? car->prt[i].pt[k].x : 0.0f; o[3 + 2 * k] = k < car->prt[i].len ? car->prt[i].pt[k].y : 0.0f; }
+    }
+    return car->n_prt;
+}
 ORC_API double orc_get_time(const OrcWorld* W) { return W->t; }
 ORC_API int orc_get_fixed_point_iter(const OrcWorld* W) { return W->vel_iters_used; }
 /* mass constants: hull mass, invMass, I, invI, lc.x, lc.y, wheel mass, invMass, I, invI, lc.x, lc.y */

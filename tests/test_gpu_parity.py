@@ -24,7 +24,7 @@ def _setup(oracle, mcr, B, A, seed, directions=None, **kw):
     venv = mcr.BatchedMultiCarRacing(B, num_agents=A, auto_reset=False, max_episode_steps=0, **kw)
     obs0 = venv.reset(tracks=tracks, car_orders=orders, directions=directions).cpu().numpy()
     okw = dict(h_ratio=kw.get("h_ratio", 0.25), backwards_flag=kw.get("backwards_flag", True),
-               use_ego_color=kw.get("use_ego_color", False))
+               use_ego_color=kw.get("use_ego_color", False), particles=kw.get("particles", False))
     worlds = make_oracle_worlds(oracle, tracks, orders, directions, A, **okw)
     oobs0 = np.stack([w.step(None)[0] for w in worlds])
     return venv, worlds, tracks, obs0, oobs0
@@ -152,6 +152,44 @@ def test_render_modes_between_steps(oracle, mcr):
                 want = np.stack([w.render(mode) for w in worlds])
                 bad = int((got != want).any(axis=-1).sum())
                 assert bad == 0, "%s, step %d: %d pixels differ" % (mode, s, bad)
+
+
+def test_rgb_array_skid_particles(oracle, mcr):
+    """particles=True: the skid traces of gym car_dynamics.Car (Car.step "Skid trace" block, Car.particles ring of
+    30 polylines of <= 30 points) are kept on the device and drawn by render('rgb_array') before
+    each car, like Car.draw(viewer, draw_particles=True) (mcr:564); state_pixels frames never show them.
+    Bit-exact against the oracle: particle lists (order, grass flag, points) and the 600 x 400 frames, over
+    enough hard-braking steps for the ring to wrap."""
+    import torch
+    venv, worlds, tracks, obs0, oobs0 = _setup(oracle, mcr, B=2, A=2, seed=51, particles=True)
+    tape = action_tape(51, 400, 2, 2, brake_p=0.3)
+    N = 4
+    wrapped = False
+    for s in range(400):
+        obs, _, _, _ = venv.step(torch.from_numpy(tape[s]).to(venv.device))
+        oo = [w.step(tape[s, e].astype(np.float64)) for e, w in enumerate(worlds)]
+        if s % 40 == 39:
+            assert np.array_equal(obs.cpu().numpy(), np.stack([x[0] for x in oo])), "state pixels, step %d" % s
+            hdr = venv.buffers["prt_hdr"].cpu().numpy()
+            meta = venv.buffers["prt_meta"].cpu().numpy()
+            pts = venv.buffers["prt_pts"].cpu().numpy().reshape(30, 30, 2, N)
+            for e, w in enumerate(worlds):
+                for c in range(2):
+                    car = e * 2 + c
+                    want = w.particles(c)
+                    head, count = int(hdr[0, car]), int(hdr[1, car])
+                    assert count == len(want), "particle count, step %d car %d" % (s, car)
+                    wrapped |= head != 0
+                    for i, (grass, p) in enumerate(want):
+                        slot = (head + i) % 30
+                        ln = int(meta[slot, car]) & 0xff
+                        assert ln == len(p) and bool(int(meta[slot, car]) & 256) == grass
+                        assert np.array_equal(pts[slot, :ln, :, car], p), "particle points, step %d car %d" % (s, car)
+            got = venv.render('rgb_array').cpu().numpy()
+            want_img = np.stack([w.render('rgb_array') for w in worlds])
+            bad = int((got != want_img).any(axis=-1).sum())
+            assert bad == 0, "rgb_array with particles, step %d: %d pixels differ" % (s, bad)
+    assert wrapped, "the test tape must make the particle ring wrap"
 
 
 def test_viewport_tiling_partial_tiles_ego_color(oracle, mcr):

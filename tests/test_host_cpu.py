@@ -22,7 +22,7 @@ def test_library_exports_every_header_symbol(mcr):
     for sym in sorted(declared):
         assert hasattr(L, sym), "libmcr.so does not export %s" % sym
     assert set(_lib.EXPORTS) == declared
-    assert L.mcr_abi_version() == 1
+    assert L.mcr_abi_version() == 2
 
 
 def test_config_validation_and_error_strings(mcr):
@@ -120,7 +120,7 @@ def test_obs_format_abi(mcr):
     import ctypes
     from multi_car_racing_b200 import _lib
     L = _lib.load()
-    cfg = _lib.McrConfig(2, 2, 512, 1024, 2, 1, 0, 1000, 0.25, 0, 1, 0, 1, 0)
+    cfg = _lib.McrConfig(2, 2, 512, 1024, 2, 1, 0, 1000, 0.25, 0, 1, 0, 1, 0, 0)
     h = ctypes.c_void_p()
     assert L.mcr_create(ctypes.byref(cfg), ctypes.byref(h)) == 0
     assert L.mcr_obs_bytes(h) == 96 * 96 * 3
