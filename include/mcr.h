@@ -151,7 +151,7 @@ int mcr_render(mcr_handle h, const uint8_t* d_env_mask, uint8_t* d_obs, double* 
 /* render(mode) outside step(), mcr:511-604, for any glViewport size: (96, 96) = 'state_pixels',
  * (600, 400) = 'rgb_array'.  d_out: [B][A][vh][vw][3] u8.  Shows the env as it is NOW (current
  * reward in the score label, current backward flags), like a render() call between steps.  Skid
- * particles (only drawn in the non-state modes, mcr:564) are not drawn. */
+ * particles (only drawn in the non-state modes, mcr:564) are drawn when mcr_config.particles is set. */
 int mcr_render_viewport(mcr_handle h, const uint8_t* d_env_mask, int32_t vw, int32_t vh, uint8_t* d_out, void* stream);
 
 /* Select the layout every later mcr_reset / mcr_step / mcr_render call writes into d_obs (one of

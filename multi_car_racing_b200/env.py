@@ -391,7 +391,8 @@ class BatchedMultiCarRacing:
         """render(mode) between steps, reference :511-604: 'state_pixels' -> (B, A, 96, 96, 3),
         'rgb_array' -> (B, A, 400, 600, 3) uint8 on the device, showing the envs as they are now
         (current score and backward flags).  Same rasteriser, tiled over the larger viewport; skid
-        particles are not drawn.  'human' opens windows in the reference; there is no display here."""
+        particles are drawn when the env was built with particles=True.  'human' opens windows in the
+        reference; there is no display here."""
         assert mode in ['human', 'state_pixels', 'rgb_array']
         if mode == 'human':
             raise NotImplementedError("mode='human' needs a display; use 'rgb_array' (same picture at 600x400)")

@@ -1656,7 +1656,7 @@ ORC_API void orc_render(OrcWorld* W, uint8_t* obs) {
     for (int c = 0; c < W->A; ++c) render_view(W, c, obs + (size_t)c * STATE_W * STATE_H * 3);
 }
 /* render(mode) for any viewport: state_pixels (96, 96), rgb_array (600, 400), mcr:566-575.  Skid
- * particles (drawn in the non-state modes, mcr:564) are not restated (documented deviation D6). */
+ * particles (drawn in the non-state modes, mcr:564) are drawn when orc_set_particles(1) (wide lines restated as D6). */
 ORC_API void orc_render_vp(OrcWorld* W, int vw, int vh, uint8_t* out) {
     for (int c = 0; c < W->A; ++c) render_view_vp(W, c, out + (size_t)c * vw * vh * 3, vw, vh);
 }
