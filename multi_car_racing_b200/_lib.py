@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmcr.so")
+LIB_PATH = os.environ.get("MCR_LIB_PATH") or os.path.join(_HERE, "libmcr.so")     # MCR_LIB_PATH: A/B another build
 
 MCR_U8, MCR_I32, MCR_U32, MCR_F32, MCR_F64, MCR_I16 = range(6)
 STATE_W = 96
@@ -103,7 +103,7 @@ def load():
     L.mcr_trackgen_scratch_bytes.argtypes = []
     L.mcr_render_viewport.restype = i32
     L.mcr_render_viewport.argtypes = [vp, vp, i32, i32, vp, vp]
-    if L.mcr_abi_version() != 2:
+    if L.mcr_abi_version() != 2 and not os.environ.get("MCR_LIB_PATH"):
         raise McrError("libmcr.so ABI version mismatch")
     _lib = L
     return L

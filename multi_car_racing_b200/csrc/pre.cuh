@@ -5,6 +5,54 @@
 #pragma once
 #include "solver.cuh"
 
+// Skid trace of gym car_dynamics Car.step for the four wheels of one car (only with mcr_config.particles;
+// kept out of line so that the step's hot path does not carry its code): skid_bits / grass_bits = per wheel
+// |force| > 2 friction_limit / no tile under the wheel; (wx, wy) = wheel.position (the wheel body's origin).
+static __device__ __noinline__ void skid_traces(const Dims& d, const DevBuffers& b, int car, unsigned skid_bits, unsigned grass_bits,
+                                         float wx0, float wy0, float wx1, float wy1, float wx2, float wy2, float wx3, float wy3) {
+    const int N = d.N;
+    for (int k = 0; k < 4; ++k) {
+        const float wx = k == 0 ? wx0 : (k == 1 ? wx1 : (k == 2 ? wx2 : wx3)), wy = k == 0 ? wy0 : (k == 1 ? wy1 : (k == 2 ? wy2 : wy3));
+        const bool grass = (grass_bits >> k) & 1u;
+        int meta = b.skid_meta[(size_t)k * N + car];
+        if ((skid_bits >> k) & 1u) {
+            const bool ref_valid = (meta & 2) != 0, ref_grass = (meta & 4) != 0;
+            const int ref_len = (meta >> 8) & 0xff, ref_slot = ((meta >> 16) & 0xff) - 1;
+            if (ref_valid && ref_grass == grass && ref_len < PRT_PTS) {
+                if (ref_slot >= 0) {             // still in Car.particles: the drawn polyline grows
+                    float* pt = b.prt_pts + ((size_t)(ref_slot * PRT_PTS + ref_len) * 2) * N + car;
+                    pt[0] = wx; pt[N] = wy;
+                    b.prt_meta[(size_t)ref_slot * N + car] = (ref_len + 1) | (ref_grass ? 256 : 0);
+                }
+                meta = (meta & ~0xff00) | ((ref_len + 1) << 8);
+            } else if (!(meta & 1)) {
+                b.skid_start[(size_t)(k * 2 + 0) * N + car] = wx; b.skid_start[(size_t)(k * 2 + 1) * N + car] = wy;
+                meta |= 1;
+            } else {
+                // _create_particle(skid_start, position, grass): append, pop(0) while more than PRT_MAX
+                int head = b.prt_hdr[car], count = b.prt_hdr[(size_t)N + car], slot;
+                if (count < PRT_MAX) { slot = head + count; if (slot >= PRT_MAX) slot -= PRT_MAX; ++count; }
+                else {
+                    slot = head; head = head + 1 == PRT_MAX ? 0 : head + 1;
+                    for (int k2 = 0; k2 < 4; ++k2) {     // wheels still extending the popped particle keep doing so, unseen
+                        const size_t mi = (size_t)k2 * N + car;
+                        if (k2 != k) { const int m2 = b.skid_meta[mi]; if (((m2 >> 16) & 0xff) - 1 == slot) b.skid_meta[mi] = m2 & ~0xff0000; }
+                    }
+                }
+                b.prt_hdr[car] = head; b.prt_hdr[(size_t)N + car] = count;
+                float* pt = b.prt_pts + ((size_t)(slot * PRT_PTS) * 2) * N + car;
+                pt[0] = b.skid_start[(size_t)(k * 2 + 0) * N + car]; pt[N] = b.skid_start[(size_t)(k * 2 + 1) * N + car];
+                pt[(size_t)2 * N] = wx; pt[(size_t)3 * N] = wy;
+                b.prt_meta[(size_t)slot * N + car] = 2 | (grass ? 256 : 0);
+                meta = 2 | (grass ? 4 : 0) | (2 << 8) | ((slot + 1) << 16);      // skid_start = None
+            }
+        } else {
+            meta = 0;                             // skid_start = None, skid_particle = None
+        }
+        b.skid_meta[(size_t)k * N + car] = meta;
+    }
+}
+
 // take_action = false: the action=None path of mcr:421 (reset()'s implicit step, next-step auto reset)
 template <typename ActT>
 __device__ __forceinline__ void pre_car(const Dims& d, const DevBuffers& b, const CarConst& cc, int car, int env,
@@ -61,6 +109,7 @@ __device__ __forceinline__ void pre_car(const Dims& d, const DevBuffers& b, cons
     const double FRICTION_LIMIT = 1000000 * SIZE * SIZE;
     const double dt = 1.0 / 50;
     float motorSpeed[4], Fx[4], Fy[4];
+    unsigned skid_bits = 0u;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int bi = 1 + k;
@@ -95,46 +144,7 @@ __device__ __forceinline__ void pre_car(const Dims& d, const DevBuffers& b, cons
         f_force *= 205000 * SIZE * SIZE;
         p_force *= 205000 * SIZE * SIZE;
         double force = sqrt(f_force * f_force + p_force * p_force);
-        if (d.particles) {
-            // Skid trace (gym car_dynamics Car.step): wheel.position is the wheel body's origin = its centre
-            const bool grass = !on_road[k];
-            int meta = b.skid_meta[(size_t)k * N + car];
-            if (fabs(force) > 2.0 * friction_limit) {
-                const bool ref_valid = (meta & 2) != 0, ref_grass = (meta & 4) != 0;
-                const int ref_len = (meta >> 8) & 0xff, ref_slot = ((meta >> 16) & 0xff) - 1;
-                if (ref_valid && ref_grass == grass && ref_len < PRT_PTS) {
-                    if (ref_slot >= 0) {             // still in Car.particles: the drawn polyline grows
-                        float* pt = b.prt_pts + ((size_t)(ref_slot * PRT_PTS + ref_len) * 2) * N + car;
-                        pt[0] = cx[bi]; pt[N] = cy[bi];
-                        b.prt_meta[(size_t)ref_slot * N + car] = (ref_len + 1) | (ref_grass ? 256 : 0);
-                    }
-                    meta = (meta & ~0xff00) | ((ref_len + 1) << 8);
-                } else if (!(meta & 1)) {
-                    b.skid_start[(size_t)(k * 2 + 0) * N + car] = cx[bi]; b.skid_start[(size_t)(k * 2 + 1) * N + car] = cy[bi];
-                    meta |= 1;
-                } else {
-                    // _create_particle(skid_start, position, grass): append, pop(0) while more than PRT_MAX
-                    int head = b.prt_hdr[car], count = b.prt_hdr[(size_t)N + car], slot;
-                    if (count < PRT_MAX) { slot = head + count; if (slot >= PRT_MAX) slot -= PRT_MAX; ++count; }
-                    else {
-                        slot = head; head = head + 1 == PRT_MAX ? 0 : head + 1;
-                        for (int k2 = 0; k2 < 4; ++k2) {     // wheels still extending the popped particle keep doing so, unseen
-                            const size_t mi = (size_t)k2 * N + car;
-                            if (k2 != k) { const int m2 = b.skid_meta[mi]; if (((m2 >> 16) & 0xff) - 1 == slot) b.skid_meta[mi] = m2 & ~0xff0000; }
-                        }
-                    }
-                    b.prt_hdr[car] = head; b.prt_hdr[(size_t)N + car] = count;
-                    float* pt = b.prt_pts + ((size_t)(slot * PRT_PTS) * 2) * N + car;
-                    pt[0] = b.skid_start[(size_t)(k * 2 + 0) * N + car]; pt[N] = b.skid_start[(size_t)(k * 2 + 1) * N + car];
-                    pt[(size_t)2 * N] = cx[bi]; pt[(size_t)3 * N] = cy[bi];
-                    b.prt_meta[(size_t)slot * N + car] = 2 | (grass ? 256 : 0);
-                    meta = 2 | (grass ? 4 : 0) | (2 << 8) | ((slot + 1) << 16);      // skid_start = None
-                }
-            } else {
-                meta = 0;                             // skid_start = None, skid_particle = None
-            }
-            b.skid_meta[(size_t)k * N + car] = meta;
-        }
+        skid_bits |= (fabs(force) > 2.0 * friction_limit ? 1u : 0u) << k;     // Car.step's "Skid trace" condition
         if (fabs(force) > friction_limit) {
             f_force /= force; p_force /= force;
             force = friction_limit;
@@ -144,6 +154,11 @@ __device__ __forceinline__ void pre_car(const Dims& d, const DevBuffers& b, cons
         Fx[k] = (float)(p_force * (double)side_x + f_force * (double)forw_x);
         Fy[k] = (float)(p_force * (double)side_y + f_force * (double)forw_y);
         if (!awake[bi]) { awake[bi] = true; slp[bi] = 0.0f; }   // ApplyForceToCenter(wake=True)
+    }
+
+    if (d.particles) {
+        const unsigned grass_bits = (on_road[0] ? 0u : 1u) | (on_road[1] ? 0u : 2u) | (on_road[2] ? 0u : 4u) | (on_road[3] ? 0u : 8u);
+        skid_traces(d, b, car, skid_bits, grass_bits, cx[1], cy[1], cx[2], cy[2], cx[3], cy[3], cx[4], cy[4]);
     }
 
     // ---- b2Island::Solve ---------------------------------------------------------------
