@@ -20,7 +20,8 @@ for s in range(WARM): venv.step(tape[s % 128])
 tl = venv.buffers["timeline"].view(torch.int64)
 acc = np.zeros(len(names)); n = 0; tot = 0.0
 for s in range(STEPS):
-    flush.zero_(); tl.zero_()
+    if not os.environ.get("NOFLUSH"): flush.zero_()      # NOFLUSH=1: leave the previous step's lines in L2
+    tl.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); venv.step(tape[(WARM + s) % 128]); e1.record()
     torch.cuda.synchronize()
