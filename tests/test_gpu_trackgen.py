@@ -97,3 +97,11 @@ def test_full_pool_device_reset_and_auto_reset(mcr):
         obs, rew, done, _ = venv.step(torch.from_numpy(tape[s]).to(venv.device))
         seen_reset += int((done.cpu().numpy() != 0).sum())
     assert seen_reset >= 8 and venv.status().tolist() == [0, 0, 0, 0]
+
+
+def test_device_generator_reports_capacity_errors(mcr):
+    """A pool whose slots are too small for the generated track: the kernel reports the error code per track
+    (-3: more tiles than max_tiles) and the Python side raises instead of stepping on a half-written slot."""
+    venv = mcr.BatchedMultiCarRacing(2, num_agents=1, max_tiles=64, max_quads=128, auto_reset=False, max_episode_steps=0)
+    with pytest.raises(mcr.McrError, match="code -3"):
+        venv.generate_tracks_device([0, 1], [np.random.RandomState(1), np.random.RandomState(2)])
