@@ -346,6 +346,67 @@ class BatchedMultiCarRacing:
             torch.cuda.current_stream(self.device).synchronize()
         return hb["obs"].numpy(), hb["reward"].numpy(), hb["done"].numpy(), {}
 
+    # ---- pipelined host API: the copy of step k's results overlaps the compute of step k+1 -------------
+    def step_host_async(self, action):
+        """Enqueue one step whose results go to pinned host memory, without waiting for them: host ->
+        device copy of the action and the step on the compute stream, device -> host copies of
+        (obs, reward, done) on a copy stream behind it.  Two steps may be in flight (double-buffered
+        device and host result buffers); step_host_wait() returns the oldest one.  For consumers whose
+        next action does not depend on the newest observation (asynchronous / delayed policies, data
+        collection): throughput is then bound by the PCIe link alone instead of copy + compute."""
+        torch = _torch()
+        B, A = self.batch_envs, self.num_agents
+        if getattr(self, "_pipe", None) is None:
+            with torch.cuda.device(self.device):
+                self._pipe = [dict(
+                    obs=torch.zeros((B, A) + self.obs_shape, dtype=torch.uint8, device=self.device),
+                    reward=torch.zeros((B, A), dtype=torch.float64, device=self.device),
+                    done=torch.zeros((B,), dtype=torch.uint8, device=self.device),
+                    h_obs=torch.zeros((B, A) + self.obs_shape, dtype=torch.uint8).pin_memory(),
+                    h_reward=torch.zeros((B, A), dtype=torch.float64).pin_memory(),
+                    h_done=torch.zeros((B,), dtype=torch.uint8).pin_memory(),
+                    computed=torch.cuda.Event(), copied=torch.cuda.Event(), busy=False) for _ in range(2)]
+                self._pipe_copy_stream = torch.cuda.Stream(device=self.device)
+            self._pipe_issue, self._pipe_retire = 0, 0
+        if self._pipe_issue - self._pipe_retire >= 2:
+            raise RuntimeError("two steps are already in flight: call step_host_wait() first")
+        hb = self.host_buffers()
+        a = np.reshape(action, (B, A, 3))
+        p = self._pipe[self._pipe_issue & 1]
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream(self.device)
+            if a.dtype == np.float64:
+                hb["action64"].numpy()[...] = a
+                src, dev_a, dt = hb["action64"], self._dev_action64, _lib.MCR_F64
+            else:
+                hb["action"].numpy()[...] = a
+                src, dev_a, dt = hb["action"], self._dev_action, _lib.MCR_F32
+            if p["busy"]:
+                cur.wait_event(p["copied"])            # the buffers' previous results have reached the host
+            dev_a.copy_(src, non_blocking=True)
+            _lib.check(self.L.mcr_step(self._h, dev_a.data_ptr(), dt, p["obs"].data_ptr(), p["reward"].data_ptr(),
+                                       p["done"].data_ptr(), self._step_flags, self._stream()), "mcr_step")
+            p["computed"].record(cur)
+            cs = self._pipe_copy_stream
+            cs.wait_event(p["computed"])
+            with torch.cuda.stream(cs):
+                p["h_obs"].copy_(p["obs"], non_blocking=True)
+                p["h_reward"].copy_(p["reward"], non_blocking=True)
+                p["h_done"].copy_(p["done"], non_blocking=True)
+                p["copied"].record(cs)
+            p["busy"] = True
+        self._pipe_issue += 1
+
+    def step_host_wait(self):
+        """Results of the oldest step in flight: numpy views of pinned host buffers (valid until the
+        second step_host_async() call from now)."""
+        if getattr(self, "_pipe", None) is None or self._pipe_issue == self._pipe_retire:
+            raise RuntimeError("step_host_wait() without a step in flight")
+        p = self._pipe[self._pipe_retire & 1]
+        p["copied"].synchronize()
+        self._pipe_retire += 1
+        return p["h_obs"].numpy(), p["h_reward"].numpy(), p["h_done"].numpy(), {}
+
     def host_buffers(self):
         """Pinned host staging buffers of step_host (allocated on first use)."""
         if getattr(self, "_host", None) is None:

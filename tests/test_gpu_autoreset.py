@@ -164,3 +164,32 @@ def test_graph_replay_equals_direct_launches(mcr, monkeypatch):
 
     (a, la), (b, lb) = run(False), run(True)
     assert a == b and la == lb
+
+
+def test_pipelined_host_api_matches_synchronous(mcr):
+    """step_host_async / step_host_wait (copy of step k under the compute of step k+1, double-buffered) returns
+    exactly what step_host returns, one call later."""
+    np.random.seed(4)
+    a = mcr.BatchedMultiCarRacing(8, num_agents=2, seed=21, max_episode_steps=20, auto_reset='next_step')
+    np.random.seed(4)
+    b = mcr.BatchedMultiCarRacing(8, num_agents=2, seed=21, max_episode_steps=20, auto_reset='next_step')
+    np.random.seed(6); a.reset()
+    np.random.seed(6); b.reset()
+    tape = action_tape(15, 50, 8, 2)
+    want = []
+    for s in range(50):
+        o, r, d, _ = a.step_host(tape[s])
+        want.append((o.copy(), r.copy(), d.copy()))
+    got = []
+    for s in range(50):
+        b.step_host_async(tape[s])
+        if s:
+            o, r, d, _ = b.step_host_wait()
+            got.append((o.copy(), r.copy(), d.copy()))
+    o, r, d, _ = b.step_host_wait()
+    got.append((o.copy(), r.copy(), d.copy()))
+    with pytest.raises(RuntimeError):
+        b.step_host_wait()
+    assert len(got) == 50
+    for s, (w, g) in enumerate(zip(want, got)):
+        assert all(np.array_equal(x, y) for x, y in zip(w, g)), "step %d" % s
