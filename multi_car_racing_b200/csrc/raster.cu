@@ -871,14 +871,18 @@ score_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, const uint8
     }
 }
 
+// One-time set-up per DEVICE (function attributes and __constant__ data belong to the device's context; a
+// process that drives several GPUs has one handle per device).
 static bool configure_render() {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    if (!configured[dev]) {
         const size_t smem = sizeof(RasterSmem);
         if (cudaMemcpyToSymbol(c_palette, mcr_host_palette(), sizeof(uint8_t) * PAL_COUNT * 4) != cudaSuccess) return false;
         if (cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
         if (cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
-        configured = true;
+        configured[dev] = true;
     }
     return true;
 }

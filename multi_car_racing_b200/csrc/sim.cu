@@ -549,12 +549,15 @@ int launch_stripes(const Dims& d, const DevBuffers& b, const uint8_t* mask, void
 // launchers
 // ---------------------------------------------------------------------------------------
 int launch_contacts(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, void* stream) {
-    static int configured_for = -1;
+    static bool configured[64] = {};       // per device: function attributes belong to the device's context
     const size_t per_warp = (sim_smem_bytes(d.A) + 15) & ~(size_t)15;
     const size_t smem = per_warp * CT_WARPS;
-    if (smem > 48 * 1024 && configured_for != d.A) {
-        if (cudaFuncSetAttribute(contacts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        configured_for = d.A;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    if (!configured[dev]) {                // once, for the largest num_agents a handle may ask for
+        const size_t smem_max = ((sim_smem_bytes(MCR_MAX_AGENTS) + 15) & ~(size_t)15) * CT_WARPS;
+        if (cudaFuncSetAttribute(contacts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) != cudaSuccess) return -1;
+        configured[dev] = true;
     }
     contacts_kernel<<<(d.B + CT_WARPS - 1) / CT_WARPS, CT_WARPS * 32, smem, (cudaStream_t)stream>>>(d, b, cc, mask, per_warp);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
