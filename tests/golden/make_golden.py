@@ -6,7 +6,7 @@ modules (tests/golden/refstub.py).  Run in the build container only:
 
 Each fixture records one seeded episode: constructor kwargs, both RNG seeds, the action tape,
 and what the reference returned / held after every step -- step rewards, done, env.reward,
-tile_visited_count, driving_backward, hull poses, a SHA-1 of every observation and every 20th
+tile_visited_count, driving_backward, driving_on_grass, hull poses, a SHA-1 of every observation and every 20th
 observation in full.  tests/test_golden.py replays the tapes through the CPU oracle (CPU suite)
 and through the CUDA path (GPU suite).
 
@@ -70,7 +70,7 @@ def run_case(ref, case):
     np.random.seed(case["np_seed"])
     env = ref.MultiCarRacing(verbose=0, **case["kwargs"])
     env.seed(case["env_seed"])
-    out = dict(rewards=[], dones=[], env_reward=[], counts=[], backward=[], poses=[], sha=[], frames=[], frame_idx=[],
+    out = dict(rewards=[], dones=[], env_reward=[], counts=[], backward=[], grass=[], poses=[], sha=[], frames=[], frame_idx=[],
                reset_sha=[], reset_frames=[], track_len=[], direction=[], car_order=[])
     acts = tape(case["kind"], case["env_seed"], case["steps"], A)
     for ep in range(case.get("episodes", 1)):
@@ -89,6 +89,7 @@ def run_case(ref, case):
             out["env_reward"].append(np.array(env.reward, np.float64))
             out["counts"].append(np.array(env.tile_visited_count, np.int32))
             out["backward"].append(np.array(env.driving_backward, np.uint8))
+            out["grass"].append(np.array(env.driving_on_grass, np.uint8))
             out["poses"].append(np.array([[c.hull.position[0], c.hull.position[1], c.hull.angle] for c in env.cars], np.float32))
             out["sha"].append(hashlib.sha1(obs.tobytes()).digest())
             if s % 20 == 0:
@@ -102,7 +103,7 @@ def run_case(ref, case):
         kwargs=np.array(repr(case["kwargs"])), np_seed=case["np_seed"], env_seed=case["env_seed"],
         episodes=case.get("episodes", 1), steps_per_episode=case["steps"], actions=acts.astype(np.float32),
         rewards=np.array(out["rewards"]), dones=np.array(out["dones"]), env_reward=np.array(out["env_reward"]),
-        counts=np.array(out["counts"]), backward=np.array(out["backward"]), poses=np.array(out["poses"]),
+        counts=np.array(out["counts"]), backward=np.array(out["backward"]), grass=np.array(out["grass"]), poses=np.array(out["poses"]),
         sha=np.frombuffer(b"".join(out["sha"]), np.uint8).reshape(n, 20),
         frames=np.array(out["frames"]), frame_idx=np.array(out["frame_idx"], np.int32),
         reset_sha=np.frombuffer(b"".join(out["reset_sha"]), np.uint8).reshape(-1, 20),

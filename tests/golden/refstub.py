@@ -545,15 +545,27 @@ class _EzPickle:
 
 class _Point:
     def __init__(self, xy):
-        self.xy = xy
+        self.xy = (float(xy[0]), float(xy[1]))
 
     def within(self, poly):
-        return False
+        """shapely Point.within(Polygon) for the convex road / border quads: strictly inside, float64."""
+        px, py = self.xy
+        pos = neg = 0
+        n = len(poly.pts)
+        for k in range(n):
+            x0, y0 = poly.pts[k]
+            x1, y1 = poly.pts[(k + 1) % n]
+            cr = (x1 - x0) * (py - y0) - (y1 - y0) * (px - x0)
+            if cr > 0:
+                pos += 1
+            elif cr < 0:
+                neg += 1
+        return pos == n or neg == n
 
 
 class _Polygon:
     def __init__(self, pts):
-        self.pts = pts
+        self.pts = [(float(p[0]), float(p[1])) for p in pts]
 
 
 def install():

@@ -44,6 +44,7 @@ def _replay(env_cls, z, kwargs, check_state):
                 assert np.array_equal(np.asarray(env.reward, np.float64), z["env_reward"][n]), "env.reward at %d" % n
                 assert [int(v) for v in env.tile_visited_count] == list(z["counts"][n]), "tile_visited_count at %d" % n
                 assert np.array_equal(np.asarray(env.driving_backward, np.uint8), z["backward"][n]), "driving_backward at %d" % n
+                assert np.array_equal(np.asarray(env.driving_on_grass, np.uint8), z["grass"][n]), "driving_on_grass at %d" % n
             if n in frame_at:
                 assert np.array_equal(obs, z["frames"][frame_at[n]]), "observation pixels at step %d" % n
             assert hashlib.sha1(np.ascontiguousarray(obs).tobytes()).digest() == z["sha"][n].tobytes(), "observation hash at step %d" % n
