@@ -184,10 +184,26 @@ __device__ void carcontacts_warp(const Dims& d, const DevBuffers& b, const CarCo
     float* gman = b.manifold + (size_t)env * MAXM * MW;
     if (A < 2) { if (lane == 0) b.n_manifold[env] = 0; return; }
     const int nold = b.n_manifold[env];
+    const int ncp = A * (A - 1) / 2;
+    if (nold == 0) {
+        // The common case costs two loads: with no manifold to carry over, fixtures can only touch if two
+        // hull origins are within reach of each other.  Every fixture vertex lies within 2.9 m of its car's
+        // hull origin (hull polygon <= 2.87 m, wheel anchor + wheel half diagonal + joint slack <= 2.7 m), so
+        // 7 m between origins rules every pair out (2 x 2.9 + polygon radii + a wide margin).
+        bool close = false;
+        for (int cp = lane; cp < ncp; cp += 32) {
+            int a = 0, rem = cp;
+            while (rem >= A - 1 - a) { rem -= A - 1 - a; ++a; }
+            const int carA = env * A + a, carB = env * A + a + 1 + rem;
+            const float dx = b.body[(size_t)BF_PX * N + carA] - b.body[(size_t)BF_PX * N + carB];
+            const float dy = b.body[(size_t)BF_PY * N + carA] - b.body[(size_t)BF_PY * N + carB];
+            close = close || !(dx * dx + dy * dy > 49.0f);
+        }
+        if (!__any_sync(0xffffffffu, close)) { if (lane == 0) b.n_manifold[env] = 0; return; }
+    }
     for (int i = lane; i < nold * MW; i += 32) s_old_w[i] = gman[i];
     __syncwarp();
     const float r = B2_POLYGON_RADIUS;
-    const int ncp = A * (A - 1) / 2;
     int nnew = 0;
     for (int base = 0; base < ncp * 64; base += 32) {
         const int idx = base + lane;
