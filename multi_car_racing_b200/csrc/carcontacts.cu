@@ -511,6 +511,8 @@ coupled_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
     __shared__ int s_root[MCR_MAX_AGENTS];
     __shared__ float s_minsep[MCR_MAX_AGENTS];
     __shared__ int s_changed;
+    __shared__ unsigned char s_list[MAXM];                 // manifold indices grouped by island root, ascending inside an island
+    __shared__ int s_lstart[MCR_MAX_AGENTS + 1];
     tl_stamp(b.timeline, TL_COUPLED);
     const int env = blockIdx.x, lane = threadIdx.x;
     if (mask && !mask[env]) return;
@@ -591,7 +593,19 @@ coupled_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
         s_vc[lane].root = s_root[m.key & 0xff];
     }
     __syncwarp();
-    if (lane == 0) for (int i = 0; i < nman; ++i) contact_warm_start(s_vc[i], s_bm);
+    // Islands do not share bodies, so their contact constraints are independent: every island's ROOT lane solves
+    // its own manifolds (in manifold order, as Box2D does inside one island) while the other roots solve theirs.
+    if (lane == 0) {
+        int pos = 0;
+        for (int r = 0; r < A; ++r) {
+            s_lstart[r] = pos;
+            for (int i = 0; i < nman; ++i) if (s_vc[i].root == r) s_list[pos++] = (unsigned char)i;
+        }
+        s_lstart[A] = pos;
+    }
+    __syncwarp();
+    const int my_first = mine ? s_lstart[lane] : 0, my_count = mine ? s_lstart[lane + 1] - s_lstart[lane] : 0;
+    for (int k = 0; k < my_count; ++k) contact_warm_start(s_vc[s_list[my_first + k]], s_bm);
     __syncwarp();
     pull_vel();
     // ---- joints: InitVelocityConstraints + warm start, then the 180 sweeps in lock step ----------------
@@ -614,7 +628,7 @@ coupled_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
             if (no_limits) sweep<0>(s, J, m); else sweep<-1>(s, J, m);
             push_vel();
             __syncwarp();
-            if (lane == 0) for (int i = 0; i < nman; ++i) contact_solve_vel(s_vc[i], s_bm);
+            for (int k = 0; k < my_count; ++k) contact_solve_vel(s_vc[s_list[my_first + k]], s_bm);
             __syncwarp();
             pull_vel();
         }
@@ -663,14 +677,10 @@ coupled_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
         push_pos();
         if (lane < A) s_minsep[lane] = 0.0f;
         __syncwarp();
-        if (lane == 0) {
-            for (int i = 0; i < nman; ++i) {
-                const int r = s_vc[i].root;
-                if (!((act >> r) & 1u)) continue;         // the island's root lane is active iff the island is
-                float ms = s_minsep[r];
-                contact_solve_pos(s_vc[i], s_bm, ms);
-                s_minsep[r] = ms;
-            }
+        if (my_count > 0 && ((act >> lane) & 1u)) {       // the island's root lane is active iff the island is
+            float ms = s_minsep[lane];
+            for (int k = 0; k < my_count; ++k) contact_solve_pos(s_vc[s_list[my_first + k]], s_bm, ms);
+            s_minsep[lane] = ms;
         }
         __syncwarp();
         bool ok = true, moved = false;
