@@ -179,6 +179,10 @@ __device__ __forceinline__ XF body_xf(const DevBuffers& b, int N, int car, int b
 
 // Narrow phase of one env by one warp (lanes over the fixture pairs of every car pair); s_old = this
 // warp's MAXM * MW floats of shared memory.
+// MANY = more than three cars per env: the car pairs worth a fixture-pair sweep are selected first.  The two
+// variants are separate kernels on purpose: the step's head is a cold-code latency chain, and the selection
+// code costs the two-car configuration 3 us when it is merely present.
+template <bool MANY>
 __device__ void carcontacts_warp(const Dims& d, const DevBuffers& b, const CarConst& cc, int env, int lane, float* s_old_w) {
     const int A = d.A, N = d.N;
     float* gman = b.manifold + (size_t)env * MAXM * MW;
@@ -204,10 +208,49 @@ __device__ void carcontacts_warp(const Dims& d, const DevBuffers& b, const CarCo
     for (int i = lane; i < nold * MW; i += 32) s_old_w[i] = gman[i];
     __syncwarp();
     const float r = B2_POLYGON_RADIUS;
+    // Car pairs worth a fixture-pair sweep, in pair order: hull origins within reach (see above), or a manifold
+    // of the pair to carry over (sleeping bodies keep theirs wherever they are).  With 8 or 16 cars per env most
+    // of the A (A - 1) / 2 pairs are far apart.
+    uint32_t pair_bits[4] = {0u, 0u, 0u, 0u};          // MCR_MAX_AGENTS = 16 -> at most 120 pairs
+    if (!MANY) pair_bits[0] = (1u << ncp) - 1u;        // 2 or 3 cars: every pair
+    else for (int c0 = 0; c0 < ncp; c0 += 32) {
+        const int cp = c0 + lane;
+        bool keep = false;
+        if (cp < ncp) {
+            int a = 0, rem = cp;
+            while (rem >= A - 1 - a) { rem -= A - 1 - a; ++a; }
+            const int bc = a + 1 + rem, carA = env * A + a, carB = env * A + bc;
+            const float dx = b.body[(size_t)BF_PX * N + carA] - b.body[(size_t)BF_PX * N + carB];
+            const float dy = b.body[(size_t)BF_PY * N + carA] - b.body[(size_t)BF_PY * N + carB];
+            keep = !(dx * dx + dy * dy > 49.0f);
+            for (int i = 0; i < nold && !keep; ++i) {
+                const uint32_t key = __float_as_uint(s_old_w[i * MW]);
+                keep = (int)(key & 0xff) == a && (int)((key >> 16) & 0xff) == bc;
+            }
+        }
+        pair_bits[c0 >> 5] = __ballot_sync(0xffffffffu, keep);
+    }
+    const int nclose = __popc(pair_bits[0]) + __popc(pair_bits[1]) + __popc(pair_bits[2]) + __popc(pair_bits[3]);
     int nnew = 0;
-    for (int base = 0; base < ncp * 64; base += 32) {
+    for (int base = 0; base < nclose * 64; base += 32) {
         const int idx = base + lane;
-        const int cp = idx >> 6, fa = (idx >> 3) & 7, fb = idx & 7;
+        const int rank = idx >> 6, fa = (idx >> 3) & 7, fb = idx & 7;
+        // the rank-th kept pair -> its pair index cp (uniform over the two 32-lane halves of a pair's 64 tests)
+        int cp = ncp;
+        if (!MANY) cp = rank;
+        else {
+            int left = rank;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const int cnt = __popc(pair_bits[w]);
+                if (cp == ncp && left >= 0 && left < cnt) {
+                    uint32_t m = pair_bits[w];
+                    for (int q = 0; q < left; ++q) m &= m - 1u;      // drop the `left` lowest kept pairs
+                    cp = 32 * w + (__ffs((int)m) - 1);
+                }
+                left -= cnt;
+            }
+        }
         // decode the car pair (a < b) from its rank cp in the order (0,1),(0,2),...,(1,2),...
         int a = 0, rem = cp;
         if (cp < ncp) { while (rem >= A - 1 - a) { rem -= A - 1 - a; ++a; } }
@@ -273,14 +316,14 @@ carcontacts_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict_
     const int env = blockIdx.x * CC_WARPS + warp;
     if (env >= d.B) return;
     if (mask && !mask[env]) return;
-    carcontacts_warp(d, b, cc, env, lane, s_old[warp]);
+    if (d.A > 3) carcontacts_warp<true>(d, b, cc, env, lane, s_old[warp]); else carcontacts_warp<false>(d, b, cc, env, lane, s_old[warp]);
 }
 
 // The head of mcr_step's pipeline as ONE launch, one warp per env: the next-step auto reset of the
 // envs whose previous step ended the episode (reset.cuh), the car-car narrow phase (above), then the
 // per-car head of the step (pre.cuh) on lanes 0 .. A-1.  Three dependent latency-bound launches
 // (auto_reset -> carcontacts -> pre, 3 + 7 + 9 us plus two launch gaps) become one.
-template <typename ActT>
+template <typename ActT, bool MANY>
 __global__ void __launch_bounds__(CC_WARPS * 32)
 head_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ reset_flags,
             AutoResetCfg ar, const ActT* __restrict__ action, int collisions) {
@@ -301,7 +344,7 @@ head_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
         }
         __syncwarp();                                  // the respawned poses are visible to every lane
     }
-    if (collisions && d.A > 1) carcontacts_warp(d, b, cc, env, lane, s_old[warp]);
+    if (collisions && d.A > 1) carcontacts_warp<MANY>(d, b, cc, env, lane, s_old[warp]);
     __syncwarp();                                      // n_manifold[env]
     // a respawned env takes reset()'s implicit step(None) (mcr:408): its action is ignored
     if (lane < d.A) pre_car<ActT>(d, b, cc, env * d.A + lane, env, action != nullptr && !respawned, action);
@@ -747,10 +790,15 @@ int launch_carcontacts(const Dims& d, const DevBuffers& b, const CarConst& cc, c
 int launch_head(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* reset_flags,
                 const AutoResetCfg& ar, const void* action, int action_dtype, int collisions, void* stream) {
     const int nb = (d.B + CC_WARPS - 1) / CC_WARPS;
-    if (action_dtype == MCR_F64)
-        head_kernel<double><<<nb, CC_WARPS * 32, 0, (cudaStream_t)stream>>>(d, b, cc, mask, reset_flags, ar, (const double*)action, collisions);
-    else
-        head_kernel<float><<<nb, CC_WARPS * 32, 0, (cudaStream_t)stream>>>(d, b, cc, mask, reset_flags, ar, (const float*)action, collisions);
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool many = d.A > 3;
+    if (action_dtype == MCR_F64) {
+        if (many) head_kernel<double, true><<<nb, CC_WARPS * 32, 0, s>>>(d, b, cc, mask, reset_flags, ar, (const double*)action, collisions);
+        else head_kernel<double, false><<<nb, CC_WARPS * 32, 0, s>>>(d, b, cc, mask, reset_flags, ar, (const double*)action, collisions);
+    } else {
+        if (many) head_kernel<float, true><<<nb, CC_WARPS * 32, 0, s>>>(d, b, cc, mask, reset_flags, ar, (const float*)action, collisions);
+        else head_kernel<float, false><<<nb, CC_WARPS * 32, 0, s>>>(d, b, cc, mask, reset_flags, ar, (const float*)action, collisions);
+    }
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

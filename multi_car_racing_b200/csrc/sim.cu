@@ -196,6 +196,9 @@ __device__ void contacts_warp(const Dims& d, const DevBuffers& b, const CarConst
         if (!(meta >> 8)) continue;              // sleeping body: contact not updated
         touched[t] = 1;                          // tile.color = ROAD_COLOR, mcr:102-104 (any body, idempotent)
         if (fi >= 4) continue;                   // hull.userData is None, mcr:108
+        // only a FIRST visit changes anything in the replay below (mcr:113); visited[] is not written before
+        // phase 4, so the test is safe here and keeps the serial replay list to the step's new visits
+        if ((b.visited[(size_t)env * d.Tmax + t] >> c) & 1u) continue;
         const int slot_c = atomicAdd(&S.counts[1], 1);
         if (slot_c < cand_cap) S.cands[slot_c] = ((uint32_t)t << 8) | (uint32_t)c;
         else atomicExch(&b.status[ST_EVENT_OVERFLOW], 1);
