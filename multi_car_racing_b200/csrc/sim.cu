@@ -191,6 +191,8 @@ __device__ void contacts_warp(const Dims& d, const DevBuffers& b, const CarConst
         const float tx[4] = {v0.x, v0.z, v1.x, v1.z}, ty[4] = {v0.y, v0.w, v1.y, v1.w};
         const float* o = S.fixt + (size_t)f * FIX_STRIDE;
         const int meta = __float_as_int(o[20]);
+        // a hull fixture's contact only ever recolours the tile (mcr:102-108): nothing to learn once it is grey
+        if (fi >= 4 && touched[t]) continue;
         if (!poly_touch(tx, ty, o, o + 8, meta & 0xff)) continue;
         if (fi < 4) atomicOr(&S.road_bits[(c * 4 + fi) >> 5], 1u << ((c * 4 + fi) & 31));   // len(wheel.tiles) > 0
         if (!(meta >> 8)) continue;              // sleeping body: contact not updated
