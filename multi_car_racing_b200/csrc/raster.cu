@@ -802,23 +802,38 @@ score_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, const uint8
         const int Q = b.trk_Q[slot], nchunks = (Q + MCR_QUAD_CHUNK - 1) / MCR_QUAD_CHUNK;
         const float4* chunk = (const float4*)(b.trk_chunk + (size_t)slot * (d.Qmax / MCR_QUAD_CHUNK) * 4);
         const double* quad64 = b.trk_quad64 + (size_t)slot * d.Qmax * 8;
-        bool inside = false;
-        for (int c = lane; c < nchunks; c += 32) {
-            const float4 cc4 = chunk[c];
-            const float dx = posxf - cc4.x, dy = posyf - cc4.y;
-            if (dx * dx + dy * dy > cc4.z * cc4.z + 1.0f) continue;
-            const int q1 = min(Q, (c + 1) * MCR_QUAD_CHUNK);
-            for (int q = c * MCR_QUAD_CHUNK; q < q1 && !inside; ++q) {
-                const double* v = quad64 + (size_t)q * 8;
-                int pos = 0, neg = 0;
+        // pass 1: the chunks in reach (warp-wide bitmask); pass 2: one cross product per lane -- lane = (quad of the
+        // chunk, edge) -- and two ballots decide "all four edges on the same strict side" for the chunk's 8 quads
+        unsigned reach[MAX_CHUNKS / 32];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int k2 = (k + 1) & 3;
+        for (int w = 0; w < MAX_CHUNKS / 32; ++w) {
+            const int c = 32 * w + lane;
+            bool hit = false;
+            if (c < nchunks) {
+                const float4 cc4 = chunk[c];
+                const float dx = posxf - cc4.x, dy = posyf - cc4.y;
+                hit = !(dx * dx + dy * dy > cc4.z * cc4.z + 1.0f);
+            }
+            reach[w] = __ballot_sync(0xffffffffu, hit);
+        }
+        bool inside = false;
+#pragma unroll
+        for (int w = 0; w < MAX_CHUNKS / 32; ++w) {
+            unsigned m = reach[w];
+            while (m) {
+                const int c = 32 * w + (__ffs((int)m) - 1);
+                m &= m - 1u;
+                const int q = c * MCR_QUAD_CHUNK + (lane >> 2), k = lane & 3, k2 = (k + 1) & 3;
+                double cr = 0.0;
+                if (q < Q) {
+                    const double* v = quad64 + (size_t)q * 8;
                     const double ex = v[2 * k2] - v[2 * k], ey = v[2 * k2 + 1] - v[2 * k + 1];
-                    const double cr = ex * (posy - v[2 * k + 1]) - ey * (posx - v[2 * k]);
-                    if (cr > 0) ++pos; else if (cr < 0) ++neg;
+                    cr = ex * (posy - v[2 * k + 1]) - ey * (posx - v[2 * k]);
                 }
-                inside = pos == 4 || neg == 4;
+                const unsigned pm = __ballot_sync(0xffffffffu, cr > 0), nm = __ballot_sync(0xffffffffu, cr < 0);
+                const unsigned allp = pm & (pm >> 1) & (pm >> 2) & (pm >> 3) & 0x11111111u;
+                const unsigned alln = nm & (nm >> 1) & (nm >> 2) & (nm >> 3) & 0x11111111u;
+                inside = inside || (allp | alln) != 0u;
             }
         }
         const bool any_inside = __any_sync(0xffffffffu, inside);
