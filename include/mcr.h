@@ -138,8 +138,9 @@ int mcr_reset(mcr_handle h, const uint8_t* d_env_mask, const int32_t* d_track_sl
 int mcr_step(mcr_handle h, const void* d_action, int32_t action_dtype, uint8_t* d_obs, double* d_reward,
              uint8_t* d_done, int32_t flags, void* stream);
 
-/* Split entry points (benchmarks / ncu / tests).  mcr_step = mcr_simulate + mcr_render;
- * mcr_simulate = mcr_contacts and mcr_physics fused into one launch (one CTA per env). */
+/* Split entry points (benchmarks / ncu / tests): the same results as mcr_step without auto reset, issued as
+ * separate stages.  mcr_simulate = mcr_contacts (side stream) beside mcr_physics; mcr_render with
+ * post_step = 1 also runs the reward / done block.  mcr_step itself issues one pipelined CUDA graph. */
 int mcr_simulate(mcr_handle h, const uint8_t* d_env_mask, const void* d_action, int32_t action_dtype,
                  void* stream);                                                      /* mcr:84-123 + mcr:421-428 */
 int mcr_contacts(mcr_handle h, const uint8_t* d_env_mask, void* stream);            /* FrictionDetector + b2 Collide, mcr:84-123 */
