@@ -40,11 +40,14 @@ def needs_build():
     return any(os.path.getmtime(p) > t for p in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, extra=()):
+    """out / extra: an instrumented side build (e.g. out='libmcr_clk.so', extra=['-DMCR_PHASE_CLOCKS'],
+    loaded through MCR_LIB_PATH) -- diagnostics only, the product library is always LIB."""
+    global_lib = LIB if out is None else os.path.join(HERE, out)
+    if out is None and not force and not needs_build():
         return LIB
-    tmp = LIB + ".tmp%d" % os.getpid()
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    tmp = global_lib + ".tmp%d" % os.getpid()
+    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + \
         ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
@@ -52,10 +55,13 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libmcr.so")
     if verbose:
         print(proc.stdout)
-    os.replace(tmp, LIB)
-    return LIB
+    os.replace(tmp, global_lib)
+    return global_lib
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    if "--phase-clocks" in sys.argv:
+        path = build(out="libmcr_clk.so", extra=["-DMCR_PHASE_CLOCKS"], verbose="--verbose" in sys.argv)
+    else:
+        path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(path)

@@ -89,21 +89,41 @@ __constant__ uint8_t c_font[11][5] = {
 
 struct Affine { float m00, m01, m02, m10, m11, m12; };
 
+// Diagnostics build (python -m multi_car_racing_b200.build --phase-clocks -> libmcr_clk.so): thread 0 of every
+// render CTA adds the SM clock cycles it spent in each phase to g_phase_clk (scripts/render_phases.py).
+#ifdef MCR_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clk[16];
+#define PHASE_T0() long long ph_t_ = clock64()
+#define PHASE(k) do { if (threadIdx.x == 0) { const long long n_ = clock64(); atomicAdd(&g_phase_clk[k], (unsigned long long)(n_ - ph_t_)); ph_t_ = n_; } } while (0)
+extern "C" int mcr_debug_phase_clocks(unsigned long long* out16, int reset) {
+    if (out16 && cudaMemcpyFromSymbol(out16, g_phase_clk, sizeof(g_phase_clk)) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[16] = {}; if (cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z)) != cudaSuccess) return -1; }
+    return 0;
+}
+#else
+#define PHASE_T0() do {} while (0)
+#define PHASE(k) do {} while (0)
+#endif
+
 // One display-list entry = 4 canonical edges.  The hull octagon takes two consecutive
 // entries (ne = 8 on the first, a row-less continuation after it).
 struct __align__(16) RasterSmem {
-    float e_ax[4][LIST_CAP];      // x at the lower endpoint
-    float e_ay[4][LIST_CAP];      // y of the lower endpoint (+inf: unused / horizontal edge)
-    float e_by[4][LIST_CAP];      // y of the upper endpoint
-    float e_sl[4][LIST_CAP];      // (bx - ax) / (by - ay)
-    int base[LIST_CAP];           // span pool offset of viewport row 0 of this polygon: off - y0
-    uint16_t off[LIST_CAP];       // first span slot (continuations: the next polygon's)
-    uint8_t ne[LIST_CAP], col[LIST_CAP];
+    // canonical edge = (x at the lower endpoint, y of the lower endpoint (+inf: unused / horizontal edge), y of the
+    // upper endpoint, slope (bx - ax) / (by - ay)): one LDS.128 per edge.  Entries LIST_CAP + c hold edges 4..7
+    // of car c's hull octagon (the only polygon with more than four edges).
+    float4 edge[4][LIST_CAP + MCR_MAX_AGENTS];
+    int base[LIST_CAP];           // span pool offset of viewport row 0 of this polygon: first slot - y0
+    uint8_t ne[LIST_CAP], col[LIST_CAP];   // ne = 4, or 8 + c for car c's octagon
+    // slot -> polygon without a search: polygon p's first slot sets a bit in startbits (unless it is word aligned),
+    // slot32_owner[k] = owner of slot 32 k; owner(32 k + l) = slot32_owner[k] + popc(startbits[k] & bits 0..l)
+    uint32_t startbits[SPAN_POOL / 32];
+    uint8_t slot32_owner[SPAN_POOL / 32];
     uchar2 span[SPAN_POOL];
     uint32_t rowmask[MASK_WORDS][SH * 3];   // per (32-pixel segment, row) = fill thread: polygons whose span touches it (word-major: conflict-free)
     Affine M;
     int first_bad;
     int ck_j0x, ck_nx, ck_j0y, ck_ny;   // visible checker index range
+    int grass_full;                     // the playfield quad covers every pixel centre of this tile
     uint32_t chunk_ballot[RS_WARPS];
     int n_vis_chunks;
     uint8_t vis_chunk[MAX_CHUNKS];    // ids of the road_poly chunks whose bounding circle touches the viewport, ascending
@@ -125,7 +145,7 @@ __device__ __forceinline__ double py_mod(double a, double m) {
 
 struct View {
     int env, agent, A, N, Q;
-    int n_checker, ck_j0x, ck_j0y, ck_ny;
+    int n_checker, ck_j0x, ck_j0y, ck_ny, grass_full;
     int c_road, c_cars, c_hud;           // first candidate index of each class (warp aligned)
     int n_road;                          // 8 * visible chunks
     const uint8_t* vis_chunk;
@@ -144,11 +164,12 @@ __device__ __forceinline__ void xf_pt(const Affine& M, float x, float y, float& 
 
 // Candidate polygon i in painter's order.  Returns the vertex count (0 = nothing to draw).
 __device__ int gen_candidate(int i, const View& V, const Affine& M, const CarConst& cc, float (&px)[MCR_MAXV],
-                             float (&py)[MCR_MAXV], int& col) {
+                             float (&py)[MCR_MAXV], int& col, int& aux) {
     const double PLAYFIELD = 2000 / 6.0;
     // candidate classes start on warp boundaries so that a warp executes one kind of polygon
     if (i < V.c_road) {
         if (i == 0) {                               // playfield, mcr:615-619
+            if (V.grass_full) return 0;             // covers the whole tile: the pixels start out as grass instead
             const float pf = (float)PLAYFIELD;
             xf_pt(M, -pf, +pf, px[0], py[0]); xf_pt(M, +pf, +pf, px[1], py[1]);
             xf_pt(M, +pf, -pf, px[2], py[2]); xf_pt(M, -pf, -pf, px[3], py[3]);
@@ -252,6 +273,7 @@ __device__ int gen_candidate(int i, const View& V, const Affine& M, const CarCon
             }
             if (V.use_ego_color) col = (c == V.agent) ? PAL_CAR0 + 0 : PAL_CAR0 + 1;   // mcr:560-563
             else col = PAL_CAR0 + (c % 8);                                              // mcr:402
+            aux = c;
             return P.n;
         }
     }
@@ -305,9 +327,9 @@ __device__ int gen_candidate(int i, const View& V, const Affine& M, const CarCon
 // Evaluate one canonical edge on the row through yc; identical arithmetic to the CPU
 // restatement: x = ax + (yc - ay) * ((bx - ax) / (by - ay)), edge taken lower -> upper.
 __device__ __forceinline__ void edge_row(const RasterSmem& S, int e, int p, float yc, float& xl, float& xr) {
-    const float ay = S.e_ay[e][p];
-    if (yc >= ay && yc < S.e_by[e][p]) {
-        const float x = S.e_ax[e][p] + (yc - ay) * S.e_sl[e][p];
+    const float4 ed = S.edge[e][p];                 // (ax, ay, by, slope)
+    if (yc >= ed.y && yc < ed.z) {
+        const float x = ed.x + (yc - ed.y) * ed.w;
         xl = fminf(xl, x); xr = fmaxf(xr, x);
     }
 }
@@ -318,23 +340,24 @@ __device__ __forceinline__ void edge_row(const RasterSmem& S, int e, int p, floa
 template <bool VP>
 __device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pix)[8], int n, int nslots, bool last,
                                            int ox, int oy, int vw) {
+    PHASE_T0();
+    // only the mask words this list can set are read by the fill below
+    for (int i = tid; i < ((n + 31) >> 5) * (SH * 3); i += RS_THREADS) (&S.rowmask[0][0])[i] = 0;
     __syncthreads();
+    PHASE(5);
     // ---- spans: one thread per (polygon,row) slot ---------------------------------------------
     for (int s = tid; s < nslots; s += RS_THREADS) {
-        int lo = 0, hi = n - 1;                    // last p with off[p] <= s
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if ((int)S.off[mid] <= s) lo = mid; else hi = mid - 1;
-        }
-        const int p = lo;
+        // RS_THREADS is a multiple of 32: the lanes of a warp share the word s >> 5
+        const int p = (int)S.slot32_owner[s >> 5] + __popc(S.startbits[s >> 5] & (0xffffffffu >> (31 - (s & 31))));
         const int row = s - S.base[p];
         const float yc = (float)(VP ? row + oy : row) + 0.5f;
         float xl = 3.402823466e+38f, xr = -3.402823466e+38f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) edge_row(S, e, p, yc, xl, xr);
-        if (S.ne[p] == 8) {
+        const int ne = S.ne[p];
+        if (ne >= 8) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) edge_row(S, e, p + 1, yc, xl, xr);
+            for (int e = 0; e < 4; ++e) edge_row(S, e, LIST_CAP + (ne - 8), yc, xl, xr);
         }
         int x0 = 0, x1 = 0;
         if (xl < xr) {
@@ -357,6 +380,7 @@ __device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pi
         }
     }
     __syncthreads();
+    PHASE(6);
     // ---- fill: one thread per (row, 32-pixel segment), top-most polygon first ------------------
     // pix[k] holds the palette indices of pixels 4k..4k+3 of this thread's segment.  Polygons of a
     // later flush are later in painter's order, so they overwrite what earlier flushes left.
@@ -397,9 +421,10 @@ __device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pi
             }
         }
     }
+    PHASE(7);
     if (last) return;                                  // nothing reads the list or the masks again
     __syncthreads();
-    for (int i = tid; i < SH * 3 * MASK_WORDS; i += RS_THREADS) (&S.rowmask[0][0])[i] = 0;
+    if (tid < SPAN_POOL / 32) S.startbits[tid] = 0;
     __syncthreads();
 }
 
@@ -415,6 +440,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
               int backwards_flag, int use_ego_color, int cls, int obs_format, VpParams vp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
+    PHASE_T0();
     if (!VP) cudaGridDependencySynchronize();      // programmatic dependent launch behind post_kernel (mcr_launch_pdl)
     if (!VP) tl_stamp(b.timeline, cls == 2 ? TL_RENDER2 : TL_RENDER);
     // VP = false: grid (B, A) -- env and agent come from the block index, no integer division per thread
@@ -432,6 +458,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     const int slot = b.env_track[env];
     const int Q = b.trk_Q[slot];
 
+    PHASE(0);
     // ---- camera (mcr:540-556) was evaluated by the physics kernel for this car ---------------
     if (tid < 6) (&S.M.m00)[tid] = camera[(size_t)tid * N + car];
     if (tid >= 32 && tid < 32 + PAL_COUNT) {
@@ -466,7 +493,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
         const float m00 = camera[(size_t)0 * N + car], m01 = camera[(size_t)1 * N + car], m02 = camera[(size_t)2 * N + car];
         const float m10 = camera[(size_t)3 * N + car], m11 = camera[(size_t)4 * N + car], m12 = camera[(size_t)5 * N + car];
         const float det = m00 * m11 - m01 * m10;
-        int j0x = 0, j1x = N_CHECKER_AXIS - 1, j0y = 0, j1y = N_CHECKER_AXIS - 1;
+        int j0x = 0, j1x = N_CHECKER_AXIS - 1, j0y = 0, j1y = N_CHECKER_AXIS - 1, grass_full = 0;
         if (fabsf(det) > 1e-12f) {
             const float inv = 1.0f / det;
             float wxmin = 3.0e38f, wxmax = -3.0e38f, wymin = 3.0e38f, wymax = -3.0e38f;
@@ -476,6 +503,10 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
                 const float wx = (m11 * u - m01 * v) * inv, wy = (-m10 * u + m00 * v) * inv;
                 wxmin = fminf(wxmin, wx); wxmax = fmaxf(wxmax, wx); wymin = fminf(wymin, wy); wymax = fmaxf(wymax, wy);
             }
+            // the tile lies inside the playfield square by >= 4 world units (>= 0.2 px at the smallest zoom, far above
+            // the fp32 error of the fill): every pixel centre of the tile is inside the playfield quad
+            const float pfm = (float)(2000 / 6.0) - 4.0f;
+            grass_full = (wxmin > -pfm && wxmax < pfm && wymin > -pfm && wymax < pfm) ? 1 : 0;
             const float ik = 20.0f / (float)(2000 / 6.0), margin = 2.0f;
             // square j spans k*(2j-20) .. k*(2j-19) on its axis
             const float a0 = floorf(((wxmin - margin) * ik + 19.0f) * 0.5f - 1e-3f), a1 = ceilf(((wxmax + margin) * ik + 20.0f) * 0.5f + 1e-3f);
@@ -487,8 +518,9 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
         }
         S.ck_j0x = j0x; S.ck_nx = j1x >= j0x ? j1x - j0x + 1 : 0;
         S.ck_j0y = j0y; S.ck_ny = j1y >= j0y ? j1y - j0y + 1 : 0;
+        S.grass_full = grass_full;
     }
-    for (int i = tid; i < SH * 3 * MASK_WORDS; i += RS_THREADS) (&S.rowmask[0][0])[i] = 0;
+    if (tid >= 128 && tid < 128 + SPAN_POOL / 32) S.startbits[tid - 128] = 0;   // (the row masks are zeroed per list, in flush_list)
     // ---- road_poly chunk culling: bounding circle of every 8 consecutive quads vs the viewport ------
     const int nchunks = (Q + MCR_QUAD_CHUNK - 1) / MCR_QUAD_CHUNK;
     {
@@ -506,6 +538,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
         const uint32_t bal = __ballot_sync(0xffffffffu, vis);
         if (lane == 0) S.chunk_ballot[warp] = bal;
         __syncthreads();
+        PHASE(1);
         if (tid < nchunks && vis) {
             int pos = __popc(bal & ((1u << lane) - 1u));
             for (int wq = 0; wq < warp; ++wq) pos += __popc(S.chunk_ballot[wq]);
@@ -518,11 +551,12 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
         }
     }
     __syncthreads();
+    PHASE(2);
 
     View V;
     V.env = env; V.agent = agent; V.A = d.A; V.N = N; V.Q = Q;
     V.ck_j0x = S.ck_j0x; V.ck_j0y = S.ck_j0y; V.ck_ny = S.ck_ny > 0 ? S.ck_ny : 1;
-    V.n_checker = S.ck_nx * S.ck_ny;
+    V.n_checker = S.ck_nx * S.ck_ny; V.grass_full = S.grass_full;
     V.n_road = S.n_vis_chunks * MCR_QUAD_CHUNK; V.vis_chunk = S.vis_chunk;
     V.c_road = (1 + V.n_checker + 31) & ~31;
     V.c_cars = V.c_road + ((V.n_road + 31) & ~31);
@@ -541,7 +575,14 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
 
     uint32_t pix[8];                       // this thread's 32 pixels (palette indices); glClear -> black
 #pragma unroll
-    for (int k = 0; k < 8; ++k) pix[k] = PAL_BLACK * 0x01010101u;
+    for (int k = 0; k < 8; ++k) pix[k] = (V.grass_full ? PAL_GRASS : PAL_BLACK) * 0x01010101u;
+    // The HUD bar (mcr:637-642, drawn after the world) covers viewport rows [0, hud_rows) over the full width:
+    // nothing of the world shows there, so world polygons start at row hud_rows (same picture, fewer spans).
+    int hud_rows = 0;
+    {
+        const float bar_top = (float)(5 * (800 / 40.0)) * V.hud_sy, bar_right = (float)1000.0 * V.hud_sx;
+        if (bar_right >= (float)VW) hud_rows = min(VH, max(0, (int)ceilf(bar_top - 0.5f)));
+    }
 
     // ---- candidates -> ordered display list -> flush -----------------------------------------
     const int NC = V.c_hud + 9;
@@ -549,8 +590,8 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     while (base < NC) {
         const int i = base + tid;
         float px[MCR_MAXV], py[MCR_MAXV];
-        int nv = 0, col = 0, y0 = 0, y1 = 0;
-        if (i < NC) nv = gen_candidate(i, V, M, cc, px, py, col);
+        int nv = 0, col = 0, y0 = 0, y1 = 0, aux = 0;
+        if (i < NC) nv = gen_candidate(i, V, M, cc, px, py, col, aux);
         bool valid = nv >= 3;
         if (valid) {
             float ymin = py[0], ymax = py[0], xmin = px[0], xmax = px[0];
@@ -566,6 +607,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
                 // rows of the VIEWPORT the polygon covers (as the full-frame fill takes them), then this tile's share
                 y0 = (int)ceilf(fmaxf(ymin, 0.0f) - 0.5f); if (y0 < 0) y0 = 0;
                 y1 = (int)ceilf(fminf(ymax, (float)VH) - 0.5f); if (y1 > VH) y1 = VH;
+                if (i < V.c_hud) y0 = max(y0, hud_rows);
                 if (VP) { y0 = max(y0, oy) - oy; y1 = min(y1, min(oy + SH, VH)) - oy; }
                 if (y1 <= y0) valid = false;
                 // same test along x: a polygon whose bounding box holds no pixel-centre column fills nothing
@@ -577,17 +619,19 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
             }
         }
         const int rows = valid ? y1 - y0 : 0;
-        const int ents = valid ? (nv > 4 ? 2 : 1) : 0;
+        const int ents = valid ? 1 : 0;
         // block-wide exclusive scan of (entries, rows)
-        int cnt_inc = ents, rows_inc = rows;
+        const int cnt_inc = __popc(__ballot_sync(0xffffffffu, valid) & (0xffffffffu >> (31 - lane)));
+        int rows_inc = rows;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int a = __shfl_up_sync(0xffffffffu, cnt_inc, o), r = __shfl_up_sync(0xffffffffu, rows_inc, o);
-            if (lane >= o) { cnt_inc += a; rows_inc += r; }
+            const int r = __shfl_up_sync(0xffffffffu, rows_inc, o);
+            if (lane >= o) rows_inc += r;
         }
         const int par = round & 1; ++round;             // double-buffered warp totals: one barrier per round
         if (lane == 31) { S.warp_cnt[par][warp] = cnt_inc; S.warp_rows[par][warp] = rows_inc; }
         __syncthreads();
+        PHASE(3);
         int cnt_before = 0, rows_before = 0, cnt_total = 0, rows_total = 0;
 #pragma unroll
         for (int wq = 0; wq < RS_WARPS; ++wq) {
@@ -616,24 +660,22 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
                 if (k < 4 || nv > 4) {
                     const int k2 = (k + 1 < nv) ? k + 1 : 0;
                     float ax = px[k], ay = py[k], bx = px[k2], by = py[k2];
-                    const int ent = sl + (k >> 2), e = k & 3;
+                    const int ent = k < 4 ? sl : LIST_CAP + aux, e = k & 3;
                     if (k >= nv || ay == by) {
-                        S.e_ay[e][ent] = 3.402823466e+38f; S.e_by[e][ent] = 3.402823466e+38f;
-                        S.e_ax[e][ent] = 0.0f; S.e_sl[e][ent] = 0.0f;
+                        S.edge[e][ent] = make_float4(0.0f, 3.402823466e+38f, 3.402823466e+38f, 0.0f);
                     } else {
                         if (ay > by) { float t = ax; ax = bx; bx = t; t = ay; ay = by; by = t; }
-                        S.e_ax[e][ent] = ax; S.e_ay[e][ent] = ay; S.e_by[e][ent] = by;
-                        S.e_sl[e][ent] = (bx - ax) / (by - ay);
+                        S.edge[e][ent] = make_float4(ax, ay, by, (bx - ax) / (by - ay));
                     }
                 }
             }
-            S.ne[sl] = (uint8_t)(nv > 4 ? 8 : 4); S.col[sl] = (uint8_t)col;
-            S.off[sl] = (uint16_t)(pc + row_rel); S.base[sl] = pc + row_rel - y0;
-            if (nv > 4) {   // row-less continuation entry: shares the NEXT polygon's first slot
-                S.ne[sl + 1] = 0; S.col[sl + 1] = (uint8_t)col;
-                S.off[sl + 1] = (uint16_t)(pc + row_rel + rows); S.base[sl + 1] = 0;
-            }
+            S.ne[sl] = (uint8_t)(nv > 4 ? 8 + aux : 4); S.col[sl] = (uint8_t)col;
+            const int first = pc + row_rel;                 // this polygon's slots: [first, first + rows)
+            S.base[sl] = first - y0;
+            if (first & 31) atomicOr(&S.startbits[first >> 5], 1u << (first & 31));
+            for (int k = (first + 31) >> 5; (k << 5) < first + rows; ++k) S.slot32_owner[k] = (uint8_t)sl;
         }
+        PHASE(4);
         if (first_bad < RS_THREADS) {
             // accepted prefix = everything before the first candidate that did not fit
             if (tid == first_bad) { S.bc_cnt = lc + slot_rel; S.bc_rows = pc + row_rel; }
@@ -743,6 +785,10 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
         }
     }
     if (!VP && cls != 2 && tid == 0) atomicMax(b.timeline + TL_RENDER_END, mcr_globaltimer());
+    PHASE(8);
+#ifdef MCR_PHASE_CLOCKS
+    if (threadIdx.x == 0) atomicAdd(&g_phase_clk[15], 1ull);
+#endif
 }
 
 

@@ -2,6 +2,7 @@
 import csv, collections, sys
 rows = list(csv.reader(open(sys.argv[1])))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+by_samples = len(sys.argv) > 3 and sys.argv[3] == "samples"
 hdr = None
 agg = collections.defaultdict(lambda: [0, 0, ''])
 cur = None
@@ -21,5 +22,5 @@ for r in rows:
     agg[cur][0] += ie; agg[cur][1] += sm
 tot = sum(v[0] for v in agg.values()); tots = sum(v[1] for v in agg.values())
 print("total warp-inst", tot, "samples", tots)
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1 if by_samples else 0])[:top]:
     print("%-14s %4d inst=%5.1f%% samp=%5.1f%%  %s" % (k[0][:14], k[1], 100 * v[0] / tot, 100 * v[1] / max(1, tots), v[2].strip()[:100]))

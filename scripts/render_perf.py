@@ -20,8 +20,11 @@ for name, upto in (("t=0.02", 0), ("t=0.5", 24), ("mid(170)", 170)):
     while done < upto:
         venv.step(tape[done % 128]); done += 1
     torch.cuda.synchronize()
-    if os.environ.get("NCU"):
-        venv.render_only(); venv.render_only(); torch.cuda.synchronize()
+    if os.environ.get("NCU"):                       # ncu --profile-from-start off: only these launches are captured
+        if os.environ["NCU"] in ("all", name):
+            torch.cuda.cudart().cudaProfilerStart()
+            venv.render_only(); torch.cuda.synchronize()
+            torch.cuda.cudart().cudaProfilerStop()
         continue
     for _ in range(3): venv.render_only()
     ts = []
