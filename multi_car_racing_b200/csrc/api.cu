@@ -416,7 +416,8 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
     if (cfg->pool_tracks < 1) return fail(-1, "pool_tracks must be >= 1");
     mcr_handle_t* h = new mcr_handle_t();
     h->cfg = *cfg;
-    h->d = Dims{cfg->batch_envs, cfg->num_agents, cfg->batch_envs * cfg->num_agents, cfg->max_tiles, cfg->max_quads, cfg->pool_tracks, cfg->particles ? 1 : 0};
+    h->d = Dims{cfg->batch_envs, cfg->num_agents, cfg->batch_envs * cfg->num_agents, cfg->max_tiles, cfg->max_quads, cfg->pool_tracks, cfg->particles ? 1 : 0,
+                MCR_DL_CAP(cfg->max_quads, cfg->num_agents)};
     if (!build_car_const(h->cc)) { delete h; return fail(-2, "car geometry set-up failed"); }
     std::memset(&h->buf, 0, sizeof(h->buf));
     std::memset(h->ptr, 0, sizeof(h->ptr));
@@ -476,6 +477,11 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
     set_spec(h, BUF_TRK_SLOT_POSE, "trk_slot_pose", MCR_F64, {P, 2, A, 3});
     set_spec(h, BUF_TRK_CHUNK, "trk_chunk", MCR_F32, {P, Q / MCR_QUAD_CHUNK, 4});
     set_spec(h, BUF_TRK_QUAD64, "trk_quad64", MCR_F64, {P, Q, 8});
+    set_spec(h, BUF_DL_HDR, "dl_hdr", MCR_I32, {N, 4});
+    set_spec(h, BUF_DL_META, "dl_meta", MCR_U32, {N, h->d.dl_cap, 2});
+    set_spec(h, BUF_DL_EDGE, "dl_edge", MCR_F32, {N, h->d.dl_cap, 16});
+    set_spec(h, BUF_DL_OCT, "dl_oct", MCR_F32, {N, A, 16});
+    set_spec(h, BUF_FILL_CTR, "fill_ctr", MCR_I32, {4});
     *out = h;
     return 0;
 }
@@ -560,6 +566,11 @@ extern "C" int mcr_bind_buffer(mcr_handle h, int i, void* p) {
         case BUF_TRK_QUAD_TILE: b.trk_quad_tile = (int16_t*)p; break;
         case BUF_TRK_SLOT_POSE: b.trk_slot_pose = (double*)p; break;
         case BUF_TRK_CHUNK: b.trk_chunk = (float*)p; break;
+        case BUF_DL_HDR: b.dl_hdr = (int32_t*)p; break;
+        case BUF_DL_META: b.dl_meta = (uint32_t*)p; break;
+        case BUF_DL_EDGE: b.dl_edge = (float*)p; break;
+        case BUF_DL_OCT: b.dl_oct = (float*)p; break;
+        case BUF_FILL_CTR: b.fill_ctr = (int32_t*)p; break;
     }
     return 0;
 }

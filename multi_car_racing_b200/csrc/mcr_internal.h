@@ -46,6 +46,7 @@ enum {
     BUF_VISITED, BUF_TOUCHED, BUF_RESET_MASK, BUF_STATUS, BUF_SCRATCH, BUF_MANIFOLD, BUF_N_MANIFOLD, BUF_SCORE_SNAP, BUF_BACKWARD_SNAP, BUF_PENDING, BUF_ACTION_STAGE, BUF_CAMERA_VP, BUF_TIMELINE, BUF_ON_GRASS, BUF_PRT_PTS, BUF_PRT_META, BUF_PRT_HDR, BUF_SKID_START, BUF_SKID_META,
     BUF_TRK_T, BUF_TRK_Q, BUF_TRK_NODE, BUF_TRK_TILE, BUF_TRK_TILE_AABB, BUF_TRK_QUAD, BUF_TRK_QUAD_COL,
     BUF_TRK_QUAD_TILE, BUF_TRK_SLOT_POSE, BUF_TRK_CHUNK, BUF_TRK_QUAD64,
+    BUF_DL_HDR, BUF_DL_META, BUF_DL_EDGE, BUF_DL_OCT, BUF_FILL_CTR,
     BUF_COUNT
 };
 
@@ -101,9 +102,17 @@ struct DevBuffers {
     float* trk_quad; uint8_t* trk_quad_col; int16_t* trk_quad_tile; double* trk_slot_pose;
     float* trk_chunk;                    // [P][Qmax/8][4] bounding circle (cx, cy, r, 0) of 8 consecutive road_poly quads
     double* trk_quad64;                  // [P][Qmax][8] road_poly vertices in float64 (what shapely's polygons hold, mcr:336-337)
+    // per-frame display lists, project_kernel -> fill_kernel (raster.cu): painter-ordered polygons that can fill a pixel
+    int32_t* dl_hdr;                     // [N][4] entries, span slots, "playfield covers the frame", score glyphs (4 x i8)
+    uint32_t* dl_meta;                   // [N][dl_cap][2] y0 | rows << 8 | palette << 16 | ne << 24 ; first span slot
+    float* dl_edge;                      // [N][dl_cap][4][4] canonical edges (ax, ay, by, slope)
+    float* dl_oct;                       // [N][A][4][4] edges 4..7 of car c's hull octagon
+    int32_t* fill_ctr;                   // [4] fill_kernel's frame queue heads, one per env class (cls)
 };
 
-struct Dims { int B, A, N, Tmax, Qmax, P; int particles; };
+struct Dims { int B, A, N, Tmax, Qmax, P; int particles; int dl_cap; };
+// display-list capacity per frame: every candidate of a state frame (playfield, 100 checker squares, road_poly, 12 parts per car, 9 HUD polygons)
+#define MCR_DL_CAP(Qmax, A) ((1 + 100 + (Qmax) + 12 * (A) + 9 + 7) & ~7)
 // skid traces (gym car_dynamics Car.particles): per car a ring of PRT_MAX polylines of <= PRT_PTS wheel positions
 #define PRT_MAX 30
 #define PRT_PTS 30

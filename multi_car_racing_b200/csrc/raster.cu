@@ -30,6 +30,8 @@
 //      frame) -- the only HBM traffic that scales with the frame count.
 #include "mcr_internal.h"
 #include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdlib>
 
 #define RS_THREADS 288
 #define RS_WARPS (RS_THREADS / 32)
@@ -344,6 +346,7 @@ __device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pi
     // only the mask words this list can set are read by the fill below
     for (int i = tid; i < ((n + 31) >> 5) * (SH * 3); i += RS_THREADS) (&S.rowmask[0][0])[i] = 0;
     __syncthreads();
+    if (nslots < 0) nslots = S.bc_rows;                // fill_kernel: written by the thread that loaded the chunk's last entry
     PHASE(5);
     // ---- spans: one thread per (polygon,row) slot ---------------------------------------------
     for (int s = tid; s < nslots; s += RS_THREADS) {
@@ -428,65 +431,41 @@ __device__ __forceinline__ void flush_list(RasterSmem& S, int tid, uint32_t (&pi
     __syncthreads();
 }
 
-// VP = false: the 96 x 96 observation of step() (one CTA per agent-frame, camera and score snapshots
-// taken by post_kernel).  VP = true: render(mode) for any viewport (rgb_array 600 x 400, mcr:566-575)
-// as a grid of 96 x 96 tiles, blockIdx.y = tile; camera from vp.camera, live score / backward flag
-// (what a render() call outside step() shows), RGB rows of vp.vw pixels.
-struct VpParams { int vw, vh, tiles_x; float hud_sx, hud_sy; const float* camera; };
+// coverage byte -> two PRMT selectors (low half: pixels 0-3, high half: pixels 4-7): byte i comes from operand b
+// (4 + i) if its bit is set, else from a (i)
+__device__ __forceinline__ uint32_t prmt_selector(int byte) {
+    const uint32_t lo = byte & 15u, hi = (uint32_t)byte >> 4;
+    const uint32_t slo = 0x3210u | ((lo & 1u) << 2) | ((lo & 2u) << 5) | ((lo & 4u) << 8) | ((lo & 8u) << 11);
+    const uint32_t shi = 0x3210u | ((hi & 1u) << 2) | ((hi & 2u) << 5) | ((hi & 4u) << 8) | ((hi & 8u) << 11);
+    return slo | (shi << 16);
+}
 
-template <bool VP>
-__global__ void __launch_bounds__(RS_THREADS, 4)
-render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, uint8_t* __restrict__ obs,
-              int backwards_flag, int use_ego_color, int cls, int obs_format, VpParams vp) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
-    PHASE_T0();
-    if (!VP) cudaGridDependencySynchronize();      // programmatic dependent launch behind post_kernel (mcr_launch_pdl)
-    if (!VP) tl_stamp(b.timeline, cls == 2 ? TL_RENDER2 : TL_RENDER);
-    // VP = false: grid (B, A) -- env and agent come from the block index, no integer division per thread
-    const int frame = VP ? (int)blockIdx.x : (int)(blockIdx.x * d.A + blockIdx.y);
-    const int ox = VP ? (int)(blockIdx.y % vp.tiles_x) * SW : 0, oy = VP ? (int)(blockIdx.y / vp.tiles_x) * SH : 0;
-    const int VW = VP ? vp.vw : SW, VH = VP ? vp.vh : SH;
-    const float* __restrict__ camera = VP ? vp.camera : b.camera;
-    // this tile's rectangle in viewport pixels (partial tiles at the right / top edge)
-    const float tx0 = (float)ox, ty0 = (float)oy, tx1 = (float)min(ox + SW, VW), ty1 = (float)min(oy + SH, VH);
-    const int env = VP ? frame / d.A : (int)blockIdx.x, agent = VP ? frame % d.A : (int)blockIdx.y;
-    if (mask && !mask[env]) return;
-    if (cls && (cls == 2) != (b.n_manifold[env] > 0)) return;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int N = d.N, car = frame;
-    const int slot = b.env_track[env];
-    const int Q = b.trk_Q[slot];
+// score label "%04i" % reward (mcr:665; drawn before reward -= 0.1) as glyph indices (10 = '-', -1 = none)
+__device__ __forceinline__ void score_glyphs(double rw, signed char* glyph) {
+    int val = (int)rw;
+    const bool neg = rw < 0 && val != 0;
+    int mag = val < 0 ? -val : val;
+    signed char digs[12]; int nd = 0;
+    do { digs[nd++] = (signed char)(mag % 10); mag /= 10; } while (mag > 0);
+    signed char buf[16]; int len = 0;
+    const int width = nd + (neg ? 1 : 0), pad = width < 4 ? 4 - width : 0;
+    if (neg) buf[len++] = 10;
+    for (int i = 0; i < pad; ++i) buf[len++] = 0;
+    for (int i = nd - 1; i >= 0; --i) buf[len++] = digs[i];
+    for (int i = 0; i < 4; ++i) glyph[i] = i < len ? buf[i] : (signed char)-1;
+}
 
-    PHASE(0);
+// Front of a frame (fused kernel) (NT threads; SM has the fields used below):
+// camera -> S.M, the score label's glyphs, the visible checker index range, "the playfield quad covers the tile",
+// and the ascending list of road_poly chunks (8 consecutive quads, bounding circle) that can touch the tile.
+// Ends with a __syncthreads().  rw = env.reward as the label shows it.
+template <int NT, class SM>
+__device__ __forceinline__ void frame_front(SM& S, const Dims& d, const DevBuffers& b, const float* __restrict__ camera, double rw,
+                                            int car, int slot, int tid, float tx0, float ty0, float tx1, float ty1) {
+    const int N = d.N, warp = tid >> 5, lane = tid & 31;
     // ---- camera (mcr:540-556) was evaluated by the physics kernel for this car ---------------
     if (tid < 6) (&S.M.m00)[tid] = camera[(size_t)tid * N + car];
-    if (tid >= 32 && tid < 32 + PAL_COUNT) {
-        const int i = tid - 32;
-        S.pal32[i] = (uint32_t)c_palette[i][0] | ((uint32_t)c_palette[i][1] << 8) | ((uint32_t)c_palette[i][2] << 16);
-        S.palY[i] = (uint32_t)c_palette[i][3];
-    }
-    if (tid < 256) {
-        const uint32_t lo = tid & 15u, hi = (uint32_t)tid >> 4;
-        const uint32_t slo = 0x3210u | ((lo & 1u) << 2) | ((lo & 2u) << 5) | ((lo & 4u) << 8) | ((lo & 8u) << 11);
-        const uint32_t shi = 0x3210u | ((hi & 1u) << 2) | ((hi & 2u) << 5) | ((hi & 4u) << 8) | ((hi & 8u) << 11);
-        S.prmt_sel[tid] = slo | (shi << 16);
-    }
-    if (tid == 64) {
-        // score label "%04i" % reward  (mcr:665; drawn before reward -= 0.1)
-        const double rw = VP ? b.reward[car] : b.score_snap[car];   // env.reward as it is when the reference draws the label
-        int val = (int)rw;
-        const bool neg = rw < 0 && val != 0;
-        int mag = val < 0 ? -val : val;
-        signed char digs[12]; int nd = 0;
-        do { digs[nd++] = (signed char)(mag % 10); mag /= 10; } while (mag > 0);
-        signed char buf[16]; int len = 0;
-        const int width = nd + (neg ? 1 : 0), pad = width < 4 ? 4 - width : 0;
-        if (neg) buf[len++] = 10;
-        for (int i = 0; i < pad; ++i) buf[len++] = 0;
-        for (int i = nd - 1; i >= 0; --i) buf[len++] = digs[i];
-        for (int i = 0; i < 4; ++i) S.glyph[i] = i < len ? buf[i] : (signed char)-1;
-    }
+    if (tid == 64) score_glyphs(rw, S.glyph);
     if (tid == 96) {
         // Checker squares the camera can see: invert the affine for the four viewport corners
         // (+ a two-unit margin, far above fp32 error) and keep the index ranges that overlap.
@@ -520,177 +499,80 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
         S.ck_j0y = j0y; S.ck_ny = j1y >= j0y ? j1y - j0y + 1 : 0;
         S.grass_full = grass_full;
     }
-    if (tid >= 128 && tid < 128 + SPAN_POOL / 32) S.startbits[tid - 128] = 0;   // (the row masks are zeroed per list, in flush_list)
     // ---- road_poly chunk culling: bounding circle of every 8 consecutive quads vs the viewport ------
-    const int nchunks = (Q + MCR_QUAD_CHUNK - 1) / MCR_QUAD_CHUNK;
-    {
-        bool vis = false;
-        if (tid < nchunks) {
-            const float4 cc4 = *(const float4*)(b.trk_chunk + ((size_t)slot * (d.Qmax / MCR_QUAD_CHUNK) + tid) * 4);
-            const float m00 = camera[(size_t)0 * N + car], m01 = camera[(size_t)1 * N + car], m02 = camera[(size_t)2 * N + car];
-            const float m10 = camera[(size_t)3 * N + car], m11 = camera[(size_t)4 * N + car], m12 = camera[(size_t)5 * N + car];
-            const float cxp = (m00 * cc4.x + m01 * cc4.y) + m02, cyp = (m10 * cc4.x + m11 * cc4.y) + m12;
-            // |M v| <= ||M||_F |v|: conservative pixel radius, plus a 2-pixel margin
-            const float rp = cc4.z * sqrtf(m00 * m00 + m01 * m01 + m10 * m10 + m11 * m11) * 1.001f + 2.0f;
-            vis = (cxp + rp >= tx0) && (cxp - rp <= tx1) && (cyp + rp >= ty0) && (cyp - rp <= ty1);
-            if (!(rp == rp) || !(cxp == cxp) || !(cyp == cyp)) vis = true;
-        }
-        const uint32_t bal = __ballot_sync(0xffffffffu, vis);
-        if (lane == 0) S.chunk_ballot[warp] = bal;
-        __syncthreads();
-        PHASE(1);
-        if (tid < nchunks && vis) {
-            int pos = __popc(bal & ((1u << lane) - 1u));
-            for (int wq = 0; wq < warp; ++wq) pos += __popc(S.chunk_ballot[wq]);
-            S.vis_chunk[pos] = (uint8_t)tid;
-        }
-        if (tid == 0) {
-            int n = 0;
-            for (int wq = 0; wq < RS_WARPS; ++wq) n += __popc(S.chunk_ballot[wq]);
-            S.n_vis_chunks = n;
-        }
+    // (chunks past the track's last quad have radius 0 in the pool: no dependency on trk_Q here)
+    const int nchunks = d.Qmax / MCR_QUAD_CHUNK;
+    bool vis = false;
+    if (tid < nchunks) {
+        const float4 cc4 = *(const float4*)(b.trk_chunk + ((size_t)slot * nchunks + tid) * 4);
+        const float m00 = camera[(size_t)0 * N + car], m01 = camera[(size_t)1 * N + car], m02 = camera[(size_t)2 * N + car];
+        const float m10 = camera[(size_t)3 * N + car], m11 = camera[(size_t)4 * N + car], m12 = camera[(size_t)5 * N + car];
+        const float cxp = (m00 * cc4.x + m01 * cc4.y) + m02, cyp = (m10 * cc4.x + m11 * cc4.y) + m12;
+        // |M v| <= ||M||_F |v|: conservative pixel radius, plus a 2-pixel margin
+        const float rp = cc4.z * sqrtf(m00 * m00 + m01 * m01 + m10 * m10 + m11 * m11) * 1.001f + 2.0f;
+        vis = (cxp + rp >= tx0) && (cxp - rp <= tx1) && (cyp + rp >= ty0) && (cyp - rp <= ty1);
+        if (!(rp == rp) || !(cxp == cxp) || !(cyp == cyp)) vis = true;
+        if (!(cc4.z > 0.0f)) vis = false;
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, vis);
+    if (lane == 0) S.chunk_ballot[warp] = bal;
+    __syncthreads();
+    if (vis) {
+        int pos = __popc(bal & ((1u << lane) - 1u));
+        for (int wq = 0; wq < warp; ++wq) pos += __popc(S.chunk_ballot[wq]);
+        S.vis_chunk[pos] = (uint8_t)tid;
+    }
+    if (tid == 0) {
+        int n = 0;
+        for (int wq = 0; wq < NT / 32; ++wq) n += __popc(S.chunk_ballot[wq]);
+        S.n_vis_chunks = n;
     }
     __syncthreads();
-    PHASE(2);
+}
 
-    View V;
-    V.env = env; V.agent = agent; V.A = d.A; V.N = N; V.Q = Q;
-    V.ck_j0x = S.ck_j0x; V.ck_j0y = S.ck_j0y; V.ck_ny = S.ck_ny > 0 ? S.ck_ny : 1;
-    V.n_checker = S.ck_nx * S.ck_ny; V.grass_full = S.grass_full;
-    V.n_road = S.n_vis_chunks * MCR_QUAD_CHUNK; V.vis_chunk = S.vis_chunk;
-    V.c_road = (1 + V.n_checker + 31) & ~31;
-    V.c_cars = V.c_road + ((V.n_road + 31) & ~31);
-    V.car_slots = CAR_PARTS + ((VP && d.particles) ? PRT_MAX * (PRT_PTS - 1) : 0);
-    V.prt_pts = b.prt_pts; V.prt_meta = b.prt_meta; V.prt_hdr = b.prt_hdr;
-    V.c_hud = V.c_cars + ((V.car_slots * d.A + 31) & ~31);
-    V.body = b.body; V.wheel = b.wheel; V.stripe = b.stripe;
-    V.quad = b.trk_quad + (size_t)slot * d.Qmax * 8;
-    V.quad_col = b.trk_quad_col + (size_t)slot * d.Qmax;
-    V.quad_tile = b.trk_quad_tile + (size_t)slot * d.Qmax;
-    V.touched = b.touched + (size_t)env * d.Tmax;
-    V.use_ego_color = use_ego_color;
-    V.backward_flag_on = ((VP ? b.backward[car] : b.backward_snap[car]) != 0) && backwards_flag;   // step(): flag of the PREVIOUS step (render precedes mcr:445-495)
-    V.hud_sx = VP ? vp.hud_sx : (float)(96.0 / 1000.0); V.hud_sy = VP ? vp.hud_sy : (float)(96.0 / 800.0);
-    const Affine M = S.M;
-
-    uint32_t pix[8];                       // this thread's 32 pixels (palette indices); glClear -> black
+// Rows [y0, y1) of this tile a candidate polygon can touch (false: it fills nothing here).  world: the polygon is
+// drawn before the HUD bar, which hides viewport rows [0, hud_rows).
+template <bool VP>
+__device__ __forceinline__ bool cand_rows(int nv, const float (&px)[MCR_MAXV], const float (&py)[MCR_MAXV], bool world, int hud_rows,
+                                          float tx0, float ty0, float tx1, float ty1, int oy, int VH, int& y0, int& y1) {
+    if (nv < 3) return false;
+    float ymin = py[0], ymax = py[0], xmin = px[0], xmax = px[0];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) pix[k] = (V.grass_full ? PAL_GRASS : PAL_BLACK) * 0x01010101u;
-    // The HUD bar (mcr:637-642, drawn after the world) covers viewport rows [0, hud_rows) over the full width:
-    // nothing of the world shows there, so world polygons start at row hud_rows (same picture, fewer spans).
-    int hud_rows = 0;
-    {
-        const float bar_top = (float)(5 * (800 / 40.0)) * V.hud_sy, bar_right = (float)1000.0 * V.hud_sx;
-        if (bar_right >= (float)VW) hud_rows = min(VH, max(0, (int)ceilf(bar_top - 0.5f)));
-    }
-
-    // ---- candidates -> ordered display list -> flush -----------------------------------------
-    const int NC = V.c_hud + 9;
-    int base = 0, lc = 0, pc = 0, round = 0;   // display-list / span-pool fill (same in every thread)
-    while (base < NC) {
-        const int i = base + tid;
-        float px[MCR_MAXV], py[MCR_MAXV];
-        int nv = 0, col = 0, y0 = 0, y1 = 0, aux = 0;
-        if (i < NC) nv = gen_candidate(i, V, M, cc, px, py, col, aux);
-        bool valid = nv >= 3;
-        if (valid) {
-            float ymin = py[0], ymax = py[0], xmin = px[0], xmax = px[0];
-#pragma unroll
-            for (int k = 1; k < MCR_MAXV; ++k) {
-                if (k < nv) {
-                    ymin = fminf(ymin, py[k]); ymax = fmaxf(ymax, py[k]);
-                    xmin = fminf(xmin, px[k]); xmax = fmaxf(xmax, px[k]);
-                }
-            }
-            if (!(ymax > ty0) || !(ymin < ty1) || !(xmax > tx0) || !(xmin < tx1)) valid = false;
-            else {
-                // rows of the VIEWPORT the polygon covers (as the full-frame fill takes them), then this tile's share
-                y0 = (int)ceilf(fmaxf(ymin, 0.0f) - 0.5f); if (y0 < 0) y0 = 0;
-                y1 = (int)ceilf(fminf(ymax, (float)VH) - 0.5f); if (y1 > VH) y1 = VH;
-                if (i < V.c_hud) y0 = max(y0, hud_rows);
-                if (VP) { y0 = max(y0, oy) - oy; y1 = min(y1, min(oy + SH, VH)) - oy; }
-                if (y1 <= y0) valid = false;
-                // same test along x: a polygon whose bounding box holds no pixel-centre column fills nothing
-                // (every span lies inside [xmin, xmax]); most road quads of a zoomed-out frame go here
-                // (such a box is < 1 px wide, so |x| <= vw + 1 and the interpolated crossings stay within a few
-                // ulp(vw) ~ 1e-4 of [xmin, xmax]: the 1e-3 margin keeps the cull conservative, hence exact)
-                const float cx0 = ceilf((fmaxf(xmin, tx0) - 1e-3f) - 0.5f), cx1 = ceilf((fminf(xmax, tx1) + 1e-3f) - 0.5f);
-                if (!(cx1 > cx0)) valid = false;
-            }
-        }
-        const int rows = valid ? y1 - y0 : 0;
-        const int ents = valid ? 1 : 0;
-        // block-wide exclusive scan of (entries, rows)
-        const int cnt_inc = __popc(__ballot_sync(0xffffffffu, valid) & (0xffffffffu >> (31 - lane)));
-        int rows_inc = rows;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int r = __shfl_up_sync(0xffffffffu, rows_inc, o);
-            if (lane >= o) rows_inc += r;
-        }
-        const int par = round & 1; ++round;             // double-buffered warp totals: one barrier per round
-        if (lane == 31) { S.warp_cnt[par][warp] = cnt_inc; S.warp_rows[par][warp] = rows_inc; }
-        __syncthreads();
-        PHASE(3);
-        int cnt_before = 0, rows_before = 0, cnt_total = 0, rows_total = 0;
-#pragma unroll
-        for (int wq = 0; wq < RS_WARPS; ++wq) {
-            const int c = S.warp_cnt[par][wq], r = S.warp_rows[par][wq];
-            if (wq < warp) { cnt_before += c; rows_before += r; }
-            cnt_total += c; rows_total += r;
-        }
-        const int slot_rel = cnt_before + cnt_inc - ents;
-        const int row_rel = rows_before + rows_inc - rows;
-        // (lc, pc) are tracked in registers: every thread sees the same totals
-        const bool all_fit = (lc + cnt_total <= LIST_CAP) && (pc + rows_total <= SPAN_POOL);
-        int first_bad = RS_THREADS;
-        if (!all_fit) {                                 // rare (zoomed-out frames): find the first candidate that does not fit
-            if (tid == 0) S.first_bad = RS_THREADS;
-            __syncthreads();
-            const bool fits = (lc + slot_rel + ents <= LIST_CAP) && (pc + row_rel + rows <= SPAN_POOL);
-            if (valid && !fits) atomicMin(&S.first_bad, tid);
-            __syncthreads();
-            first_bad = S.first_bad;
-        }
-        if (valid && tid < first_bad) {
-            const int sl = lc + slot_rel;
-            // canonical edges: lower endpoint first, slope hoisted out of the row loop
-#pragma unroll
-            for (int k = 0; k < MCR_MAXV; ++k) {
-                if (k < 4 || nv > 4) {
-                    const int k2 = (k + 1 < nv) ? k + 1 : 0;
-                    float ax = px[k], ay = py[k], bx = px[k2], by = py[k2];
-                    const int ent = k < 4 ? sl : LIST_CAP + aux, e = k & 3;
-                    if (k >= nv || ay == by) {
-                        S.edge[e][ent] = make_float4(0.0f, 3.402823466e+38f, 3.402823466e+38f, 0.0f);
-                    } else {
-                        if (ay > by) { float t = ax; ax = bx; bx = t; t = ay; ay = by; by = t; }
-                        S.edge[e][ent] = make_float4(ax, ay, by, (bx - ax) / (by - ay));
-                    }
-                }
-            }
-            S.ne[sl] = (uint8_t)(nv > 4 ? 8 + aux : 4); S.col[sl] = (uint8_t)col;
-            const int first = pc + row_rel;                 // this polygon's slots: [first, first + rows)
-            S.base[sl] = first - y0;
-            if (first & 31) atomicOr(&S.startbits[first >> 5], 1u << (first & 31));
-            for (int k = (first + 31) >> 5; (k << 5) < first + rows; ++k) S.slot32_owner[k] = (uint8_t)sl;
-        }
-        PHASE(4);
-        if (first_bad < RS_THREADS) {
-            // accepted prefix = everything before the first candidate that did not fit
-            if (tid == first_bad) { S.bc_cnt = lc + slot_rel; S.bc_rows = pc + row_rel; }
-            __syncthreads();
-            lc = S.bc_cnt; pc = S.bc_rows;
-            base += first_bad;
-            flush_list<VP>(S, tid, pix, lc, pc, false, ox, oy, VW);
-            lc = 0; pc = 0;
-        } else {
-            lc += cnt_total; pc += rows_total;
-            base += RS_THREADS;
+    for (int k = 1; k < MCR_MAXV; ++k) {
+        if (k < nv) {
+            ymin = fminf(ymin, py[k]); ymax = fmaxf(ymax, py[k]);
+            xmin = fminf(xmin, px[k]); xmax = fmaxf(xmax, px[k]);
         }
     }
-    flush_list<VP>(S, tid, pix, lc, pc, true, ox, oy, VW);
+    if (!(ymax > ty0) || !(ymin < ty1) || !(xmax > tx0) || !(xmin < tx1)) return false;
+    // rows of the VIEWPORT the polygon covers (as the full-frame fill takes them), then this tile's share
+    y0 = (int)ceilf(fmaxf(ymin, 0.0f) - 0.5f); if (y0 < 0) y0 = 0;
+    y1 = (int)ceilf(fminf(ymax, (float)VH) - 0.5f); if (y1 > VH) y1 = VH;
+    if (world) y0 = max(y0, hud_rows);
+    if (VP) { y0 = max(y0, oy) - oy; y1 = min(y1, min(oy + SH, VH)) - oy; }
+    if (y1 <= y0) return false;
+    // same test along x: a polygon whose bounding box holds no pixel-centre column fills nothing
+    // (every span lies inside [xmin, xmax]); most road quads of a zoomed-out frame go here
+    // (such a box is < 1 px wide, so |x| <= vw + 1 and the interpolated crossings stay within a few
+    // ulp(vw) ~ 1e-4 of [xmin, xmax]: the 1e-3 margin keeps the cull conservative, hence exact)
+    const float cx0 = ceilf((fmaxf(xmin, tx0) - 1e-3f) - 0.5f), cx1 = ceilf((fminf(xmax, tx1) + 1e-3f) - 0.5f);
+    return cx1 > cx0;
+}
 
+// Canonical edge k of a polygon: lower endpoint first, slope hoisted out of the row loop (one IEEE division per edge).
+__device__ __forceinline__ float4 canon_edge(int k, int nv, const float (&px)[MCR_MAXV], const float (&py)[MCR_MAXV]) {
+    const int k2 = (k + 1 < nv) ? k + 1 : 0;
+    float ax = px[k], ay = py[k], bx = px[k2], by = py[k2];
+    if (k >= nv || ay == by) return make_float4(0.0f, 3.402823466e+38f, 3.402823466e+38f, 0.0f);
+    if (ay > by) { float t = ax; ax = bx; bx = t; t = ay; ay = by; by = t; }
+    return make_float4(ax, ay, by, (bx - ax) / (by - ay));
+}
+
+// Score label glyphs, palette expansion and the store of this thread's 32 pixels (6 x uint4 for the
+// reference's RGB HWC layout).  Shared by the fused kernel (viewport modes) and fill_kernel (step path).
+template <bool VP>
+__device__ __forceinline__ void finish_frame(RasterSmem& S, int tid, uint32_t (&pix)[8], uint8_t* __restrict__ obs, int frame,
+                                             int obs_format, int ox, int oy, int VW, int VH) {
     const int my_seg = tid / SH, my_y = tid - SH * my_seg;
     // ---- score label glyphs (D3): observation rows 87..91 (= GL rows 8..4), cols 2..13 -------------
     if (VP) {
@@ -752,7 +634,6 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
             const uint32_t w0 = c | (c << 24), w1 = (c >> 8) | (c << 16), w2 = (c >> 16) | (c << 8);
             const uint4 q0 = make_uint4(w0, w1, w2, w0), q1 = make_uint4(w1, w2, w0, w1), q2 = make_uint4(w2, w0, w1, w2);
             dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q0; dst[4] = q1; dst[5] = q2;
-            if (cls != 2 && tid == 0) atomicMax(b.timeline + TL_RENDER_END, mcr_globaltimer());
             return;
         }
 #pragma unroll
@@ -784,11 +665,400 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
             dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
         }
     }
+}
+
+// VP = false: the 96 x 96 observation of step() (one CTA per agent-frame, camera and score snapshots
+// taken by post_kernel).  VP = true: render(mode) for any viewport (rgb_array 600 x 400, mcr:566-575)
+// as a grid of 96 x 96 tiles, blockIdx.y = tile; camera from vp.camera, live score / backward flag
+// (what a render() call outside step() shows), RGB rows of vp.vw pixels.
+struct VpParams { int vw, vh, tiles_x; float hud_sx, hud_sy; const float* camera; };
+
+template <bool VP>
+__global__ void __launch_bounds__(RS_THREADS, 4)
+render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, uint8_t* __restrict__ obs,
+              int backwards_flag, int use_ego_color, int cls, int obs_format, VpParams vp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
+    PHASE_T0();
+    if (!VP) cudaGridDependencySynchronize();      // programmatic dependent launch behind post_kernel (mcr_launch_pdl)
+    if (!VP) tl_stamp(b.timeline, cls == 2 ? TL_RENDER2 : TL_RENDER);
+    // VP = false: grid (B, A) -- env and agent come from the block index, no integer division per thread
+    const int frame = VP ? (int)blockIdx.x : (int)(blockIdx.x * d.A + blockIdx.y);
+    const int ox = VP ? (int)(blockIdx.y % vp.tiles_x) * SW : 0, oy = VP ? (int)(blockIdx.y / vp.tiles_x) * SH : 0;
+    const int VW = VP ? vp.vw : SW, VH = VP ? vp.vh : SH;
+    const float* __restrict__ camera = VP ? vp.camera : b.camera;
+    // this tile's rectangle in viewport pixels (partial tiles at the right / top edge)
+    const float tx0 = (float)ox, ty0 = (float)oy, tx1 = (float)min(ox + SW, VW), ty1 = (float)min(oy + SH, VH);
+    const int env = VP ? frame / d.A : (int)blockIdx.x, agent = VP ? frame % d.A : (int)blockIdx.y;
+    if (mask && !mask[env]) return;
+    if (cls && (cls == 2) != (b.n_manifold[env] > 0)) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = d.N, car = frame;
+    const int slot = b.env_track[env];
+    const int Q = b.trk_Q[slot];
+
+    PHASE(0);
+    if (tid >= 32 && tid < 32 + PAL_COUNT) {
+        const int i = tid - 32;
+        S.pal32[i] = (uint32_t)c_palette[i][0] | ((uint32_t)c_palette[i][1] << 8) | ((uint32_t)c_palette[i][2] << 16);
+        S.palY[i] = (uint32_t)c_palette[i][3];
+    }
+    if (tid < 256) S.prmt_sel[tid] = prmt_selector(tid);
+    if (tid >= 128 && tid < 128 + SPAN_POOL / 32) S.startbits[tid - 128] = 0;   // (the row masks are zeroed per list, in flush_list)
+    frame_front<RS_THREADS>(S, d, b, camera, VP ? b.reward[car] : b.score_snap[car], car, slot, tid, tx0, ty0, tx1, ty1);
+    PHASE(2);
+
+    View V;
+    V.env = env; V.agent = agent; V.A = d.A; V.N = N; V.Q = Q;
+    V.ck_j0x = S.ck_j0x; V.ck_j0y = S.ck_j0y; V.ck_ny = S.ck_ny > 0 ? S.ck_ny : 1;
+    V.n_checker = S.ck_nx * S.ck_ny; V.grass_full = S.grass_full;
+    V.n_road = S.n_vis_chunks * MCR_QUAD_CHUNK; V.vis_chunk = S.vis_chunk;
+    V.c_road = (1 + V.n_checker + 31) & ~31;
+    V.c_cars = V.c_road + ((V.n_road + 31) & ~31);
+    V.car_slots = CAR_PARTS + ((VP && d.particles) ? PRT_MAX * (PRT_PTS - 1) : 0);
+    V.prt_pts = b.prt_pts; V.prt_meta = b.prt_meta; V.prt_hdr = b.prt_hdr;
+    V.c_hud = V.c_cars + ((V.car_slots * d.A + 31) & ~31);
+    V.body = b.body; V.wheel = b.wheel; V.stripe = b.stripe;
+    V.quad = b.trk_quad + (size_t)slot * d.Qmax * 8;
+    V.quad_col = b.trk_quad_col + (size_t)slot * d.Qmax;
+    V.quad_tile = b.trk_quad_tile + (size_t)slot * d.Qmax;
+    V.touched = b.touched + (size_t)env * d.Tmax;
+    V.use_ego_color = use_ego_color;
+    V.backward_flag_on = ((VP ? b.backward[car] : b.backward_snap[car]) != 0) && backwards_flag;   // step(): flag of the PREVIOUS step (render precedes mcr:445-495)
+    V.hud_sx = VP ? vp.hud_sx : (float)(96.0 / 1000.0); V.hud_sy = VP ? vp.hud_sy : (float)(96.0 / 800.0);
+    const Affine M = S.M;
+
+    uint32_t pix[8];                       // this thread's 32 pixels (palette indices); glClear -> black
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pix[k] = (V.grass_full ? PAL_GRASS : PAL_BLACK) * 0x01010101u;
+    // The HUD bar (mcr:637-642, drawn after the world) covers viewport rows [0, hud_rows) over the full width:
+    // nothing of the world shows there, so world polygons start at row hud_rows (same picture, fewer spans).
+    int hud_rows = 0;
+    {
+        const float bar_top = (float)(5 * (800 / 40.0)) * V.hud_sy, bar_right = (float)1000.0 * V.hud_sx;
+        if (bar_right >= (float)VW) hud_rows = min(VH, max(0, (int)ceilf(bar_top - 0.5f)));
+    }
+
+    // ---- candidates -> ordered display list -> flush -----------------------------------------
+    const int NC = V.c_hud + 9;
+    int base = 0, lc = 0, pc = 0, round = 0;   // display-list / span-pool fill (same in every thread)
+    while (base < NC) {
+        const int i = base + tid;
+        float px[MCR_MAXV], py[MCR_MAXV];
+        int nv = 0, col = 0, y0 = 0, y1 = 0, aux = 0;
+        if (i < NC) nv = gen_candidate(i, V, M, cc, px, py, col, aux);
+        const bool valid = cand_rows<VP>(nv, px, py, i < V.c_hud, hud_rows, tx0, ty0, tx1, ty1, oy, VH, y0, y1);
+        const int rows = valid ? y1 - y0 : 0;
+        const int ents = valid ? 1 : 0;
+        // block-wide exclusive scan of (entries, rows)
+        const int cnt_inc = __popc(__ballot_sync(0xffffffffu, valid) & (0xffffffffu >> (31 - lane)));
+        int rows_inc = rows;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int r = __shfl_up_sync(0xffffffffu, rows_inc, o);
+            if (lane >= o) rows_inc += r;
+        }
+        const int par = round & 1; ++round;             // double-buffered warp totals: one barrier per round
+        if (lane == 31) { S.warp_cnt[par][warp] = cnt_inc; S.warp_rows[par][warp] = rows_inc; }
+        __syncthreads();
+        PHASE(3);
+        int cnt_before = 0, rows_before = 0, cnt_total = 0, rows_total = 0;
+#pragma unroll
+        for (int wq = 0; wq < RS_WARPS; ++wq) {
+            const int c = S.warp_cnt[par][wq], r = S.warp_rows[par][wq];
+            if (wq < warp) { cnt_before += c; rows_before += r; }
+            cnt_total += c; rows_total += r;
+        }
+        const int slot_rel = cnt_before + cnt_inc - ents;
+        const int row_rel = rows_before + rows_inc - rows;
+        // (lc, pc) are tracked in registers: every thread sees the same totals
+        const bool all_fit = (lc + cnt_total <= LIST_CAP) && (pc + rows_total <= SPAN_POOL);
+        int first_bad = RS_THREADS;
+        if (!all_fit) {                                 // rare (zoomed-out frames): find the first candidate that does not fit
+            if (tid == 0) S.first_bad = RS_THREADS;
+            __syncthreads();
+            const bool fits = (lc + slot_rel + ents <= LIST_CAP) && (pc + row_rel + rows <= SPAN_POOL);
+            if (valid && !fits) atomicMin(&S.first_bad, tid);
+            __syncthreads();
+            first_bad = S.first_bad;
+        }
+        if (valid && tid < first_bad) {
+            const int sl = lc + slot_rel;
+            // canonical edges: lower endpoint first, slope hoisted out of the row loop
+#pragma unroll
+            for (int k = 0; k < MCR_MAXV; ++k)
+                if (k < 4 || nv > 4) S.edge[k & 3][k < 4 ? sl : LIST_CAP + aux] = canon_edge(k, nv, px, py);
+            S.ne[sl] = (uint8_t)(nv > 4 ? 8 + aux : 4); S.col[sl] = (uint8_t)col;
+            const int first = pc + row_rel;                 // this polygon's slots: [first, first + rows)
+            S.base[sl] = first - y0;
+            if (first & 31) atomicOr(&S.startbits[first >> 5], 1u << (first & 31));
+            for (int k = (first + 31) >> 5; (k << 5) < first + rows; ++k) S.slot32_owner[k] = (uint8_t)sl;
+        }
+        PHASE(4);
+        if (first_bad < RS_THREADS) {
+            // accepted prefix = everything before the first candidate that did not fit
+            if (tid == first_bad) { S.bc_cnt = lc + slot_rel; S.bc_rows = pc + row_rel; }
+            __syncthreads();
+            lc = S.bc_cnt; pc = S.bc_rows;
+            base += first_bad;
+            flush_list<VP>(S, tid, pix, lc, pc, false, ox, oy, VW);
+            lc = 0; pc = 0;
+        } else {
+            lc += cnt_total; pc += rows_total;
+            base += RS_THREADS;
+        }
+    }
+    flush_list<VP>(S, tid, pix, lc, pc, true, ox, oy, VW);
+
+    finish_frame<VP>(S, tid, pix, obs, frame, obs_format, ox, oy, VW, VH);
     if (!VP && cls != 2 && tid == 0) atomicMax(b.timeline + TL_RENDER_END, mcr_globaltimer());
     PHASE(8);
 #ifdef MCR_PHASE_CLOCKS
     if (threadIdx.x == 0) atomicAdd(&g_phase_clk[15], 1ull);
 #endif
+}
+
+
+// ---------------------------------------------------------------------------------------
+// The step path renders in two kernels (the fused render_kernel above stays for the viewport modes):
+//   project_kernel  front end, one CTA of 256 threads per agent-frame: candidates in painter's order -> camera ->
+//                   cull -> ordered compaction (block scan) -> canonical edges, written as the frame's display list
+//                   to global memory (stays in L2).  Latency bound (three dependent load levels), light on
+//                   registers and shared memory: many CTAs per SM hide the latency the fused kernel's idle warps
+//                   used to wait out at block barriers.
+//   fill_kernel     back end, one CTA of 288 threads per agent-frame: display list -> shared memory in chunks that
+//                   fit the list / span pool -> spans -> fill -> palette expansion -> 6 x uint4 per thread.
+// Same arithmetic as the fused kernel, polygon by polygon (cand_rows, canon_edge, flush_list, finish_frame are shared).
+// ---------------------------------------------------------------------------------------
+#ifndef FILL_CTAS
+#define FILL_CTAS 4
+#endif
+#define PJ_THREADS 256
+#define PJ_WARPS (PJ_THREADS / 32)
+
+// checker index range the camera can see + "the playfield quad covers the whole frame" (see frame_front)
+struct CheckerRange { int j0x, nx, j0y, ny, grass_full; };
+__device__ __forceinline__ CheckerRange checker_range(float m00, float m01, float m02, float m10, float m11, float m12,
+                                                      float tx0, float ty0, float tx1, float ty1) {
+    const float det = m00 * m11 - m01 * m10;
+    int j0x = 0, j1x = N_CHECKER_AXIS - 1, j0y = 0, j1y = N_CHECKER_AXIS - 1, grass_full = 0;
+    if (fabsf(det) > 1e-12f) {
+        const float inv = 1.0f / det;
+        float wxmin = 3.0e38f, wxmax = -3.0e38f, wymin = 3.0e38f, wymax = -3.0e38f;
+#pragma unroll
+        for (int cnr = 0; cnr < 4; ++cnr) {
+            const float u = ((cnr & 1) ? tx1 : tx0) - m02, v = ((cnr & 2) ? ty1 : ty0) - m12;
+            const float wx = (m11 * u - m01 * v) * inv, wy = (-m10 * u + m00 * v) * inv;
+            wxmin = fminf(wxmin, wx); wxmax = fmaxf(wxmax, wx); wymin = fminf(wymin, wy); wymax = fmaxf(wymax, wy);
+        }
+        const float pfm = (float)(2000 / 6.0) - 4.0f;
+        grass_full = (wxmin > -pfm && wxmax < pfm && wymin > -pfm && wymax < pfm) ? 1 : 0;
+        const float ik = 20.0f / (float)(2000 / 6.0), margin = 2.0f;
+        const float a0 = floorf(((wxmin - margin) * ik + 19.0f) * 0.5f - 1e-3f), a1 = ceilf(((wxmax + margin) * ik + 20.0f) * 0.5f + 1e-3f);
+        const float c0 = floorf(((wymin - margin) * ik + 19.0f) * 0.5f - 1e-3f), c1 = ceilf(((wymax + margin) * ik + 20.0f) * 0.5f + 1e-3f);
+        if (a0 == a0 && a1 == a1 && c0 == c0 && c1 == c1) {
+            j0x = (int)fmaxf(0.0f, fminf(a0, 20.0f)); j1x = (int)fminf((float)(N_CHECKER_AXIS - 1), fmaxf(a1, -1.0f));
+            j0y = (int)fmaxf(0.0f, fminf(c0, 20.0f)); j1y = (int)fminf((float)(N_CHECKER_AXIS - 1), fmaxf(c1, -1.0f));
+        }
+    }
+    CheckerRange r;
+    r.j0x = j0x; r.nx = j1x >= j0x ? j1x - j0x + 1 : 0; r.j0y = j0y; r.ny = j1y >= j0y ? j1y - j0y + 1 : 0; r.grass_full = grass_full;
+    return r;
+}
+
+// One WARP per agent-frame, no block barriers: every warp walks its frame's candidates 32 at a time in painter's
+// order (ballot / shuffle-scan compaction), so a warp waiting on a load never holds another frame back.
+__global__ void __launch_bounds__(PJ_THREADS, 4)
+project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, int backwards_flag, int use_ego_color, int cls) {
+    __shared__ uint8_t s_vis_chunk[PJ_WARPS][MAX_CHUNKS];
+    cudaGridDependencySynchronize();               // programmatic dependent launch behind post_kernel (mcr_launch_pdl)
+    tl_stamp(b.timeline, cls == 2 ? TL_RENDER2 : TL_RENDER);
+    if (blockIdx.x == 0 && threadIdx.x == 0) b.fill_ctr[cls] = 0;          // fill_kernel's frame queue
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int frame = (int)blockIdx.x * PJ_WARPS + warp;
+    if (frame >= d.N) return;
+    const int env = frame / d.A, agent = frame - env * d.A;
+    if (mask && !mask[env]) return;
+    if (cls && (cls == 2) != (b.n_manifold[env] > 0)) return;
+    const int N = d.N, car = frame;
+    const int slot = b.env_track[env];
+    Affine M;
+    M.m00 = b.camera[(size_t)0 * N + car]; M.m01 = b.camera[(size_t)1 * N + car]; M.m02 = b.camera[(size_t)2 * N + car];
+    M.m10 = b.camera[(size_t)3 * N + car]; M.m11 = b.camera[(size_t)4 * N + car]; M.m12 = b.camera[(size_t)5 * N + car];
+    const int Q = b.trk_Q[slot];
+    // ---- road_poly chunk culling (bounding circle of every 8 consecutive quads vs the frame), lane per chunk; chunks
+    // past the track's last quad have radius 0 in the pool, so the loop bound does not wait for trk_Q
+    uint8_t* vis_chunk = s_vis_chunk[warp];
+    int n_vis = 0;
+    {
+        const int nchunks = d.Qmax / MCR_QUAD_CHUNK;
+        const float rscale = sqrtf(M.m00 * M.m00 + M.m01 * M.m01 + M.m10 * M.m10 + M.m11 * M.m11) * 1.001f;
+        for (int c0 = 0; c0 < nchunks; c0 += 32) {
+            const int c = c0 + lane;
+            bool vis = false;
+            if (c < nchunks) {
+                const float4 cc4 = *(const float4*)(b.trk_chunk + ((size_t)slot * nchunks + c) * 4);
+                const float cxp = (M.m00 * cc4.x + M.m01 * cc4.y) + M.m02, cyp = (M.m10 * cc4.x + M.m11 * cc4.y) + M.m12;
+                const float rp = cc4.z * rscale + 2.0f;      // |M v| <= ||M||_F |v|: conservative pixel radius, plus a 2-pixel margin
+                vis = (cxp + rp >= 0.0f) && (cxp - rp <= (float)SW) && (cyp + rp >= 0.0f) && (cyp - rp <= (float)SH);
+                if (!(rp == rp) || !(cxp == cxp) || !(cyp == cyp)) vis = true;
+                if (!(cc4.z > 0.0f)) vis = false;
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, vis);
+            if (vis) vis_chunk[n_vis + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)c;
+            n_vis += __popc(bal);
+        }
+        __syncwarp();
+    }
+    const CheckerRange ck = checker_range(M.m00, M.m01, M.m02, M.m10, M.m11, M.m12, 0.0f, 0.0f, (float)SW, (float)SH);
+
+    View V;
+    V.env = env; V.agent = agent; V.A = d.A; V.N = N; V.Q = Q;
+    V.ck_j0x = ck.j0x; V.ck_j0y = ck.j0y; V.ck_ny = ck.ny > 0 ? ck.ny : 1;
+    V.n_checker = ck.nx * ck.ny; V.grass_full = ck.grass_full;
+    V.n_road = n_vis * MCR_QUAD_CHUNK; V.vis_chunk = vis_chunk;
+    V.c_road = (1 + V.n_checker + 31) & ~31;
+    V.c_cars = V.c_road + ((V.n_road + 31) & ~31);
+    V.car_slots = CAR_PARTS;
+    V.prt_pts = b.prt_pts; V.prt_meta = b.prt_meta; V.prt_hdr = b.prt_hdr;
+    V.c_hud = V.c_cars + ((V.car_slots * d.A + 31) & ~31);
+    V.body = b.body; V.wheel = b.wheel; V.stripe = b.stripe;
+    V.quad = b.trk_quad + (size_t)slot * d.Qmax * 8;
+    V.quad_col = b.trk_quad_col + (size_t)slot * d.Qmax;
+    V.quad_tile = b.trk_quad_tile + (size_t)slot * d.Qmax;
+    V.touched = b.touched + (size_t)env * d.Tmax;
+    V.use_ego_color = use_ego_color;
+    V.backward_flag_on = (b.backward_snap[car] != 0) && backwards_flag;     // step(): flag of the PREVIOUS step (render precedes mcr:445-495)
+    V.hud_sx = (float)(96.0 / 1000.0); V.hud_sy = (float)(96.0 / 800.0);
+    int hud_rows = 0;                              // see render_kernel
+    {
+        const float bar_top = (float)(5 * (800 / 40.0)) * V.hud_sy, bar_right = (float)1000.0 * V.hud_sx;
+        if (bar_right >= (float)SW) hud_rows = min(SH, max(0, (int)ceilf(bar_top - 0.5f)));
+    }
+    uint2* __restrict__ meta = reinterpret_cast<uint2*>(b.dl_meta) + (size_t)frame * d.dl_cap;
+    float4* __restrict__ edge = reinterpret_cast<float4*>(b.dl_edge) + (size_t)frame * d.dl_cap * 4;
+    float4* __restrict__ oct = reinterpret_cast<float4*>(b.dl_oct) + (size_t)frame * d.A * 4;
+
+    const int NC = V.c_hud + 9;
+    int lc = 0, pc = 0;                            // entries / span slots so far (warp uniform)
+    for (int base = 0; base < NC; base += 32) {
+        const int i = base + lane;
+        float px[MCR_MAXV], py[MCR_MAXV];
+        int nv = 0, col = 0, y0 = 0, y1 = 0, aux = 0;
+        if (i < NC) nv = gen_candidate(i, V, M, cc, px, py, col, aux);
+        const bool valid = cand_rows<false>(nv, px, py, i < V.c_hud, hud_rows, 0.0f, 0.0f, (float)SW, (float)SH, 0, SH, y0, y1);
+        const uint32_t bal = __ballot_sync(0xffffffffu, valid);
+        if (bal == 0u) continue;
+        const int rows = valid ? y1 - y0 : 0;
+        int rows_inc = rows;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int r = __shfl_up_sync(0xffffffffu, rows_inc, o);
+            if (lane >= o) rows_inc += r;
+        }
+        if (valid) {
+            const int sl = lc + __popc(bal & ((1u << lane) - 1u));          // < dl_cap: the list holds every candidate
+            const int first = pc + rows_inc - rows;                         // this polygon's span slots: [first, first + rows)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) edge[(size_t)sl * 4 + k] = canon_edge(k, nv, px, py);
+            if (nv > 4) {
+#pragma unroll
+                for (int k = 4; k < MCR_MAXV; ++k) oct[(size_t)aux * 4 + (k - 4)] = canon_edge(k, nv, px, py);
+            }
+            meta[sl] = make_uint2((uint32_t)y0 | ((uint32_t)rows << 8) | ((uint32_t)col << 16) | ((uint32_t)(nv > 4 ? 8 + aux : 4) << 24),
+                                  (uint32_t)first);
+        }
+        lc += __popc(bal);
+        pc += __shfl_sync(0xffffffffu, rows_inc, 31);
+    }
+    if (lane == 0) *reinterpret_cast<int4*>(b.dl_hdr + (size_t)frame * 4) = make_int4(lc, pc, V.grass_full, 0);
+}
+
+// Persistent: gridDim.x = resident CTAs of the device; a CTA takes frame blockIdx.x first and then draws frames from
+// b.fill_ctr[cls] (reset by project_kernel) until none are left -- no CTA relaunch gap between frames, the tables are
+// built once, and the tail of the launch is balanced by whoever finishes first.
+__global__ void __launch_bounds__(RS_THREADS, FILL_CTAS)
+fill_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, uint8_t* __restrict__ obs, int cls, int obs_format) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    PHASE_T0();
+    // tables that do not depend on project_kernel's output: built while it drains (programmatic dependent launch)
+    if (tid >= 32 && tid < 32 + PAL_COUNT) {
+        const int i = tid - 32;
+        S.pal32[i] = (uint32_t)c_palette[i][0] | ((uint32_t)c_palette[i][1] << 8) | ((uint32_t)c_palette[i][2] << 16);
+        S.palY[i] = (uint32_t)c_palette[i][3];
+    }
+    if (tid < 256) S.prmt_sel[tid] = prmt_selector(tid);
+    if (tid >= 128 && tid < 128 + SPAN_POOL / 32) S.startbits[tid - 128] = 0;
+    cudaGridDependencySynchronize();
+    int frame = (int)blockIdx.x;
+    while (frame < d.N) {
+        int next = 0;
+        if (tid == 0) next = atomicAdd(b.fill_ctr + cls, 1) + (int)gridDim.x;      // needed at the end of this frame only
+        const int env = frame / d.A;
+        const bool skip = (mask && !mask[env]) || (cls && (cls == 2) != (b.n_manifold[env] > 0));
+        if (!skip) {
+            const uint2* __restrict__ meta = reinterpret_cast<const uint2*>(b.dl_meta) + (size_t)frame * d.dl_cap;
+            const float4* __restrict__ edge = reinterpret_cast<const float4*>(b.dl_edge) + (size_t)frame * d.dl_cap * 4;
+            const float4* __restrict__ oct = reinterpret_cast<const float4*>(b.dl_oct) + (size_t)frame * d.A * 4;
+            // header, metadata and the first edges are loaded side by side (no load waits for the entry count)
+            const int4 hdr = *reinterpret_cast<const int4*>(b.dl_hdr + (size_t)frame * 4);
+            uint2 mt = make_uint2(0u, 0u);
+            if (tid < LIST_CAP) mt = meta[min(tid, d.dl_cap - 1)];
+            const float4 ed0 = edge[min(tid, d.dl_cap * 4 - 1)], ed1 = edge[min(tid + RS_THREADS, d.dl_cap * 4 - 1)];
+            const int n = hdr.x;
+            if (tid == 64) score_glyphs(b.score_snap[frame], S.glyph);
+            uint32_t pix[8];               // this thread's 32 pixels (palette indices); glClear -> black
+#pragma unroll
+            for (int k = 0; k < 8; ++k) pix[k] = (hdr.z ? PAL_GRASS : PAL_BLACK) * 0x01010101u;
+            PHASE(0);
+            int e0 = 0;
+            uint32_t rs0 = 0u;             // first span slot of the chunk (the frame's first polygon starts at slot 0)
+            do {
+                // this chunk = the longest run of entries from e0 that fits the shared-memory list and the span pool
+                if (e0 > 0) {
+                    rs0 = meta[e0].y;
+                    if (tid < LIST_CAP) mt = meta[min(e0 + tid, d.dl_cap - 1)];
+                }
+                const bool fits = tid < LIST_CAP && e0 + tid < n && mt.y + ((mt.x >> 8) & 0xffu) - rs0 <= (uint32_t)SPAN_POOL;
+                const int cnt = __syncthreads_count(fits);     // slot offsets are monotone: the entries that fit are a prefix
+                if (tid < cnt) {
+                    const int y0 = (int)(mt.x & 0xffu), rows = (int)((mt.x >> 8) & 0xffu), ne = (int)(mt.x >> 24);
+                    const int first = (int)(mt.y - rs0);
+                    S.base[tid] = first - y0; S.ne[tid] = (uint8_t)ne; S.col[tid] = (uint8_t)((mt.x >> 16) & 0xffu);
+                    if (first & 31) atomicOr(&S.startbits[first >> 5], 1u << (first & 31));
+                    for (int k = (first + 31) >> 5; (k << 5) < first + rows; ++k) S.slot32_owner[k] = (uint8_t)tid;
+                    if (ne >= 8) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) S.edge[k][LIST_CAP + (ne - 8)] = oct[(size_t)(ne - 8) * 4 + k];
+                    }
+                    if (tid == cnt - 1) S.bc_rows = first + rows;
+                }
+                if (e0 == 0) {
+                    if (tid < cnt * 4) S.edge[tid & 3][tid >> 2] = ed0;
+                    if (tid + RS_THREADS < cnt * 4) S.edge[(tid + RS_THREADS) & 3][(tid + RS_THREADS) >> 2] = ed1;
+                    for (int i = tid + 2 * RS_THREADS; i < cnt * 4; i += RS_THREADS) S.edge[i & 3][i >> 2] = edge[i];
+                } else {
+                    for (int i = tid; i < cnt * 4; i += RS_THREADS) S.edge[i & 3][i >> 2] = edge[(size_t)e0 * 4 + i];
+                }
+                PHASE(3);
+                const bool last = e0 + cnt >= n;
+                flush_list<false>(S, tid, pix, cnt, -1, last, 0, 0, SW);
+                e0 += cnt;
+            } while (e0 < n);
+            finish_frame<false>(S, tid, pix, obs, frame, obs_format, 0, 0, SW, SH);
+#ifdef MCR_PHASE_CLOCKS
+            if (threadIdx.x == 0) atomicAdd(&g_phase_clk[15], 1ull);
+#endif
+        }
+        __syncthreads();                   // every thread is done with this frame's list, spans and masks
+        if (tid == 0) S.first_bad = next;
+        if (!skip && tid >= 128 && tid < 128 + SPAN_POOL / 32) S.startbits[tid - 128] = 0;
+        __syncthreads();
+        frame = S.first_bad;
+    }
+    if (cls != 2 && tid == 0) atomicMax(b.timeline + TL_RENDER_END, mcr_globaltimer());
 }
 
 
@@ -943,6 +1213,7 @@ static bool configure_render() {
         if (cudaMemcpyToSymbol(c_palette, mcr_host_palette(), sizeof(uint8_t) * PAL_COUNT * 4) != cudaSuccess) return false;
         if (cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
         if (cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+        if (cudaFuncSetAttribute(fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
         configured[dev] = true;
     }
     return true;
@@ -951,9 +1222,26 @@ static bool configure_render() {
 int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* obs,
                   int backwards_flag, int use_ego_color, int cls, int obs_format, void* stream) {
     if (!configure_render()) return -1;
-    mcr_launch_pdl(render_kernel<false>, dim3(d.B, d.A), dim3(RS_THREADS), sizeof(RasterSmem), (cudaStream_t)stream,
-                   d, b, cc, mask, obs, backwards_flag, use_ego_color, cls, obs_format, VpParams{});
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    static const bool fused = std::getenv("MCR_RENDER_FUSED") != nullptr;     // diagnostics: the single-kernel rasteriser (A/B)
+    if (fused) {
+        mcr_launch_pdl(render_kernel<false>, dim3(d.B, d.A), dim3(RS_THREADS), sizeof(RasterSmem), (cudaStream_t)stream,
+                       d, b, cc, mask, obs, backwards_flag, use_ego_color, cls, obs_format, VpParams{});
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    }
+    mcr_launch_pdl(project_kernel, dim3((d.N + PJ_WARPS - 1) / PJ_WARPS), dim3(PJ_THREADS), 0, (cudaStream_t)stream,
+                   d, b, cc, mask, backwards_flag, use_ego_color, cls);
+    static int resident[64] = {};
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && resident[dev] == 0) {
+        int per_sm = 0, sms = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_kernel, RS_THREADS, sizeof(RasterSmem)) != cudaSuccess || per_sm < 1) per_sm = 1;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 1;
+        resident[dev] = per_sm * sms;
+    }
+    const int fill_grid = std::min(d.N, dev >= 0 && dev < 64 ? resident[dev] : d.N);
+    mcr_launch_pdl(fill_kernel, dim3(fill_grid), dim3(RS_THREADS), sizeof(RasterSmem), (cudaStream_t)stream,
+                   d, b, mask, obs, cls, obs_format);
+    return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
 
 // camera of mcr:540-556 for a viewport of vw x vh pixels (post_kernel evaluates the 96 x 96 one); same

@@ -14,7 +14,7 @@ venv = mcr.BatchedMultiCarRacing(B, num_agents=A, auto_reset=False, max_episode_
 venv.reset(device_tracks=True)
 g = torch.Generator(device=venv.device); g.manual_seed(1234)
 tape = torch.rand((128, B, A, 3), device=venv.device, generator=g); tape[..., 0] = tape[..., 0] * 2 - 1
-names = ["0 pdl wait+ids", "1 setup..ballot", "2 vis chunks", "3 candidates+scan", "4 edges", "5 zero masks", "6 spans", "7 fill", "8 glyph+store"]
+names = ["0 tables+pdl wait+hdr", "1 -", "2 -", "3 list -> smem", "4 -", "5 zero masks+barrier", "6 spans", "7 fill", "8 -"]   # fill_kernel (MCR_RENDER_FUSED=1: the fused kernel's phases 0-8)
 done = 0
 buf = (ctypes.c_ulonglong * 16)()
 for name, upto in (("t=0.02", 0), ("t=0.5", 24), ("mid(170)", 170)):
