@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MCR_ABI_VERSION 2
+#define MCR_ABI_VERSION 3
 #define MCR_STATE_W 96
 #define MCR_STATE_H 96
 #define MCR_MAX_AGENTS 16
@@ -51,6 +51,12 @@ typedef struct mcr_config {
     uint64_t seed;             /* stream id of the device-side auto-reset RNG             */
     int32_t particles;         /* 1: keep the skid traces of gym car_dynamics.Car (Car.particles, "Skid trace" block of
                                   Car.step) so that the non-state render modes draw them (mcr:564); 0: no bookkeeping */
+    int32_t fresh_tracks;      /* R > 0: the device-side auto reset gives every episode a NEW track generated on the env's
+                                  own RandomState stream, like reset() does (mcr:359-364): env e owns pool slots
+                                  e + batch_envs * j, j = 0..R (pool_tracks must be batch_envs * (R + 1)); a low-priority
+                                  refill kernel keeps R tracks ready ahead of the episode in progress, and an env whose
+                                  next track is not ready generates it in place (the track sequence of an env never
+                                  depends on timing).  0: auto reset draws from the shared pool filled at reset(). */
 } mcr_config;
 
 /* Observation layouts the rasteriser can store (mcr_set_obs_format).  The reference returns
@@ -58,8 +64,14 @@ typedef struct mcr_config {
  * pre-processing fused into the store, so the frame never makes an extra HBM round trip:
  *   MCR_OBS_RGB_HWC  [96][96][3] u8   (27 648 B per agent-frame, the default)
  *   MCR_OBS_GRAY     [96][96]    u8   ( 9 216 B) ITU-R 601 luma, (299 R + 587 G + 114 B + 500) / 1000
- *   MCR_OBS_RGB_CHW  [3][96][96] u8   (27 648 B) planar, what a convolution stack wants */
-enum { MCR_OBS_RGB_HWC = 0, MCR_OBS_GRAY = 1, MCR_OBS_RGB_CHW = 2 };
+ *   MCR_OBS_RGB_CHW  [3][96][96] u8   (27 648 B) planar, what a convolution stack wants
+ *   MCR_OBS_GRAY_STACK [K][96][96] u8 (K x 9 216 B) frame stack of the last K luma frames as a ring: the frame of the
+ *                    episode's step s is stored in slot s % K, the first frame of an episode (s = 0) in every slot
+ *                    (what gym's FrameStack wrapper does on reset); K = mcr_set_frame_stack(), default 4.  The
+ *                    caller's d_obs persists between steps -- only one slot per agent is written per step.
+ *   MCR_OBS_RGB_CHW_F16 [3][96][96] fp16 (55 296 B) planar, value / 255 rounded to nearest fp16: the learner's
+ *                    uint8 -> float normalisation fused into the store (README.md:82-95 downstream learners) */
+enum { MCR_OBS_RGB_HWC = 0, MCR_OBS_GRAY = 1, MCR_OBS_RGB_CHW = 2, MCR_OBS_GRAY_STACK = 3, MCR_OBS_RGB_CHW_F16 = 4 };
 
 /* dtype codes used by mcr_buffer_spec */
 enum { MCR_U8 = 0, MCR_I32 = 1, MCR_U32 = 2, MCR_F32 = 3, MCR_F64 = 4, MCR_I16 = 5 };
@@ -94,6 +106,14 @@ int mcr_track_generate(uint32_t* mt_state, int32_t max_tiles, int32_t max_quads,
 /* MT19937 init_by_array, the seeding RandomState.seed(list) performs (gym seeding.np_random,
  * used at mcr:169-171). */
 int mcr_mt_seed(uint32_t* mt_state, const uint32_t* key, int32_t key_len);
+/* The same for n streams at once: states[n][625], keys[n][key_stride] of which key_len[i] words are used. */
+int mcr_mt_seed_batch(uint32_t* h_states, const uint32_t* h_keys, const int32_t* h_key_len, int32_t n, int32_t key_stride);
+/* reset()'s draws from the GLOBAL numpy RNG (mcr:351-357) for n envs in a row: direction
+ * (np.random.choice(['CW','CCW']) when use_random_direction, else default_cw) and car order
+ * (np.random.choice(ids, size=A, replace=False)).  mt_state[625] = np.random.get_state() in/out, so the
+ * global stream advances exactly as n reference reset() calls would advance it.  h_cw[n], h_order[n][A]. */
+int mcr_reset_draws(uint32_t* mt_state, int32_t n, int32_t A, int32_t use_random_direction, int32_t default_cw,
+                    uint8_t* h_cw, int32_t* h_order);
 /* Spawn grid of reset() (mcr:366-393): poses[A][3] = (angle, x, y) f64 for car_order[A]. */
 int mcr_spawn_poses(const double* h_nodes, int32_t T, const int32_t* car_order, int32_t A, int32_t cw,
                     double* h_poses);
@@ -111,7 +131,7 @@ int mcr_load_track(mcr_handle h, int32_t slot, int32_t T, const double* h_nodes,
  * generator to ~1e-12 rather than bit for bit; the host generator remains the bit-exact path.
  * d_scratch: n * mcr_trackgen_scratch_bytes() bytes; afterwards track i's path nodes
  * (alpha, beta, x, y) f64 are rows [i1, i1 + T) of its scratch block.
- * d_result[i][4] = { T (> 0) or an error code (< 0), attempts, i1, i2 }. */
+ * d_result[i][4] = { T (> 0) or an error code (< 0), attempts, i1, i2 }.  d_slot = NULL: track i goes to slot i. */
 int mcr_tracks_generate_device(mcr_handle h, int32_t n, uint32_t* d_mt_state, const int32_t* d_slot,
                                void* d_scratch, int32_t* d_result, void* stream);
 int64_t mcr_trackgen_scratch_bytes(void);
@@ -158,6 +178,8 @@ int mcr_render_viewport(mcr_handle h, const uint8_t* d_env_mask, int32_t vw, int
 /* Select the layout every later mcr_reset / mcr_step / mcr_render call writes into d_obs (one of
  * MCR_OBS_*).  mcr_obs_bytes() = bytes per agent-frame of the current layout. */
 int mcr_set_obs_format(mcr_handle h, int32_t format);
+/* Ring depth K of MCR_OBS_GRAY_STACK (1..16, default 4). */
+int mcr_set_frame_stack(mcr_handle h, int32_t k);
 int64_t mcr_obs_bytes(mcr_handle h);
 
 /* Car-constant readback for parity tests: 12 floats hull(mass,invMass,I,invI,lc.x,lc.y),

@@ -18,9 +18,9 @@ EXPORTS = [
     "mcr_buffer_spec", "mcr_bind_buffer", "mcr_track_generate", "mcr_mt_seed", "mcr_spawn_poses",
     "mcr_load_track", "mcr_reset", "mcr_step", "mcr_simulate", "mcr_contacts", "mcr_physics", "mcr_render",
     "mcr_get_mass", "mcr_get_shape", "mcr_launch_count", "mcr_set_obs_format", "mcr_obs_bytes",
-    "mcr_tracks_generate_device", "mcr_trackgen_scratch_bytes", "mcr_render_viewport",
+    "mcr_tracks_generate_device", "mcr_trackgen_scratch_bytes", "mcr_render_viewport", "mcr_set_frame_stack", "mcr_mt_seed_batch", "mcr_reset_draws",
 ]
-OBS_FORMATS = {"rgb": 0, "gray": 1, "rgb_chw": 2}     # MCR_OBS_RGB_HWC / MCR_OBS_GRAY / MCR_OBS_RGB_CHW
+OBS_FORMATS = {"rgb": 0, "gray": 1, "rgb_chw": 2, "gray_stack": 3, "rgb_chw_f16": 4}     # MCR_OBS_* of include/mcr.h
 
 
 class McrConfig(ctypes.Structure):
@@ -32,6 +32,7 @@ class McrConfig(ctypes.Structure):
         ("h_ratio", ctypes.c_double), ("device", ctypes.c_int32),
         ("use_random_direction", ctypes.c_int32), ("direction_cw", ctypes.c_int32),
         ("collisions", ctypes.c_int32), ("seed", ctypes.c_uint64), ("particles", ctypes.c_int32),
+        ("fresh_tracks", ctypes.c_int32),
     ]
 
 
@@ -71,6 +72,10 @@ def load():
     L.mcr_track_generate.argtypes = [vp, i32, i32, vp, vp, vp, vp, ctypes.POINTER(i32), vp]
     L.mcr_mt_seed.restype = i32
     L.mcr_mt_seed.argtypes = [vp, vp, i32]
+    L.mcr_mt_seed_batch.restype = i32
+    L.mcr_mt_seed_batch.argtypes = [vp, vp, vp, i32, i32]
+    L.mcr_reset_draws.restype = i32
+    L.mcr_reset_draws.argtypes = [vp, i32, i32, i32, i32, vp, vp]
     L.mcr_spawn_poses.restype = i32
     L.mcr_spawn_poses.argtypes = [vp, i32, vp, i32, i32, vp]
     L.mcr_load_track.restype = i32
@@ -95,6 +100,8 @@ def load():
     L.mcr_launch_count.argtypes = [vp]
     L.mcr_set_obs_format.restype = i32
     L.mcr_set_obs_format.argtypes = [vp, i32]
+    L.mcr_set_frame_stack.restype = i32
+    L.mcr_set_frame_stack.argtypes = [vp, i32]
     L.mcr_obs_bytes.restype = i64
     L.mcr_obs_bytes.argtypes = [vp]
     L.mcr_tracks_generate_device.restype = i32
@@ -103,7 +110,7 @@ def load():
     L.mcr_trackgen_scratch_bytes.argtypes = []
     L.mcr_render_viewport.restype = i32
     L.mcr_render_viewport.argtypes = [vp, vp, i32, i32, vp, vp]
-    if L.mcr_abi_version() != 2 and not os.environ.get("MCR_LIB_PATH"):
+    if L.mcr_abi_version() != 3 and not os.environ.get("MCR_LIB_PATH"):
         raise McrError("libmcr.so ABI version mismatch")
     _lib = L
     return L

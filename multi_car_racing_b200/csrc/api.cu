@@ -223,6 +223,41 @@ extern "C" int mcr_mt_seed(uint32_t* st, const uint32_t* key, int32_t key_len) {
     return 0;
 }
 
+extern "C" int mcr_mt_seed_batch(uint32_t* states, const uint32_t* keys, const int32_t* key_len, int32_t n, int32_t key_stride) {
+    if (!states || !keys || !key_len || n < 1 || key_stride < 1) return fail(-1, "mcr_mt_seed_batch: bad arguments");
+    for (int i = 0; i < n; ++i) {
+        if (key_len[i] < 1 || key_len[i] > key_stride) return fail(-1, "mcr_mt_seed_batch: key %d has length %d", i, key_len[i]);
+        const int rc = mcr_mt_seed(states + (size_t)i * 625, keys + (size_t)i * key_stride, key_len[i]);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// reset()'s draws from the GLOBAL numpy RandomState for n envs in a row (mcr:351-357), on a copy of its MT19937 state:
+//   np.random.choice(['CW', 'CCW'])              -> randint(0, 2): one 32-bit draw, masked (legacy _rand_int64, rng = 1)
+//   np.random.choice(ids, size=A, replace=False) -> permutation(A)[:A]: Fisher-Yates from the top, j = random_interval(i)
+//                                                   (masked rejection on 32-bit draws)
+extern "C" int mcr_reset_draws(uint32_t* mt_state, int32_t n, int32_t A, int32_t use_random_direction, int32_t default_cw,
+                               uint8_t* h_cw, int32_t* h_order) {
+    if (!mt_state || !h_cw || !h_order || n < 1 || A < 1) return fail(-1, "mcr_reset_draws: bad arguments");
+    MT rng(mt_state);
+    for (int e = 0; e < n; ++e) {
+        int cw = default_cw ? 1 : 0;
+        if (use_random_direction) cw = (rng.next32() & 1u) ? 0 : 1;        // index 0 = 'CW', 1 = 'CCW'
+        h_cw[e] = (uint8_t)cw;
+        int32_t* o = h_order + (size_t)e * A;
+        for (int i = 0; i < A; ++i) o[i] = i;
+        for (int i = A - 1; i > 0; --i) {
+            uint32_t mask = (uint32_t)i;
+            mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+            uint32_t j;
+            do { j = rng.next32() & mask; } while (j > (uint32_t)i);
+            const int32_t t = o[i]; o[i] = o[j]; o[j] = t;
+        }
+    }
+    return 0;
+}
+
 // One attempt of _create_track (mcr:183-338).
 extern "C" int mcr_track_generate(uint32_t* mt_state, int32_t max_tiles, int32_t max_quads, double* h_nodes,
                                   double* h_quads, float* h_quad_rgb, int32_t* h_quad_tile, int32_t* out_q,
@@ -385,6 +420,9 @@ struct mcr_handle_t {
     cudaEvent_t ev_fork, ev_join;
     cudaStream_t side2;          // the chain of envs with touching cars: coupled -> post -> score -> render
     cudaStream_t side3;          // score_kernel of the touching-car envs, beside their rasteriser
+    cudaStream_t refill;         // lowest priority: ring_refill_kernel tops up the envs' track rings beside the steps
+    cudaEvent_t ev_refill, ev_refill_go;
+    int64_t steps_since_refill;
     cudaEvent_t ev_pre, ev_contacts, ev_chain2, ev_score, ev_post2, ev_score2;
     bool side_ready;
     // mcr_step replays a captured CUDA graph of its launches (one graph per argument tuple)
@@ -393,6 +431,7 @@ struct mcr_handle_t {
     int64_t eager_steps;
     bool use_graphs;
     int obs_format;              // MCR_OBS_*
+    int stack_k;                 // ring depth of MCR_OBS_GRAY_STACK
 };
 
 
@@ -414,6 +453,9 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
     if (cfg->max_quads < cfg->max_tiles || cfg->max_quads > 2048 || cfg->max_quads % MCR_QUAD_CHUNK)
         return fail(-1, "max_quads must be a multiple of %d in [max_tiles, 2048]", MCR_QUAD_CHUNK);
     if (cfg->pool_tracks < 1) return fail(-1, "pool_tracks must be >= 1");
+    if (cfg->fresh_tracks < 0 || cfg->fresh_tracks > 7) return fail(-1, "fresh_tracks (spare tracks per env) must be in [0, 7]");
+    if (cfg->fresh_tracks > 0 && (int64_t)cfg->pool_tracks != (int64_t)cfg->batch_envs * (cfg->fresh_tracks + 1))
+        return fail(-1, "fresh_tracks = R needs pool_tracks == batch_envs * (R + 1): env e owns slots e + batch_envs * j");
     mcr_handle_t* h = new mcr_handle_t();
     h->cfg = *cfg;
     h->d = Dims{cfg->batch_envs, cfg->num_agents, cfg->batch_envs * cfg->num_agents, cfg->max_tiles, cfg->max_quads, cfg->pool_tracks, cfg->particles ? 1 : 0,
@@ -422,7 +464,8 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
     std::memset(&h->buf, 0, sizeof(h->buf));
     std::memset(h->ptr, 0, sizeof(h->ptr));
     h->launches = 0; h->palette_ready = false; h->side_ready = false;
-    h->obs_format = MCR_OBS_RGB_HWC;
+    h->obs_format = MCR_OBS_RGB_HWC; h->stack_k = 4;
+    h->steps_since_refill = 0;
     h->eager_steps = 0; h->use_graphs = std::getenv("MCR_NO_GRAPH") == nullptr;
     const int64_t N = h->d.N, B = h->d.B, A = h->d.A, T = h->d.Tmax, Q = h->d.Qmax, P = h->d.P;
     set_spec(h, BUF_BODY, "body", MCR_F32, {5, BODY_FIELDS, N});
@@ -481,7 +524,11 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
     set_spec(h, BUF_DL_META, "dl_meta", MCR_U32, {N, h->d.dl_cap, 2});
     set_spec(h, BUF_DL_EDGE, "dl_edge", MCR_F32, {N, h->d.dl_cap, 16});
     set_spec(h, BUF_DL_OCT, "dl_oct", MCR_F32, {N, A, 16});
-    set_spec(h, BUF_FILL_CTR, "fill_ctr", MCR_I32, {4});
+    set_spec(h, BUF_MT_STATE, "mt_state", MCR_U32, {B, 625});
+    set_spec(h, BUF_TRK_CONSUMED, "trk_consumed", MCR_I32, {B});
+    set_spec(h, BUF_TRK_PRODUCED, "trk_produced", MCR_I32, {B});
+    set_spec(h, BUF_TRK_LOCK, "trk_lock", MCR_I32, {B});
+    set_spec(h, BUF_TG_SCRATCH, "tg_scratch", MCR_U8, {cfg->fresh_tracks > 0 ? B : 1, mcr_trackgen_scratch_bytes()});
     *out = h;
     return 0;
 }
@@ -491,6 +538,7 @@ extern "C" int mcr_destroy(mcr_handle h) {
     if (h && h->side_ready) {
         cudaStreamDestroy(h->side); cudaStreamDestroy(h->cap); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
         cudaStreamDestroy(h->side3); cudaEventDestroy(h->ev_post2); cudaEventDestroy(h->ev_score2);
+        cudaStreamSynchronize(h->refill); cudaStreamDestroy(h->refill); cudaEventDestroy(h->ev_refill); cudaEventDestroy(h->ev_refill_go);
         cudaStreamDestroy(h->side2); cudaEventDestroy(h->ev_pre); cudaEventDestroy(h->ev_contacts); cudaEventDestroy(h->ev_chain2); cudaEventDestroy(h->ev_score);
     }
     delete h;
@@ -570,7 +618,11 @@ extern "C" int mcr_bind_buffer(mcr_handle h, int i, void* p) {
         case BUF_DL_META: b.dl_meta = (uint32_t*)p; break;
         case BUF_DL_EDGE: b.dl_edge = (float*)p; break;
         case BUF_DL_OCT: b.dl_oct = (float*)p; break;
-        case BUF_FILL_CTR: b.fill_ctr = (int32_t*)p; break;
+        case BUF_MT_STATE: b.mt_state = (uint32_t*)p; break;
+        case BUF_TRK_CONSUMED: b.trk_consumed = (int32_t*)p; break;
+        case BUF_TRK_PRODUCED: b.trk_produced = (int32_t*)p; break;
+        case BUF_TRK_LOCK: b.trk_lock = (int32_t*)p; break;
+        case BUF_TG_SCRATCH: b.tg_scratch = (unsigned char*)p; break;
     }
     return 0;
 }
@@ -601,7 +653,7 @@ extern "C" int64_t mcr_launch_count(mcr_handle h) { return h ? h->launches : -1;
 
 extern "C" int mcr_set_obs_format(mcr_handle h, int32_t format) {
     if (!h) return fail(-1, "null handle");
-    if (format != MCR_OBS_RGB_HWC && format != MCR_OBS_GRAY && format != MCR_OBS_RGB_CHW)
+    if (format < MCR_OBS_RGB_HWC || format > MCR_OBS_RGB_CHW_F16)
         return fail(-1, "mcr_set_obs_format: unknown format %d", format);
     if (format != h->obs_format) {
         // captured step graphs bake the layout in
@@ -612,9 +664,25 @@ extern "C" int mcr_set_obs_format(mcr_handle h, int32_t format) {
     return 0;
 }
 
+extern "C" int mcr_set_frame_stack(mcr_handle h, int32_t k) {
+    if (!h) return fail(-1, "null handle");
+    if (k < 1 || k > 16) return fail(-1, "mcr_set_frame_stack: depth must be in [1, 16]");
+    if (k != h->stack_k) {
+        for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);    // captured step graphs bake the depth in
+        h->graphs.clear();
+        h->stack_k = k;
+    }
+    return 0;
+}
+
 extern "C" int64_t mcr_obs_bytes(mcr_handle h) {
     if (!h) return -1;
-    return h->obs_format == MCR_OBS_GRAY ? MCR_STATE_W * MCR_STATE_H : MCR_OBS_BYTES;
+    switch (h->obs_format) {
+        case MCR_OBS_GRAY: return MCR_STATE_W * MCR_STATE_H;
+        case MCR_OBS_GRAY_STACK: return (int64_t)h->stack_k * MCR_STATE_W * MCR_STATE_H;
+        case MCR_OBS_RGB_CHW_F16: return 2 * MCR_OBS_BYTES;
+        default: return MCR_OBS_BYTES;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -712,7 +780,7 @@ extern "C" int mcr_load_track(mcr_handle h, int32_t slot, int32_t T, const doubl
 extern "C" int mcr_tracks_generate_device(mcr_handle h, int32_t n, uint32_t* d_mt_state, const int32_t* d_slot,
                                           void* d_scratch, int32_t* d_result, void* stream) {
     int rc = check_bound(h); if (rc) return rc;
-    if (n < 1 || !d_mt_state || !d_slot || !d_scratch || !d_result) return fail(-1, "mcr_tracks_generate_device: bad arguments");
+    if (n < 1 || !d_mt_state || !d_scratch || !d_result) return fail(-1, "mcr_tracks_generate_device: bad arguments");
     CUDA_OK(cudaSetDevice(h->cfg.device));
     LAUNCH(launch_trackgen(h->d, h->buf, n, d_mt_state, d_slot, d_scratch, d_result, 64, stream));
     return 0;
@@ -733,6 +801,11 @@ static int ensure_side(mcr_handle h) {
         CUDA_OK(cudaStreamCreateWithFlags(&h->side3, cudaStreamNonBlocking));
         CUDA_OK(cudaEventCreateWithFlags(&h->ev_post2, cudaEventDisableTiming));
         CUDA_OK(cudaEventCreateWithFlags(&h->ev_score2, cudaEventDisableTiming));
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUDA_OK(cudaStreamCreateWithPriority(&h->refill, cudaStreamNonBlocking, prio_lo));
+        CUDA_OK(cudaEventCreateWithFlags(&h->ev_refill, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&h->ev_refill_go, cudaEventDisableTiming));
         h->side_ready = true;
     }
     return 0;
@@ -787,7 +860,7 @@ static int render_and_score(mcr_handle h, const uint8_t* mask, uint8_t* obs, dou
         LAUNCH(launch_score(h->d, h->buf, mask, noact, reward, done, h->cfg.max_episode_steps, 0, h->side));
         CUDA_OK(cudaEventRecord(h->ev_join, h->side));
     }
-    LAUNCH(launch_render(h->d, h->buf, h->cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, 0, h->obs_format, s));
+    LAUNCH(launch_render(h->d, h->buf, h->cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, 0, h->obs_format, h->stack_k, s));
     if (post_step) CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));
     return 0;
 }
@@ -811,11 +884,31 @@ extern "C" int mcr_render_viewport(mcr_handle h, const uint8_t* mask, int32_t vw
 static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, const void* action, int32_t action_dtype,
                     uint8_t* obs, double* reward, uint8_t* done, int post_step, void* stream, const uint8_t* reset_flags = nullptr);
 
+// Top up the track rings on the refill stream, ordered behind what `after` holds so far (mcr_reset: the spawn kernel
+// that zeroes the ring counters; steps: nothing to wait for, the kernel only looks at the counters).
+static int kick_refill(mcr_handle h, cudaStream_t after) {
+    if (after) {
+        CUDA_OK(cudaEventRecord(h->ev_refill_go, after));
+        CUDA_OK(cudaStreamWaitEvent(h->refill, h->ev_refill_go, 0));
+    }
+    LAUNCH(launch_ring_refill(h->d, h->buf, h->cfg.fresh_tracks, h->refill));
+    CUDA_OK(cudaEventRecord(h->ev_refill, h->refill));
+    h->steps_since_refill = 0;
+    return 0;
+}
+
 extern "C" int mcr_reset(mcr_handle h, const uint8_t* mask, const int32_t* track_slot, const uint8_t* cw,
                          const double* spawn_pose, uint8_t* obs, void* stream) {
     int rc = check_bound(h); if (rc) return rc;
     if (!track_slot || !cw || !spawn_pose || !obs) return fail(-1, "mcr_reset: null argument");
+    const bool fresh = h->cfg.fresh_tracks > 0;
+    if (fresh) {
+        rc = ensure_side(h); if (rc) return rc;
+        // a refill of the previous episodes may still be writing the rings this reset re-initialises
+        CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_refill, 0));
+    }
     LAUNCH(launch_spawn(h->d, h->buf, h->cc, mask, track_slot, cw, spawn_pose, stream));
+    if (fresh) { rc = kick_refill(h, (cudaStream_t)stream); if (rc) return rc; }
     // the implicit step(None), mcr:408
     return pipeline(h, mask, nullptr, nullptr, MCR_F32, obs, nullptr, nullptr, 0, stream);
 }
@@ -835,7 +928,7 @@ static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, con
     const Dims& d = h->d; const DevBuffers& b = h->buf; const CarConst& cc = h->cc;
     const bool split = h->cfg.collisions && d.A > 1;
     static const int early_exit = std::getenv("MCR_NO_EARLY_EXIT") ? 0 : 1;   // diagnostics only
-    const AutoResetCfg ar{h->cfg.use_random_direction, h->cfg.direction_cw, (unsigned long long)h->cfg.seed};
+    const AutoResetCfg ar{h->cfg.use_random_direction, h->cfg.direction_cw, (unsigned long long)h->cfg.seed, h->cfg.fresh_tracks};
     if (reset_flags) {
         // next-step auto reset: the head kernel respawns the flagged envs first, so the contact pass
         // (which reads the start poses) has to follow it
@@ -870,7 +963,7 @@ static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, con
             LAUNCH(launch_score(d, b, mask, noact, reward, done, h->cfg.max_episode_steps, 2, h->side3));
             CUDA_OK(cudaEventRecord(h->ev_score2, h->side3));
         }
-        LAUNCH(launch_render(d, b, cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, 2, h->obs_format, h->side2));
+        LAUNCH(launch_render(d, b, cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, 2, h->obs_format, h->stack_k, h->side2));
         if (post_step) CUDA_OK(cudaStreamWaitEvent(h->side2, h->ev_score2, 0));
         CUDA_OK(cudaEventRecord(h->ev_chain2, h->side2));
     }
@@ -884,7 +977,7 @@ static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, con
         LAUNCH(launch_score(d, b, mask, noact, reward, done, h->cfg.max_episode_steps, cls, h->side));
         CUDA_OK(cudaEventRecord(h->ev_score, h->side));
     }
-    LAUNCH(launch_render(d, b, cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, cls, h->obs_format, s));
+    LAUNCH(launch_render(d, b, cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, cls, h->obs_format, h->stack_k, s));
     if (post_step) CUDA_OK(cudaStreamWaitEvent(s, h->ev_score, 0));
     if (split) CUDA_OK(cudaStreamWaitEvent(s, h->ev_chain2, 0));
     return 0;
@@ -901,7 +994,7 @@ static int step_enqueue(mcr_handle h, const void* action, int32_t action_dtype, 
     }
     rc = pipeline(h, nullptr, nullptr, action, action_dtype, obs, reward, done, 1, stream); if (rc) return rc;
     if (flags & 1) {
-        AutoResetCfg ar{h->cfg.use_random_direction, h->cfg.direction_cw, (unsigned long long)h->cfg.seed};
+        AutoResetCfg ar{h->cfg.use_random_direction, h->cfg.direction_cw, (unsigned long long)h->cfg.seed, h->cfg.fresh_tracks};
         LAUNCH(launch_auto_reset(h->d, h->buf, h->cc, done, ar, stream));
         rc = pipeline(h, h->buf.reset_mask, nullptr, nullptr, MCR_F32, obs, nullptr, nullptr, 0, stream); if (rc) return rc;
     }
@@ -920,9 +1013,12 @@ extern "C" int mcr_step(mcr_handle h, const void* action, int32_t action_dtype, 
     if (action_dtype != MCR_F32 && action_dtype != MCR_F64) return fail(-1, "action dtype must be MCR_F32 or MCR_F64");
     if ((flags & 3) == 3) return fail(-1, "mcr_step: flags bit0 (same-step) and bit1 (next-step) auto reset are exclusive");
     cudaStream_t s = (cudaStream_t)stream;
+    const bool refill_now = h->cfg.fresh_tracks > 0 && (flags & 3) && ++h->steps_since_refill >= 4;
     if (!h->use_graphs || h->eager_steps < 2) {
         ++h->eager_steps;
-        return step_enqueue(h, action, action_dtype, obs, reward, done, flags, stream);
+        rc = step_enqueue(h, action, action_dtype, obs, reward, done, flags, stream);
+        if (!rc && refill_now) rc = kick_refill(h, nullptr);
+        return rc;
     }
     mcr_handle_t::StepGraph* g = nullptr;
     for (auto& c : h->graphs)
@@ -945,7 +1041,9 @@ extern "C" int mcr_step(mcr_handle h, const void* action, int32_t action_dtype, 
             // graphs are an optimisation of the launch path only: issue this and all later steps directly
             (void)cudaGetLastError();
             h->use_graphs = false;
-            return step_enqueue(h, action, action_dtype, obs, reward, done, flags, stream);
+            rc = step_enqueue(h, action, action_dtype, obs, reward, done, flags, stream);
+            if (!rc && refill_now) rc = kick_refill(h, nullptr);
+            return rc;
         }
         h->graphs.push_back(mcr_handle_t::StepGraph{action_dtype, flags, obs, reward, done, exec, per_step});
         g = &h->graphs.back();
@@ -955,5 +1053,6 @@ extern "C" int mcr_step(mcr_handle h, const void* action, int32_t action_dtype, 
         CUDA_OK(cudaMemcpyAsync(h->buf.action_stage, action, abytes, cudaMemcpyDeviceToDevice, s));
     CUDA_OK(cudaGraphLaunch(g->exec, s));
     h->launches += g->launches;
+    if (refill_now) { rc = kick_refill(h, nullptr); if (rc) return rc; }
     return 0;
 }

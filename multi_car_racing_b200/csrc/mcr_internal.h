@@ -46,12 +46,13 @@ enum {
     BUF_VISITED, BUF_TOUCHED, BUF_RESET_MASK, BUF_STATUS, BUF_SCRATCH, BUF_MANIFOLD, BUF_N_MANIFOLD, BUF_SCORE_SNAP, BUF_BACKWARD_SNAP, BUF_PENDING, BUF_ACTION_STAGE, BUF_CAMERA_VP, BUF_TIMELINE, BUF_ON_GRASS, BUF_PRT_PTS, BUF_PRT_META, BUF_PRT_HDR, BUF_SKID_START, BUF_SKID_META,
     BUF_TRK_T, BUF_TRK_Q, BUF_TRK_NODE, BUF_TRK_TILE, BUF_TRK_TILE_AABB, BUF_TRK_QUAD, BUF_TRK_QUAD_COL,
     BUF_TRK_QUAD_TILE, BUF_TRK_SLOT_POSE, BUF_TRK_CHUNK, BUF_TRK_QUAD64,
-    BUF_DL_HDR, BUF_DL_META, BUF_DL_EDGE, BUF_DL_OCT, BUF_FILL_CTR,
+    BUF_DL_HDR, BUF_DL_META, BUF_DL_EDGE, BUF_DL_OCT,
+    BUF_MT_STATE, BUF_TRK_CONSUMED, BUF_TRK_PRODUCED, BUF_TRK_LOCK, BUF_TG_SCRATCH,
     BUF_COUNT
 };
 
 // status words
-enum { ST_EVENT_OVERFLOW = 0, ST_NAN = 1, ST_RASTER_OVERFLOW = 2, ST_MANIFOLD_OVERFLOW = 3, STATUS_WORDS = 4 };
+enum { ST_EVENT_OVERFLOW = 0, ST_NAN = 1, ST_RASTER_OVERFLOW = 2, ST_MANIFOLD_OVERFLOW = 3, ST_TRACK_ERROR = 4, STATUS_WORDS = 8 };
 
 // palette indices (rgb values in raster.cu)
 enum {
@@ -107,7 +108,11 @@ struct DevBuffers {
     uint32_t* dl_meta;                   // [N][dl_cap][2] y0 | rows << 8 | palette << 16 | ne << 24 ; first span slot
     float* dl_edge;                      // [N][dl_cap][4][4] canonical edges (ax, ay, by, slope)
     float* dl_oct;                       // [N][A][4][4] edges 4..7 of car c's hull octagon
-    int32_t* fill_ctr;                   // [4] fill_kernel's frame queue heads, one per env class (cls)
+    // fresh track per episode on the device (mcr_config.fresh_tracks = R > 0): env e's own MT19937 stream and its ring of
+    // R + 1 pool slots e + B * j (trackgen.cuh)
+    uint32_t* mt_state;                  // [B][625] numpy RandomState of every env (624 words + position)
+    int32_t* trk_consumed; int32_t* trk_produced; int32_t* trk_lock;   // [B]
+    unsigned char* tg_scratch;           // [B][mcr_trackgen_scratch_bytes()] generator scratch (one element when fresh_tracks = 0)
 };
 
 struct Dims { int B, A, N, Tmax, Qmax, P; int particles; int dl_cap; };
@@ -162,7 +167,7 @@ int launch_physics_post(const Dims& d, const DevBuffers& b, const CarConst& cc, 
 int launch_presweep(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* noact,
                     const void* action, int action_dtype, int collisions, int with_sweep, void* stream);
 int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* obs,
-                  int backwards_flag, int use_ego_color, int cls, int obs_format, void* stream);
+                  int backwards_flag, int use_ego_color, int cls, int obs_format, int stack_k, void* stream);
 int launch_score(const Dims& d, const DevBuffers& b, const uint8_t* mask, const uint8_t* noact, double* reward, uint8_t* done,
                  int max_episode_steps, int cls, void* stream);
 // render(mode) for a vw x vh viewport (rgb_array: 600 x 400): camera_kernel + tiled render_kernel<true>
@@ -173,7 +178,8 @@ int launch_trackgen(const Dims& d, const DevBuffers& b, int n, uint32_t* mt_stat
                     int32_t* result, int max_attempts, void* stream);
 int launch_spawn(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask,
                  const int32_t* track_slot, const uint8_t* cw, const double* spawn_pose, void* stream);
-struct AutoResetCfg { int use_random_direction, direction_cw; unsigned long long seed; };
+struct AutoResetCfg { int use_random_direction, direction_cw; unsigned long long seed; int fresh; /* R: ring of R + 1 slots per env, 0 = shared pool */ };
+int launch_ring_refill(const Dims& d, const DevBuffers& b, int R, void* stream);
 // auto reset (reset_flags != NULL: respawn the flagged envs, write reset_mask) + carcontacts + pre in one launch
 int launch_head(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* reset_flags,
                 const AutoResetCfg& ar, const void* action, int action_dtype, int collisions, void* stream);

@@ -30,6 +30,7 @@
 //      frame) -- the only HBM traffic that scales with the frame count.
 #include "mcr_internal.h"
 #include <cuda_runtime.h>
+#include <cstring>
 #include <algorithm>
 #include <cstdlib>
 
@@ -81,6 +82,30 @@ const uint8_t (*mcr_host_palette())[4] {
         pal[i][3] = (uint8_t)((299 * pal[i][0] + 587 * pal[i][1] + 114 * pal[i][2] + 500) / 1000);
     }
     return pal;
+}
+
+// fp16 bits of c / 255 (fp32 division, round to nearest even) per palette colour: r | g << 16, b
+__constant__ uint32_t c_pal16[PAL_COUNT][2];
+
+static uint16_t host_f2h(float f) {          // IEEE fp32 -> fp16, round to nearest even (values in [0, 1])
+    uint32_t x; std::memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    int32_t e = (int32_t)((x >> 23) & 0xffu) - 127 + 15;
+    uint32_t m = x & 0x7fffffu;
+    if (e >= 31) return (uint16_t)(sign | 0x7c00u);
+    if (e <= 0) {
+        if (e < -10) return (uint16_t)sign;
+        m |= 0x800000u;
+        const int sh = 14 - e;
+        uint32_t h = m >> sh;
+        const uint32_t rem = m & ((1u << sh) - 1u), half = 1u << (sh - 1);
+        if (rem > half || (rem == half && (h & 1u))) ++h;
+        return (uint16_t)(sign | h);
+    }
+    uint32_t h = ((uint32_t)e << 10) | (m >> 13);
+    const uint32_t rem = m & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;
+    return (uint16_t)(sign | h);
 }
 
 // 3x5 digit font for the score label (documented deviation D3: the reference uses the
@@ -135,6 +160,7 @@ struct __align__(16) RasterSmem {
     signed char glyph[4];
     uint32_t pal32[32];      // r | g << 8 | b << 16
     uint32_t palY[32];       // luma (MCR_OBS_GRAY)
+    uint2 pal16[32];         // fp16 bits of r / 255, g / 255 (x) and b / 255 (y): MCR_OBS_RGB_CHW_F16
     uint32_t prmt_sel[256];  // coverage byte -> two PRMT selectors (low half: pixels 0-3, high half: pixels 4-7):
                              // byte i comes from operand b (4 + i) if its bit is set, else from a (i)
 };
@@ -572,7 +598,7 @@ __device__ __forceinline__ float4 canon_edge(int k, int nv, const float (&px)[MC
 // reference's RGB HWC layout).  Shared by the fused kernel (viewport modes) and fill_kernel (step path).
 template <bool VP>
 __device__ __forceinline__ void finish_frame(RasterSmem& S, int tid, uint32_t (&pix)[8], uint8_t* __restrict__ obs, int frame,
-                                             int obs_format, int ox, int oy, int VW, int VH) {
+                                             int obs_format, int ox, int oy, int VW, int VH, int stack_k = 1, int stack_step = 0) {
     const int my_seg = tid / SH, my_y = tid - SH * my_seg;
     // ---- score label glyphs (D3): observation rows 87..91 (= GL rows 8..4), cols 2..13 -------------
     if (VP) {
@@ -646,10 +672,47 @@ __device__ __forceinline__ void finish_frame(RasterSmem& S, int tid, uint32_t (&
         }
 #pragma unroll
         for (int v = 0; v < 6; ++v) dst[v] = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+    } else if (obs_format == MCR_OBS_RGB_CHW_F16) {
+        // planar fp16, value / 255: 32 pixels = 64 bytes = 4 x uint4 per plane
+        uint2 v[32];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            v[4 * k + 0] = S.pal16[pix[k] & 0xff]; v[4 * k + 1] = S.pal16[(pix[k] >> 8) & 0xff];
+            v[4 * k + 2] = S.pal16[(pix[k] >> 16) & 0xff]; v[4 * k + 3] = S.pal16[pix[k] >> 24];
+        }
+        uint16_t* plane0 = reinterpret_cast<uint16_t*>(obs) + (size_t)frame * (3 * SW * SH) + (size_t)out_row * SW + my_seg * 32;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            uint32_t o[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t a = c == 2 ? v[2 * k].y : v[2 * k].x, bq = c == 2 ? v[2 * k + 1].y : v[2 * k + 1].x;
+                o[k] = c == 1 ? __byte_perm(a, bq, 0x7632) : __byte_perm(a, bq, 0x5410);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(plane0 + (size_t)c * (SW * SH));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        }
     } else {
         // planar layouts: one byte per pixel and plane, 32 pixels = 2 x uint4 per plane
-        const int planes = obs_format == MCR_OBS_GRAY ? 1 : 3;
-        const size_t frame_bytes = (size_t)planes * SW * SH;
+        // MCR_OBS_GRAY_STACK: a ring of stack_k luma frames per agent; the frame of step s goes to slot s % stack_k and
+        // the first frame of an episode (s == 0) to every slot, like gym's FrameStack does on reset
+        const bool stack = obs_format == MCR_OBS_GRAY_STACK;
+        const int planes = (obs_format == MCR_OBS_GRAY || stack) ? 1 : 3;
+        const size_t frame_bytes = (size_t)(stack ? stack_k : planes) * SW * SH;
+        if (stack) {
+            uint32_t o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                o[k] = S.palY[pix[k] & 0xff] | (S.palY[(pix[k] >> 8) & 0xff] << 8) | (S.palY[(pix[k] >> 16) & 0xff] << 16) | (S.palY[pix[k] >> 24] << 24);
+            const int s0 = stack_step == 0 ? 0 : stack_step % stack_k, s1 = stack_step == 0 ? stack_k : s0 + 1;
+            for (int sl = s0; sl < s1; ++sl) {
+                uint4* dst = reinterpret_cast<uint4*>(obs + (size_t)frame * frame_bytes + (size_t)sl * (SW * SH) + (size_t)out_row * SW + my_seg * 32);
+                dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+            return;
+        }
         for (int c = 0; c < planes; ++c) {
             const uint32_t* tab = obs_format == MCR_OBS_GRAY ? S.palY : S.pal32;
             const int sh = 8 * c;
@@ -676,7 +739,7 @@ struct VpParams { int vw, vh, tiles_x; float hud_sx, hud_sy; const float* camera
 template <bool VP>
 __global__ void __launch_bounds__(RS_THREADS, 4)
 render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, uint8_t* __restrict__ obs,
-              int backwards_flag, int use_ego_color, int cls, int obs_format, VpParams vp) {
+              int backwards_flag, int use_ego_color, int cls, int obs_format, int stack_k, VpParams vp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
     PHASE_T0();
@@ -702,6 +765,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
         const int i = tid - 32;
         S.pal32[i] = (uint32_t)c_palette[i][0] | ((uint32_t)c_palette[i][1] << 8) | ((uint32_t)c_palette[i][2] << 16);
         S.palY[i] = (uint32_t)c_palette[i][3];
+        S.pal16[i] = make_uint2(c_pal16[i][0], c_pal16[i][1]);
     }
     if (tid < 256) S.prmt_sel[tid] = prmt_selector(tid);
     if (tid >= 128 && tid < 128 + SPAN_POOL / 32) S.startbits[tid - 128] = 0;   // (the row masks are zeroed per list, in flush_list)
@@ -810,7 +874,7 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
     }
     flush_list<VP>(S, tid, pix, lc, pc, true, ox, oy, VW);
 
-    finish_frame<VP>(S, tid, pix, obs, frame, obs_format, ox, oy, VW, VH);
+    finish_frame<VP>(S, tid, pix, obs, frame, obs_format, ox, oy, VW, VH, stack_k, VP ? 0 : b.steps[car]);
     if (!VP && cls != 2 && tid == 0) atomicMax(b.timeline + TL_RENDER_END, mcr_globaltimer());
     PHASE(8);
 #ifdef MCR_PHASE_CLOCKS
@@ -873,7 +937,6 @@ project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
     __shared__ uint8_t s_vis_chunk[PJ_WARPS][MAX_CHUNKS];
     cudaGridDependencySynchronize();               // programmatic dependent launch behind post_kernel (mcr_launch_pdl)
     tl_stamp(b.timeline, cls == 2 ? TL_RENDER2 : TL_RENDER);
-    if (blockIdx.x == 0 && threadIdx.x == 0) b.fill_ctr[cls] = 0;          // fill_kernel's frame queue
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int frame = (int)blockIdx.x * PJ_WARPS + warp;
     if (frame >= d.N) return;
@@ -941,14 +1004,10 @@ project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
 
     const int NC = V.c_hud + 9;
     int lc = 0, pc = 0;                            // entries / span slots so far (warp uniform)
-    for (int base = 0; base < NC; base += 32) {
-        const int i = base + lane;
-        float px[MCR_MAXV], py[MCR_MAXV];
-        int nv = 0, col = 0, y0 = 0, y1 = 0, aux = 0;
-        if (i < NC) nv = gen_candidate(i, V, M, cc, px, py, col, aux);
-        const bool valid = cand_rows<false>(nv, px, py, i < V.c_hud, hud_rows, 0.0f, 0.0f, (float)SW, (float)SH, 0, SH, y0, y1);
+    // ordered compaction of one pass of <= 32 candidates into the frame's display list
+    auto emit = [&](bool valid, int nv, const float (&px)[MCR_MAXV], const float (&py)[MCR_MAXV], int y0, int y1, int col, int aux) {
         const uint32_t bal = __ballot_sync(0xffffffffu, valid);
-        if (bal == 0u) continue;
+        if (bal == 0u) return;
         const int rows = valid ? y1 - y0 : 0;
         int rows_inc = rows;
 #pragma unroll
@@ -970,17 +1029,62 @@ project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
         }
         lc += __popc(bal);
         pc += __shfl_sync(0xffffffffu, rows_inc, 31);
+    };
+    auto generic_passes = [&](int i0, int i1) {    // playfield + checker squares, cars, HUD: gen_candidate's class dispatch
+        for (int base = i0; base < i1; base += 32) {
+            const int i = base + lane;
+            float px[MCR_MAXV], py[MCR_MAXV];
+            int nv = 0, col = 0, y0 = 0, y1 = 0, aux = 0;
+            if (i < i1) nv = gen_candidate(i, V, M, cc, px, py, col, aux);
+            const bool valid = cand_rows<false>(nv, px, py, i < V.c_hud, hud_rows, 0.0f, 0.0f, (float)SW, (float)SH, 0, SH, y0, y1);
+            emit(valid, nv, px, py, y0, y1, col, aux);
+        }
+    };
+    generic_passes(0, 1 + V.n_checker);
+    // ---- road_poly quads of the visible chunks (mcr:628-631): the bulk of a frame.  Four chunks per pass; the next
+    // pass's quads are loaded before this pass is processed, and the "tile colour was reset" flag (a dependent load)
+    // is only consumed when the entry is written.
+    {
+        const int n_road = V.n_road;
+        auto quad_of = [&](int r) -> int {         // r-th road candidate -> road_poly index, -1 = none
+            if (r >= n_road) return -1;
+            const int q = (int)vis_chunk[r >> 3] * MCR_QUAD_CHUNK + (r & (MCR_QUAD_CHUNK - 1));
+            return q < Q ? q : -1;
+        };
+        int q = quad_of(lane);
+        float4 qa = make_float4(0, 0, 0, 0), qb = qa; int tl = -1; int qc = 0;
+        if (q >= 0) {
+            qa = *(const float4*)(V.quad + (size_t)q * 8); qb = *(const float4*)(V.quad + (size_t)q * 8 + 4);
+            tl = V.quad_tile[q]; qc = V.quad_col[q];
+        }
+        for (int base = 0; base < n_road; base += 32) {
+            const int qn = quad_of(base + 32 + lane);
+            float4 na = make_float4(0, 0, 0, 0), nb = na; int ntl = -1, nqc = 0;
+            if (qn >= 0) {
+                na = *(const float4*)(V.quad + (size_t)qn * 8); nb = *(const float4*)(V.quad + (size_t)qn * 8 + 4);
+                ntl = V.quad_tile[qn]; nqc = V.quad_col[qn];
+            }
+            const uint8_t tch = (q >= 0 && tl >= 0) ? V.touched[tl] : (uint8_t)0;
+            float px[MCR_MAXV], py[MCR_MAXV];
+            int y0 = 0, y1 = 0;
+            xf_pt(M, qa.x, qa.y, px[0], py[0]); xf_pt(M, qa.z, qa.w, px[1], py[1]);
+            xf_pt(M, qb.x, qb.y, px[2], py[2]); xf_pt(M, qb.z, qb.w, px[3], py[3]);
+            const bool valid = cand_rows<false>(q >= 0 ? 4 : 0, px, py, true, hud_rows, 0.0f, 0.0f, (float)SW, (float)SH, 0, SH, y0, y1);
+            emit(valid, 4, px, py, y0, y1, tch ? PAL_ROAD0 : qc, 0);       // tile.color reset, mcr:102-104
+            q = qn; qa = na; qb = nb; tl = ntl; qc = nqc;
+        }
     }
+    generic_passes(V.c_cars, NC);
     if (lane == 0) *reinterpret_cast<int4*>(b.dl_hdr + (size_t)frame * 4) = make_int4(lc, pc, V.grass_full, 0);
 }
 
-// Persistent: gridDim.x = resident CTAs of the device; a CTA takes frame blockIdx.x first and then draws frames from
-// b.fill_ctr[cls] (reset by project_kernel) until none are left -- no CTA relaunch gap between frames, the tables are
-// built once, and the tail of the launch is balanced by whoever finishes first.
+// One CTA per agent-frame.  (Measured and dropped, profiles/README r02: persistent CTAs with a frame queue or a static
+// stride, register prefetch of the next frame's list, 5 CTAs per SM at 40 registers -- none beat this plain form.)
 __global__ void __launch_bounds__(RS_THREADS, FILL_CTAS)
-fill_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, uint8_t* __restrict__ obs, int cls, int obs_format) {
+fill_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, uint8_t* __restrict__ obs, int cls, int obs_format, int stack_k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
+    const int env = (int)blockIdx.x, agent = (int)blockIdx.y, frame = env * d.A + agent;
     const int tid = threadIdx.x;
     PHASE_T0();
     // tables that do not depend on project_kernel's output: built while it drains (programmatic dependent launch)
@@ -988,77 +1092,66 @@ fill_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, uint8_t* __r
         const int i = tid - 32;
         S.pal32[i] = (uint32_t)c_palette[i][0] | ((uint32_t)c_palette[i][1] << 8) | ((uint32_t)c_palette[i][2] << 16);
         S.palY[i] = (uint32_t)c_palette[i][3];
+        S.pal16[i] = make_uint2(c_pal16[i][0], c_pal16[i][1]);
     }
     if (tid < 256) S.prmt_sel[tid] = prmt_selector(tid);
     if (tid >= 128 && tid < 128 + SPAN_POOL / 32) S.startbits[tid - 128] = 0;
     cudaGridDependencySynchronize();
-    int frame = (int)blockIdx.x;
-    while (frame < d.N) {
-        int next = 0;
-        if (tid == 0) next = atomicAdd(b.fill_ctr + cls, 1) + (int)gridDim.x;      // needed at the end of this frame only
-        const int env = frame / d.A;
-        const bool skip = (mask && !mask[env]) || (cls && (cls == 2) != (b.n_manifold[env] > 0));
-        if (!skip) {
-            const uint2* __restrict__ meta = reinterpret_cast<const uint2*>(b.dl_meta) + (size_t)frame * d.dl_cap;
-            const float4* __restrict__ edge = reinterpret_cast<const float4*>(b.dl_edge) + (size_t)frame * d.dl_cap * 4;
-            const float4* __restrict__ oct = reinterpret_cast<const float4*>(b.dl_oct) + (size_t)frame * d.A * 4;
-            // header, metadata and the first edges are loaded side by side (no load waits for the entry count)
-            const int4 hdr = *reinterpret_cast<const int4*>(b.dl_hdr + (size_t)frame * 4);
-            uint2 mt = make_uint2(0u, 0u);
-            if (tid < LIST_CAP) mt = meta[min(tid, d.dl_cap - 1)];
-            const float4 ed0 = edge[min(tid, d.dl_cap * 4 - 1)], ed1 = edge[min(tid + RS_THREADS, d.dl_cap * 4 - 1)];
-            const int n = hdr.x;
-            if (tid == 64) score_glyphs(b.score_snap[frame], S.glyph);
-            uint32_t pix[8];               // this thread's 32 pixels (palette indices); glClear -> black
+    if (mask && !mask[env]) return;
+    if (cls && (cls == 2) != (b.n_manifold[env] > 0)) return;
+    const uint2* __restrict__ meta = reinterpret_cast<const uint2*>(b.dl_meta) + (size_t)frame * d.dl_cap;
+    const float4* __restrict__ edge = reinterpret_cast<const float4*>(b.dl_edge) + (size_t)frame * d.dl_cap * 4;
+    const float4* __restrict__ oct = reinterpret_cast<const float4*>(b.dl_oct) + (size_t)frame * d.A * 4;
+    // header, metadata and the first edges are loaded side by side (no load waits for the entry count)
+    const int4 hdr = *reinterpret_cast<const int4*>(b.dl_hdr + (size_t)frame * 4);
+    uint2 mt = make_uint2(0u, 0u);
+    if (tid < LIST_CAP) mt = meta[min(tid, d.dl_cap - 1)];
+    const float4 ed0 = edge[min(tid, d.dl_cap * 4 - 1)], ed1 = edge[min(tid + RS_THREADS, d.dl_cap * 4 - 1)];
+    const int n = hdr.x;
+    if (tid == 64) score_glyphs(b.score_snap[frame], S.glyph);
+    uint32_t pix[8];                       // this thread's 32 pixels (palette indices); glClear -> black
 #pragma unroll
-            for (int k = 0; k < 8; ++k) pix[k] = (hdr.z ? PAL_GRASS : PAL_BLACK) * 0x01010101u;
-            PHASE(0);
-            int e0 = 0;
-            uint32_t rs0 = 0u;             // first span slot of the chunk (the frame's first polygon starts at slot 0)
-            do {
-                // this chunk = the longest run of entries from e0 that fits the shared-memory list and the span pool
-                if (e0 > 0) {
-                    rs0 = meta[e0].y;
-                    if (tid < LIST_CAP) mt = meta[min(e0 + tid, d.dl_cap - 1)];
-                }
-                const bool fits = tid < LIST_CAP && e0 + tid < n && mt.y + ((mt.x >> 8) & 0xffu) - rs0 <= (uint32_t)SPAN_POOL;
-                const int cnt = __syncthreads_count(fits);     // slot offsets are monotone: the entries that fit are a prefix
-                if (tid < cnt) {
-                    const int y0 = (int)(mt.x & 0xffu), rows = (int)((mt.x >> 8) & 0xffu), ne = (int)(mt.x >> 24);
-                    const int first = (int)(mt.y - rs0);
-                    S.base[tid] = first - y0; S.ne[tid] = (uint8_t)ne; S.col[tid] = (uint8_t)((mt.x >> 16) & 0xffu);
-                    if (first & 31) atomicOr(&S.startbits[first >> 5], 1u << (first & 31));
-                    for (int k = (first + 31) >> 5; (k << 5) < first + rows; ++k) S.slot32_owner[k] = (uint8_t)tid;
-                    if (ne >= 8) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) S.edge[k][LIST_CAP + (ne - 8)] = oct[(size_t)(ne - 8) * 4 + k];
-                    }
-                    if (tid == cnt - 1) S.bc_rows = first + rows;
-                }
-                if (e0 == 0) {
-                    if (tid < cnt * 4) S.edge[tid & 3][tid >> 2] = ed0;
-                    if (tid + RS_THREADS < cnt * 4) S.edge[(tid + RS_THREADS) & 3][(tid + RS_THREADS) >> 2] = ed1;
-                    for (int i = tid + 2 * RS_THREADS; i < cnt * 4; i += RS_THREADS) S.edge[i & 3][i >> 2] = edge[i];
-                } else {
-                    for (int i = tid; i < cnt * 4; i += RS_THREADS) S.edge[i & 3][i >> 2] = edge[(size_t)e0 * 4 + i];
-                }
-                PHASE(3);
-                const bool last = e0 + cnt >= n;
-                flush_list<false>(S, tid, pix, cnt, -1, last, 0, 0, SW);
-                e0 += cnt;
-            } while (e0 < n);
-            finish_frame<false>(S, tid, pix, obs, frame, obs_format, 0, 0, SW, SH);
-#ifdef MCR_PHASE_CLOCKS
-            if (threadIdx.x == 0) atomicAdd(&g_phase_clk[15], 1ull);
-#endif
+    for (int k = 0; k < 8; ++k) pix[k] = (hdr.z ? PAL_GRASS : PAL_BLACK) * 0x01010101u;
+    PHASE(0);
+    int e0 = 0;
+    uint32_t rs0 = 0u;                     // first span slot of the chunk (the frame's first polygon starts at slot 0)
+    do {
+        // this chunk = the longest run of entries from e0 that fits the shared-memory list and the span pool
+        if (e0 > 0) {
+            rs0 = meta[e0].y;
+            if (tid < LIST_CAP) mt = meta[min(e0 + tid, d.dl_cap - 1)];
         }
-        __syncthreads();                   // every thread is done with this frame's list, spans and masks
-        if (tid == 0) S.first_bad = next;
-        if (!skip && tid >= 128 && tid < 128 + SPAN_POOL / 32) S.startbits[tid - 128] = 0;
-        __syncthreads();
-        frame = S.first_bad;
-    }
+        const bool fits = tid < LIST_CAP && e0 + tid < n && mt.y + ((mt.x >> 8) & 0xffu) - rs0 <= (uint32_t)SPAN_POOL;
+        const int cnt = __syncthreads_count(fits);         // slot offsets are monotone: the entries that fit are a prefix
+        if (tid < cnt) {
+            const int y0 = (int)(mt.x & 0xffu), rows = (int)((mt.x >> 8) & 0xffu), ne = (int)(mt.x >> 24);
+            const int first = (int)(mt.y - rs0);
+            S.base[tid] = first - y0; S.ne[tid] = (uint8_t)ne; S.col[tid] = (uint8_t)((mt.x >> 16) & 0xffu);
+            if (first & 31) atomicOr(&S.startbits[first >> 5], 1u << (first & 31));
+            for (int k = (first + 31) >> 5; (k << 5) < first + rows; ++k) S.slot32_owner[k] = (uint8_t)tid;
+            if (ne >= 8) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) S.edge[k][LIST_CAP + (ne - 8)] = oct[(size_t)(ne - 8) * 4 + k];
+            }
+            if (tid == cnt - 1) S.bc_rows = first + rows;
+        }
+        if (e0 == 0) {
+            if (tid < cnt * 4) S.edge[tid & 3][tid >> 2] = ed0;
+            if (tid + RS_THREADS < cnt * 4) S.edge[(tid + RS_THREADS) & 3][(tid + RS_THREADS) >> 2] = ed1;
+            for (int i = tid + 2 * RS_THREADS; i < cnt * 4; i += RS_THREADS) S.edge[i & 3][i >> 2] = edge[i];
+        } else {
+            for (int i = tid; i < cnt * 4; i += RS_THREADS) S.edge[i & 3][i >> 2] = edge[(size_t)e0 * 4 + i];
+        }
+        PHASE(3);
+        const bool last = e0 + cnt >= n;
+        flush_list<false>(S, tid, pix, cnt, -1, last, 0, 0, SW);
+        e0 += cnt;
+    } while (e0 < n);
+    finish_frame<false>(S, tid, pix, obs, frame, obs_format, 0, 0, SW, SH, stack_k, b.steps[frame]);
     if (cls != 2 && tid == 0) atomicMax(b.timeline + TL_RENDER_END, mcr_globaltimer());
+#ifdef MCR_PHASE_CLOCKS
+    if (threadIdx.x == 0) atomicAdd(&g_phase_clk[15], 1ull);
+#endif
 }
 
 
@@ -1211,6 +1304,13 @@ static bool configure_render() {
     if (!configured[dev]) {
         const size_t smem = sizeof(RasterSmem);
         if (cudaMemcpyToSymbol(c_palette, mcr_host_palette(), sizeof(uint8_t) * PAL_COUNT * 4) != cudaSuccess) return false;
+        uint32_t p16[PAL_COUNT][2];
+        for (int i = 0; i < PAL_COUNT; ++i) {
+            const uint8_t* c = mcr_host_palette()[i];
+            p16[i][0] = (uint32_t)host_f2h((float)c[0] / 255.0f) | ((uint32_t)host_f2h((float)c[1] / 255.0f) << 16);
+            p16[i][1] = (uint32_t)host_f2h((float)c[2] / 255.0f);
+        }
+        if (cudaMemcpyToSymbol(c_pal16, p16, sizeof(p16)) != cudaSuccess) return false;
         if (cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
         if (cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
         if (cudaFuncSetAttribute(fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
@@ -1220,27 +1320,18 @@ static bool configure_render() {
 }
 
 int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* obs,
-                  int backwards_flag, int use_ego_color, int cls, int obs_format, void* stream) {
+                  int backwards_flag, int use_ego_color, int cls, int obs_format, int stack_k, void* stream) {
     if (!configure_render()) return -1;
     static const bool fused = std::getenv("MCR_RENDER_FUSED") != nullptr;     // diagnostics: the single-kernel rasteriser (A/B)
     if (fused) {
         mcr_launch_pdl(render_kernel<false>, dim3(d.B, d.A), dim3(RS_THREADS), sizeof(RasterSmem), (cudaStream_t)stream,
-                       d, b, cc, mask, obs, backwards_flag, use_ego_color, cls, obs_format, VpParams{});
+                       d, b, cc, mask, obs, backwards_flag, use_ego_color, cls, obs_format, stack_k, VpParams{});
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
     }
     mcr_launch_pdl(project_kernel, dim3((d.N + PJ_WARPS - 1) / PJ_WARPS), dim3(PJ_THREADS), 0, (cudaStream_t)stream,
                    d, b, cc, mask, backwards_flag, use_ego_color, cls);
-    static int resident[64] = {};
-    int dev = 0; cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && resident[dev] == 0) {
-        int per_sm = 0, sms = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_kernel, RS_THREADS, sizeof(RasterSmem)) != cudaSuccess || per_sm < 1) per_sm = 1;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 1;
-        resident[dev] = per_sm * sms;
-    }
-    const int fill_grid = std::min(d.N, dev >= 0 && dev < 64 ? resident[dev] : d.N);
-    mcr_launch_pdl(fill_kernel, dim3(fill_grid), dim3(RS_THREADS), sizeof(RasterSmem), (cudaStream_t)stream,
-                   d, b, mask, obs, cls, obs_format);
+    mcr_launch_pdl(fill_kernel, dim3(d.B, d.A), dim3(RS_THREADS), sizeof(RasterSmem), (cudaStream_t)stream,
+                   d, b, mask, obs, cls, obs_format, stack_k);
     return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
 
@@ -1281,7 +1372,7 @@ int launch_render_viewport(const Dims& d, const DevBuffers& b, const CarConst& c
     vp.hud_sx = (float)((double)vw / 1000.0); vp.hud_sy = (float)((double)vh / 800.0); vp.camera = cam;
     const int tiles = vp.tiles_x * ((vh + SH - 1) / SH);
     render_kernel<true><<<dim3(d.N, tiles), RS_THREADS, sizeof(RasterSmem), (cudaStream_t)stream>>>(
-        d, b, cc, mask, out, backwards_flag, use_ego_color, 0, MCR_OBS_RGB_HWC, vp);
+        d, b, cc, mask, out, backwards_flag, use_ego_color, 0, MCR_OBS_RGB_HWC, 1, vp);
     return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
 

@@ -21,7 +21,10 @@ spawn_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask
     const int env = blockIdx.x;
     if (mask && !mask[env]) return;
     const int tid = threadIdx.x;
-    if (tid == 0) { b.env_track[env] = track_slot[env]; b.env_cw[env] = cw[env]; b.n_manifold[env] = 0; b.pending[env] = 0; }
+    if (tid == 0) {
+        b.env_track[env] = track_slot[env]; b.env_cw[env] = cw[env]; b.n_manifold[env] = 0; b.pending[env] = 0;
+        b.trk_consumed[env] = 0; b.trk_produced[env] = 0; b.trk_lock[env] = 0;     // track ring: this episode is ring index 0
+    }
     for (int i = tid; i < d.Tmax; i += SP_THREADS) {
         b.visited[(size_t)env * d.Tmax + i] = 0u;
         b.touched[(size_t)env * d.Tmax + i] = 0;

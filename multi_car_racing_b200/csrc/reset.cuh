@@ -4,6 +4,7 @@
 #pragma once
 #include "mcr_internal.h"
 #include <cuda_runtime.h>
+#include "trackgen.cuh"
 
 __device__ __forceinline__ void rot_set_d(float a, float& s, float& c) {
     double ds, dc;
@@ -81,6 +82,13 @@ __device__ __forceinline__ void auto_reset_draw(const Dims& d, const AutoResetCf
 __device__ __forceinline__ void auto_reset_env(const Dims& d, const DevBuffers& b, const CarConst& cc, const AutoResetCfg& cfg,
                                                int env, uint32_t episode, int tid, int nthreads) {
     ResetDraw r; auto_reset_draw(d, cfg, env, episode, r);
+    if (cfg.fresh) {
+        // a fresh track on the env's own RandomState stream (mcr:359-364): the next slot of the env's ring, generated
+        // ahead of time by the refill kernel (or right here if the episode was shorter than a track generation)
+        if (tid == 0) b.env_track[env] = ring_next_slot(d, b, env, cfg.fresh);
+        if (nthreads <= 32) __syncwarp(); else __syncthreads();
+        r.slot = ring_ld(b.env_track + env);
+    }
     if (tid == 0) { b.env_episode[env] = episode; b.env_track[env] = r.slot; b.env_cw[env] = (uint8_t)r.cw; b.n_manifold[env] = 0; }
     for (int i = tid; i < d.Tmax; i += nthreads) {
         b.visited[(size_t)env * d.Tmax + i] = 0u;

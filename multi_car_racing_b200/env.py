@@ -16,7 +16,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from .track import TrackGenerator, np_random, MAX_TILES_DEFAULT, MAX_QUADS_DEFAULT
+from .track import TrackGenerator, np_random, seed_key, MAX_TILES_DEFAULT, MAX_QUADS_DEFAULT
 
 STATE_W = 96
 STATE_H = 96
@@ -82,7 +82,14 @@ class BatchedMultiCarRacing:
     `device`, the pool/capacity knobs and `max_episode_steps` (the gym registration's TimeLimit,
     reference __init__.py:8) are additions.  `obs_format` selects what the rasteriser stores:
     'rgb' (B,A,96,96,3) as the reference returns it, 'gray' (B,A,96,96) ITU-R 601 luma, or
-    'rgb_chw' (B,A,3,96,96) -- the learner's first pre-processing stage fused into the store.
+    'rgb_chw' (B,A,3,96,96), 'gray_stack' (B,A,K,96,96) -- a ring of the last K = `frame_stack` luma
+    frames, see stacked_obs() -- or 'rgb_chw_f16' (B,A,3,96,96) float16 = value / 255: the learner's
+    first pre-processing stages fused into the store.
+    `fresh_tracks=R` (default 1 when auto_reset is on and no explicit `pool_tracks` is given): every
+    auto-reset episode runs on a NEW track generated on the GPU from the env's own RandomState stream,
+    as the reference's reset() does (:359-364) -- env e owns R + 1 pool slots, R tracks are kept ready
+    ahead of the running episode.  `fresh_tracks=0` with `pool_tracks=P` is the shared-pool mode: auto
+    reset draws one of P tracks generated at reset().
     `particles=True` keeps the cars' skid traces (gym car_dynamics Car.particles) so that
     render('rgb_array') draws them like the reference does in its non-state modes (:564).
     """
@@ -91,7 +98,7 @@ class BatchedMultiCarRacing:
                  backwards_flag=True, h_ratio=0.25, use_ego_color=False, device=None,
                  max_tiles=MAX_TILES_DEFAULT, max_quads=MAX_QUADS_DEFAULT, pool_tracks=None,
                  max_episode_steps=1000, auto_reset=True, seed=None, collisions=True, obs_format='rgb',
-                 particles=False):
+                 particles=False, frame_stack=4, fresh_tracks=None):
         torch = _torch()
         if not torch.cuda.is_available():
             raise _lib.McrError("multi_car_racing_b200 needs a CUDA device (B200, sm_100a); none is visible")
@@ -112,7 +119,15 @@ class BatchedMultiCarRacing:
             raise ValueError("auto_reset must be False, True, 'same_step' or 'next_step'")
         self.auto_reset = auto_reset if isinstance(auto_reset, str) else bool(auto_reset)
         self._step_flags = 2 if self.auto_reset == 'next_step' else (1 if self.auto_reset else 0)
-        self.pool_tracks = int(pool_tracks) if pool_tracks else self.batch_envs
+        if fresh_tracks is None:
+            fresh_tracks = 1 if (self.auto_reset and not pool_tracks) else 0
+        self.fresh_tracks = int(fresh_tracks)
+        if self.fresh_tracks:
+            if pool_tracks and int(pool_tracks) != self.batch_envs * (self.fresh_tracks + 1):
+                raise ValueError("fresh_tracks=R uses a ring of R + 1 slots per env: leave pool_tracks unset")
+            self.pool_tracks = self.batch_envs * (self.fresh_tracks + 1)
+        else:
+            self.pool_tracks = int(pool_tracks) if pool_tracks else self.batch_envs
         if self.pool_tracks < self.batch_envs:
             raise ValueError("pool_tracks must be >= batch_envs")
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
@@ -120,7 +135,7 @@ class BatchedMultiCarRacing:
                              int(bool(backwards_flag)), int(bool(use_ego_color)), self.max_episode_steps,
                              float(h_ratio), dev_index, int(bool(use_random_direction)),
                              int(direction == 'CW'), int(bool(collisions)), int(seed if seed is not None else 0) & (2 ** 64 - 1),
-                             int(bool(particles)))
+                             int(bool(particles)), self.fresh_tracks)
         self.particles = bool(particles)
         self._h = ctypes.c_void_p()
         _lib.check(self.L.mcr_create(ctypes.byref(cfg), ctypes.byref(self._h)), "mcr_create")
@@ -143,20 +158,27 @@ class BatchedMultiCarRacing:
                 raise ValueError("obs_format must be one of %s" % sorted(_lib.OBS_FORMATS))
             self.obs_format = obs_format
             _lib.check(self.L.mcr_set_obs_format(self._h, _lib.OBS_FORMATS[obs_format]), "mcr_set_obs_format")
-            self.obs_shape = {"rgb": (STATE_H, STATE_W, 3), "gray": (STATE_H, STATE_W), "rgb_chw": (3, STATE_H, STATE_W)}[obs_format]
-            assert int(np.prod(self.obs_shape)) == int(self.L.mcr_obs_bytes(self._h))
-            self.obs = torch.zeros((B, A) + self.obs_shape, dtype=torch.uint8, device=self.device)
+            self.frame_stack = int(frame_stack)
+            _lib.check(self.L.mcr_set_frame_stack(self._h, self.frame_stack), "mcr_set_frame_stack")
+            self.obs_shape = {"rgb": (STATE_H, STATE_W, 3), "gray": (STATE_H, STATE_W), "rgb_chw": (3, STATE_H, STATE_W),
+                              "gray_stack": (self.frame_stack, STATE_H, STATE_W), "rgb_chw_f16": (3, STATE_H, STATE_W)}[obs_format]
+            self.obs_dtype = torch.float16 if obs_format == "rgb_chw_f16" else torch.uint8
+            assert int(np.prod(self.obs_shape)) * (2 if self.obs_dtype == torch.float16 else 1) == int(self.L.mcr_obs_bytes(self._h))
+            self.obs = torch.zeros((B, A) + self.obs_shape, dtype=self.obs_dtype, device=self.device)
             self.reward_out = torch.zeros((B, A), dtype=torch.float64, device=self.device)
             self.done_out = torch.zeros((B,), dtype=torch.uint8, device=self.device)
             self._slot = torch.zeros((B,), dtype=torch.int32, device=self.device)
             self._cw = torch.zeros((B,), dtype=torch.uint8, device=self.device)
             self._pose = torch.zeros((B, A, 3), dtype=torch.float64, device=self.device)
         self._gen = TrackGenerator(max_tiles, max_quads)
-        self.tracks = [None] * self.pool_tracks          # HostTrack per pool slot
+        self.tracks = _TrackTable(self)                  # HostTrack / DeviceTrack per pool slot
         self.episode_direction = [direction] * self.batch_envs
         self.car_order = [None] * self.batch_envs
         self.action_space = _make_box(np.array([-1, 0, 0]), np.array([+1, +1, +1]), dtype=np.float32)
-        self.observation_space = _make_box(0, 255, shape=self.obs_shape, dtype=np.uint8)
+        if self.obs_dtype == torch.float16:
+            self.observation_space = _make_box(0.0, 1.0, shape=self.obs_shape, dtype=np.float16)
+        else:
+            self.observation_space = _make_box(0, 255, shape=self.obs_shape, dtype=np.uint8)
         self.seed(seed)
 
     # ---- plumbing ---------------------------------------------------------------------------
@@ -172,6 +194,12 @@ class BatchedMultiCarRacing:
             pass
 
     def close(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value and self.status().any():
+                import warnings
+                warnings.warn("multi_car_racing_b200: device status words set at close(): %s" % self.status().tolist())
+        except Exception:
+            pass
         self.__del__()
 
     @property
@@ -179,13 +207,84 @@ class BatchedMultiCarRacing:
         return int(self.L.mcr_launch_count(self._h))
 
     def seed(self, seed=None):
-        """Per-env RandomState streams: env i is seeded like the reference's env.seed(seed + i)."""
-        self.np_randoms, seeds = [], []
-        for i in range(self.batch_envs):
-            rng, s = np_random(None if seed is None else int(seed) + i)
-            self.np_randoms.append(rng)
-            seeds.append(s)
+        """Per-env RandomState streams: env i is seeded like the reference's env.seed(seed + i)
+        (gym seeding.np_random: sha512 of the seed -> init_by_array).  The MT19937 states are built in one
+        native call; `np_randoms` materialises numpy RandomState objects from them on first use."""
+        B = self.batch_envs
+        keys = np.zeros((B, 2), np.uint32)
+        lens = np.empty((B,), np.int32)
+        seeds = []
+        for i in range(B):
+            k, sd = seed_key(None if seed is None else int(seed) + i)
+            keys[i, :len(k)] = k
+            lens[i] = len(k)
+            seeds.append(sd)
+        self._mt_host = np.empty((B, 625), np.uint32)
+        _lib.check(self.L.mcr_mt_seed_batch(self._mt_host.ctypes.data, keys.ctypes.data, lens.ctypes.data, B, 2), "mcr_mt_seed_batch")
+        self._np_randoms = None
+        self._mt_on_device = False       # True: buffers['mt_state'] is ahead of the host copies
         return seeds
+
+    @property
+    def np_randoms(self):
+        """numpy RandomState of every env (the reference's env.np_random).  After a device-side generation the
+        streams live on the GPU (buffers['mt_state'], R tracks ahead when fresh_tracks=R); they are read back here."""
+        if self._mt_on_device:
+            self._mt_host = self.buffers["mt_state"].cpu().numpy().view(np.uint32).copy()
+            self._mt_on_device = False
+            self._np_randoms = None
+        if self._np_randoms is None:
+            self._np_randoms = []
+            for row in self._mt_host:
+                rng = np.random.RandomState()
+                rng.set_state(("MT19937", row[:624].copy(), int(row[624]), 0, 0.0))
+                self._np_randoms.append(rng)
+        return self._np_randoms
+
+    @np_randoms.setter
+    def np_randoms(self, rngs):
+        self._np_randoms = list(rngs)
+        self._mt_on_device = False
+
+    def _mt_states(self):
+        """(B, 625) uint32 MT19937 states of the envs' streams as they stand on the host."""
+        if self._np_randoms is not None:
+            for i, rng in enumerate(self._np_randoms):
+                st = rng.get_state()
+                self._mt_host[i, :624] = st[1]
+                self._mt_host[i, 624] = st[2]
+        return self._mt_host
+
+    def _reset_draws(self, car_orders=None, directions=None):
+        """reset()'s draws from the GLOBAL numpy RNG for every env in turn (reference :351-357), in one native
+        call on np.random's MT19937 state (same stream positions as B reference resets)."""
+        B, A = self.batch_envs, self.num_agents
+        cws = np.empty((B,), np.uint8)
+        orders = np.empty((B, A), np.int32)
+        if car_orders is None and (directions is None or not self.use_random_direction):
+            st = np.random.get_state()
+            mt = np.empty(625, np.uint32)
+            mt[:624] = st[1]; mt[624] = st[2]
+            rand_dir = self.use_random_direction and directions is None
+            _lib.check(self.L.mcr_reset_draws(mt.ctypes.data, B, A, int(rand_dir), int(self.direction == 'CW'),
+                                              cws.ctypes.data, orders.ctypes.data), "mcr_reset_draws")
+            np.random.set_state((st[0], mt[:624].copy(), int(mt[624]), st[3], st[4]))
+            if directions is not None:
+                cws[:] = [d == 'CW' for d in directions]
+            elif not self.use_random_direction:
+                cws[:] = [d == 'CW' for d in self.episode_direction]
+        else:
+            for e in range(B):                      # mixed injection: the reference's own calls, env by env
+                if directions is not None:
+                    d = directions[e]
+                elif self.use_random_direction:
+                    d = str(np.random.choice(['CW', 'CCW']))
+                else:
+                    d = self.episode_direction[e]
+                cws[e] = d == 'CW'
+                orders[e] = np.asarray(car_orders[e]) if car_orders is not None else \
+                    np.random.choice([i for i in range(A)], size=A, replace=False)
+        return cws, orders
 
     def load_track(self, slot, track):
         """Upload a HostTrack (or any object with nodes/quads/quad_rgb/quad_tile) into a pool slot."""
@@ -206,55 +305,80 @@ class BatchedMultiCarRacing:
         `tracks` / `car_orders` / `directions` inject host-made values (parity tests).
         device_tracks=True generates all tracks on the GPU (mcr_tracks_generate_device, one thread
         per track on the env's own MT19937 stream) instead of one by one on the host -- same draws,
-        same arithmetic, CUDA libm instead of glibc (coordinates agree to ~1e-12, not bit for bit)."""
+        same arithmetic, CUDA libm instead of glibc (coordinates agree to ~1e-12, not bit for bit);
+        nothing in that path loops over envs in Python."""
         torch = _torch()
-        B, A = self.batch_envs, self.num_agents
-        poses = np.empty((B, A, 3), np.float64)
-        cws = np.empty((B,), np.uint8)
-        orders = np.empty((B, A), np.int64)
+        B, A, P = self.batch_envs, self.num_agents, self.pool_tracks
         if device_tracks and tracks is not None:
             raise ValueError("device_tracks=True generates the tracks itself; do not pass `tracks`")
-        for e in range(B):
-            if directions is not None:
-                self.episode_direction[e] = directions[e]
-            elif self.use_random_direction:
-                self.episode_direction[e] = str(np.random.choice(['CW', 'CCW']))
-            if car_orders is not None:
-                order = np.asarray(car_orders[e])
-            else:
-                order = np.random.choice([i for i in range(A)], size=A, replace=False)
-            self.car_order[e] = {i: order[i] for i in range(A)}
-            orders[e] = order
-            cws[e] = self.episode_direction[e] == 'CW'
-            if not device_tracks:
-                tr = tracks[e] if tracks is not None else self._gen.generate(self.np_randoms[e], self.verbose)
-                self.load_track(e, tr)
-                poses[e] = self._gen.spawn_poses(tr.nodes, order, cws[e])
-        if device_tracks:
-            # every pool slot in rounds of B: slot s draws from env (s % B)'s stream, like the host path
-            for s0 in range(0, self.pool_tracks, B):
-                slots = list(range(s0, min(s0 + B, self.pool_tracks)))
-                if s0 == 0 or any(self.tracks[s] is None for s in slots):
-                    self.generate_tracks_device(slots, [self.np_randoms[s % B] for s in slots])
+        cws, orders = self._reset_draws(car_orders, directions)
+        self.episode_direction = np.where(cws != 0, 'CW', 'CCW')
+        self.car_order = orders
+        ring = self.fresh_tracks > 0
+        poses = None
+        if device_tracks and (ring or P == B):
+            self._generate_episode0_tracks()
+        elif device_tracks:
+            # shared pool larger than the batch: every slot in rounds of B, slot s draws from env (s % B)'s stream
+            rngs = self.np_randoms
+            for s0 in range(0, P, B):
+                slots = list(range(s0, min(s0 + B, P)))
+                if s0 == 0 or any(self.tracks.host.get(s) is None for s in slots):
+                    self.generate_tracks_device(slots, [rngs[s % B] for s in slots])
         else:
-            # extra pool slots (device-side auto reset draws from the whole pool)
-            for s in range(B, self.pool_tracks):
-                if self.tracks[s] is None:
-                    self.load_track(s, self._gen.generate(self.np_randoms[s % B], 0))
+            rngs = self.np_randoms
+            poses = np.empty((B, A, 3), np.float64)
+            for e in range(B):
+                tr = tracks[e] if tracks is not None else self._gen.generate(rngs[e], self.verbose)
+                self.load_track(e, tr)
+                poses[e] = self._gen.spawn_poses(tr.nodes, orders[e], cws[e])
+            if not ring:
+                for s in range(B, P):        # extra pool slots (the shared-pool auto reset draws from the whole pool)
+                    if self.tracks.host.get(s) is None:
+                        self.load_track(s, self._gen.generate(rngs[s % B], 0))
         with torch.cuda.device(self.device):
+            if ring and not (device_tracks and self._mt_on_device):
+                # the env streams continue on the device: the refill kernel generates the next episodes' tracks from them
+                self.buffers["mt_state"].copy_(torch.from_numpy(self._mt_states().view(np.int32)))
+                self._mt_on_device = True
+                self._np_randoms = None
             self._slot.copy_(torch.arange(B, dtype=torch.int32))
             self._cw.copy_(torch.from_numpy(cws))
-            if device_tracks:
+            if poses is None:
                 # spawn grid poses were evaluated per slot / direction / grid position by the generator
                 sp = self.buffers["trk_slot_pose"]                     # (P, 2, A, 3)
                 e_idx = torch.arange(B, device=self.device).view(B, 1).expand(B, A)
                 cw_idx = torch.from_numpy(cws.astype(np.int64)).to(self.device).view(B, 1).expand(B, A)
-                self._pose.copy_(sp[e_idx, cw_idx, torch.from_numpy(orders).to(self.device)])
+                self._pose.copy_(sp[e_idx, cw_idx, torch.from_numpy(orders.astype(np.int64)).to(self.device)])
             else:
                 self._pose.copy_(torch.from_numpy(poses))
             _lib.check(self.L.mcr_reset(self._h, None, self._slot.data_ptr(), self._cw.data_ptr(),
                                         self._pose.data_ptr(), self.obs.data_ptr(), self._stream()), "mcr_reset")
         return self.obs
+
+    def _generate_episode0_tracks(self):
+        """All B first-episode tracks in one launch: env e's stream (uploaded to buffers['mt_state']) -> pool slot e."""
+        torch = _torch()
+        B = self.batch_envs
+        stride = int(self.L.mcr_trackgen_scratch_bytes())
+        with torch.cuda.device(self.device):
+            self.buffers["mt_state"].copy_(torch.from_numpy(self._mt_states().view(np.int32)))
+            scratch = self.buffers["tg_scratch"] if self.fresh_tracks else torch.empty((B, stride), dtype=torch.uint8, device=self.device)
+            d_res = torch.zeros((B, 4), dtype=torch.int32, device=self.device)
+            _lib.check(self.L.mcr_tracks_generate_device(self._h, B, self.buffers["mt_state"].data_ptr(), None, scratch.data_ptr(),
+                                                         d_res.data_ptr(), self._stream()), "mcr_tracks_generate_device")
+            res = d_res.cpu().numpy()
+        if (res[:, 0] <= 0).any():
+            bad = int(np.argmax(res[:, 0] <= 0))
+            raise _lib.McrError("device track generation failed for env %d: code %d (-3: more tiles than max_tiles, "
+                                "-4: more quads than max_quads, -5: no valid track in 64 attempts)" % (bad, res[bad, 0]))
+        self._mt_on_device = True
+        self._np_randoms = None
+        self.tracks.host.clear()
+        if self.verbose == 1:
+            for i in range(B):
+                print("Track generation: %i..%i -> %i-tiles track" % (res[i, 2], res[i, 3], res[i, 3] - res[i, 2]))
+        return res
 
     def generate_tracks_device(self, slots, rngs):
         """Generate len(slots) tracks on the GPU into the given pool slots, each on its own numpy
@@ -320,6 +444,18 @@ class BatchedMultiCarRacing:
                                        self.done_out.data_ptr(), self._step_flags, self._stream()), "mcr_step")
         return self.obs, self.reward_out, self.done_out, {}
 
+    def stacked_obs(self):
+        """obs_format='gray_stack': the ring (B, A, K, 96, 96) gathered oldest -> newest.  The store writes the
+        frame of an episode's step s into slot s % K (every slot on the first frame of an episode), so slot
+        (s - K + 1 + j) % K holds the j-th oldest frame."""
+        torch = _torch()
+        if self.obs_format != "gray_stack":
+            raise ValueError("stacked_obs() needs obs_format='gray_stack'")
+        B, A, K = self.batch_envs, self.num_agents, self.frame_stack
+        s = self.buffers["steps"].view(B, A).long()
+        idx = (s.unsqueeze(-1) - (K - 1) + torch.arange(K, device=self.device).view(1, 1, K)) % K
+        return torch.gather(self.obs, 2, idx.view(B, A, K, 1, 1).expand(B, A, K, STATE_H, STATE_W))
+
     def step_host(self, action):
         """The reference-facing call with HOST buffers: `action` is a (B, A, 3) float32/float64
         numpy array (ideally a view of pinned memory, see host_buffers()); returns numpy views
@@ -359,28 +495,35 @@ class BatchedMultiCarRacing:
         if getattr(self, "_pipe", None) is None:
             with torch.cuda.device(self.device):
                 self._pipe = [dict(
-                    obs=torch.zeros((B, A) + self.obs_shape, dtype=torch.uint8, device=self.device),
+                    obs=torch.zeros((B, A) + self.obs_shape, dtype=self.obs_dtype, device=self.device),
                     reward=torch.zeros((B, A), dtype=torch.float64, device=self.device),
                     done=torch.zeros((B,), dtype=torch.uint8, device=self.device),
-                    h_obs=torch.zeros((B, A) + self.obs_shape, dtype=torch.uint8).pin_memory(),
+                    h_obs=torch.zeros((B, A) + self.obs_shape, dtype=self.obs_dtype).pin_memory(),
                     h_reward=torch.zeros((B, A), dtype=torch.float64).pin_memory(),
                     h_done=torch.zeros((B,), dtype=torch.uint8).pin_memory(),
+                    # per-slot action staging: the host buffer of a slot is only rewritten after the step that
+                    # read it was retired by step_host_wait(), and the device copy is this slot's own
+                    h_action=torch.zeros((B, A, 3), dtype=torch.float32).pin_memory(),
+                    h_action64=torch.zeros((B, A, 3), dtype=torch.float64).pin_memory(),
+                    d_action=torch.zeros((B, A, 3), dtype=torch.float32, device=self.device),
+                    d_action64=torch.zeros((B, A, 3), dtype=torch.float64, device=self.device),
                     computed=torch.cuda.Event(), copied=torch.cuda.Event(), busy=False) for _ in range(2)]
                 self._pipe_copy_stream = torch.cuda.Stream(device=self.device)
             self._pipe_issue, self._pipe_retire = 0, 0
         if self._pipe_issue - self._pipe_retire >= 2:
             raise RuntimeError("two steps are already in flight: call step_host_wait() first")
-        hb = self.host_buffers()
         a = np.reshape(action, (B, A, 3))
         p = self._pipe[self._pipe_issue & 1]
         with torch.cuda.device(self.device):
             cur = torch.cuda.current_stream(self.device)
+            # slot p was last used two calls ago and has been retired since (the in-flight check above), so its
+            # host -> device action copy has completed: the pinned buffer can be rewritten
             if a.dtype == np.float64:
-                hb["action64"].numpy()[...] = a
-                src, dev_a, dt = hb["action64"], self._dev_action64, _lib.MCR_F64
+                p["h_action64"].numpy()[...] = a
+                src, dev_a, dt = p["h_action64"], p["d_action64"], _lib.MCR_F64
             else:
-                hb["action"].numpy()[...] = a
-                src, dev_a, dt = hb["action"], self._dev_action, _lib.MCR_F32
+                p["h_action"].numpy()[...] = a
+                src, dev_a, dt = p["h_action"], p["d_action"], _lib.MCR_F32
             if p["busy"]:
                 cur.wait_event(p["copied"])            # the buffers' previous results have reached the host
             dev_a.copy_(src, non_blocking=True)
@@ -415,7 +558,7 @@ class BatchedMultiCarRacing:
             self._host = dict(
                 action=torch.zeros((B, A, 3), dtype=torch.float32).pin_memory(),
                 action64=torch.zeros((B, A, 3), dtype=torch.float64).pin_memory(),
-                obs=torch.zeros((B, A) + self.obs_shape, dtype=torch.uint8).pin_memory(),
+                obs=torch.zeros((B, A) + self.obs_shape, dtype=self.obs_dtype).pin_memory(),
                 reward=torch.zeros((B, A), dtype=torch.float64).pin_memory(),
                 done=torch.zeros((B,), dtype=torch.uint8).pin_memory())
             # the library's own action staging buffer (what its CUDA graph reads): copying the host
@@ -488,8 +631,20 @@ class BatchedMultiCarRacing:
         b = self.buffers["body"]                      # (5, 10, N)
         return b.permute(2, 0, 1).reshape(self.batch_envs, self.num_agents, 5, 10)
 
+    STATUS_NAMES = ("contact event overflow", "NaN in a body state", "rasteriser overflow", "car-car manifold overflow")
+
     def status(self):
+        """Sticky device status words (events dropped, NaN, rasteriser overflow, manifold overflow): all zero
+        means every contact / manifold / polygon of every step so far was processed."""
         return self.buffers["status"].cpu().numpy()
+
+    def check_status(self):
+        """Raise if a kernel ever had to drop work (results then differ from the reference).  One small
+        device -> host read: call it at episode or logging boundaries, not per step.  close() warns."""
+        st = self.status()
+        if st.any():
+            raise _lib.McrError("device status words are set: " + ", ".join(
+                "%s (%d)" % (n, v) for n, v in zip(self.STATUS_NAMES, st.tolist()) if v))
 
     def mass(self):
         out = np.empty(12, np.float32)
@@ -502,12 +657,43 @@ class BatchedMultiCarRacing:
         return out[:2 * n].reshape(n, 2).copy()
 
 
+class _TrackTable:
+    """venv.tracks[slot]: the HostTrack loaded into a pool slot, or a DeviceTrack view of whatever the GPU generated
+    there (read back on demand -- device-side resets never touch the host)."""
+
+    def __init__(self, venv):
+        self._venv, self.host = venv, {}
+
+    def __getitem__(self, slot):
+        slot = int(slot)
+        t = self.host.get(slot)
+        v = self._venv
+        if t is not None and v.fresh_tracks and int(v.buffers["trk_consumed"][slot % v.batch_envs].item()) > 0:
+            t = None                     # the env's ring has moved on: the slot may hold a device-generated track by now
+        return t if t is not None else DeviceTrack(v, slot)
+
+    def __setitem__(self, slot, track):
+        self.host[int(slot)] = track
+
+    def __len__(self):
+        return self._venv.pool_tracks
+
+    def __iter__(self):
+        return (self[s] for s in range(len(self)))
+
+
 class DeviceTrack:
     """A track generated on the GPU: nodes (alpha, beta, x, y) float64 on the host; the road_poly
     quads are read back from the pool on demand (fp32 -- what GL and Box2D see of them)."""
 
-    def __init__(self, venv, slot, nodes, idx_range, attempts):
-        self._venv, self.slot, self.nodes, self.idx_range, self.attempts = venv, slot, nodes, idx_range, attempts
+    def __init__(self, venv, slot, nodes=None, idx_range=None, attempts=None):
+        self._venv, self.slot, self.idx_range, self.attempts = venv, slot, idx_range, attempts
+        if nodes is None:
+            # from the pool: (beta, x, y) per tile; alpha (only used while generating) is not kept there
+            T = int(venv.buffers["trk_T"][slot].item())
+            bxy = venv.buffers["trk_node"][slot, :T].cpu().numpy()
+            nodes = np.concatenate([np.full((T, 1), np.nan), bxy], axis=1)
+        self.nodes = nodes
 
     @property
     def T(self):
@@ -723,10 +909,11 @@ class MultiCarRacingVecEnv:
         A = self.num_agents
         self.single_action_space = _make_box(np.tile(np.array([-1, 0, 0], np.float32), (A, 1)),
                                              np.tile(np.array([+1, +1, +1], np.float32), (A, 1)), dtype=np.float32)
-        self.single_observation_space = _make_box(0, 255, shape=(A,) + self.venv.obs_shape, dtype=np.uint8)
+        hi, odt = (1.0, np.float16) if self.venv.obs_format == "rgb_chw_f16" else (255, np.uint8)
+        self.single_observation_space = _make_box(0, hi, shape=(A,) + self.venv.obs_shape, dtype=odt)
         self.action_space = _make_box(np.tile(np.array([-1, 0, 0], np.float32), (self.num_envs, A, 1)),
                                       np.tile(np.array([+1, +1, +1], np.float32), (self.num_envs, A, 1)), dtype=np.float32)
-        self.observation_space = _make_box(0, 255, shape=(self.num_envs, A) + self.venv.obs_shape, dtype=np.uint8)
+        self.observation_space = _make_box(0, hi, shape=(self.num_envs, A) + self.venv.obs_shape, dtype=odt)
         self.metadata = {'render.modes': ['rgb_array', 'state_pixels'], 'video.frames_per_second': FPS,
                          'autoreset_mode': 'next_step'}
         self._pending_actions = None
@@ -738,7 +925,10 @@ class MultiCarRacingVecEnv:
 
     def step(self, actions):
         obs, reward, done, _ = self.venv.step(actions)
-        return obs, reward, (done & 1).bool(), (done & 2).bool(), {}
+        terminated = (done & 1).bool()
+        # gym's TimeLimit sets TimeLimit.truncated = not done: an env that terminated on its last allowed
+        # step is terminated, not truncated
+        return obs, reward, terminated, (done & 2).bool() & ~terminated, {}
 
     def step_async(self, actions):
         self._pending_actions = actions

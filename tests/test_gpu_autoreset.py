@@ -77,7 +77,7 @@ def test_auto_reset_matches_oracle(oracle, mcr, mode):
         g, o = gpu_state(venv), oracle_state(worlds)
         for k in ("bodies", "wheels", "joints", "reward", "counts"):
             assert np.array_equal(g[k], o[k]), "%s, step %d" % (k, s)
-    assert venv.status().tolist() == [0, 0, 0, 0]
+    assert not venv.status().any()
 
 
 def test_out_of_field_done_then_next_step_reset(mcr):
@@ -193,3 +193,99 @@ def test_pipelined_host_api_matches_synchronous(mcr):
     assert len(got) == 50
     for s, (w, g) in enumerate(zip(want, got)):
         assert all(np.array_equal(x, y) for x, y in zip(w, g)), "step %d" % s
+
+
+def test_pipelined_host_api_with_a_busy_stream(mcr):
+    """two step_host_async() calls issued while the GPU is still busy must not share one pinned
+    action buffer (step k would run with step k+1's action).  A long kernel is queued first so that both
+    host -> device action copies are still pending when the second call writes its action."""
+    import torch
+    np.random.seed(9)
+    a = mcr.BatchedMultiCarRacing(4, num_agents=2, seed=5, max_episode_steps=0, auto_reset=False)
+    np.random.seed(9)
+    b = mcr.BatchedMultiCarRacing(4, num_agents=2, seed=5, max_episode_steps=0, auto_reset=False)
+    np.random.seed(3); a.reset()
+    np.random.seed(3); b.reset()
+    tape = action_tape(33, 6, 4, 2)
+    want = []
+    for s in range(6):
+        o, r, d, _ = a.step_host(tape[s])
+        want.append((o.copy(), r.copy(), d.copy()))
+    got = []
+    for s in range(0, 6, 2):
+        torch.cuda._sleep(200_000_000)                 # ~0.1 s of GPU time in front of the two steps
+        b.step_host_async(tape[s])
+        b.step_host_async(tape[s + 1])
+        for _ in range(2):
+            o, r, d, _ = b.step_host_wait()
+            got.append((o.copy(), r.copy(), d.copy()))
+    for s, (w, g) in enumerate(zip(want, got)):
+        assert all(np.array_equal(x, y) for x, y in zip(w, g)), "step %d" % s
+
+
+def test_vecenv_truncated_excludes_terminated(mcr):
+    """gym's TimeLimit sets truncated = not done -- an env that terminates on its last allowed step
+    is terminated only."""
+    import torch
+    np.random.seed(1)
+    v = mcr.MultiCarRacingVecEnv(4, num_agents=2, seed=3, max_episode_steps=5)
+    v.reset()
+    act = torch.zeros((4, 2, 3), device=v.venv.device)
+    for s in range(5):
+        obs, rew, term, trunc, _ = v.step(act)
+    assert trunc.all() and not term.any()
+    # force a termination on the step that also hits the limit: place env 0's first car outside the playfield
+    v.step(act)                                           # next-step auto reset: the new episodes start here
+    for s in range(4):
+        v.step(act)
+    body = v.venv.buffers["body"]
+    body[0, 6, 0] = 400.0                                 # hull origin x of car 0 (env 0): |x| > PLAYFIELD
+    body[0, 0, 0] = 400.0
+    obs, rew, term, trunc, _ = v.step(act)
+    assert bool(term[0]) and not bool(trunc[0]), "terminated on the limit step must not also be truncated"
+    assert trunc[1:].all() and not term[1:].any()
+
+
+@pytest.mark.parametrize("mode,device_tracks", [("next_step", True), ("same_step", True), ("next_step", False)])
+def test_fresh_tracks_follow_each_envs_own_stream(mcr, mode, device_tracks):
+    """SURVEY 8f #1 / reference :359-364: every reset() generates a NEW track on the env's own np_random stream.
+    Device-side auto reset must do the same: the k-th episode of env i runs on the k-th successful track of the
+    host generator seeded like env.seed(SEED + i) -- T, Q, border pattern and palette identical, float64 nodes
+    within 1e-9 (CUDA libm vs glibc), whatever the timing (episodes of 4 steps are far shorter than a track
+    generation, so the in-place generation path is exercised too)."""
+    import torch
+    from multi_car_racing_b200.track import TrackGenerator, np_random
+    B, A, LIMIT, SEED, EPISODES = 8, 2, 4, 321, 4
+    venv = mcr.BatchedMultiCarRacing(B, num_agents=A, auto_reset=mode, max_episode_steps=LIMIT, seed=SEED)
+    assert venv.fresh_tracks == 1 and venv.pool_tracks == 2 * B
+    np.random.seed(0)
+    venv.reset(device_tracks=device_tracks)
+    gen = TrackGenerator()
+    host = []
+    for i in range(B):
+        rng, _ = np_random(SEED + i)
+        host.append([gen.generate(rng) for _ in range(EPISODES)])
+
+    def check(ep):
+        slots = venv.buffers["env_track"].cpu().numpy()
+        buf = {k: venv.buffers[k].cpu().numpy() for k in ("trk_T", "trk_Q", "trk_quad_tile", "trk_quad_col", "trk_node", "trk_quad")}
+        for e in range(B):
+            s, tr = int(slots[e]), host[e][ep]
+            assert s == e + B * (ep % 2), "env %d episode %d runs on slot %d" % (e, ep, s)
+            assert buf["trk_T"][s] == tr.T and buf["trk_Q"][s] == tr.Q, "env %d episode %d: T/Q" % (e, ep)
+            assert np.array_equal(buf["trk_quad_tile"][s, :tr.Q], tr.quad_tile), "border pattern, env %d episode %d" % (e, ep)
+            assert np.abs(buf["trk_node"][s, :tr.T] - tr.nodes[:, 1:4]).max() <= 1e-9
+            assert np.abs(buf["trk_quad"][s, :tr.Q].reshape(tr.Q, 4, 2) - tr.quads).max() <= 1e-4
+
+    check(0)
+    act = torch.zeros((B, A, 3), device=venv.device)
+    calls = LIMIT if mode == "same_step" else LIMIT + 1
+    for ep in range(1, EPISODES):
+        for _ in range(calls):
+            venv.step(act)
+        assert (venv.buffers["steps"].cpu().numpy() == 0).all(), "every env has just been respawned"
+        check(ep)
+    assert not venv.status().any()
+    # the streams live on the device now, one track ahead of the running episode at most
+    ahead = venv.buffers["trk_produced"].cpu().numpy() - venv.buffers["trk_consumed"].cpu().numpy()
+    assert ((ahead >= 0) & (ahead <= 1)).all()

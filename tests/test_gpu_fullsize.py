@@ -28,7 +28,7 @@ def _run(mcr, B, A, steps, tracks, orders, directions, tape, sample, **kw):
         rewards.append(rew[sample].cpu().numpy())
         sha.update(obs.cpu().numpy().tobytes()); sha.update(rew.cpu().numpy().tobytes()); sha.update(done.cpu().numpy().tobytes())
     sha.update(venv.buffers["body"].cpu().numpy().tobytes())
-    assert venv.status().tolist() == [0, 0, 0, 0]
+    assert not venv.status().any()
     return venv, np.stack(frames), np.stack(rewards), sha.hexdigest()
 
 

@@ -53,7 +53,7 @@ def test_reset_matches_oracle(oracle, mcr):
     venv, worlds, tracks, obs0, oobs0 = _setup(oracle, mcr, B=3, A=2, seed=1)
     _compare_state(venv, worlds, tracks, -1)
     assert np.array_equal(obs0, oobs0)
-    assert venv.status().tolist() == [0, 0, 0, 0]
+    assert not venv.status().any()
 
 
 @pytest.mark.parametrize("A,B,seed", [(1, 2, 2), (2, 4, 3), (4, 2, 4), (8, 1, 5), (16, 1, 6)])
@@ -69,7 +69,7 @@ def test_step_parity_300(oracle, mcr, A, B, seed):
         if s % 10 == 0 or s > 290:
             _compare_state(venv, worlds, tracks, s)
             assert np.array_equal(obs.cpu().numpy(), np.stack([x[0] for x in oo])), "observation pixels, step %d" % s
-    assert venv.status().tolist() == [0, 0, 0, 0]
+    assert not venv.status().any()
 
 
 def test_pose_after_1000_steps(oracle, mcr):
@@ -109,17 +109,20 @@ def _reformat(rgb, fmt):
         return ((299 * c[..., 0] + 587 * c[..., 1] + 114 * c[..., 2] + 500) // 1000).astype(np.uint8)
     if fmt == "rgb_chw":
         return np.ascontiguousarray(np.moveaxis(rgb, -1, -3))
+    if fmt == "rgb_chw_f16":          # uint8 -> float normalisation fused into the store: fp32 division, RN to fp16
+        return (np.moveaxis(rgb, -1, -3).astype(np.float32) / np.float32(255)).astype(np.float16)
     return rgb
 
 
-@pytest.mark.parametrize("fmt", ["gray", "rgb_chw"])
+@pytest.mark.parametrize("fmt", ["gray", "rgb_chw", "rgb_chw_f16"])
 def test_fused_observation_formats(oracle, mcr, fmt):
     """grayscale / planar layouts written straight from the rasteriser's registers;
     bit-exact against the oracle's RGB frame pushed through the same integer formula.  Covers the
     reset frame, eager steps and CUDA-graph replayed steps (the graph bakes the layout in)."""
     import torch
     venv, worlds, tracks, obs0, oobs0 = _setup(oracle, mcr, B=2, A=2, seed=21, obs_format=fmt)
-    assert obs0.shape == oobs0.shape[:2] + ({"gray": (96, 96), "rgb_chw": (3, 96, 96)}[fmt])
+    assert obs0.shape == oobs0.shape[:2] + ({"gray": (96, 96), "rgb_chw": (3, 96, 96), "rgb_chw_f16": (3, 96, 96)}[fmt])
+    assert obs0.dtype == (np.float16 if fmt == "rgb_chw_f16" else np.uint8)
     assert np.array_equal(obs0, _reformat(oobs0, fmt))
     tape = action_tape(21, 40, 2, 2)
     for s in range(40):
@@ -129,6 +132,32 @@ def test_fused_observation_formats(oracle, mcr, fmt):
             assert np.array_equal(obs.cpu().numpy(), _reformat(oo, fmt)), "%s pixels, step %d" % (fmt, s)
     hobs, _, _, _ = venv.step_host(tape[0])
     assert hobs.shape == obs.shape
+
+
+@pytest.mark.parametrize("K", [4, 3])
+def test_frame_stack_ring(oracle, mcr, K):
+    """SURVEY 8f #4 frame stack: obs_format='gray_stack' keeps the last K luma frames of every agent as a ring
+    written by the rasteriser's store (slot = episode step % K, every slot on the first frame of an episode).
+    stacked_obs() (oldest -> newest) must equal the oracle's frames pushed through the luma formula and a
+    host-side deque -- across eager steps, CUDA-graph replay and a next-step auto reset."""
+    import collections
+    import torch
+    B, A = 2, 2
+    tracks = [oracle.generate_track(np.random.RandomState(700 + e))[0] for e in range(B)]
+    orders = [np.array([0, 1]), np.array([1, 0])]
+    directions = ['CCW', 'CW']
+    venv = mcr.BatchedMultiCarRacing(B, num_agents=A, auto_reset=False, max_episode_steps=0, obs_format="gray_stack", frame_stack=K)
+    venv.reset(tracks=tracks, car_orders=orders, directions=directions)
+    worlds = make_oracle_worlds(oracle, tracks, orders, directions, A)
+    f0 = _reformat(np.stack([w.step(None)[0] for w in worlds]), "gray")
+    dq = collections.deque([f0] * K, maxlen=K)
+    assert venv.obs.shape == (B, A, K, 96, 96)
+    assert np.array_equal(venv.stacked_obs().cpu().numpy(), np.stack(dq, axis=2)), "reset fills every slot"
+    tape = action_tape(71, 3 * K + 5, B, A)
+    for s in range(len(tape)):
+        venv.step(torch.from_numpy(tape[s]).to(venv.device))
+        dq.append(_reformat(np.stack([w.step(tape[s, e].astype(np.float64))[0] for e, w in enumerate(worlds)]), "gray"))
+        assert np.array_equal(venv.stacked_obs().cpu().numpy(), np.stack(dq, axis=2)), "stack after step %d" % s
 
 
 def test_render_modes_between_steps(oracle, mcr):
@@ -264,7 +293,7 @@ def test_car_car_collisions(oracle, mcr):
         if s % 20 == 0:
             assert np.array_equal(obs.cpu().numpy(), np.stack([x[0] for x in oo])), "pixels, step %d" % s
     assert saw_manifolds >= 2, "the tape never produced a car-car contact"
-    assert venv.status().tolist() == [0, 0, 0, 0]
+    assert not venv.status().any()
 
 
 def test_collisions_keep_cars_apart(mcr):

@@ -96,7 +96,7 @@ def test_full_pool_device_reset_and_auto_reset(mcr):
     for s in range(70):
         obs, rew, done, _ = venv.step(torch.from_numpy(tape[s]).to(venv.device))
         seen_reset += int((done.cpu().numpy() != 0).sum())
-    assert seen_reset >= 8 and venv.status().tolist() == [0, 0, 0, 0]
+    assert seen_reset >= 8 and not venv.status().any()
 
 
 def test_device_generator_reports_capacity_errors(mcr):

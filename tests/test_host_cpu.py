@@ -22,7 +22,7 @@ def test_library_exports_every_header_symbol(mcr):
     for sym in sorted(declared):
         assert hasattr(L, sym), "libmcr.so does not export %s" % sym
     assert set(_lib.EXPORTS) == declared
-    assert L.mcr_abi_version() == 2
+    assert L.mcr_abi_version() == 3
 
 
 def test_config_validation_and_error_strings(mcr):
@@ -126,6 +126,10 @@ def test_obs_format_abi(mcr):
     assert L.mcr_obs_bytes(h) == 96 * 96 * 3
     assert L.mcr_set_obs_format(h, _lib.OBS_FORMATS["gray"]) == 0 and L.mcr_obs_bytes(h) == 96 * 96
     assert L.mcr_set_obs_format(h, _lib.OBS_FORMATS["rgb_chw"]) == 0 and L.mcr_obs_bytes(h) == 96 * 96 * 3
+    assert L.mcr_set_obs_format(h, _lib.OBS_FORMATS["rgb_chw_f16"]) == 0 and L.mcr_obs_bytes(h) == 2 * 96 * 96 * 3
+    assert L.mcr_set_obs_format(h, _lib.OBS_FORMATS["gray_stack"]) == 0 and L.mcr_obs_bytes(h) == 4 * 96 * 96
+    assert L.mcr_set_frame_stack(h, 6) == 0 and L.mcr_obs_bytes(h) == 6 * 96 * 96
+    assert L.mcr_set_frame_stack(h, 0) < 0 and L.mcr_set_frame_stack(h, 17) < 0
     assert L.mcr_set_obs_format(h, 7) < 0 and b"unknown format" in L.mcr_last_error()
     L.mcr_destroy(h)
 
@@ -194,3 +198,47 @@ def test_env_sharding():
         for first, count in blocks:
             assert first == nxt
             nxt += count
+
+
+def test_reset_draws_match_numpy_global_rng(mcr):
+    """mcr_reset_draws restates what reset() draws from the GLOBAL numpy RNG (reference :351-357):
+    np.random.choice(['CW','CCW']) and np.random.choice(ids, size=A, replace=False) per env, in turn.
+    Same values, and np.random ends at the same stream position."""
+    from multi_car_racing_b200 import _lib
+    L = _lib.load()
+    for A, rand_dir, seed in [(1, 1, 0), (2, 1, 1), (2, 0, 2), (3, 1, 3), (8, 1, 4), (16, 1, 5), (5, 0, 6)]:
+        n = 200
+        np.random.seed(seed)
+        want_cw, want_order = [], []
+        for e in range(n):
+            d = str(np.random.choice(['CW', 'CCW'])) if rand_dir else 'CCW'
+            want_cw.append(d == 'CW')
+            want_order.append(np.random.choice([i for i in range(A)], size=A, replace=False))
+        tail_ref = np.random.uniform(size=3)
+        np.random.seed(seed)
+        st = np.random.get_state()
+        mt = np.empty(625, np.uint32); mt[:624] = st[1]; mt[624] = st[2]
+        cws = np.empty(n, np.uint8); orders = np.empty((n, A), np.int32)
+        assert L.mcr_reset_draws(mt.ctypes.data, n, A, rand_dir, 0, cws.ctypes.data, orders.ctypes.data) == 0
+        np.random.set_state((st[0], mt[:624].copy(), int(mt[624]), st[3], st[4]))
+        assert np.array_equal(cws.astype(bool), np.array(want_cw)), (A, rand_dir)
+        assert np.array_equal(orders, np.array(want_order)), (A, rand_dir)
+        assert np.array_equal(np.random.uniform(size=3), tail_ref), "stream position after the draws"
+
+
+def test_batched_seeding_matches_np_random(mcr):
+    """mcr_mt_seed_batch == gym seeding.np_random (sha512 -> init_by_array) for a run of seeds."""
+    from multi_car_racing_b200 import _lib
+    from multi_car_racing_b200.track import np_random, seed_key
+    L = _lib.load()
+    seeds = [0, 1, 2, 12345, 2 ** 31 - 1, 2 ** 40 + 7] + list(range(100, 130))
+    keys = np.zeros((len(seeds), 2), np.uint32); lens = np.empty(len(seeds), np.int32)
+    for i, sd in enumerate(seeds):
+        k, _ = seed_key(sd)
+        keys[i, :len(k)] = k; lens[i] = len(k)
+    states = np.empty((len(seeds), 625), np.uint32)
+    assert L.mcr_mt_seed_batch(states.ctypes.data, keys.ctypes.data, lens.ctypes.data, len(seeds), 2) == 0
+    for i, sd in enumerate(seeds):
+        rng, _ = np_random(sd)
+        st = rng.get_state()
+        assert np.array_equal(states[i, :624], st[1]) and states[i, 624] == st[2], "seed %d" % sd
