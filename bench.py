@@ -11,8 +11,10 @@ random policy).  One agent-frame = one (96,96,3) uint8 observation produced by a
   value     device-resident throughput (actions already in HBM), CUDA events, max over ranks
   e2e       the same through BatchedMultiCarRacing.step_host: actions from pinned host memory,
             observations/rewards/dones copied back to pinned host memory every step
-  roofline  rasteriser kernel: algorithmic bytes (27 648 B per agent-frame) / its measured
-            launch time vs MEASURED_PEAKS.json hbm_gbs
+  roofline  the rasteriser (project_kernel + fill_kernel, timed alone with CUDA events -- no reward /
+            done block beside it): algorithmic bytes (27 648 B per agent-frame) / launch time vs
+            MEASURED_PEAKS.json hbm_gbs; fill_kernel's own share from the %globaltimer stamps the
+            kernels write (kernel_ms.fill)
   cpu_baseline  the CPU oracle (a port of the reference's algorithm, NOT the original
             Box2D+pyglet, which is not installable here) timed on host cores
 
@@ -38,7 +40,14 @@ NUM_AGENTS = 2
 BATCH_ENVS = 1024
 
 
-def workload_config(A, B, world, obs_format="rgb"):
+def workload_config(A, B, world, obs_format="rgb", extra=None):
+    cfg = _workload_config(A, B, world, obs_format)
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def _workload_config(A, B, world, obs_format="rgb"):
     return {"workload": "MultiCarRacing-v0 step+render, num_agents=%d, batch=%d envs per GPU, random policy, "
                         "use_random_direction=True, device-side next-step auto reset (done or 1000 steps)%s" % (
                             A, B, "" if obs_format == "rgb" else ", obs_format=%s (NOT the reference's layout)" % obs_format),
@@ -116,7 +125,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(args.gpus), "steps": steps,
         "warmup": warm, "ms_per_step": 1e3 * wall / max(1, frames // (cores * envs_per_proc * NUM_AGENTS)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-        "config": workload_config(NUM_AGENTS, BATCH_ENVS, int(args.gpus)),
+        "config": workload_config(NUM_AGENTS, BATCH_ENVS, int(args.gpus), extra={
+            "reference_arm_sample": "a step of THIS arm advances %d envs (%d processes x %d), not the %d of the workload: "
+                                    "a bounded sample of the same per-env work, throughput in the same unit" % (
+                                        cores * envs_per_proc, cores, envs_per_proc, BATCH_ENVS),
+            "envs_stepped_per_step": cores * envs_per_proc}),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d agent-frames: %d processes x %d envs x %d agents, oracle/mcr_oracle.c (CPU port of the "
                                    "reference algorithm; the original Box2D+pyglet stack is not installable offline)" % (
@@ -207,8 +220,8 @@ def run_ours(args):
     np.random.seed(1234 + rank)
     venv = mcr.BatchedMultiCarRacing(B, num_agents=A, use_random_direction=True, device=dev, auto_reset='next_step',
                                      max_episode_steps=1000, seed=1234 + rank * B, obs_format=args.obs_format)
-    obs_bytes = int(np.prod(venv.obs_shape))
-    venv.reset()
+    obs_bytes = int(np.prod(venv.obs_shape)) * (2 if args.obs_format == "rgb_chw_f16" else 1)
+    venv.reset(device_tracks=True)
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
     TAPE = 128
     tape = torch.rand((TAPE, B, A, 3), device=dev, generator=gen)
@@ -242,14 +255,28 @@ def run_ours(args):
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     status = venv.status().tolist()
 
-    # ---- per-kernel split (same work, no auto reset) for the roofline --------------------------
+    # ---- per-kernel split (same work, no auto reset) for the roofline: simulate, then the rasteriser ALONE
+    #      (mcr_render without the reward / done block that rides beside it in the real step) -------------------
     KS = min(K, 200)
     kev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(KS)]
+    tl = venv.buffers["timeline"].view(torch.int64)
+    fill_us = []
     for s in range(KS):
         flush.zero_()
-        venv.step_split(tape[s % TAPE], kev[s])
+        tl.zero_()
+        kev[s][0].record()
+        venv.simulate_only(tape[s % TAPE])
+        kev[s][1].record()
+        venv.render_only()
+        kev[s][2].record()
+        if s < 32:                                 # fill_kernel's own window: its first CTA's start .. its last CTA's end
+            torch.cuda.synchronize(dev)
+            t = tl.cpu().numpy()
+            if t[15] > 0 and t[8] > t[15]:
+                fill_us.append((t[8] - t[15]) / 1e3)
     torch.cuda.synchronize(dev)
     k_ms = [sum(e[i].elapsed_time(e[i + 1]) for e in kev) / KS for i in range(2)]
+    fill_ms = (sum(fill_us) / len(fill_us) / 1e3) if fill_us else None
 
     # ---- end-to-end through the host-buffer API ----------------------------------------------------
     hb = venv.host_buffers()
@@ -301,9 +328,11 @@ def run_ours(args):
         peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         render_ms = k_ms[1]
         achieved = frames_per_step * obs_bytes / (render_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None          # not measurable inside this run: taken from the committed ncu capture
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "render_traffic.json"))).get("dram_bytes_per_launch")
+            tj = json.load(open(os.path.join(ROOT, "profiles", "render_traffic.json")))
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_src = "static: profiles/render_traffic.json (%s)" % tj.get("source", "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum")
         except Exception:
             pass
         cpu = None
@@ -324,10 +353,14 @@ def run_ours(args):
                               "note": "step_host_async / step_host_wait: the device-to-host copy of step k overlaps the "
                                       "compute of step k+1 (results one call late); not usable by a synchronous policy loop"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "render_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
+            "roofline": {"bound": "hbm", "kernel": "rasteriser = project_kernel + fill_kernel (fill_kernel writes the frames)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_kind,
                          "algorithmic_bytes_per_launch": frames_per_step * obs_bytes,
-                         "kernel_ms": {"simulate": k_ms[0], "render": k_ms[1]}},
+                         "kernel_ms": {"simulate": k_ms[0], "render": k_ms[1], "fill": fill_ms},
+                         "fill_kernel_alone": None if not fill_ms else {
+                             "achieved": frames_per_step * obs_bytes / (fill_ms * 1e-3) / 1e9,
+                             "frac": frames_per_step * obs_bytes / (fill_ms * 1e-3) / 1e9 / peak}},
             "cpu_baseline": cpu,
             "status_words": status,
             "host": {"numa_node_rank0": numa_node, "cpus_rank0": len(os.sched_getaffinity(0))},
@@ -348,7 +381,7 @@ def main():
     ap.add_argument("--batch-envs", dest="batch_envs", type=int, default=BATCH_ENVS)
     ap.add_argument("--num-agents", dest="num_agents", type=int, default=NUM_AGENTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--obs-format", dest="obs_format", default="rgb", choices=["rgb", "gray", "rgb_chw"],
+    ap.add_argument("--obs-format", dest="obs_format", default="rgb", choices=["rgb", "gray", "rgb_chw", "gray_stack", "rgb_chw_f16"],
                     help="rasteriser store layout; only 'rgb' is the reference's observation (the headline config)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -158,6 +158,14 @@ int mcr_reset(mcr_handle h, const uint8_t* d_env_mask, const int32_t* d_track_sl
 int mcr_step(mcr_handle h, const void* d_action, int32_t action_dtype, uint8_t* d_obs, double* d_reward,
              uint8_t* d_done, int32_t flags, void* stream);
 
+/* The same step with HOST buffers (what a caller holding numpy arrays uses): h_action [B][A][3] in pinned (or pageable)
+ * host memory is copied in, and obs / reward / done are copied out to h_obs / h_reward / h_done (pinned) as part of the
+ * call's stream work -- the frames leave in ranges of envs as soon as each range is rendered, so most of the step hides
+ * behind the PCIe transfer.  d_obs / d_reward / d_done are the device staging buffers (also valid results).  Nothing
+ * synchronises: the host buffers are complete once `stream` has drained. */
+int mcr_step_host(mcr_handle h, const void* h_action, int32_t action_dtype, uint8_t* d_obs, double* d_reward, uint8_t* d_done,
+                  uint8_t* h_obs, double* h_reward, uint8_t* h_done, int32_t flags, void* stream);
+
 /* Split entry points (benchmarks / ncu / tests): the same results as mcr_step without auto reset, issued as
  * separate stages.  mcr_simulate = mcr_contacts (side stream) beside mcr_physics; mcr_render with
  * post_step = 1 also runs the reward / done block.  mcr_step itself issues one pipelined CUDA graph. */

@@ -18,7 +18,7 @@ EXPORTS = [
     "mcr_buffer_spec", "mcr_bind_buffer", "mcr_track_generate", "mcr_mt_seed", "mcr_spawn_poses",
     "mcr_load_track", "mcr_reset", "mcr_step", "mcr_simulate", "mcr_contacts", "mcr_physics", "mcr_render",
     "mcr_get_mass", "mcr_get_shape", "mcr_launch_count", "mcr_set_obs_format", "mcr_obs_bytes",
-    "mcr_tracks_generate_device", "mcr_trackgen_scratch_bytes", "mcr_render_viewport", "mcr_set_frame_stack", "mcr_mt_seed_batch", "mcr_reset_draws",
+    "mcr_tracks_generate_device", "mcr_trackgen_scratch_bytes", "mcr_render_viewport", "mcr_set_frame_stack", "mcr_mt_seed_batch", "mcr_reset_draws", "mcr_step_host",
 ]
 OBS_FORMATS = {"rgb": 0, "gray": 1, "rgb_chw": 2, "gray_stack": 3, "rgb_chw_f16": 4}     # MCR_OBS_* of include/mcr.h
 
@@ -84,6 +84,8 @@ def load():
     L.mcr_reset.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.mcr_step.restype = i32
     L.mcr_step.argtypes = [vp, vp, i32, vp, vp, vp, i32, vp]
+    L.mcr_step_host.restype = i32
+    L.mcr_step_host.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, vp]
     L.mcr_contacts.restype = i32
     L.mcr_contacts.argtypes = [vp, vp, vp]
     L.mcr_physics.restype = i32

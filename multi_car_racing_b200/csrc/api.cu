@@ -420,13 +420,16 @@ struct mcr_handle_t {
     cudaEvent_t ev_fork, ev_join;
     cudaStream_t side2;          // the chain of envs with touching cars: coupled -> post -> score -> render
     cudaStream_t side3;          // score_kernel of the touching-car envs, beside their rasteriser
+    cudaStream_t copy;           // mcr_step_host: device-to-host copies of the envs already filled, beside the fill of the rest
+    cudaEvent_t ev_chunk[8], ev_copy;
     cudaStream_t refill;         // lowest priority: ring_refill_kernel tops up the envs' track rings beside the steps
     cudaEvent_t ev_refill, ev_refill_go;
     int64_t steps_since_refill;
     cudaEvent_t ev_pre, ev_contacts, ev_chain2, ev_score, ev_post2, ev_score2;
     bool side_ready;
     // mcr_step replays a captured CUDA graph of its launches (one graph per argument tuple)
-    struct StepGraph { int32_t dtype, flags; uint8_t* obs; double* reward; uint8_t* done; cudaGraphExec_t exec; int64_t launches; };
+    struct StepGraph { int32_t dtype, flags; uint8_t* obs; double* reward; uint8_t* done; uint8_t* h_obs; double* h_reward; uint8_t* h_done;
+                       cudaGraphExec_t exec; int64_t launches; };
     std::vector<StepGraph> graphs;
     int64_t eager_steps;
     bool use_graphs;
@@ -538,6 +541,7 @@ extern "C" int mcr_destroy(mcr_handle h) {
     if (h && h->side_ready) {
         cudaStreamDestroy(h->side); cudaStreamDestroy(h->cap); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
         cudaStreamDestroy(h->side3); cudaEventDestroy(h->ev_post2); cudaEventDestroy(h->ev_score2);
+        cudaStreamDestroy(h->copy); for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev_chunk[i]); cudaEventDestroy(h->ev_copy);
         cudaStreamSynchronize(h->refill); cudaStreamDestroy(h->refill); cudaEventDestroy(h->ev_refill); cudaEventDestroy(h->ev_refill_go);
         cudaStreamDestroy(h->side2); cudaEventDestroy(h->ev_pre); cudaEventDestroy(h->ev_contacts); cudaEventDestroy(h->ev_chain2); cudaEventDestroy(h->ev_score);
     }
@@ -801,6 +805,9 @@ static int ensure_side(mcr_handle h) {
         CUDA_OK(cudaStreamCreateWithFlags(&h->side3, cudaStreamNonBlocking));
         CUDA_OK(cudaEventCreateWithFlags(&h->ev_post2, cudaEventDisableTiming));
         CUDA_OK(cudaEventCreateWithFlags(&h->ev_score2, cudaEventDisableTiming));
+        CUDA_OK(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 8; ++i) CUDA_OK(cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
         int prio_lo = 0, prio_hi = 0;
         CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CUDA_OK(cudaStreamCreateWithPriority(&h->refill, cudaStreamNonBlocking, prio_lo));
@@ -881,8 +888,10 @@ extern "C" int mcr_render_viewport(mcr_handle h, const uint8_t* mask, int32_t vw
     return 0;
 }
 
+struct HostOut { uint8_t* h_obs; double* h_reward; uint8_t* h_done; };   // pinned host destinations of mcr_step_host
 static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, const void* action, int32_t action_dtype,
-                    uint8_t* obs, double* reward, uint8_t* done, int post_step, void* stream, const uint8_t* reset_flags = nullptr);
+                    uint8_t* obs, double* reward, uint8_t* done, int post_step, void* stream, const uint8_t* reset_flags = nullptr,
+                    const HostOut* ho = nullptr);
 
 // Top up the track rings on the refill stream, ordered behind what `after` holds so far (mcr_reset: the spawn kernel
 // that zeroes the ring counters; steps: nothing to wait for, the kernel only looks at the counters).
@@ -922,7 +931,8 @@ extern "C" int mcr_reset(mcr_handle h, const uint8_t* mask, const int32_t* track
 // batch has touching cars) no longer stalls the other envs' post/render; the classes are disjoint
 // sets of envs, so the chains never touch the same state.
 static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, const void* action, int32_t action_dtype,
-                    uint8_t* obs, double* reward, uint8_t* done, int post_step, void* stream, const uint8_t* reset_flags) {
+                    uint8_t* obs, double* reward, uint8_t* done, int post_step, void* stream, const uint8_t* reset_flags,
+                    const HostOut* ho) {
     cudaStream_t s = (cudaStream_t)stream;
     { int rc_ = ensure_side(h); if (rc_) return rc_; }
     const Dims& d = h->d; const DevBuffers& b = h->buf; const CarConst& cc = h->cc;
@@ -977,26 +987,63 @@ static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, con
         LAUNCH(launch_score(d, b, mask, noact, reward, done, h->cfg.max_episode_steps, cls, h->side));
         CUDA_OK(cudaEventRecord(h->ev_score, h->side));
     }
-    LAUNCH(launch_render(d, b, cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, cls, h->obs_format, h->stack_k, s));
+    const size_t frame_bytes = (size_t)mcr_obs_bytes(h);
+    const bool chunked = ho && render_is_split() && d.B >= 64;
+    if (chunked) {
+        // mcr_step_host: the frames go to the host in up to 8 ranges of envs; the copy of a range starts as soon as it is
+        // filled, beside the fill of the next ranges -- only the physics and the first range's fill are not hidden
+        // behind the PCIe transfer.  (The touching-car chain's frames lie scattered in every range: wait for it first.)
+        LAUNCH(launch_project(d, b, cc, mask, h->cfg.backwards_flag, h->cfg.use_ego_color, cls, s));
+        if (split) CUDA_OK(cudaStreamWaitEvent(h->copy, h->ev_chain2, 0));
+        const int nch = 8, per = (d.B + nch - 1) / nch;
+        for (int c = 0; c < nch; ++c) {
+            const int env0 = c * per, nenv = std::min(per, d.B - env0);
+            if (nenv <= 0) break;
+            LAUNCH(launch_fill(d, b, mask, obs, cls, h->obs_format, h->stack_k, env0, nenv, true, s));
+            CUDA_OK(cudaEventRecord(h->ev_chunk[c], s));
+            CUDA_OK(cudaStreamWaitEvent(h->copy, h->ev_chunk[c], 0));
+            const size_t off = (size_t)env0 * d.A * frame_bytes;
+            CUDA_OK(cudaMemcpyAsync(ho->h_obs + off, obs + off, (size_t)nenv * d.A * frame_bytes, cudaMemcpyDeviceToHost, h->copy));
+        }
+        CUDA_OK(cudaEventRecord(h->ev_copy, h->copy));
+    } else {
+        LAUNCH(launch_render(d, b, cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, cls, h->obs_format, h->stack_k, s));
+    }
     if (post_step) CUDA_OK(cudaStreamWaitEvent(s, h->ev_score, 0));
     if (split) CUDA_OK(cudaStreamWaitEvent(s, h->ev_chain2, 0));
+    if (ho) {
+        if (!chunked) CUDA_OK(cudaMemcpyAsync(ho->h_obs, obs, (size_t)d.N * frame_bytes, cudaMemcpyDeviceToHost, s));
+        if (post_step) {
+            CUDA_OK(cudaMemcpyAsync(ho->h_reward, reward, (size_t)d.N * sizeof(double), cudaMemcpyDeviceToHost, s));
+            CUDA_OK(cudaMemcpyAsync(ho->h_done, done, (size_t)d.B, cudaMemcpyDeviceToHost, s));
+        }
+        if (chunked) CUDA_OK(cudaStreamWaitEvent(s, h->ev_copy, 0));
+    }
     return 0;
 }
 
 static int step_enqueue(mcr_handle h, const void* action, int32_t action_dtype, uint8_t* obs, double* reward,
-                        uint8_t* done, int32_t flags, void* stream) {
+                        uint8_t* done, int32_t flags, void* stream, const HostOut* ho = nullptr) {
     int rc;
     if (flags & 2) {
         // next-step auto reset: envs whose previous step ended the episode respawn now and take
         // reset()'s step(None) inside this very pass -- one pass, no masked second pass
         // (the respawn itself is the first stage of the pipeline's head kernel; it writes reset_mask)
-        return pipeline(h, nullptr, h->buf.reset_mask, action, action_dtype, obs, reward, done, 1, stream, h->buf.pending);
+        return pipeline(h, nullptr, h->buf.reset_mask, action, action_dtype, obs, reward, done, 1, stream, h->buf.pending, ho);
     }
-    rc = pipeline(h, nullptr, nullptr, action, action_dtype, obs, reward, done, 1, stream); if (rc) return rc;
+    // same-step auto reset rewrites the frames of the envs that ended: their host copy has to follow the second pass
+    const HostOut* ho1 = (flags & 1) ? nullptr : ho;
+    rc = pipeline(h, nullptr, nullptr, action, action_dtype, obs, reward, done, 1, stream, nullptr, ho1); if (rc) return rc;
     if (flags & 1) {
         AutoResetCfg ar{h->cfg.use_random_direction, h->cfg.direction_cw, (unsigned long long)h->cfg.seed, h->cfg.fresh_tracks};
         LAUNCH(launch_auto_reset(h->d, h->buf, h->cc, done, ar, stream));
         rc = pipeline(h, h->buf.reset_mask, nullptr, nullptr, MCR_F32, obs, nullptr, nullptr, 0, stream); if (rc) return rc;
+        if (ho) {
+            cudaStream_t s = (cudaStream_t)stream;
+            CUDA_OK(cudaMemcpyAsync(ho->h_obs, obs, (size_t)h->d.N * (size_t)mcr_obs_bytes(h), cudaMemcpyDeviceToHost, s));
+            CUDA_OK(cudaMemcpyAsync(ho->h_reward, reward, (size_t)h->d.N * sizeof(double), cudaMemcpyDeviceToHost, s));
+            CUDA_OK(cudaMemcpyAsync(ho->h_done, done, (size_t)h->d.B, cudaMemcpyDeviceToHost, s));
+        }
     }
     return 0;
 }
@@ -1006,29 +1053,51 @@ static int step_enqueue(mcr_handle h, const void* action, int32_t action_dtype, 
 // kernel attributes and constant uploads are done by then) the launch sequence is captured once per
 // argument tuple into a CUDA graph that reads the action from the bound `action_stage` buffer; a
 // step is then one device-to-device copy of the action plus one cudaGraphLaunch.
+static int step_impl(mcr_handle h, const void* action, bool action_on_host, int32_t action_dtype, uint8_t* obs, double* reward,
+                     uint8_t* done, int32_t flags, void* stream, const HostOut* ho);
+
 extern "C" int mcr_step(mcr_handle h, const void* action, int32_t action_dtype, uint8_t* obs, double* reward,
                         uint8_t* done, int32_t flags, void* stream) {
+    return step_impl(h, action, false, action_dtype, obs, reward, done, flags, stream, nullptr);
+}
+
+extern "C" int mcr_step_host(mcr_handle h, const void* h_action, int32_t action_dtype, uint8_t* d_obs, double* d_reward, uint8_t* d_done,
+                             uint8_t* h_obs, double* h_reward, uint8_t* h_done, int32_t flags, void* stream) {
+    if (!h_obs || !h_reward || !h_done) return fail(-1, "mcr_step_host: null host buffer");
+    const HostOut ho{h_obs, h_reward, h_done};
+    return step_impl(h, h_action, true, action_dtype, d_obs, d_reward, d_done, flags, stream, &ho);
+}
+
+static int step_impl(mcr_handle h, const void* action, bool action_on_host, int32_t action_dtype, uint8_t* obs, double* reward,
+                     uint8_t* done, int32_t flags, void* stream, const HostOut* ho) {
     int rc = check_bound(h); if (rc) return rc;
     if (!action || !obs || !reward || !done) return fail(-1, "mcr_step: null argument");
     if (action_dtype != MCR_F32 && action_dtype != MCR_F64) return fail(-1, "action dtype must be MCR_F32 or MCR_F64");
     if ((flags & 3) == 3) return fail(-1, "mcr_step: flags bit0 (same-step) and bit1 (next-step) auto reset are exclusive");
     cudaStream_t s = (cudaStream_t)stream;
+    const size_t abytes = (size_t)h->d.N * 3 * (action_dtype == MCR_F64 ? 8 : 4);
+    if (action_on_host) {
+        // the action goes straight into the library's staging buffer (what the kernels and the captured graph read)
+        CUDA_OK(cudaMemcpyAsync(h->buf.action_stage, action, abytes, cudaMemcpyHostToDevice, s));
+        action = h->buf.action_stage;
+    }
     const bool refill_now = h->cfg.fresh_tracks > 0 && (flags & 3) && ++h->steps_since_refill >= 4;
     if (!h->use_graphs || h->eager_steps < 2) {
         ++h->eager_steps;
-        rc = step_enqueue(h, action, action_dtype, obs, reward, done, flags, stream);
+        rc = step_enqueue(h, action, action_dtype, obs, reward, done, flags, stream, ho);
         if (!rc && refill_now) rc = kick_refill(h, nullptr);
         return rc;
     }
     mcr_handle_t::StepGraph* g = nullptr;
     for (auto& c : h->graphs)
-        if (c.dtype == action_dtype && c.flags == flags && c.obs == obs && c.reward == reward && c.done == done) { g = &c; break; }
+        if (c.dtype == action_dtype && c.flags == flags && c.obs == obs && c.reward == reward && c.done == done &&
+            c.h_obs == (ho ? ho->h_obs : nullptr) && c.h_reward == (ho ? ho->h_reward : nullptr) && c.h_done == (ho ? ho->h_done : nullptr)) { g = &c; break; }
     if (!g) {
         if (h->graphs.size() >= 16) { cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
         rc = ensure_side(h); if (rc) return rc;
         const int64_t before = h->launches;
         CUDA_OK(cudaStreamBeginCapture(h->cap, cudaStreamCaptureModeRelaxed));
-        rc = step_enqueue(h, h->buf.action_stage, action_dtype, obs, reward, done, flags, h->cap);
+        rc = step_enqueue(h, h->buf.action_stage, action_dtype, obs, reward, done, flags, h->cap, ho);
         cudaGraph_t graph = nullptr;
         const cudaError_t ce = cudaStreamEndCapture(h->cap, &graph);
         const int64_t per_step = h->launches - before;
@@ -1041,14 +1110,14 @@ extern "C" int mcr_step(mcr_handle h, const void* action, int32_t action_dtype, 
             // graphs are an optimisation of the launch path only: issue this and all later steps directly
             (void)cudaGetLastError();
             h->use_graphs = false;
-            rc = step_enqueue(h, action, action_dtype, obs, reward, done, flags, stream);
+            rc = step_enqueue(h, action, action_dtype, obs, reward, done, flags, stream, ho);
             if (!rc && refill_now) rc = kick_refill(h, nullptr);
             return rc;
         }
-        h->graphs.push_back(mcr_handle_t::StepGraph{action_dtype, flags, obs, reward, done, exec, per_step});
+        h->graphs.push_back(mcr_handle_t::StepGraph{action_dtype, flags, obs, reward, done, ho ? ho->h_obs : nullptr,
+                                                    ho ? ho->h_reward : nullptr, ho ? ho->h_done : nullptr, exec, per_step});
         g = &h->graphs.back();
     }
-    const size_t abytes = (size_t)h->d.N * 3 * (action_dtype == MCR_F64 ? 8 : 4);
     if (action != (const void*)h->buf.action_stage)
         CUDA_OK(cudaMemcpyAsync(h->buf.action_stage, action, abytes, cudaMemcpyDeviceToDevice, s));
     CUDA_OK(cudaGraphLaunch(g->exec, s));

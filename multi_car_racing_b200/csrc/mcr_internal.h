@@ -123,7 +123,7 @@ struct Dims { int B, A, N, Tmax, Qmax, P; int particles; int dl_cap; };
 #define PRT_PTS 30
 // skid_meta[wheel] bits: 0 skid_start valid, 1 skid_particle valid, 2 its grass flag, 8-15 its length, 16-23 its ring slot + 1 (0 = popped from Car.particles)
 // timeline slots: kernel start stamps (block 0, thread 0) and the latest CTA end of the rasteriser
-enum { TL_HEAD = 0, TL_CONTACTS, TL_STRIPES, TL_SWEEP, TL_COUPLED, TL_POST, TL_SCORE, TL_RENDER, TL_RENDER_END, TL_POST2, TL_RENDER2, TL_SWEEP_END, TL_SWEEP_END_PACKED, TL_COUPLED_VEL_END, TL_COUPLED_POS_END, TL_COUNT = 16 };
+enum { TL_HEAD = 0, TL_CONTACTS, TL_STRIPES, TL_SWEEP, TL_COUPLED, TL_POST, TL_SCORE, TL_RENDER, TL_RENDER_END, TL_POST2, TL_RENDER2, TL_SWEEP_END, TL_SWEEP_END_PACKED, TL_COUPLED_VEL_END, TL_COUPLED_POS_END, TL_FILL = 15 /* fill_kernel start (cls != 2) */, TL_COUNT = 16 };
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned long long mcr_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void tl_stamp(const unsigned long long* tl_base, int slot) {
@@ -170,6 +170,11 @@ int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const 
                   int backwards_flag, int use_ego_color, int cls, int obs_format, int stack_k, void* stream);
 int launch_score(const Dims& d, const DevBuffers& b, const uint8_t* mask, const uint8_t* noact, double* reward, uint8_t* done,
                  int max_episode_steps, int cls, void* stream);
+bool render_is_split();
+int launch_project(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, int backwards_flag, int use_ego_color,
+                   int cls, void* stream);
+int launch_fill(const Dims& d, const DevBuffers& b, const uint8_t* mask, uint8_t* obs, int cls, int obs_format, int stack_k,
+                int env0, int nenv, bool pdl, void* stream);
 // render(mode) for a vw x vh viewport (rgb_array: 600 x 400): camera_kernel + tiled render_kernel<true>
 int launch_render_viewport(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* out, float* cam,
                            int vw, int vh, double h_ratio, int backwards_flag, int use_ego_color, void* stream);

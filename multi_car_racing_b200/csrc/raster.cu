@@ -1081,10 +1081,10 @@ project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
 // One CTA per agent-frame.  (Measured and dropped, profiles/README r02: persistent CTAs with a frame queue or a static
 // stride, register prefetch of the next frame's list, 5 CTAs per SM at 40 registers -- none beat this plain form.)
 __global__ void __launch_bounds__(RS_THREADS, FILL_CTAS)
-fill_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, uint8_t* __restrict__ obs, int cls, int obs_format, int stack_k) {
+fill_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, uint8_t* __restrict__ obs, int cls, int obs_format, int stack_k, int env0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
-    const int env = (int)blockIdx.x, agent = (int)blockIdx.y, frame = env * d.A + agent;
+    const int env = env0 + (int)blockIdx.x, agent = (int)blockIdx.y, frame = env * d.A + agent;   // env0: launches over a range of envs (step_host chunks)
     const int tid = threadIdx.x;
     PHASE_T0();
     // tables that do not depend on project_kernel's output: built while it drains (programmatic dependent launch)
@@ -1097,6 +1097,7 @@ fill_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, uint8_t* __r
     if (tid < 256) S.prmt_sel[tid] = prmt_selector(tid);
     if (tid >= 128 && tid < 128 + SPAN_POOL / 32) S.startbits[tid - 128] = 0;
     cudaGridDependencySynchronize();
+    if (cls != 2) tl_stamp(b.timeline, TL_FILL);
     if (mask && !mask[env]) return;
     if (cls && (cls == 2) != (b.n_manifold[env] > 0)) return;
     const uint2* __restrict__ meta = reinterpret_cast<const uint2*>(b.dl_meta) + (size_t)frame * d.dl_cap;
@@ -1331,8 +1332,32 @@ int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const 
     mcr_launch_pdl(project_kernel, dim3((d.N + PJ_WARPS - 1) / PJ_WARPS), dim3(PJ_THREADS), 0, (cudaStream_t)stream,
                    d, b, cc, mask, backwards_flag, use_ego_color, cls);
     mcr_launch_pdl(fill_kernel, dim3(d.B, d.A), dim3(RS_THREADS), sizeof(RasterSmem), (cudaStream_t)stream,
-                   d, b, mask, obs, cls, obs_format, stack_k);
+                   d, b, mask, obs, cls, obs_format, stack_k, 0);
     return cudaGetLastError() == cudaSuccess ? 2 : -1;
+}
+
+bool render_is_split() {
+    static const bool fused = std::getenv("MCR_RENDER_FUSED") != nullptr;
+    return !fused;
+}
+
+// The two halves of launch_render for callers that interleave something with the fill (mcr_step_host: the device-to-host
+// copy of a range of envs starts as soon as that range is filled).
+int launch_project(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, int backwards_flag, int use_ego_color,
+                   int cls, void* stream) {
+    if (!configure_render()) return -1;
+    mcr_launch_pdl(project_kernel, dim3((d.N + PJ_WARPS - 1) / PJ_WARPS), dim3(PJ_THREADS), 0, (cudaStream_t)stream,
+                   d, b, cc, mask, backwards_flag, use_ego_color, cls);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_fill(const Dims& d, const DevBuffers& b, const uint8_t* mask, uint8_t* obs, int cls, int obs_format, int stack_k,
+                int env0, int nenv, bool pdl, void* stream) {
+    if (!configure_render()) return -1;
+    if (pdl) mcr_launch_pdl(fill_kernel, dim3(nenv, d.A), dim3(RS_THREADS), sizeof(RasterSmem), (cudaStream_t)stream,
+                            d, b, mask, obs, cls, obs_format, stack_k, env0);
+    else fill_kernel<<<dim3(nenv, d.A), RS_THREADS, sizeof(RasterSmem), (cudaStream_t)stream>>>(d, b, mask, obs, cls, obs_format, stack_k, env0);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 // camera of mcr:540-556 for a viewport of vw x vh pixels (post_kernel evaluates the 96 x 96 one); same

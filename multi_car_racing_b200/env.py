@@ -472,13 +472,12 @@ class BatchedMultiCarRacing:
             if a.ctypes.data != hb["action"].data_ptr():
                 hb["action"].numpy()[...] = a
             src = hb["action"]
+        dt = _lib.MCR_F64 if src.dtype == torch.float64 else _lib.MCR_F32
         with torch.cuda.device(self.device):
-            dev_a = self._dev_action64 if src.dtype == torch.float64 else self._dev_action
-            dev_a.copy_(src, non_blocking=True)
-            self.step(dev_a)
-            hb["obs"].copy_(self.obs, non_blocking=True)
-            hb["reward"].copy_(self.reward_out, non_blocking=True)
-            hb["done"].copy_(self.done_out, non_blocking=True)
+            # one native call: action in, step, and the results out in ranges of envs as they are rendered
+            _lib.check(self.L.mcr_step_host(self._h, src.data_ptr(), dt, self.obs.data_ptr(), self.reward_out.data_ptr(),
+                                            self.done_out.data_ptr(), hb["obs"].data_ptr(), hb["reward"].data_ptr(),
+                                            hb["done"].data_ptr(), self._step_flags, self._stream()), "mcr_step_host")
             torch.cuda.current_stream(self.device).synchronize()
         return hb["obs"].numpy(), hb["reward"].numpy(), hb["done"].numpy(), {}
 
@@ -621,6 +620,10 @@ class BatchedMultiCarRacing:
     def physics_only(self, action):
         dt = _lib.MCR_F32 if action.dtype == _torch().float32 else _lib.MCR_F64
         _lib.check(self.L.mcr_physics(self._h, None, action.data_ptr(), dt, self._stream()), "mcr_physics")
+
+    def simulate_only(self, action):
+        dt = _lib.MCR_F32 if action.dtype == _torch().float32 else _lib.MCR_F64
+        _lib.check(self.L.mcr_simulate(self._h, None, action.data_ptr(), dt, self._stream()), "mcr_simulate")
 
     def render_only(self):
         _lib.check(self.L.mcr_render(self._h, None, self.obs.data_ptr(), None, None, 0, self._stream()), "mcr_render")

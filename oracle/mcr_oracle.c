@@ -291,6 +291,10 @@ typedef struct OrcWorld {
     /* config */
     double h_ratio; int backwards_flag, use_ego_color;
     int collisions;      /* car-car rigid contacts on/off */
+    /* EXPOSURE VARIANTS (tests/test_oracle_exposure.py): what the two orders this restatement could not check against a
+     * real Box2D would change if they were the other way round.  0 = the documented choice (D1). */
+    int var_tie_ascending;    /* same-step shared-tile tie break: LOWER car id first */
+    int var_joint_ascending;  /* island joint order [j0, j1, j2, j3] */
     Manifold manifolds[MAX_MANIFOLDS]; int n_manifolds; int manifold_overflow;
     int vel_iters_used;  /* diagnostics: last fixed-point iteration index */
 } OrcWorld;
@@ -355,6 +359,9 @@ static void free_track(OrcWorld* W) {
 ORC_API void orc_destroy(OrcWorld* W) { if (!W) return; free_track(W); free(W); }
 
 ORC_API void orc_set_collisions(OrcWorld* W, int on) { W->collisions = on; }
+ORC_API void orc_set_variant(OrcWorld* W, int tie_ascending, int joint_ascending) {
+    W->var_tie_ascending = tie_ascending; W->var_joint_ascending = joint_ascending;
+}
 
 /* Load a track: what _create_track leaves behind (mcr:310-335).  quad_verts are the float64
  * vertices of road_poly in draw order, quad_tile[q] = tile index for road quads, -1 for
@@ -600,7 +607,8 @@ static int collect_pairs(OrcWorld* W, Pair* out, int max) {
     }
     for (int t = T - 1; t >= 0; --t) {
         const float* ta = &W->tile_aabb[4 * t]; const Poly* TP = &W->tile_poly[t];
-        for (int c = A - 1; c >= 0; --c) {
+        for (int cc_ = A - 1; cc_ >= 0; --cc_) {
+            const int c = W->var_tie_ascending ? A - 1 - cc_ : cc_;
             for (int f = 7; f >= 0; --f) {
                 const float* fa = wa[c][f];
                 if (fa[0] - ta[2] > AABB_MARGIN || fa[1] - ta[3] > AABB_MARGIN ||
@@ -1218,14 +1226,14 @@ static void solve_island(OrcWorld* W, const int* cars, int ncars, Manifold** man
     for (int i = 0; i < nmans; ++i) contact_warm_start(&vcs[i]);
     for (int ci = 0; ci < ncars; ++ci) {
         Car* car = &W->car[cars[ci]];
-        for (int k = 0; k < 4; ++k) { int j = JOINT_ORDER[k]; joint_init(&car->j[j], &car->b[0], &car->b[1 + j], dtRatio); }
+        for (int k = 0; k < 4; ++k) { int j = W->var_joint_ascending ? k : JOINT_ORDER[k]; joint_init(&car->j[j], &car->b[0], &car->b[1 + j], dtRatio); }
     }
     int fixed_at = -1;
     for (int it = 0; it < velIters; ++it) {
         Car before; if (fixed_at < 0 && ncars == 1) before = W->car[cars[0]];
         for (int ci = 0; ci < ncars; ++ci) {
             Car* car = &W->car[cars[ci]];
-            for (int k = 0; k < 4; ++k) { int j = JOINT_ORDER[k]; joint_solve_vel(&car->j[j], &car->b[0], &car->b[1 + j], h); }
+            for (int k = 0; k < 4; ++k) { int j = W->var_joint_ascending ? k : JOINT_ORDER[k]; joint_solve_vel(&car->j[j], &car->b[0], &car->b[1 + j], h); }
         }
         for (int i = 0; i < nmans; ++i) contact_solve_vel(&vcs[i]);
         if (fixed_at < 0 && ncars == 1 && state_equal(&before, &W->car[cars[0]])) fixed_at = it; /* diagnostics only */
@@ -1257,7 +1265,7 @@ static void solve_island(OrcWorld* W, const int* cars, int ncars, Manifold** man
         for (int ci = 0; ci < ncars; ++ci) {
             Car* car = &W->car[cars[ci]];
             for (int k = 0; k < 4; ++k) {
-                int j = JOINT_ORDER[k];
+                int j = W->var_joint_ascending ? k : JOINT_ORDER[k];
                 int ok = joint_solve_pos(&car->j[j], &car->b[0], &car->b[1 + j]);
                 jointsOkay = jointsOkay && ok;
             }

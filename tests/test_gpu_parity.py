@@ -315,3 +315,32 @@ def test_collisions_keep_cars_apart(mcr):
             dmin = min(dmin, float(np.linalg.norm(p[2] - p[0])))
         mins[coll] = dmin
     assert mins[True] > 4.0 and mins[False] < 2.0, mins
+
+
+@pytest.mark.parametrize("A,B,seed", [(8, 2, 41), (2, 64, 43)])
+def test_1000_steps_random_policy_with_collisions(oracle, mcr, A, B, seed):
+    """the 1000-step bar with car-car contacts in play -- BASELINE.json configs[3]'s 8 agents
+    (use_ego_color=True; manifolds in most steps) and a 64-env batch of 2 agents.  Rewards and done every step,
+    manifold counts, full state bit-exact every 100 steps and at the end, pixels at a few steps."""
+    import torch
+    kw = dict(use_ego_color=True) if A == 8 else {}
+    venv, worlds, tracks, obs0, oobs0 = _setup(oracle, mcr, B=B, A=A, seed=seed, **kw)
+    assert np.array_equal(obs0, oobs0)
+    tape = action_tape(seed, 1000, B, A, brake_p=0.15)
+    steps_with_manifolds = 0
+    for s in range(1000):
+        obs, rew, done, _ = venv.step(torch.from_numpy(tape[s]).to(venv.device))
+        want_pixels = s in (0, 499, 999)
+        oo = [w.step(tape[s, e].astype(np.float64), render=want_pixels) for e, w in enumerate(worlds)]
+        assert np.array_equal(rew.cpu().numpy(), np.stack([x[1] for x in oo])), "step_reward, step %d" % s
+        assert np.array_equal(done.cpu().numpy() & 1, np.array([x[2] for x in oo], np.uint8)), "done, step %d" % s
+        if s % 100 == 99:
+            nman = venv.buffers["n_manifold"].cpu().numpy()
+            assert list(nman) == [len(w.manifolds()) for w in worlds], "manifold count, step %d" % s
+            steps_with_manifolds += int(nman.max() > 0)
+            _compare_state(venv, worlds, tracks, s)
+        if want_pixels:
+            assert np.array_equal(obs.cpu().numpy(), np.stack([x[0] for x in oo])), "pixels, step %d" % s
+    if A == 8:
+        assert steps_with_manifolds >= 1, "eight cars on one track never touched"
+    assert not venv.status().any()
