@@ -995,15 +995,18 @@ static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, con
         // behind the PCIe transfer.  (The touching-car chain's frames lie scattered in every range: wait for it first.)
         LAUNCH(launch_project(d, b, cc, mask, h->cfg.backwards_flag, h->cfg.use_ego_color, cls, s));
         if (split) CUDA_OK(cudaStreamWaitEvent(h->copy, h->ev_chain2, 0));
-        const int nch = 8, per = (d.B + nch - 1) / nch;
-        for (int c = 0; c < nch; ++c) {
-            const int env0 = c * per, nenv = std::min(per, d.B - env0);
-            if (nenv <= 0) break;
+        // ranges grow geometrically (B/16, B/16, B/8, B/4, B/2): the first copy starts after a sixteenth of the fill, and
+        // the later, larger copies keep the per-copy set-up cost off the link
+        int env0 = 0;
+        for (int c = 0; c < 5 && env0 < d.B; ++c) {
+            const int want = std::max(1, c == 0 ? d.B / 16 : (d.B >> (5 - c)));
+            const int nenv = c == 4 ? d.B - env0 : std::min(want, d.B - env0);
             LAUNCH(launch_fill(d, b, mask, obs, cls, h->obs_format, h->stack_k, env0, nenv, true, s));
             CUDA_OK(cudaEventRecord(h->ev_chunk[c], s));
             CUDA_OK(cudaStreamWaitEvent(h->copy, h->ev_chunk[c], 0));
             const size_t off = (size_t)env0 * d.A * frame_bytes;
             CUDA_OK(cudaMemcpyAsync(ho->h_obs + off, obs + off, (size_t)nenv * d.A * frame_bytes, cudaMemcpyDeviceToHost, h->copy));
+            env0 += nenv;
         }
         CUDA_OK(cudaEventRecord(h->ev_copy, h->copy));
     } else {

@@ -455,10 +455,9 @@ __device__ __forceinline__ void apply2(const VC& vc, V2& vA, float& wA, V2& vB, 
     wB += vc.iB * (cross(mk(vc.rBx[0], vc.rBy[0]), P1) + cross(mk(vc.rBx[1], vc.rBy[1]), P2));
 }
 
-__device__ void contact_solve_vel(VC& vc, BodyMirror* bm) {
-    BodyMirror& A = bm[vc.bA]; BodyMirror& B = bm[vc.bB];
+// b2ContactSolver::SolveVelocityConstraints for one manifold on the velocities of its two bodies (registers)
+__device__ __forceinline__ void contact_solve_vel_reg(VC& vc, V2& vA, float& wA, V2& vB, float& wB) {
     const float mA = vc.mA, mB = vc.mB, iA = vc.iA, iB = vc.iB;
-    V2 vA = mk(A.vx, A.vy), vB = mk(B.vx, B.vy); float wA = A.w, wB = B.w;
     const V2 normal = mk(vc.nx, vc.ny), tangent = cross_vs(normal, 1.0f);
     for (int j = 0; j < vc.pointCount; ++j) {
         const V2 rA = mk(vc.rAx[j], vc.rAy[j]), rB = mk(vc.rBx[j], vc.rBy[j]);
@@ -507,6 +506,12 @@ __device__ void contact_solve_vel(VC& vc, BodyMirror* bm) {
             break;
         }
     }
+}
+
+__device__ void contact_solve_vel(VC& vc, BodyMirror* bm) {
+    BodyMirror& A = bm[vc.bA]; BodyMirror& B = bm[vc.bB];
+    V2 vA = mk(A.vx, A.vy), vB = mk(B.vx, B.vy); float wA = A.w, wB = B.w;
+    contact_solve_vel_reg(vc, vA, wA, vB, wB);
     A.vx = vA.x; A.vy = vA.y; A.w = wA; B.vx = vB.x; B.vy = vB.y; B.w = wB;
 }
 
@@ -514,9 +519,13 @@ __device__ void contact_solve_pos(const VC& vc, BodyMirror* bm, float& minSepara
     BodyMirror& A = bm[vc.bA]; BodyMirror& B = bm[vc.bB];
     const float mA = vc.mA, mB = vc.mB, iA = vc.iA, iB = vc.iB;
     V2 cA = mk(A.cx, A.cy), cB = mk(B.cx, B.cy); float aA = A.a, aB = B.a;
+    XF xfA, xfB;
+    float aA_set = 0.0f, aB_set = 0.0f;
     for (int j = 0; j < vc.manifoldPoints; ++j) {
-        XF xfA, xfB;
-        rot_set(aA, xfA.s, xfA.c); rot_set(aB, xfB.s, xfB.c);
+        // b2Rot::Set per point (fp64 sincos, D5): an angle the previous point left untouched (zero impulse: the point is
+        // not penetrating) gives the same rotation bit for bit
+        if (j == 0 || __float_as_uint(aA) != __float_as_uint(aA_set)) { rot_set(aA, xfA.s, xfA.c); aA_set = aA; }
+        if (j == 0 || __float_as_uint(aB) != __float_as_uint(aB_set)) { rot_set(aB, xfB.s, xfB.c); aB_set = aB; }
         xfA.p = cA - rmul(xfA.s, xfA.c, mk(vc.lcAx, vc.lcAy));
         xfB.p = cB - rmul(xfB.s, xfB.c, mk(vc.lcBx, vc.lcBy));
         V2 normal, point; float separation;
@@ -546,6 +555,22 @@ __device__ void contact_solve_pos(const VC& vc, BodyMirror* bm, float& minSepara
     }
     A.cx = cA.x; A.cy = cA.y; A.a = aA; B.cx = cB.x; B.cy = cB.y; B.a = aB;
 }
+
+// Diagnostics build (-DMCR_PHASE_CLOCKS): lane 0 of every coupled warp adds the cycles of each part of a velocity
+// iteration to g_coupled_clk (0 joints, 1 push + sync, 2 contacts + sync, 3 pull; 7 = iterations).
+#ifdef MCR_PHASE_CLOCKS
+__device__ unsigned long long g_coupled_clk[8];
+#define CK_T0() long long ck_t_ = clock64()
+#define CK(k) do { if (threadIdx.x == 0) { const long long n_ = clock64(); atomicAdd(&g_coupled_clk[k], (unsigned long long)(n_ - ck_t_)); ck_t_ = n_; if (k == 3) atomicAdd(&g_coupled_clk[7], 1ull); } } while (0)
+extern "C" int mcr_debug_coupled_clocks(unsigned long long* out8, int reset) {
+    if (out8 && cudaMemcpyFromSymbol(out8, g_coupled_clk, sizeof(g_coupled_clk)) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[8] = {}; if (cudaMemcpyToSymbol(g_coupled_clk, z, sizeof(z)) != cudaSuccess) return -1; }
+    return 0;
+}
+#else
+#define CK_T0() do {} while (0)
+#define CK(k) do {} while (0)
+#endif
 
 __global__ void __launch_bounds__(32)
 coupled_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, int early_exit) {
@@ -590,25 +615,28 @@ coupled_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
         motorSpeed[k] = sc[(size_t)(SC_JOINT + k * SC_JOINT_FIELDS + 14) * N];
         lim[k] = b.limit_state[(size_t)k * N + car];
     }
+    // The contact solver only reads and writes the bodies some manifold refers to (`touched`, set below): inside the
+    // iteration loops only those are exchanged through the shared-memory mirror (typically one body per car).
+    unsigned touched = 0x1fu;
     auto push_vel = [&]() {
         if (mine) {
 #pragma unroll
-            for (int i = 0; i < 5; ++i) { BodyMirror& m = s_bm[lane * 5 + i]; m.vx = s.vx[i]; m.vy = s.vy[i]; m.w = s.w[i]; }
+            for (int i = 0; i < 5; ++i) if ((touched >> i) & 1u) { BodyMirror& m = s_bm[lane * 5 + i]; m.vx = s.vx[i]; m.vy = s.vy[i]; m.w = s.w[i]; }
         }
     };
     auto pull_vel = [&]() {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) { const BodyMirror& m = s_bm[(mine ? lane : A - 1) * 5 + i]; s.vx[i] = m.vx; s.vy[i] = m.vy; s.w[i] = m.w; }
+        for (int i = 0; i < 5; ++i) if ((touched >> i) & 1u) { const BodyMirror& m = s_bm[(mine ? lane : A - 1) * 5 + i]; s.vx[i] = m.vx; s.vy[i] = m.vy; s.w[i] = m.w; }
     };
     auto push_pos = [&]() {
         if (mine) {
 #pragma unroll
-            for (int i = 0; i < 5; ++i) { BodyMirror& m = s_bm[lane * 5 + i]; m.cx = cx[i]; m.cy = cy[i]; m.a = ang[i]; }
+            for (int i = 0; i < 5; ++i) if ((touched >> i) & 1u) { BodyMirror& m = s_bm[lane * 5 + i]; m.cx = cx[i]; m.cy = cy[i]; m.a = ang[i]; }
         }
     };
     auto pull_pos = [&]() {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) { const BodyMirror& m = s_bm[(mine ? lane : A - 1) * 5 + i]; cx[i] = m.cx; cy[i] = m.cy; ang[i] = m.a; }
+        for (int i = 0; i < 5; ++i) if ((touched >> i) & 1u) { const BodyMirror& m = s_bm[(mine ? lane : A - 1) * 5 + i]; cx[i] = m.cx; cy[i] = m.cy; ang[i] = m.a; }
     };
 
     // ---- islands: union-find over cars linked by manifolds, root = lowest car index -------------------
@@ -650,6 +678,16 @@ coupled_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
     const int my_first = mine ? s_lstart[lane] : 0, my_count = mine ? s_lstart[lane + 1] - s_lstart[lane] : 0;
     for (int k = 0; k < my_count; ++k) contact_warm_start(s_vc[s_list[my_first + k]], s_bm);
     __syncwarp();
+    {   // bodies of this lane's car that a manifold refers to (mirror slot = car * 5 + body)
+        unsigned t = 0u;
+        const int me = mine ? lane : A - 1;
+        for (int i = 0; i < nman; ++i) {
+            const int a = s_vc[i].bA, bq = s_vc[i].bB;
+            if (a / 5 == me) t |= 1u << (a % 5);
+            if (bq / 5 == me) t |= 1u << (bq % 5);
+        }
+        touched = t;
+    }
     pull_vel();
     // ---- joints: InitVelocityConstraints + warm start, then the 180 sweeps in lock step ----------------
     JointC J[4];
@@ -668,12 +706,19 @@ coupled_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
         if (lane < nman) { ci_before[0][0] = s_vc[lane].ni[0]; ci_before[0][1] = s_vc[lane].ni[1]; ci_before[0][2] = s_vc[lane].ti[0]; ci_before[0][3] = s_vc[lane].ti[1]; }
 #pragma unroll 1
         for (int rep = 0; rep < 4; ++rep) {
+            CK_T0();
             if (no_limits) sweep<0>(s, J, m); else sweep<-1>(s, J, m);
+            CK(0);
+            // (measured and dropped, profiles/README r02: fetching the manifold's two bodies from their owners' registers
+            // with shuffles instead of this shared-memory mirror -- 12 shuffles per manifold -- was 17 % slower)
             push_vel();
             __syncwarp();
+            CK(1);
             for (int k = 0; k < my_count; ++k) contact_solve_vel(s_vc[s_list[my_first + k]], s_bm);
             __syncwarp();
+            CK(2);
             pull_vel();
+            CK(3);
         }
         bool changed = mine && state_diff(before, s) != 0u;
         if (lane < nman) {

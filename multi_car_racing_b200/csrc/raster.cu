@@ -1324,7 +1324,9 @@ int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const 
                   int backwards_flag, int use_ego_color, int cls, int obs_format, int stack_k, void* stream) {
     if (!configure_render()) return -1;
     static const bool fused = std::getenv("MCR_RENDER_FUSED") != nullptr;     // diagnostics: the single-kernel rasteriser (A/B)
-    if (fused) {
+    // cls 2 = the few envs with touching cars, at the end of the step's longest chain: one wave of the fused kernel
+    // (~18 us) ends earlier there than project + fill (two latency-bound launches, ~30 us for a handful of frames)
+    if (fused || cls == 2) {
         mcr_launch_pdl(render_kernel<false>, dim3(d.B, d.A), dim3(RS_THREADS), sizeof(RasterSmem), (cudaStream_t)stream,
                        d, b, cc, mask, obs, backwards_flag, use_ego_color, cls, obs_format, stack_k, VpParams{});
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
