@@ -40,17 +40,18 @@ NUM_AGENTS = 2
 BATCH_ENVS = 1024
 
 
-def workload_config(A, B, world, obs_format="rgb", extra=None):
-    cfg = _workload_config(A, B, world, obs_format)
+def workload_config(A, B, world, obs_format="rgb", extra=None, ego=False):
+    cfg = _workload_config(A, B, world, obs_format, ego)
     if extra:
         cfg.update(extra)
     return cfg
 
 
-def _workload_config(A, B, world, obs_format="rgb"):
+def _workload_config(A, B, world, obs_format="rgb", ego=False):
     return {"workload": "MultiCarRacing-v0 step+render, num_agents=%d, batch=%d envs per GPU, random policy, "
                         "use_random_direction=True, device-side next-step auto reset (done or 1000 steps)%s" % (
-                            A, B, "" if obs_format == "rgb" else ", obs_format=%s (NOT the reference's layout)" % obs_format),
+                            A, B, ("" if obs_format == "rgb" else ", obs_format=%s (NOT the reference's layout)" % obs_format) +
+                            (", use_ego_color=True" if ego else "")),
             "batch_envs_per_gpu": B, "num_agents": A, "l2": "256 MiB flush between timed steps",
             "parallelism": "env-sharded x%d, no data-path collective" % world}
 
@@ -219,7 +220,8 @@ def run_ours(args):
 
     np.random.seed(1234 + rank)
     venv = mcr.BatchedMultiCarRacing(B, num_agents=A, use_random_direction=True, device=dev, auto_reset='next_step',
-                                     max_episode_steps=1000, seed=1234 + rank * B, obs_format=args.obs_format)
+                                     max_episode_steps=1000, seed=1234 + rank * B, obs_format=args.obs_format,
+                                     use_ego_color=bool(args.use_ego_color))
     obs_bytes = int(np.prod(venv.obs_shape)) * (2 if args.obs_format == "rgb_chw_f16" else 1)
     venv.reset(device_tracks=True)
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
@@ -279,35 +281,37 @@ def run_ours(args):
     fill_ms = (sum(fill_us) / len(fill_us) / 1e3) if fill_us else None
 
     # ---- end-to-end through the host-buffer API ----------------------------------------------------
-    hb = venv.host_buffers()
-    host_tape = tape[:16].cpu().numpy()
     KE = min(K, 200)
-    for s in range(3):
-        venv.step_host(host_tape[s % 16])
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(KE):
-        hb["action"].numpy()[...] = host_tape[s % 16]
-        venv.step_host(hb["action"].numpy())
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = pipe_s = float("nan")
+    if not args.no_e2e:
+      hb = venv.host_buffers()
+      host_tape = tape[:16].cpu().numpy()
+      for s in range(3):
+          venv.step_host(host_tape[s % 16])
+      barrier()
+      t0 = time.perf_counter()
+      for s in range(KE):
+          hb["action"].numpy()[...] = host_tape[s % 16]
+          venv.step_host(hb["action"].numpy())
+      barrier()
+      e2e_s = time.perf_counter() - t0
 
-    # ---- the same with the copy of step k overlapping the compute of step k+1 (not the headline: a
-    #      synchronous caller cannot use it; reported as e2e_pipelined) ---------------------------------------
-    for s in range(3):
-        venv.step_host_async(host_tape[s % 16])
-        if s:
-            venv.step_host_wait()
-    venv.step_host_wait()
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(KE):
-        venv.step_host_async(host_tape[s % 16])
-        if s:
-            venv.step_host_wait()
-    venv.step_host_wait()
-    barrier()
-    pipe_s = time.perf_counter() - t0
+      # ---- the same with the copy of step k overlapping the compute of step k+1 (not the headline: a
+      #      synchronous caller cannot use it; reported as e2e_pipelined) ---------------------------------------
+      for s in range(3):
+          venv.step_host_async(host_tape[s % 16])
+          if s:
+              venv.step_host_wait()
+      venv.step_host_wait()
+      barrier()
+      t0 = time.perf_counter()
+      for s in range(KE):
+          venv.step_host_async(host_tape[s % 16])
+          if s:
+              venv.step_host_wait()
+      venv.step_host_wait()
+      barrier()
+      pipe_s = time.perf_counter() - t0
 
     # ---- reduce over ranks: MAX time, SUM frames -------------------------------------------------------
     times = torch.tensor([dev_ms, e2e_s * 1e3, pipe_s * 1e3], dtype=torch.float64, device=dev)
@@ -345,11 +349,11 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 rigid bodies + f64 tyre/reward (u8 frames)", "data": "synthetic",
-            "config": workload_config(A, B, world, args.obs_format),
+            "config": workload_config(A, B, world, args.obs_format, ego=bool(args.use_ego_color)),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * A * 3 * 4,
+            "e2e": None if args.no_e2e else {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * A * 3 * 4,
                     "d2h_bytes_per_step": B * A * obs_bytes + B * A * 8 + B, "steps": KE},
-            "e2e_pipelined": {"value": frames_per_step * KE * world / (pipe_ms_max * 1e-3), "unit": UNIT, "steps": KE,
+            "e2e_pipelined": None if args.no_e2e else {"value": frames_per_step * KE * world / (pipe_ms_max * 1e-3), "unit": UNIT, "steps": KE,
                               "note": "step_host_async / step_host_wait: the device-to-host copy of step k overlaps the "
                                       "compute of step k+1 (results one call late); not usable by a synchronous policy loop"},
             "gpu_launches": int(launches),
@@ -381,6 +385,8 @@ def main():
     ap.add_argument("--batch-envs", dest="batch_envs", type=int, default=BATCH_ENVS)
     ap.add_argument("--num-agents", dest="num_agents", type=int, default=NUM_AGENTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", dest="no_e2e", action="store_true", help="skip the host-buffer legs (large-batch sweeps)")
+    ap.add_argument("--use-ego-color", dest="use_ego_color", action="store_true", help="BASELINE.json configs[3]")
     ap.add_argument("--obs-format", dest="obs_format", default="rgb", choices=["rgb", "gray", "rgb_chw", "gray_stack", "rgb_chw_f16"],
                     help="rasteriser store layout; only 'rgb' is the reference's observation (the headline config)")
     args = ap.parse_args()

@@ -60,7 +60,9 @@ def build(force=False, verbose=False, out=None, extra=()):
 
 
 if __name__ == "__main__":
-    if "--phase-clocks" in sys.argv:
+    if "--stg-store" in sys.argv:
+        path = build(out="libmcr_stg.so", extra=["-DMCR_FILL_STG_STORE"], verbose="--verbose" in sys.argv)
+    elif "--phase-clocks" in sys.argv:
         path = build(out="libmcr_clk.so", extra=["-DMCR_PHASE_CLOCKS"], verbose="--verbose" in sys.argv)
     else:
         path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)

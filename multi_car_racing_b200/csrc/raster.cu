@@ -31,6 +31,7 @@
 #include "mcr_internal.h"
 #include <cuda_runtime.h>
 #include <cstring>
+#include <cstddef>
 #include <algorithm>
 #include <cstdlib>
 
@@ -1148,6 +1149,29 @@ fill_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, uint8_t* __r
         flush_list<false>(S, tid, pix, cnt, -1, last, 0, 0, SW);
         e0 += cnt;
     } while (e0 < n);
+#ifndef MCR_FILL_STG_STORE
+    // The reference's RGB HWC frame is staged in shared memory (over the display list / span pool / row masks, which
+    // are dead by now) and leaves as ONE cp.async.bulk (TMA, UBLKCP.G.S) of 27 648 contiguous bytes issued by thread 0.
+    // Each warp-level STG.128 of the direct store touches 32 rows at 16 bytes -- half a sector each: the bulk copy
+    // writes whole sectors (L2 write requests 4.8 M -> 0.68 M, sectors 5.2 M -> 2.7 M per 2048 frames) and is 5-8 % faster
+    // end to end (profiles/README r02; A/B build: python -m multi_car_racing_b200.build --stg-store -> libmcr_stg.so).
+    if (obs_format == MCR_OBS_RGB_HWC || obs_format == MCR_OBS_GRAY || obs_format == MCR_OBS_RGB_CHW) {   // one contiguous block per frame
+        __syncthreads();                               // every thread is done with the spans and masks
+        unsigned char* stage = reinterpret_cast<unsigned char*>(&S.edge[0][0]);
+        static_assert(offsetof(RasterSmem, rowmask) + sizeof(((RasterSmem*)0)->rowmask) - offsetof(RasterSmem, edge) >= MCR_OBS_BYTES, "staging area");
+        finish_frame<false>(S, tid, pix, stage, 0, obs_format, 0, 0, SW, SH, 1, 0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned frame_bytes = obs_format == MCR_OBS_GRAY ? (unsigned)(SW * SH) : (unsigned)MCR_OBS_BYTES;
+            const unsigned long long gdst = (unsigned long long)(obs + (size_t)frame * frame_bytes);
+            const unsigned ssrc = (unsigned)__cvta_generic_to_shared(stage);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(ssrc), "r"(frame_bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    } else
+#endif
     finish_frame<false>(S, tid, pix, obs, frame, obs_format, 0, 0, SW, SH, stack_k, b.steps[frame]);
     if (cls != 2 && tid == 0) atomicMax(b.timeline + TL_RENDER_END, mcr_globaltimer());
 #ifdef MCR_PHASE_CLOCKS
