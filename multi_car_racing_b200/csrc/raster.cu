@@ -931,16 +931,36 @@ __device__ __forceinline__ CheckerRange checker_range(float m00, float m01, floa
     return r;
 }
 
-// One WARP per agent-frame, no block barriers: every warp walks its frame's candidates 32 at a time in painter's
-// order (ballot / shuffle-scan compaction), so a warp waiting on a load never holds another frame back.
-__global__ void __launch_bounds__(PJ_THREADS, 4)
+// PJ_W warps per agent-frame (one CTA per frame).  The frame's candidates are cut into passes of 32 in painter's order;
+// pass p is worked by warp p % PJ_W -- loads, camera transform, cull and the row scan of different passes run side by
+// side -- and only the hand-off of the running (entries, span slots) prefix goes in pass order: the warp of pass p
+// waits for the prefix pass p - 1 published in shared memory, publishes its own and writes its entries.  Dependencies
+// only point to earlier passes and every warp takes its passes in increasing order, so the wait always ends.
+#ifdef MCR_PHASE_CLOCKS
+#define PJCLK_T0() long long pj_t_ = clock64()
+#define PJCLK(k) do { if (threadIdx.x == 0) { const long long n_ = clock64(); atomicAdd(&g_phase_clk[k], (unsigned long long)(n_ - pj_t_)); pj_t_ = n_; } } while (0)
+#else
+#define PJCLK_T0() do {} while (0)
+#define PJCLK(k) do {} while (0)
+#endif
+#ifndef PJ_W
+#define PJ_W 2
+#endif
+#define PJ_MAX_PASS 96           // (1 + 100) / 32 + 2048 / 32 + (12 * 16 + 9) / 32 + slack
+
+__global__ void __launch_bounds__(PJ_W * 32, 32 / PJ_W)
 project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, int backwards_flag, int use_ego_color, int cls) {
-    __shared__ uint8_t s_vis_chunk[PJ_WARPS][MAX_CHUNKS];
+    __shared__ uint8_t s_vis_chunk[MAX_CHUNKS];
+    __shared__ int s_nvis;
+    __shared__ int s_pre_cnt[PJ_MAX_PASS + 1], s_pre_rows[PJ_MAX_PASS + 1];   // prefix BEFORE pass p; cnt < 0: not published yet
+    __shared__ __align__(16) uint8_t s_touched[2048];   // this env's "tile colour was reset" flags (Tmax <= Qmax <= 2048): loaded
+                                                        // beside the camera, so the road passes do not wait for a dependent load
+    PJCLK_T0();
     cudaGridDependencySynchronize();               // programmatic dependent launch behind post_kernel (mcr_launch_pdl)
     tl_stamp(b.timeline, cls == 2 ? TL_RENDER2 : TL_RENDER);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int frame = (int)blockIdx.x * PJ_WARPS + warp;
-    if (frame >= d.N) return;
+    const int frame = (int)blockIdx.x;
+    PJCLK(9);
     const int env = frame / d.A, agent = frame - env * d.A;
     if (mask && !mask[env]) return;
     if (cls && (cls == 2) != (b.n_manifold[env] > 0)) return;
@@ -950,31 +970,46 @@ project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
     M.m00 = b.camera[(size_t)0 * N + car]; M.m01 = b.camera[(size_t)1 * N + car]; M.m02 = b.camera[(size_t)2 * N + car];
     M.m10 = b.camera[(size_t)3 * N + car]; M.m11 = b.camera[(size_t)4 * N + car]; M.m12 = b.camera[(size_t)5 * N + car];
     const int Q = b.trk_Q[slot];
-    // ---- road_poly chunk culling (bounding circle of every 8 consecutive quads vs the frame), lane per chunk; chunks
-    // past the track's last quad have radius 0 in the pool, so the loop bound does not wait for trk_Q
-    uint8_t* vis_chunk = s_vis_chunk[warp];
-    int n_vis = 0;
-    {
+    for (int i = threadIdx.x; i <= PJ_MAX_PASS; i += PJ_W * 32) { s_pre_cnt[i] = i == 0 ? 0 : -1; s_pre_rows[i] = 0; }
+    if ((d.Tmax & 15) == 0) {
+        const uint4* src = reinterpret_cast<const uint4*>(b.touched + (size_t)env * d.Tmax);
+        for (int i = threadIdx.x; i < d.Tmax / 16; i += PJ_W * 32) reinterpret_cast<uint4*>(s_touched)[i] = src[i];
+    } else {
+        for (int i = threadIdx.x; i < d.Tmax; i += PJ_W * 32) s_touched[i] = b.touched[(size_t)env * d.Tmax + i];
+    }
+    // ---- road_poly chunk culling (bounding circle of every 8 consecutive quads vs the frame), warp 0, lane per chunk;
+    // chunks past the track's last quad have radius 0 in the pool, so the loop bound does not wait for trk_Q
+    if (warp == 0) {
+        int n_vis = 0;
         const int nchunks = d.Qmax / MCR_QUAD_CHUNK;
         const float rscale = sqrtf(M.m00 * M.m00 + M.m01 * M.m01 + M.m10 * M.m10 + M.m11 * M.m11) * 1.001f;
-        for (int c0 = 0; c0 < nchunks; c0 += 32) {
-            const int c = c0 + lane;
-            bool vis = false;
-            if (c < nchunks) {
-                const float4 cc4 = *(const float4*)(b.trk_chunk + ((size_t)slot * nchunks + c) * 4);
-                const float cxp = (M.m00 * cc4.x + M.m01 * cc4.y) + M.m02, cyp = (M.m10 * cc4.x + M.m11 * cc4.y) + M.m12;
-                const float rp = cc4.z * rscale + 2.0f;      // |M v| <= ||M||_F |v|: conservative pixel radius, plus a 2-pixel margin
-                vis = (cxp + rp >= 0.0f) && (cxp - rp <= (float)SW) && (cyp + rp >= 0.0f) && (cyp - rp <= (float)SH);
-                if (!(rp == rp) || !(cxp == cxp) || !(cyp == cyp)) vis = true;
-                if (!(cc4.z > 0.0f)) vis = false;
+        for (int c0 = 0; c0 < nchunks; c0 += 128) {          // four circles per lane in flight: one memory round trip per 128 chunks
+            float4 cc4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + 32 * u + lane;
+                cc4[u] = c < nchunks ? *(const float4*)(b.trk_chunk + ((size_t)slot * nchunks + c) * 4) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             }
-            const uint32_t bal = __ballot_sync(0xffffffffu, vis);
-            if (vis) vis_chunk[n_vis + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)c;
-            n_vis += __popc(bal);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + 32 * u + lane;
+                const float cxp = (M.m00 * cc4[u].x + M.m01 * cc4[u].y) + M.m02, cyp = (M.m10 * cc4[u].x + M.m11 * cc4[u].y) + M.m12;
+                const float rp = cc4[u].z * rscale + 2.0f;   // |M v| <= ||M||_F |v|: conservative pixel radius, plus a 2-pixel margin
+                bool vis = (cxp + rp >= 0.0f) && (cxp - rp <= (float)SW) && (cyp + rp >= 0.0f) && (cyp - rp <= (float)SH);
+                if (!(rp == rp) || !(cxp == cxp) || !(cyp == cyp)) vis = true;
+                if (!(cc4[u].z > 0.0f)) vis = false;
+                const uint32_t bal = __ballot_sync(0xffffffffu, vis);
+                if (vis) s_vis_chunk[n_vis + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)c;
+                n_vis += __popc(bal);
+            }
         }
-        __syncwarp();
+        if (lane == 0) s_nvis = n_vis;
     }
     const CheckerRange ck = checker_range(M.m00, M.m01, M.m02, M.m10, M.m11, M.m12, 0.0f, 0.0f, (float)SW, (float)SH);
+    __syncthreads();
+    PJCLK(10);
+    const uint8_t* vis_chunk = s_vis_chunk;
+    const int n_vis = s_nvis;
 
     View V;
     V.env = env; V.agent = agent; V.A = d.A; V.N = N; V.Q = Q;
@@ -990,7 +1025,7 @@ project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
     V.quad = b.trk_quad + (size_t)slot * d.Qmax * 8;
     V.quad_col = b.trk_quad_col + (size_t)slot * d.Qmax;
     V.quad_tile = b.trk_quad_tile + (size_t)slot * d.Qmax;
-    V.touched = b.touched + (size_t)env * d.Tmax;
+    V.touched = s_touched;
     V.use_ego_color = use_ego_color;
     V.backward_flag_on = (b.backward_snap[car] != 0) && backwards_flag;     // step(): flag of the PREVIOUS step (render precedes mcr:445-495)
     V.hud_sx = (float)(96.0 / 1000.0); V.hud_sy = (float)(96.0 / 800.0);
@@ -1003,12 +1038,47 @@ project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
     float4* __restrict__ edge = reinterpret_cast<float4*>(b.dl_edge) + (size_t)frame * d.dl_cap * 4;
     float4* __restrict__ oct = reinterpret_cast<float4*>(b.dl_oct) + (size_t)frame * d.A * 4;
 
+    // passes in painter's order: [0, P0) playfield + checker squares, [P0, P0 + P1) road_poly, [P0 + P1, NP) cars + HUD
     const int NC = V.c_hud + 9;
-    int lc = 0, pc = 0;                            // entries / span slots so far (warp uniform)
-    // ordered compaction of one pass of <= 32 candidates into the frame's display list
-    auto emit = [&](bool valid, int nv, const float (&px)[MCR_MAXV], const float (&py)[MCR_MAXV], int y0, int y1, int col, int aux) {
+    const int P0 = V.c_road >> 5, P1 = (V.c_cars - V.c_road) >> 5, NP = min(P0 + P1 + ((NC - V.c_cars + 31) >> 5), PJ_MAX_PASS);
+    // road_poly quads of the visible chunks (mcr:628-631), four chunks per pass: a warp loads the quads of its NEXT road
+    // pass before it works on the current pass
+    struct RoadQuad { int q; float4 a, b; int tile, col; };
+    auto road_load = [&](int p) {
+        RoadQuad r; r.q = -1; r.a = make_float4(0, 0, 0, 0); r.b = r.a; r.tile = -1; r.col = 0;
+        if (p >= P0 && p < P0 + P1) {
+            const int k = p * 32 + lane - V.c_road;
+            if (k < V.n_road) { r.q = (int)vis_chunk[k >> 3] * MCR_QUAD_CHUNK + (k & (MCR_QUAD_CHUNK - 1)); if (r.q >= Q) r.q = -1; }
+            if (r.q >= 0) {
+                r.a = *(const float4*)(V.quad + (size_t)r.q * 8); r.b = *(const float4*)(V.quad + (size_t)r.q * 8 + 4);
+                r.tile = V.quad_tile[r.q]; r.col = V.quad_col[r.q];
+            }
+        }
+        return r;
+    };
+    RoadQuad nextq = road_load(warp);
+    for (int p = warp; p < NP; p += PJ_W) {
+        const int i = p * 32 + lane;               // candidate index (the classes start on multiples of 32)
+        float px[MCR_MAXV], py[MCR_MAXV];
+        int nv = 0, col = 0, y0 = 0, y1 = 0, aux = 0;
+        const RoadQuad rq = nextq;
+        nextq = road_load(p + PJ_W);
+        if (p >= P0 && p < P0 + P1) {
+            const int q = rq.q;
+            if (q >= 0) {
+                const float4 qa = rq.a, qb = rq.b;
+                const int tl = rq.tile;
+                col = rq.col;
+                if (tl >= 0 && V.touched[tl]) col = PAL_ROAD0;                // tile.color reset, mcr:102-104
+                xf_pt(M, qa.x, qa.y, px[0], py[0]); xf_pt(M, qa.z, qa.w, px[1], py[1]);
+                xf_pt(M, qb.x, qb.y, px[2], py[2]); xf_pt(M, qb.z, qb.w, px[3], py[3]);
+                nv = 4;
+            }
+        } else if (i < NC) {
+            nv = gen_candidate(i, V, M, cc, px, py, col, aux);
+        }
+        const bool valid = cand_rows<false>(nv, px, py, i < V.c_hud, hud_rows, 0.0f, 0.0f, (float)SW, (float)SH, 0, SH, y0, y1);
         const uint32_t bal = __ballot_sync(0xffffffffu, valid);
-        if (bal == 0u) return;
         const int rows = valid ? y1 - y0 : 0;
         int rows_inc = rows;
 #pragma unroll
@@ -1016,6 +1086,21 @@ project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
             const int r = __shfl_up_sync(0xffffffffu, rows_inc, o);
             if (lane >= o) rows_inc += r;
         }
+        const int pass_rows = __shfl_sync(0xffffffffu, rows_inc, 31);
+        PJCLK(11);
+        // ---- in-order hand-off of the running prefix -------------------------------------------------------------
+        int lc = 0, pc = 0;
+        if (lane == 0) {
+            volatile int* vc = s_pre_cnt; volatile int* vr = s_pre_rows;
+            while ((lc = vc[p]) < 0) __nanosleep(20);
+            __threadfence_block();
+            pc = vr[p];
+            vr[p + 1] = pc + pass_rows;
+            __threadfence_block();
+            vc[p + 1] = lc + __popc(bal);
+        }
+        lc = __shfl_sync(0xffffffffu, lc, 0); pc = __shfl_sync(0xffffffffu, pc, 0);
+        PJCLK(12);
         if (valid) {
             const int sl = lc + __popc(bal & ((1u << lane) - 1u));          // < dl_cap: the list holds every candidate
             const int first = pc + rows_inc - rows;                         // this polygon's span slots: [first, first + rows)
@@ -1028,55 +1113,13 @@ project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
             meta[sl] = make_uint2((uint32_t)y0 | ((uint32_t)rows << 8) | ((uint32_t)col << 16) | ((uint32_t)(nv > 4 ? 8 + aux : 4) << 24),
                                   (uint32_t)first);
         }
-        lc += __popc(bal);
-        pc += __shfl_sync(0xffffffffu, rows_inc, 31);
-    };
-    auto generic_passes = [&](int i0, int i1) {    // playfield + checker squares, cars, HUD: gen_candidate's class dispatch
-        for (int base = i0; base < i1; base += 32) {
-            const int i = base + lane;
-            float px[MCR_MAXV], py[MCR_MAXV];
-            int nv = 0, col = 0, y0 = 0, y1 = 0, aux = 0;
-            if (i < i1) nv = gen_candidate(i, V, M, cc, px, py, col, aux);
-            const bool valid = cand_rows<false>(nv, px, py, i < V.c_hud, hud_rows, 0.0f, 0.0f, (float)SW, (float)SH, 0, SH, y0, y1);
-            emit(valid, nv, px, py, y0, y1, col, aux);
-        }
-    };
-    generic_passes(0, 1 + V.n_checker);
-    // ---- road_poly quads of the visible chunks (mcr:628-631): the bulk of a frame.  Four chunks per pass; the next
-    // pass's quads are loaded before this pass is processed, and the "tile colour was reset" flag (a dependent load)
-    // is only consumed when the entry is written.
-    {
-        const int n_road = V.n_road;
-        auto quad_of = [&](int r) -> int {         // r-th road candidate -> road_poly index, -1 = none
-            if (r >= n_road) return -1;
-            const int q = (int)vis_chunk[r >> 3] * MCR_QUAD_CHUNK + (r & (MCR_QUAD_CHUNK - 1));
-            return q < Q ? q : -1;
-        };
-        int q = quad_of(lane);
-        float4 qa = make_float4(0, 0, 0, 0), qb = qa; int tl = -1; int qc = 0;
-        if (q >= 0) {
-            qa = *(const float4*)(V.quad + (size_t)q * 8); qb = *(const float4*)(V.quad + (size_t)q * 8 + 4);
-            tl = V.quad_tile[q]; qc = V.quad_col[q];
-        }
-        for (int base = 0; base < n_road; base += 32) {
-            const int qn = quad_of(base + 32 + lane);
-            float4 na = make_float4(0, 0, 0, 0), nb = na; int ntl = -1, nqc = 0;
-            if (qn >= 0) {
-                na = *(const float4*)(V.quad + (size_t)qn * 8); nb = *(const float4*)(V.quad + (size_t)qn * 8 + 4);
-                ntl = V.quad_tile[qn]; nqc = V.quad_col[qn];
-            }
-            const uint8_t tch = (q >= 0 && tl >= 0) ? V.touched[tl] : (uint8_t)0;
-            float px[MCR_MAXV], py[MCR_MAXV];
-            int y0 = 0, y1 = 0;
-            xf_pt(M, qa.x, qa.y, px[0], py[0]); xf_pt(M, qa.z, qa.w, px[1], py[1]);
-            xf_pt(M, qb.x, qb.y, px[2], py[2]); xf_pt(M, qb.z, qb.w, px[3], py[3]);
-            const bool valid = cand_rows<false>(q >= 0 ? 4 : 0, px, py, true, hud_rows, 0.0f, 0.0f, (float)SW, (float)SH, 0, SH, y0, y1);
-            emit(valid, 4, px, py, y0, y1, tch ? PAL_ROAD0 : qc, 0);       // tile.color reset, mcr:102-104
-            q = qn; qa = na; qb = nb; tl = ntl; qc = nqc;
-        }
+        if (p == NP - 1 && lane == 0)
+            *reinterpret_cast<int4*>(b.dl_hdr + (size_t)frame * 4) = make_int4(lc + __popc(bal), pc + pass_rows, V.grass_full, 0);
+        PJCLK(13);
     }
-    generic_passes(V.c_cars, NC);
-    if (lane == 0) *reinterpret_cast<int4*>(b.dl_hdr + (size_t)frame * 4) = make_int4(lc, pc, V.grass_full, 0);
+#ifdef MCR_PHASE_CLOCKS
+    if (threadIdx.x == 0) atomicAdd(&g_phase_clk[14], 1ull);
+#endif
 }
 
 // One CTA per agent-frame.  (Measured and dropped, profiles/README r02: persistent CTAs with a frame queue or a static
@@ -1355,7 +1398,7 @@ int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const 
                        d, b, cc, mask, obs, backwards_flag, use_ego_color, cls, obs_format, stack_k, VpParams{});
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
     }
-    mcr_launch_pdl(project_kernel, dim3((d.N + PJ_WARPS - 1) / PJ_WARPS), dim3(PJ_THREADS), 0, (cudaStream_t)stream,
+    mcr_launch_pdl(project_kernel, dim3(d.N), dim3(PJ_W * 32), 0, (cudaStream_t)stream,
                    d, b, cc, mask, backwards_flag, use_ego_color, cls);
     mcr_launch_pdl(fill_kernel, dim3(d.B, d.A), dim3(RS_THREADS), sizeof(RasterSmem), (cudaStream_t)stream,
                    d, b, mask, obs, cls, obs_format, stack_k, 0);
@@ -1372,7 +1415,7 @@ bool render_is_split() {
 int launch_project(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, int backwards_flag, int use_ego_color,
                    int cls, void* stream) {
     if (!configure_render()) return -1;
-    mcr_launch_pdl(project_kernel, dim3((d.N + PJ_WARPS - 1) / PJ_WARPS), dim3(PJ_THREADS), 0, (cudaStream_t)stream,
+    mcr_launch_pdl(project_kernel, dim3(d.N), dim3(PJ_W * 32), 0, (cudaStream_t)stream,
                    d, b, cc, mask, backwards_flag, use_ego_color, cls);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

@@ -29,3 +29,6 @@ for name, upto in (("t=0.02", 0), ("t=0.5", 24), ("mid(170)", 170)):
     print("%s: %d CTAs, %.0f cycles per CTA" % (name, n, v[:9].sum() / n))
     for k, nm in enumerate(names):
         print("   %-20s %8.0f cycles  %5.1f %%" % (nm, v[k] / n, 100 * v[k] / max(v[:9].sum(), 1)))
+    npj = max(v[14], 1)
+    print("   project_kernel, warp 0 of %d CTAs: pdl wait+ids %.0f | loads+cull+barrier %.0f | passes: candidates+scan %.0f, prefix hand-off %.0f, edges+stores %.0f  (cycles per CTA)"
+          % (npj, v[9] / npj, v[10] / npj, v[11] / npj, v[12] / npj, v[13] / npj))
