@@ -1152,6 +1152,9 @@ fill_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, uint8_t* __r
     uint2 mt = make_uint2(0u, 0u);
     if (tid < LIST_CAP) mt = meta[min(tid, d.dl_cap - 1)];
     const float4 ed0 = edge[min(tid, d.dl_cap * 4 - 1)], ed1 = edge[min(tid + RS_THREADS, d.dl_cap * 4 - 1)];
+    // edges 4..7 of every car's hull octagon go to their fixed place behind the list, whether or not the octagon made it
+    // into the list (no load waits for the metadata)
+    if (tid < d.A * 4) S.edge[tid & 3][LIST_CAP + (tid >> 2)] = oct[tid];
     const int n = hdr.x;
     if (tid == 64) score_glyphs(b.score_snap[frame], S.glyph);
     uint32_t pix[8];                       // this thread's 32 pixels (palette indices); glClear -> black
@@ -1174,10 +1177,6 @@ fill_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, uint8_t* __r
             S.base[tid] = first - y0; S.ne[tid] = (uint8_t)ne; S.col[tid] = (uint8_t)((mt.x >> 16) & 0xffu);
             if (first & 31) atomicOr(&S.startbits[first >> 5], 1u << (first & 31));
             for (int k = (first + 31) >> 5; (k << 5) < first + rows; ++k) S.slot32_owner[k] = (uint8_t)tid;
-            if (ne >= 8) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) S.edge[k][LIST_CAP + (ne - 8)] = oct[(size_t)(ne - 8) * 4 + k];
-            }
             if (tid == cnt - 1) S.bc_rows = first + rows;
         }
         if (e0 == 0) {
