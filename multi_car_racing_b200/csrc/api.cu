@@ -361,6 +361,12 @@ extern "C" int mcr_track_generate(uint32_t* mt_state, int32_t max_tiles, int32_t
                                 x2 + TRACK_WIDTH * std::cos(b2), y2 + TRACK_WIDTH * std::sin(b2),
                                 x2 - TRACK_WIDTH * std::cos(b2), y2 - TRACK_WIDTH * std::sin(b2)};
         const double c = 0.01 * (k % 3);
+        {   // D8: a tile quad that b2PolygonShape::Set cannot keep as four vertices (fd_tile.shape.vertices = ..., mcr:318:
+            // the reference's CreateStaticBody asserts) fails the attempt, like the device generator does (trackgen.cuh)
+            std::vector<P2> raw;
+            for (int v = 0; v < 4; ++v) raw.push_back(P2{(float)road[2 * v], (float)road[2 * v + 1]});
+            if (b2_polygon_set(raw).size() != 4) return 0;
+        }
         if (!put(road, (float)(0.4 + c), (float)(0.4 + c), (float)(0.4 + c), k)) return fail(-3, "max_quads too small");
         if (border[k]) {
             const double side = npsign(b2 - b1);

@@ -359,6 +359,19 @@ static void free_track(OrcWorld* W) {
 ORC_API void orc_destroy(OrcWorld* W) { if (!W) return; free_track(W); free(W); }
 
 ORC_API void orc_set_collisions(OrcWorld* W, int on) { W->collisions = on; }
+/* Vertex count b2PolygonShape::Set leaves of a tile quad given as 8 floats (fd_tile.shape.vertices = ..., mcr:318). */
+ORC_API int orc_tile_vertex_count(const float* xy8) {
+    V2 vv[4], ps[4]; Poly P; int n = 0;
+    for (int k = 0; k < 4; ++k) vv[k] = v2(xy8[2 * k], xy8[2 * k + 1]);
+    for (int i = 0; i < 4; ++i) {               /* the weld step of Set: fewer than 3 vertices left -> b2Assert in Box2D */
+        int unique = 1;
+        for (int j = 0; j < n; ++j) { V2 d = vsub(vv[i], ps[j]); if (vdot(d, d) < 0.5f * B2_LINEAR_SLOP) { unique = 0; break; } }
+        if (unique) ps[n++] = vv[i];
+    }
+    if (n < 3) return n;
+    poly_set(&P, vv, 4);
+    return P.n;
+}
 ORC_API void orc_set_variant(OrcWorld* W, int tie_ascending, int joint_ascending) {
     W->var_tie_ascending = tie_ascending; W->var_joint_ascending = joint_ascending;
 }

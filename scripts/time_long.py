@@ -5,7 +5,7 @@ import multi_car_racing_b200 as mcr
 B = 1024
 np.random.seed(1234)
 venv = mcr.BatchedMultiCarRacing(B, num_agents=2, auto_reset=False, max_episode_steps=0, seed=1234)
-venv.reset()
+venv.reset(device_tracks=True)
 g = torch.Generator(device=venv.device); g.manual_seed(1234)
 tape = torch.rand((128, B, 2, 3), device=venv.device, generator=g); tape[..., 0] = tape[..., 0] * 2 - 1
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]

@@ -13,7 +13,7 @@ A = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 names = ["head", "contacts", "stripes", "sweep", "coupled", "post", "score", "render", "render_end", "post2", "render2", "sweep_end_percar", "sweep_end_packed", "coupled_vel_end", "coupled_pos_end", "fill"]
 np.random.seed(1234)
 venv = mcr.BatchedMultiCarRacing(B, num_agents=A, auto_reset="next_step", max_episode_steps=1000, seed=1234)
-venv.reset()
+venv.reset(device_tracks=True)
 g = torch.Generator(device=venv.device); g.manual_seed(1234)
 tape = torch.rand((128, B, A, 3), device=venv.device, generator=g); tape[..., 0] = tape[..., 0] * 2 - 1
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
