@@ -945,18 +945,25 @@ static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, con
     const bool split = h->cfg.collisions && d.A > 1;
     static const int early_exit = std::getenv("MCR_NO_EARLY_EXIT") ? 0 : 1;   // diagnostics only
     const AutoResetCfg ar{h->cfg.use_random_direction, h->cfg.direction_cw, (unsigned long long)h->cfg.seed, h->cfg.fresh_tracks};
+    // The fused head kernel (warp per env: auto reset + car-car narrow phase + the per-car head on lanes 0..A-1) takes two
+    // launch latencies off the chain.  MCR_HEAD_SPLIT=1 runs the three stages as packed kernels instead (thread per car
+    // for the per-car head): measured slower at every batch size, 1 k to 16 k envs (profiles/README r02) -- diagnostics only.
+    static const char* head_env = std::getenv("MCR_HEAD_SPLIT");
+    const bool head_split = head_env && head_env[0] == '1';
     if (reset_flags) {
-        // next-step auto reset: the head kernel respawns the flagged envs first, so the contact pass
-        // (which reads the start poses) has to follow it
-        LAUNCH(launch_head(d, b, cc, mask, reset_flags, ar, action, action_dtype, h->cfg.collisions, s));
+        // next-step auto reset: the flagged envs are respawned first, so the contact pass (which reads the start poses)
+        // has to follow it
+        if (head_split) LAUNCH(launch_auto_reset(d, b, cc, reset_flags, ar, s));
+        else LAUNCH(launch_head(d, b, cc, mask, reset_flags, ar, action, action_dtype, h->cfg.collisions, s));
         CUDA_OK(cudaEventRecord(h->ev_fork, s));
         CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
         LAUNCH(launch_contacts(d, b, cc, mask, h->side));
+        if (head_split) LAUNCH(launch_presweep(d, b, cc, mask, noact, action, action_dtype, h->cfg.collisions, 0, s));
     } else {
         CUDA_OK(cudaEventRecord(h->ev_fork, s));
         CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
         LAUNCH(launch_contacts(d, b, cc, mask, h->side));
-        if (noact) LAUNCH(launch_presweep(d, b, cc, mask, noact, action, action_dtype, h->cfg.collisions, 0, s));
+        if (noact || head_split) LAUNCH(launch_presweep(d, b, cc, mask, noact, action, action_dtype, h->cfg.collisions, 0, s));
         else LAUNCH(launch_head(d, b, cc, mask, nullptr, ar, action, action_dtype, h->cfg.collisions, s));
     }
     CUDA_OK(cudaEventRecord(h->ev_pre, s));

@@ -943,11 +943,13 @@ __device__ __forceinline__ CheckerRange checker_range(float m00, float m01, floa
 #define PJCLK_T0() do {} while (0)
 #define PJCLK(k) do {} while (0)
 #endif
-#ifndef PJ_W
-#define PJ_W 2
-#endif
+// small batches (one wave of CTAs) are latency bound and finish earlier with two warps per frame; large batches are
+// throughput bound and do less redundant set-up work with one
+#define PJ_W_SMALL 2
+#define PJ_SMALL_FRAMES 8192
 #define PJ_MAX_PASS 96           // (1 + 100) / 32 + 2048 / 32 + (12 * 16 + 9) / 32 + slack
 
+template <int PJ_W>
 __global__ void __launch_bounds__(PJ_W * 32, 32 / PJ_W)
 project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, int backwards_flag, int use_ego_color, int cls) {
     __shared__ uint8_t s_vis_chunk[MAX_CHUNKS];
@@ -1397,8 +1399,12 @@ int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const 
                        d, b, cc, mask, obs, backwards_flag, use_ego_color, cls, obs_format, stack_k, VpParams{});
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
     }
-    mcr_launch_pdl(project_kernel, dim3(d.N), dim3(PJ_W * 32), 0, (cudaStream_t)stream,
-                   d, b, cc, mask, backwards_flag, use_ego_color, cls);
+    if (d.N <= PJ_SMALL_FRAMES)
+        mcr_launch_pdl(project_kernel<PJ_W_SMALL>, dim3(d.N), dim3(PJ_W_SMALL * 32), 0, (cudaStream_t)stream,
+                       d, b, cc, mask, backwards_flag, use_ego_color, cls);
+    else
+        mcr_launch_pdl(project_kernel<1>, dim3(d.N), dim3(32), 0, (cudaStream_t)stream,
+                       d, b, cc, mask, backwards_flag, use_ego_color, cls);
     mcr_launch_pdl(fill_kernel, dim3(d.B, d.A), dim3(RS_THREADS), sizeof(RasterSmem), (cudaStream_t)stream,
                    d, b, mask, obs, cls, obs_format, stack_k, 0);
     return cudaGetLastError() == cudaSuccess ? 2 : -1;
@@ -1414,8 +1420,12 @@ bool render_is_split() {
 int launch_project(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, int backwards_flag, int use_ego_color,
                    int cls, void* stream) {
     if (!configure_render()) return -1;
-    mcr_launch_pdl(project_kernel, dim3(d.N), dim3(PJ_W * 32), 0, (cudaStream_t)stream,
-                   d, b, cc, mask, backwards_flag, use_ego_color, cls);
+    if (d.N <= PJ_SMALL_FRAMES)
+        mcr_launch_pdl(project_kernel<PJ_W_SMALL>, dim3(d.N), dim3(PJ_W_SMALL * 32), 0, (cudaStream_t)stream,
+                       d, b, cc, mask, backwards_flag, use_ego_color, cls);
+    else
+        mcr_launch_pdl(project_kernel<1>, dim3(d.N), dim3(32), 0, (cudaStream_t)stream,
+                       d, b, cc, mask, backwards_flag, use_ego_color, cls);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

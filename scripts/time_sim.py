@@ -6,7 +6,7 @@ from multi_car_racing_b200 import _lib
 for B in [int(x) for x in sys.argv[1:]]:
     np.random.seed(0)
     venv = mcr.BatchedMultiCarRacing(B, num_agents=2, auto_reset=False, max_episode_steps=0, seed=0)
-    venv.reset()
+    venv.reset(device_tracks=True)
     g = torch.Generator(device=venv.device); g.manual_seed(0)
     tape = torch.rand((64, B, 2, 3), device=venv.device, generator=g); tape[..., 0] = tape[..., 0] * 2 - 1
     for s in range(60): venv.step(tape[s % 64])

@@ -12,7 +12,7 @@ for mode in ("graph", "direct"):
     else: os.environ.pop("MCR_NO_GRAPH", None)
     np.random.seed(1234)
     venv = mcr.BatchedMultiCarRacing(B, num_agents=2, auto_reset="next_step", max_episode_steps=1000, seed=1234)
-    venv.reset()
+    venv.reset(device_tracks=True)
     g = torch.Generator(device=venv.device); g.manual_seed(1234)
     tape = torch.rand((128, B, 2, 3), device=venv.device, generator=g); tape[..., 0] = tape[..., 0] * 2 - 1
     for s in range(50): venv.step(tape[s % 128])
