@@ -140,6 +140,10 @@ struct __align__(16) RasterSmem {
     // upper endpoint, slope (bx - ax) / (by - ay)): one LDS.128 per edge.  Entries LIST_CAP + c hold edges 4..7
     // of car c's hull octagon (the only polygon with more than four edges).
     float4 edge[4][LIST_CAP + MCR_MAX_AGENTS];
+    // fill_kernel stages the finished frame in `edge` + `stage_tail` (27 648 bytes, contiguous) for its bulk store: the
+    // edges are dead once the last list's spans are computed, so a warp can stage its rows as soon as its own fill is
+    // done, while other warps still read the spans and masks
+    unsigned char stage_tail[MCR_OBS_BYTES - sizeof(float4) * 4 * (LIST_CAP + MCR_MAX_AGENTS)];
     int base[LIST_CAP];           // span pool offset of viewport row 0 of this polygon: first slot - y0
     uint8_t ne[LIST_CAP], col[LIST_CAP];   // ne = 4, or 8 + c for car c's octagon
     // slot -> polygon without a search: polygon p's first slot sets a bit in startbits (unless it is word aligned),
@@ -954,7 +958,7 @@ __global__ void __launch_bounds__(PJ_W * 32, 32 / PJ_W)
 project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, int backwards_flag, int use_ego_color, int cls) {
     __shared__ uint8_t s_vis_chunk[MAX_CHUNKS];
     __shared__ int s_nvis;
-    __shared__ int s_pre_cnt[PJ_MAX_PASS + 1], s_pre_rows[PJ_MAX_PASS + 1];   // prefix BEFORE pass p; cnt < 0: not published yet
+    __shared__ unsigned long long s_pre[PJ_MAX_PASS + 1];   // prefix BEFORE pass p: entries << 32 | span slots; ~0 = not published yet
     __shared__ __align__(16) uint8_t s_touched[2048];   // this env's "tile colour was reset" flags (Tmax <= Qmax <= 2048): loaded
                                                         // beside the camera, so the road passes do not wait for a dependent load
     PJCLK_T0();
@@ -972,7 +976,7 @@ project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
     M.m00 = b.camera[(size_t)0 * N + car]; M.m01 = b.camera[(size_t)1 * N + car]; M.m02 = b.camera[(size_t)2 * N + car];
     M.m10 = b.camera[(size_t)3 * N + car]; M.m11 = b.camera[(size_t)4 * N + car]; M.m12 = b.camera[(size_t)5 * N + car];
     const int Q = b.trk_Q[slot];
-    for (int i = threadIdx.x; i <= PJ_MAX_PASS; i += PJ_W * 32) { s_pre_cnt[i] = i == 0 ? 0 : -1; s_pre_rows[i] = 0; }
+    for (int i = threadIdx.x; i <= PJ_MAX_PASS; i += PJ_W * 32) s_pre[i] = i == 0 ? 0ull : ~0ull;
     if ((d.Tmax & 15) == 0) {
         const uint4* src = reinterpret_cast<const uint4*>(b.touched + (size_t)env * d.Tmax);
         for (int i = threadIdx.x; i < d.Tmax / 16; i += PJ_W * 32) reinterpret_cast<uint4*>(s_touched)[i] = src[i];
@@ -1093,13 +1097,12 @@ project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
         // ---- in-order hand-off of the running prefix -------------------------------------------------------------
         int lc = 0, pc = 0;
         if (lane == 0) {
-            volatile int* vc = s_pre_cnt; volatile int* vr = s_pre_rows;
-            while ((lc = vc[p]) < 0) __nanosleep(20);
-            __threadfence_block();
-            pc = vr[p];
-            vr[p + 1] = pc + pass_rows;
-            __threadfence_block();
-            vc[p + 1] = lc + __popc(bal);
+            // one 64-bit word per pass carries the prefix AND its "published" state, read and written with shared-memory
+            // atomics (nothing else has to be ordered around it; compute-sanitizer racecheck accepts atomics only)
+            unsigned long long v;
+            while ((v = atomicAdd(&s_pre[p], 0ull)) == ~0ull) __nanosleep(20);
+            lc = (int)(v >> 32); pc = (int)(v & 0xffffffffull);
+            atomicExch(&s_pre[p + 1], ((unsigned long long)(unsigned)(lc + __popc(bal)) << 32) | (unsigned long long)(unsigned)(pc + pass_rows));
         }
         lc = __shfl_sync(0xffffffffu, lc, 0); pc = __shfl_sync(0xffffffffu, pc, 0);
         PJCLK(12);
@@ -1200,9 +1203,9 @@ fill_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, uint8_t* __r
     // writes whole sectors (L2 write requests 4.8 M -> 0.68 M, sectors 5.2 M -> 2.7 M per 2048 frames) and is 5-8 % faster
     // end to end (profiles/README r02; A/B build: python -m multi_car_racing_b200.build --stg-store -> libmcr_stg.so).
     if (obs_format == MCR_OBS_RGB_HWC || obs_format == MCR_OBS_GRAY || obs_format == MCR_OBS_RGB_CHW) {   // one contiguous block per frame
-        __syncthreads();                               // every thread is done with the spans and masks
         unsigned char* stage = reinterpret_cast<unsigned char*>(&S.edge[0][0]);
-        static_assert(offsetof(RasterSmem, rowmask) + sizeof(((RasterSmem*)0)->rowmask) - offsetof(RasterSmem, edge) >= MCR_OBS_BYTES, "staging area");
+        static_assert(offsetof(RasterSmem, stage_tail) == offsetof(RasterSmem, edge) + sizeof(((RasterSmem*)0)->edge) &&
+                      offsetof(RasterSmem, base) - offsetof(RasterSmem, edge) >= MCR_OBS_BYTES, "staging area = edge + stage_tail");
         finish_frame<false>(S, tid, pix, stage, 0, obs_format, 0, 0, SW, SH, 1, 0);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
