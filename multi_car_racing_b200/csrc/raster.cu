@@ -471,19 +471,21 @@ __device__ __forceinline__ uint32_t prmt_selector(int byte) {
     return slo | (shi << 16);
 }
 
-// score label "%04i" % reward (mcr:665; drawn before reward -= 0.1) as glyph indices (10 = '-', -1 = none)
-__device__ __forceinline__ void score_glyphs(double rw, signed char* glyph) {
-    int val = (int)rw;
+// Character i (0..3) of the score label "%04i" % reward (mcr:665; drawn before reward -= 0.1) as a glyph index
+// (0-9, 10 = '-', -1 = none): straight-line, one thread per character.
+__device__ __forceinline__ signed char score_glyph(double rw, int i) {
+    const int val = (int)rw;
     const bool neg = rw < 0 && val != 0;
-    int mag = val < 0 ? -val : val;
-    signed char digs[12]; int nd = 0;
-    do { digs[nd++] = (signed char)(mag % 10); mag /= 10; } while (mag > 0);
-    signed char buf[16]; int len = 0;
-    const int width = nd + (neg ? 1 : 0), pad = width < 4 ? 4 - width : 0;
-    if (neg) buf[len++] = 10;
-    for (int i = 0; i < pad; ++i) buf[len++] = 0;
-    for (int i = nd - 1; i >= 0; --i) buf[len++] = digs[i];
-    for (int i = 0; i < 4; ++i) glyph[i] = i < len ? buf[i] : (signed char)-1;
+    const unsigned mag = (unsigned)(val < 0 ? -(long long)val : (long long)val);
+    int nd = 1;
+    for (unsigned p = 10u; nd < 10 && mag >= p; p *= 10u) ++nd;      // decimal digits of |val| (p overflows only after nd = 10)
+    // "%04i": zero padded to a width of 4 (the sign counts), longer numbers are cut after four characters
+    int e;                                                           // power of ten of the digit shown at position i
+    if (!neg) e = nd <= 4 ? 3 - i : nd - 1 - i;
+    else { if (i == 0) return 10; e = nd <= 3 ? 3 - i : nd - i; }
+    unsigned p10 = 1u;
+    for (int k = 0; k < e; ++k) p10 *= 10u;
+    return (signed char)((mag / p10) % 10u);
 }
 
 // Front of a frame (fused kernel) (NT threads; SM has the fields used below):
@@ -496,7 +498,7 @@ __device__ __forceinline__ void frame_front(SM& S, const Dims& d, const DevBuffe
     const int N = d.N, warp = tid >> 5, lane = tid & 31;
     // ---- camera (mcr:540-556) was evaluated by the physics kernel for this car ---------------
     if (tid < 6) (&S.M.m00)[tid] = camera[(size_t)tid * N + car];
-    if (tid == 64) score_glyphs(rw, S.glyph);
+    if (tid >= 64 && tid < 68) S.glyph[tid - 64] = score_glyph(rw, tid - 64);
     if (tid == 96) {
         // Checker squares the camera can see: invert the affine for the four viewport corners
         // (+ a two-unit margin, far above fp32 error) and keep the index ranges that overlap.
@@ -1161,7 +1163,7 @@ fill_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, uint8_t* __r
     // into the list (no load waits for the metadata)
     if (tid < d.A * 4) S.edge[tid & 3][LIST_CAP + (tid >> 2)] = oct[tid];
     const int n = hdr.x;
-    if (tid == 64) score_glyphs(b.score_snap[frame], S.glyph);
+    if (tid >= 64 && tid < 68) S.glyph[tid - 64] = score_glyph(b.score_snap[frame], tid - 64);
     uint32_t pix[8];                       // this thread's 32 pixels (palette indices); glClear -> black
 #pragma unroll
     for (int k = 0; k < 8; ++k) pix[k] = (hdr.z ? PAL_GRASS : PAL_BLACK) * 0x01010101u;
