@@ -994,19 +994,23 @@ static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, con
     CUDA_OK(cudaStreamWaitEvent(s, h->ev_contacts, 0));
     const int cls = split ? 1 : 0;
     LAUNCH(launch_physics_post(d, b, cc, mask, noact, action != nullptr, h->cfg.h_ratio, cls, s));
-    if (post_step) {
+    // the reward / done block: inside the projector's launch (nothing between post_kernel and it in this stream, so the
+    // programmatic dependent launch holds), or -- fused rasteriser -- as its own kernel on the side stream
+    const bool score_in_render = post_step && render_runs_score(cls);
+    if (post_step && !score_in_render) {
         CUDA_OK(cudaEventRecord(h->ev_join, s));
         CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_join, 0));
         LAUNCH(launch_score(d, b, mask, noact, reward, done, h->cfg.max_episode_steps, cls, h->side));
         CUDA_OK(cudaEventRecord(h->ev_score, h->side));
     }
+    double* sc_reward = score_in_render ? reward : nullptr;
     const size_t frame_bytes = (size_t)mcr_obs_bytes(h);
     const bool chunked = ho && render_is_split() && d.B >= 64;
     if (chunked) {
         // mcr_step_host: the frames go to the host in up to 8 ranges of envs; the copy of a range starts as soon as it is
         // filled, beside the fill of the next ranges -- only the physics and the first range's fill are not hidden
         // behind the PCIe transfer.  (The touching-car chain's frames lie scattered in every range: wait for it first.)
-        LAUNCH(launch_project(d, b, cc, mask, h->cfg.backwards_flag, h->cfg.use_ego_color, cls, s));
+        LAUNCH(launch_project(d, b, cc, mask, h->cfg.backwards_flag, h->cfg.use_ego_color, cls, s, noact, sc_reward, done, h->cfg.max_episode_steps));
         if (split) CUDA_OK(cudaStreamWaitEvent(h->copy, h->ev_chain2, 0));
         // ranges grow geometrically (B/16, B/16, B/8, B/4, B/2): the first copy starts after a sixteenth of the fill, and
         // the later, larger copies keep the per-copy set-up cost off the link
@@ -1023,9 +1027,10 @@ static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, con
         }
         CUDA_OK(cudaEventRecord(h->ev_copy, h->copy));
     } else {
-        LAUNCH(launch_render(d, b, cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, cls, h->obs_format, h->stack_k, s));
+        LAUNCH(launch_render(d, b, cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, cls, h->obs_format, h->stack_k, s,
+                             noact, sc_reward, done, h->cfg.max_episode_steps));
     }
-    if (post_step) CUDA_OK(cudaStreamWaitEvent(s, h->ev_score, 0));
+    if (post_step && !score_in_render) CUDA_OK(cudaStreamWaitEvent(s, h->ev_score, 0));
     if (split) CUDA_OK(cudaStreamWaitEvent(s, h->ev_chain2, 0));
     if (ho) {
         if (!chunked) CUDA_OK(cudaMemcpyAsync(ho->h_obs, obs, (size_t)d.N * frame_bytes, cudaMemcpyDeviceToHost, s));

@@ -348,6 +348,7 @@ head_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
     __syncwarp();                                      // n_manifold[env]
     // a respawned env takes reset()'s implicit step(None) (mcr:408): its action is ignored
     if (lane < d.A) pre_car<ActT>(d, b, cc, env * d.A + lane, env, action != nullptr && !respawned, action);
+    if (threadIdx.x == 0) atomicMax(b.timeline + TL_HEAD_END, mcr_globaltimer());
 }
 
 // ---------------------------------------------------------------------------------------

@@ -123,9 +123,11 @@ struct Dims { int B, A, N, Tmax, Qmax, P; int particles; int dl_cap; };
 #define PRT_PTS 30
 // skid_meta[wheel] bits: 0 skid_start valid, 1 skid_particle valid, 2 its grass flag, 8-15 its length, 16-23 its ring slot + 1 (0 = popped from Car.particles)
 // timeline slots: kernel start stamps (block 0, thread 0) and the latest CTA end of the rasteriser
-enum { TL_HEAD = 0, TL_CONTACTS, TL_STRIPES, TL_SWEEP, TL_COUPLED, TL_POST, TL_SCORE, TL_RENDER, TL_RENDER_END, TL_POST2, TL_RENDER2, TL_SWEEP_END, TL_SWEEP_END_PACKED, TL_COUPLED_VEL_END, TL_COUPLED_POS_END, TL_FILL = 15 /* fill_kernel start (cls != 2) */, TL_COUNT = 16 };
+enum { TL_HEAD = 0, TL_CONTACTS, TL_STRIPES, TL_SWEEP, TL_COUPLED, TL_POST, TL_SCORE, TL_RENDER, TL_RENDER_END, TL_POST2, TL_RENDER2, TL_SWEEP_END, TL_SWEEP_END_PACKED, TL_COUPLED_VEL_END, TL_COUPLED_POS_END, TL_FILL = 15 /* fill_kernel start (cls != 2) */,
+       TL_POST_END = 16, TL_PROJECT_END = 17, TL_HEAD_END = 18 /* latest CTA end of post (cls != 2) / project / head */, TL_COUNT = 24 };
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned long long mcr_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void tl_stamp_any(const unsigned long long* tl_base, int slot) { const_cast<unsigned long long*>(tl_base)[slot] = mcr_globaltimer(); }
 __device__ __forceinline__ void tl_stamp(const unsigned long long* tl_base, int slot) {
     if ((blockIdx.x | blockIdx.y | threadIdx.x) == 0) const_cast<unsigned long long*>(tl_base)[slot] = mcr_globaltimer();
 }
@@ -166,13 +168,17 @@ int launch_physics_post(const Dims& d, const DevBuffers& b, const CarConst& cc, 
                         int has_action, double h_ratio, int cls, void* stream);
 int launch_presweep(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* noact,
                     const void* action, int action_dtype, int collisions, int with_sweep, void* stream);
+// score_reward != NULL (only when render_runs_score(cls)): the reward / done block (launch_score's work) runs inside the launch
 int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* obs,
-                  int backwards_flag, int use_ego_color, int cls, int obs_format, int stack_k, void* stream);
+                  int backwards_flag, int use_ego_color, int cls, int obs_format, int stack_k, void* stream,
+                  const uint8_t* score_noact = nullptr, double* score_reward = nullptr, uint8_t* score_done = nullptr, int max_episode_steps = 0);
+bool render_runs_score(int cls);
 int launch_score(const Dims& d, const DevBuffers& b, const uint8_t* mask, const uint8_t* noact, double* reward, uint8_t* done,
                  int max_episode_steps, int cls, void* stream);
 bool render_is_split();
 int launch_project(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, int backwards_flag, int use_ego_color,
-                   int cls, void* stream);
+                   int cls, void* stream, const uint8_t* score_noact = nullptr, double* score_reward = nullptr, uint8_t* score_done = nullptr,
+                   int max_episode_steps = 0);
 int launch_fill(const Dims& d, const DevBuffers& b, const uint8_t* mask, uint8_t* obs, int cls, int obs_format, int stack_k,
                 int env0, int nenv, bool pdl, void* stream);
 // render(mode) for a vw x vh viewport (rgb_array: 600 x 400): camera_kernel + tiled render_kernel<true>

@@ -891,6 +891,154 @@ render_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mas
 
 
 // ---------------------------------------------------------------------------------------
+// score_kernel: mcr:433-507 for one car per warp.  Runs concurrently with render_kernel (which
+// reads the snapshots post_kernel took of env.reward / driving_backward, because the reference
+// renders BEFORE this block).
+// ---------------------------------------------------------------------------------------
+#define SCORE_WARPS 4
+
+// One car of the block above on one warp; s_cand[32] / s_ncand are that warp's shared scratch.
+__device__ __forceinline__ void score_car(const Dims& d, const DevBuffers& b, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ noact,
+                                          double* __restrict__ out_reward, uint8_t* __restrict__ out_done, int max_episode_steps, int cls,
+                                          int car, int lane, int* s_cand_w, int* s_ncand_w) {
+    const int env = car / d.A, agent = car - env * d.A;
+    if (mask && !mask[env]) return;
+    if (cls && (cls == 2) != (b.n_manifold[env] > 0)) return;
+    if (noact && noact[env]) {
+        // this env was respawned at the start of the step and took reset()'s step(None): the whole
+        // `if action is not None` block of mcr:433-507 is skipped, the caller sees reward 0, done 0
+        if (lane == 0) { out_reward[car] = 0.0; if (agent == 0) { out_done[env] = 0; b.pending[env] = 0; } }
+        return;
+    }
+    const int N = d.N;
+    const int slot = b.env_track[env];
+    const int T = b.trk_T[slot];
+    // nearest track node: argmin_i || pos - track[i].xy ||, first minimum wins (np.argmin over
+    // sqrt(dx^2 + dy^2) in float64).  Pass 1 finds the minimal squared distance in fp32 (error
+    // < 1e-3 near the minimum); pass 2 queues every node within 0.05 of it; lane 0 then evaluates
+    // those few exactly as the reference does.
+    const float posxf = b.body[(size_t)BF_PX * N + car], posyf = b.body[(size_t)BF_PY * N + car];
+    const double* node = b.trk_node + (size_t)slot * d.Tmax * 3;
+    float best2 = 3.0e38f;
+    for (int i = lane; i < T; i += 32) {
+        const float dx = posxf - (float)node[(size_t)i * 3 + 1], dy = posyf - (float)node[(size_t)i * 3 + 2];
+        best2 = fminf(best2, dx * dx + dy * dy);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best2 = fminf(best2, __shfl_xor_sync(0xffffffffu, best2, o));
+    if (lane == 0) (*s_ncand_w) = 0;
+    __syncwarp();
+    for (int i = lane; i < T; i += 32) {
+        const float dx = posxf - (float)node[(size_t)i * 3 + 1], dy = posyf - (float)node[(size_t)i * 3 + 2];
+        if (dx * dx + dy * dy <= best2 + 0.05f) { const int q = atomicAdd(&(*s_ncand_w), 1); if (q < 32) s_cand_w[q] = i; }
+    }
+    __syncwarp();
+    // driving_on_grass, mcr:469-472: the hull position is strictly inside none of the road_poly quads (shapely
+    // Point.within(Polygon), float64).  Lanes take the culling chunks (8 quads, fp32 bounding circle whose radius
+    // is padded far beyond the fp32 / float64 vertex difference) and test the quads of the chunks in reach exactly.
+    {
+        const double posx = posxf, posy = posyf;
+        const int Q = b.trk_Q[slot], nchunks = (Q + MCR_QUAD_CHUNK - 1) / MCR_QUAD_CHUNK;
+        const float4* chunk = (const float4*)(b.trk_chunk + (size_t)slot * (d.Qmax / MCR_QUAD_CHUNK) * 4);
+        const double* quad64 = b.trk_quad64 + (size_t)slot * d.Qmax * 8;
+        // pass 1: the chunks in reach (warp-wide bitmask); pass 2: one cross product per lane -- lane = (quad of the
+        // chunk, edge) -- and two ballots decide "all four edges on the same strict side" for the chunk's 8 quads
+        unsigned reach[MAX_CHUNKS / 32];
+#pragma unroll
+        for (int w = 0; w < MAX_CHUNKS / 32; ++w) {
+            const int c = 32 * w + lane;
+            bool hit = false;
+            if (c < nchunks) {
+                const float4 cc4 = chunk[c];
+                const float dx = posxf - cc4.x, dy = posyf - cc4.y;
+                hit = !(dx * dx + dy * dy > cc4.z * cc4.z + 1.0f);
+            }
+            reach[w] = __ballot_sync(0xffffffffu, hit);
+        }
+        bool inside = false;
+#pragma unroll
+        for (int w = 0; w < MAX_CHUNKS / 32; ++w) {
+            unsigned m = reach[w];
+            while (m) {
+                const int c = 32 * w + (__ffs((int)m) - 1);
+                m &= m - 1u;
+                const int q = c * MCR_QUAD_CHUNK + (lane >> 2), k = lane & 3, k2 = (k + 1) & 3;
+                double cr = 0.0;
+                if (q < Q) {
+                    const double* v = quad64 + (size_t)q * 8;
+                    const double ex = v[2 * k2] - v[2 * k], ey = v[2 * k2 + 1] - v[2 * k + 1];
+                    cr = ex * (posy - v[2 * k + 1]) - ey * (posx - v[2 * k]);
+                }
+                const unsigned pm = __ballot_sync(0xffffffffu, cr > 0), nm = __ballot_sync(0xffffffffu, cr < 0);
+                const unsigned allp = pm & (pm >> 1) & (pm >> 2) & (pm >> 3) & 0x11111111u;
+                const unsigned alln = nm & (nm >> 1) & (nm >> 2) & (nm >> 3) & 0x11111111u;
+                inside = inside || (allp | alln) != 0u;
+            }
+        }
+        const bool any_inside = __any_sync(0xffffffffu, inside);
+        if (lane == 0) b.on_grass[car] = any_inside ? 0 : 1;
+    }
+    if (lane == 0) {
+        const double posx = posxf, posy = posyf;
+        double bestd = 1.0e300; int besti = 0x7fffffff;
+        const int nc = (*s_ncand_w);
+        if (nc <= 32) {
+            for (int q = 0; q < nc; ++q) {
+                const int i = s_cand_w[q];
+                const double dx = posx - node[(size_t)i * 3 + 1], dy = posy - node[(size_t)i * 3 + 2];
+                const double dd = sqrt(dx * dx + dy * dy);
+                if (dd < bestd || (dd == bestd && i < besti)) { bestd = dd; besti = i; }
+            }
+        } else {                                    // pathological (many equidistant nodes): exact scan
+            for (int i = 0; i < T; ++i) {
+                const double dx = posx - node[(size_t)i * 3 + 1], dy = posy - node[(size_t)i * 3 + 2];
+                const double dd = sqrt(dx * dx + dy * dy);
+                if (dd < bestd) { bestd = dd; besti = i; }
+            }
+        }
+        const double PI = 3.141592653589793, PLAYFIELD = 2000 / 6.0;
+        double reward = b.reward[car] - 0.1;                     // mcr:436
+        double step_reward = reward - b.prev_reward[car];        // mcr:443
+        const double car_angle = b.heading[car];                 // mcr:449-456, evaluated in the physics kernel
+        double desired = node[(size_t)besti * 3 + 0];
+        if (b.env_cw[env]) desired += PI;
+        desired = py_mod(desired + 2 * PI, 2 * PI);
+        double diff = fabs(desired - car_angle);
+        if (diff > PI) diff = fabs(diff - 2 * PI);
+        uint8_t backward = 0;
+        if (diff > PI / 2) { backward = 1; step_reward -= 0 * diff; }   // K_BACKWARD = 0, mcr:78
+        b.backward[car] = backward;
+        b.reward[car] = reward;
+        b.prev_reward[car] = reward;
+        // done: ANY agent finished all tiles or left the playfield (evaluated identically by
+        // every agent's CTA of this env; only agent 0 stores it)
+        uint8_t done = 0;
+        for (int c = 0; c < d.A; ++c) {
+            const int oc = env * d.A + c;
+            if (b.visit_count[oc] == T) done = 1;
+            const double x = b.body[(size_t)BF_PX * N + oc], y = b.body[(size_t)BF_PY * N + oc];
+            if (fabs(x) > PLAYFIELD || fabs(y) > PLAYFIELD) { done = 1; if (c == agent) step_reward = -100; }
+        }
+        if (max_episode_steps > 0 && b.steps[car] >= max_episode_steps) done |= 2;   // TimeLimit
+        out_reward[car] = step_reward;
+        if (agent == 0) { out_done[env] = done; b.pending[env] = done; }
+    }
+}
+
+__global__ void __launch_bounds__(SCORE_WARPS * 32)
+score_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ noact,
+             double* __restrict__ out_reward, uint8_t* __restrict__ out_done, int max_episode_steps, int cls) {
+    tl_stamp(b.timeline, TL_SCORE);
+    __shared__ int s_cand[SCORE_WARPS][32];
+    __shared__ int s_ncand[SCORE_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int car = blockIdx.x * SCORE_WARPS + warp;
+    if (car >= d.N) return;
+    score_car(d, b, mask, noact, out_reward, out_done, max_episode_steps, cls, car, lane, s_cand[warp], &s_ncand[warp]);
+}
+
+
+// ---------------------------------------------------------------------------------------
 // The step path renders in two kernels (the fused render_kernel above stays for the viewport modes):
 //   project_kernel  front end, one CTA of 256 threads per agent-frame: candidates in painter's order -> camera ->
 //                   cull -> ordered compaction (block scan) -> canonical edges, written as the frame's display list
@@ -955,9 +1103,16 @@ __device__ __forceinline__ CheckerRange checker_range(float m00, float m01, floa
 #define PJ_SMALL_FRAMES 8192
 #define PJ_MAX_PASS 96           // (1 + 100) / 32 + 2048 / 32 + (12 * 16 + 9) / 32 + slack
 
+// The reward / done block of the step (score_car, mcr:433-507) rides in the same launch: CTAs past the last frame take
+// PJ_W cars each, one warp per car.  It only needs what post_kernel left, like the projector, so it used to be a kernel
+// of its own on a side stream -- but the event record that forked it sat between post_kernel and this kernel in the
+// main stream and cost the programmatic dependent launch (6-7 us of launch latency on the critical chain).
+struct ScoreArgs { const uint8_t* noact; double* out_reward; uint8_t* out_done; int max_episode_steps; int enabled; };
+
 template <int PJ_W>
 __global__ void __launch_bounds__(PJ_W * 32, 32 / PJ_W)
-project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, int backwards_flag, int use_ego_color, int cls) {
+project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, int backwards_flag, int use_ego_color, int cls,
+               ScoreArgs sa) {
     __shared__ uint8_t s_vis_chunk[MAX_CHUNKS];
     __shared__ int s_nvis;
     __shared__ unsigned long long s_pre[PJ_MAX_PASS + 1];   // prefix BEFORE pass p: entries << 32 | span slots; ~0 = not published yet
@@ -967,6 +1122,14 @@ project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
     cudaGridDependencySynchronize();               // programmatic dependent launch behind post_kernel (mcr_launch_pdl)
     tl_stamp(b.timeline, cls == 2 ? TL_RENDER2 : TL_RENDER);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if ((int)blockIdx.x >= d.N) {                  // score CTAs
+        __shared__ int s_cand[PJ_W][32];
+        __shared__ int s_ncand[PJ_W];
+        if ((int)blockIdx.x == d.N && threadIdx.x == 0) tl_stamp_any(b.timeline, TL_SCORE);
+        const int car = ((int)blockIdx.x - d.N) * PJ_W + warp;
+        if (car < d.N) score_car(d, b, mask, sa.noact, sa.out_reward, sa.out_done, sa.max_episode_steps, cls, car, lane, s_cand[warp], &s_ncand[warp]);
+        return;
+    }
     const int frame = (int)blockIdx.x;
     PJCLK(9);
     const int env = frame / d.A, agent = frame - env * d.A;
@@ -1124,6 +1287,7 @@ project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
             *reinterpret_cast<int4*>(b.dl_hdr + (size_t)frame * 4) = make_int4(lc + __popc(bal), pc + pass_rows, V.grass_full, 0);
         PJCLK(13);
     }
+    if (cls != 2 && threadIdx.x == 0) atomicMax(b.timeline + TL_PROJECT_END, mcr_globaltimer());
 #ifdef MCR_PHASE_CLOCKS
     if (threadIdx.x == 0) atomicAdd(&g_phase_clk[14], 1ull);
 #endif
@@ -1229,146 +1393,6 @@ fill_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, uint8_t* __r
 }
 
 
-// ---------------------------------------------------------------------------------------
-// score_kernel: mcr:433-507 for one car per warp.  Runs concurrently with render_kernel (which
-// reads the snapshots post_kernel took of env.reward / driving_backward, because the reference
-// renders BEFORE this block).
-// ---------------------------------------------------------------------------------------
-#define SCORE_WARPS 4
-
-__global__ void __launch_bounds__(SCORE_WARPS * 32)
-score_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ noact,
-             double* __restrict__ out_reward, uint8_t* __restrict__ out_done, int max_episode_steps, int cls) {
-    tl_stamp(b.timeline, TL_SCORE);
-    __shared__ int s_cand[SCORE_WARPS][32];
-    __shared__ int s_ncand[SCORE_WARPS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int car = blockIdx.x * SCORE_WARPS + warp;
-    if (car >= d.N) return;
-    const int env = car / d.A, agent = car - env * d.A;
-    if (mask && !mask[env]) return;
-    if (cls && (cls == 2) != (b.n_manifold[env] > 0)) return;
-    if (noact && noact[env]) {
-        // this env was respawned at the start of the step and took reset()'s step(None): the whole
-        // `if action is not None` block of mcr:433-507 is skipped, the caller sees reward 0, done 0
-        if (lane == 0) { out_reward[car] = 0.0; if (agent == 0) { out_done[env] = 0; b.pending[env] = 0; } }
-        return;
-    }
-    const int N = d.N;
-    const int slot = b.env_track[env];
-    const int T = b.trk_T[slot];
-    // nearest track node: argmin_i || pos - track[i].xy ||, first minimum wins (np.argmin over
-    // sqrt(dx^2 + dy^2) in float64).  Pass 1 finds the minimal squared distance in fp32 (error
-    // < 1e-3 near the minimum); pass 2 queues every node within 0.05 of it; lane 0 then evaluates
-    // those few exactly as the reference does.
-    const float posxf = b.body[(size_t)BF_PX * N + car], posyf = b.body[(size_t)BF_PY * N + car];
-    const double* node = b.trk_node + (size_t)slot * d.Tmax * 3;
-    float best2 = 3.0e38f;
-    for (int i = lane; i < T; i += 32) {
-        const float dx = posxf - (float)node[(size_t)i * 3 + 1], dy = posyf - (float)node[(size_t)i * 3 + 2];
-        best2 = fminf(best2, dx * dx + dy * dy);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) best2 = fminf(best2, __shfl_xor_sync(0xffffffffu, best2, o));
-    if (lane == 0) s_ncand[warp] = 0;
-    __syncwarp();
-    for (int i = lane; i < T; i += 32) {
-        const float dx = posxf - (float)node[(size_t)i * 3 + 1], dy = posyf - (float)node[(size_t)i * 3 + 2];
-        if (dx * dx + dy * dy <= best2 + 0.05f) { const int q = atomicAdd(&s_ncand[warp], 1); if (q < 32) s_cand[warp][q] = i; }
-    }
-    __syncwarp();
-    // driving_on_grass, mcr:469-472: the hull position is strictly inside none of the road_poly quads (shapely
-    // Point.within(Polygon), float64).  Lanes take the culling chunks (8 quads, fp32 bounding circle whose radius
-    // is padded far beyond the fp32 / float64 vertex difference) and test the quads of the chunks in reach exactly.
-    {
-        const double posx = posxf, posy = posyf;
-        const int Q = b.trk_Q[slot], nchunks = (Q + MCR_QUAD_CHUNK - 1) / MCR_QUAD_CHUNK;
-        const float4* chunk = (const float4*)(b.trk_chunk + (size_t)slot * (d.Qmax / MCR_QUAD_CHUNK) * 4);
-        const double* quad64 = b.trk_quad64 + (size_t)slot * d.Qmax * 8;
-        // pass 1: the chunks in reach (warp-wide bitmask); pass 2: one cross product per lane -- lane = (quad of the
-        // chunk, edge) -- and two ballots decide "all four edges on the same strict side" for the chunk's 8 quads
-        unsigned reach[MAX_CHUNKS / 32];
-#pragma unroll
-        for (int w = 0; w < MAX_CHUNKS / 32; ++w) {
-            const int c = 32 * w + lane;
-            bool hit = false;
-            if (c < nchunks) {
-                const float4 cc4 = chunk[c];
-                const float dx = posxf - cc4.x, dy = posyf - cc4.y;
-                hit = !(dx * dx + dy * dy > cc4.z * cc4.z + 1.0f);
-            }
-            reach[w] = __ballot_sync(0xffffffffu, hit);
-        }
-        bool inside = false;
-#pragma unroll
-        for (int w = 0; w < MAX_CHUNKS / 32; ++w) {
-            unsigned m = reach[w];
-            while (m) {
-                const int c = 32 * w + (__ffs((int)m) - 1);
-                m &= m - 1u;
-                const int q = c * MCR_QUAD_CHUNK + (lane >> 2), k = lane & 3, k2 = (k + 1) & 3;
-                double cr = 0.0;
-                if (q < Q) {
-                    const double* v = quad64 + (size_t)q * 8;
-                    const double ex = v[2 * k2] - v[2 * k], ey = v[2 * k2 + 1] - v[2 * k + 1];
-                    cr = ex * (posy - v[2 * k + 1]) - ey * (posx - v[2 * k]);
-                }
-                const unsigned pm = __ballot_sync(0xffffffffu, cr > 0), nm = __ballot_sync(0xffffffffu, cr < 0);
-                const unsigned allp = pm & (pm >> 1) & (pm >> 2) & (pm >> 3) & 0x11111111u;
-                const unsigned alln = nm & (nm >> 1) & (nm >> 2) & (nm >> 3) & 0x11111111u;
-                inside = inside || (allp | alln) != 0u;
-            }
-        }
-        const bool any_inside = __any_sync(0xffffffffu, inside);
-        if (lane == 0) b.on_grass[car] = any_inside ? 0 : 1;
-    }
-    if (lane == 0) {
-        const double posx = posxf, posy = posyf;
-        double bestd = 1.0e300; int besti = 0x7fffffff;
-        const int nc = s_ncand[warp];
-        if (nc <= 32) {
-            for (int q = 0; q < nc; ++q) {
-                const int i = s_cand[warp][q];
-                const double dx = posx - node[(size_t)i * 3 + 1], dy = posy - node[(size_t)i * 3 + 2];
-                const double dd = sqrt(dx * dx + dy * dy);
-                if (dd < bestd || (dd == bestd && i < besti)) { bestd = dd; besti = i; }
-            }
-        } else {                                    // pathological (many equidistant nodes): exact scan
-            for (int i = 0; i < T; ++i) {
-                const double dx = posx - node[(size_t)i * 3 + 1], dy = posy - node[(size_t)i * 3 + 2];
-                const double dd = sqrt(dx * dx + dy * dy);
-                if (dd < bestd) { bestd = dd; besti = i; }
-            }
-        }
-        const double PI = 3.141592653589793, PLAYFIELD = 2000 / 6.0;
-        double reward = b.reward[car] - 0.1;                     // mcr:436
-        double step_reward = reward - b.prev_reward[car];        // mcr:443
-        const double car_angle = b.heading[car];                 // mcr:449-456, evaluated in the physics kernel
-        double desired = node[(size_t)besti * 3 + 0];
-        if (b.env_cw[env]) desired += PI;
-        desired = py_mod(desired + 2 * PI, 2 * PI);
-        double diff = fabs(desired - car_angle);
-        if (diff > PI) diff = fabs(diff - 2 * PI);
-        uint8_t backward = 0;
-        if (diff > PI / 2) { backward = 1; step_reward -= 0 * diff; }   // K_BACKWARD = 0, mcr:78
-        b.backward[car] = backward;
-        b.reward[car] = reward;
-        b.prev_reward[car] = reward;
-        // done: ANY agent finished all tiles or left the playfield (evaluated identically by
-        // every agent's CTA of this env; only agent 0 stores it)
-        uint8_t done = 0;
-        for (int c = 0; c < d.A; ++c) {
-            const int oc = env * d.A + c;
-            if (b.visit_count[oc] == T) done = 1;
-            const double x = b.body[(size_t)BF_PX * N + oc], y = b.body[(size_t)BF_PY * N + oc];
-            if (fabs(x) > PLAYFIELD || fabs(y) > PLAYFIELD) { done = 1; if (c == agent) step_reward = -100; }
-        }
-        if (max_episode_steps > 0 && b.steps[car] >= max_episode_steps) done |= 2;   // TimeLimit
-        out_reward[car] = step_reward;
-        if (agent == 0) { out_done[env] = done; b.pending[env] = done; }
-    }
-}
-
 // One-time set-up per DEVICE (function attributes and __constant__ data belong to the device's context; a
 // process that drives several GPUs has one handle per device).
 static bool configure_render() {
@@ -1393,9 +1417,26 @@ static bool configure_render() {
     return true;
 }
 
+static void launch_project_impl(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, int backwards_flag,
+                                int use_ego_color, int cls, const ScoreArgs& sa, cudaStream_t stream) {
+    if (d.N <= PJ_SMALL_FRAMES) {
+        const int score_ctas = sa.enabled ? (d.N + PJ_W_SMALL - 1) / PJ_W_SMALL : 0;
+        mcr_launch_pdl(project_kernel<PJ_W_SMALL>, dim3(d.N + score_ctas), dim3(PJ_W_SMALL * 32), 0, stream,
+                       d, b, cc, mask, backwards_flag, use_ego_color, cls, sa);
+    } else {
+        const int score_ctas = sa.enabled ? d.N : 0;
+        mcr_launch_pdl(project_kernel<1>, dim3(d.N + score_ctas), dim3(32), 0, stream,
+                       d, b, cc, mask, backwards_flag, use_ego_color, cls, sa);
+    }
+}
+
 int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* obs,
-                  int backwards_flag, int use_ego_color, int cls, int obs_format, int stack_k, void* stream) {
+                  int backwards_flag, int use_ego_color, int cls, int obs_format, int stack_k, void* stream,
+                  const uint8_t* score_noact, double* score_reward, uint8_t* score_done, int max_episode_steps) {
     if (!configure_render()) return -1;
+    // score_reward != NULL: the step's reward / done block runs inside this launch (project_kernel's extra CTAs); callers
+    // must check render_runs_score(cls) first -- the fused kernel has no such CTAs
+    const ScoreArgs sa{score_noact, score_reward, score_done, max_episode_steps, score_reward != nullptr ? 1 : 0};
     static const bool fused = std::getenv("MCR_RENDER_FUSED") != nullptr;     // diagnostics: the single-kernel rasteriser (A/B)
     // cls 2 = the few envs with touching cars, at the end of the step's longest chain: one wave of the fused kernel
     // (~18 us) ends earlier there than project + fill (two latency-bound launches, ~30 us for a handful of frames)
@@ -1404,12 +1445,7 @@ int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const 
                        d, b, cc, mask, obs, backwards_flag, use_ego_color, cls, obs_format, stack_k, VpParams{});
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
     }
-    if (d.N <= PJ_SMALL_FRAMES)
-        mcr_launch_pdl(project_kernel<PJ_W_SMALL>, dim3(d.N), dim3(PJ_W_SMALL * 32), 0, (cudaStream_t)stream,
-                       d, b, cc, mask, backwards_flag, use_ego_color, cls);
-    else
-        mcr_launch_pdl(project_kernel<1>, dim3(d.N), dim3(32), 0, (cudaStream_t)stream,
-                       d, b, cc, mask, backwards_flag, use_ego_color, cls);
+    launch_project_impl(d, b, cc, mask, backwards_flag, use_ego_color, cls, sa, (cudaStream_t)stream);
     mcr_launch_pdl(fill_kernel, dim3(d.B, d.A), dim3(RS_THREADS), sizeof(RasterSmem), (cudaStream_t)stream,
                    d, b, mask, obs, cls, obs_format, stack_k, 0);
     return cudaGetLastError() == cudaSuccess ? 2 : -1;
@@ -1422,15 +1458,19 @@ bool render_is_split() {
 
 // The two halves of launch_render for callers that interleave something with the fill (mcr_step_host: the device-to-host
 // copy of a range of envs starts as soon as that range is filled).
+// MCR_SCORE_IN_PROJECT=1 (diagnostics): the reward / done block as extra CTAs of project_kernel instead of its own kernel
+// on the side stream.  Measured slower (profiles/README r02): the projector is on the critical chain and gets 3 us longer,
+// and the gap it was meant to close (post_kernel -> projector) is the tail of post_kernel's slowest cars, not launch latency.
+bool render_runs_score(int cls) {
+    static const bool on = std::getenv("MCR_SCORE_IN_PROJECT") != nullptr;
+    return on && render_is_split() && cls != 2;
+}
+
 int launch_project(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, int backwards_flag, int use_ego_color,
-                   int cls, void* stream) {
+                   int cls, void* stream, const uint8_t* score_noact, double* score_reward, uint8_t* score_done, int max_episode_steps) {
     if (!configure_render()) return -1;
-    if (d.N <= PJ_SMALL_FRAMES)
-        mcr_launch_pdl(project_kernel<PJ_W_SMALL>, dim3(d.N), dim3(PJ_W_SMALL * 32), 0, (cudaStream_t)stream,
-                       d, b, cc, mask, backwards_flag, use_ego_color, cls);
-    else
-        mcr_launch_pdl(project_kernel<1>, dim3(d.N), dim3(32), 0, (cudaStream_t)stream,
-                       d, b, cc, mask, backwards_flag, use_ego_color, cls);
+    const ScoreArgs sa{score_noact, score_reward, score_done, max_episode_steps, score_reward != nullptr ? 1 : 0};
+    launch_project_impl(d, b, cc, mask, backwards_flag, use_ego_color, cls, sa, (cudaStream_t)stream);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -359,150 +359,238 @@ sweep_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask
     }
 }
 
+// Diagnostics build (-DMCR_PHASE_CLOCKS): thread 0 of every post CTA adds the cycles of each part to g_post_clk
+// (0 grid-dependency wait, 1 loads, 2 integrate + position iterations, 3 transforms + sleep, 4 stores, 5 camera; 7 = CTAs).
+#ifdef MCR_PHASE_CLOCKS
+__device__ unsigned long long g_post_clk[8];
+#define PK_T0() long long pk_t_ = clock64()
+#define PK(k) do { if (threadIdx.x == 0) { const long long n_ = clock64(); atomicAdd(&g_post_clk[k], (unsigned long long)(n_ - pk_t_)); pk_t_ = n_; } } while (0)
+extern "C" int mcr_debug_post_clocks(unsigned long long* out8, int reset) {
+    if (out8 && cudaMemcpyFromSymbol(out8, g_post_clk, sizeof(g_post_clk)) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[8] = {}; if (cudaMemcpyToSymbol(g_post_clk, z, sizeof(z)) != cudaSuccess) return -1; }
+    return 0;
+}
+#else
+#define PK_T0() do {} while (0)
+#define PK(k) do {} while (0)
+#endif
+
+// Two lanes per car (even lane = solver, odd lane = view): the solver lane integrates the positions, runs the position
+// iterations, synchronises the transforms, takes the sleep decision and stores the bodies and joints; the view lane
+// meanwhile evaluates what only depends on the solved VELOCITIES -- the camera's angle (atan2 + two sincos, mcr:544-556)
+// and the heading of the backward test (mcr:449-456) --, takes the score / backward snapshots, advances the env clock,
+// and finishes the camera once the solver lane hands it the final hull pose (one shuffle).  Both are serial fp64-trig
+// chains; side by side the kernel is as long as the longer one instead of their sum.
 __global__ void __launch_bounds__(128)
 post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ noact, int has_action,
             double h_ratio, int cls) {
+    PK_T0();
     cudaGridDependencySynchronize();               // programmatic dependent launch behind the sweep / coupled kernel
-    const int car = blockIdx.x * blockDim.x + threadIdx.x;
+    PK(0);
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int car_raw = gt >> 1;
+    const bool view = (gt & 1) != 0;
     tl_stamp(b.timeline, cls == 2 ? TL_POST2 : TL_POST);
-    if (car >= d.N) return;
+    // both lanes of a pair take the same early exits, so the pair's shuffle below is always executed by both or none
+    bool live = car_raw < d.N;
+    const int car = live ? car_raw : d.N - 1;
     const int env = car / d.A;
-    if (mask && !mask[env]) return;
-    if (cls && (cls == 2) != (b.n_manifold[env] > 0)) return;
+    if (mask && !mask[env]) live = false;
+    const bool coupled = b.n_manifold[env] > 0;
+    if (cls && (cls == 2) != coupled) live = false;
     const int N = d.N;
     const float h = (float)(1.0 / 50);
     const float mA = cc.hull_invMass, iA = cc.hull_invI, mB = cc.wheel_invMass, iB = cc.wheel_invI;
-
-    float cx[5], cy[5], ang[5], vx[5], vy[5], w[5], qs[5], qc[5], slp[5];
-    bool awake[5];
+    (void)mA; (void)iA; (void)mB; (void)iB;
     const float* sc = b.scratch + car;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        const float* p = b.body + (size_t)(i * BODY_FIELDS) * N + car;
-        cx[i] = p[(size_t)BF_CX * N]; cy[i] = p[(size_t)BF_CY * N]; ang[i] = p[(size_t)BF_A * N];
-        vx[i] = sc[(size_t)(SC_VX + i) * N]; vy[i] = sc[(size_t)(SC_VY + i) * N]; w[i] = sc[(size_t)(SC_W + i) * N];
-        slp[i] = b.sleep_time[(size_t)i * N + car];
-        awake[i] = b.awake[(size_t)i * N + car] != 0;
-    }
-    float jix[4], jiy[4], jiz[4], jmot[4], motorMassK[4];
-    int lim[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        jix[k] = sc[(size_t)(SC_JIX + k) * N]; jiy[k] = sc[(size_t)(SC_JIY + k) * N];
-        jiz[k] = sc[(size_t)(SC_JIZ + k) * N]; jmot[k] = sc[(size_t)(SC_JMOT + k) * N];
-        motorMassK[k] = sc[(size_t)(SC_JOINT + k * SC_JOINT_FIELDS + 13) * N];
-        lim[k] = b.limit_state[(size_t)k * N + car];
-    }
-    const bool coupled = b.n_manifold[env] > 0;
-    float px[5], py[5];
-    if (coupled) {
-        // coupled_kernel already integrated, position-solved and took the sleep decision for this car
+    float hull_px = 0.0f, hull_py = 0.0f, hull_ang = 0.0f;       // the solver lane's result the view lane needs
+
+    if (live && !view) {
+        // ================================ solver lane ================================================
+        float cx[5], cy[5], ang[5], vx[5], vy[5], w[5], qs[5], qc[5], slp[5];
+        bool awake[5];
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-            slp[i] = sc[(size_t)(SC_SLP + i) * N]; awake[i] = sc[(size_t)(SC_AWAKE + i) * N] != 0.0f;
-            rot_set(ang[i], qs[i], qc[i]);
-            float lx = i == 0 ? cc.hull_lcx : 0.0f, ly = i == 0 ? cc.hull_lcy : 0.0f;
-            px[i] = cx[i] - (qc[i] * lx - qs[i] * ly);
-            py[i] = cy[i] - (qs[i] * lx + qc[i] * ly);
+            const float* p = b.body + (size_t)(i * BODY_FIELDS) * N + car;
+            cx[i] = p[(size_t)BF_CX * N]; cy[i] = p[(size_t)BF_CY * N]; ang[i] = p[(size_t)BF_A * N];
+            vx[i] = sc[(size_t)(SC_VX + i) * N]; vy[i] = sc[(size_t)(SC_VY + i) * N]; w[i] = sc[(size_t)(SC_W + i) * N];
+            slp[i] = b.sleep_time[(size_t)i * N + car];
+            awake[i] = b.awake[(size_t)i * N + car] != 0;
         }
-    } else {
-    if (!awake[0]) { awake[0] = true; slp[0] = 0.0f; }           // island DFS wakes the hull
-    // integrate positions
+        float jix[4], jiy[4], jiz[4], jmot[4], motorMassK[4];
+        int lim[4];
+        uint8_t on_road_next[4];
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        float tx = h * vx[i], ty = h * vy[i];
-        if (tx * tx + ty * ty > B2_MAX_TRANSLATION * B2_MAX_TRANSLATION) {
-            float ratio = B2_MAX_TRANSLATION / sqrtf(tx * tx + ty * ty);
-            vx[i] = ratio * vx[i]; vy[i] = ratio * vy[i];
+        for (int k = 0; k < 4; ++k) {
+            jix[k] = sc[(size_t)(SC_JIX + k) * N]; jiy[k] = sc[(size_t)(SC_JIY + k) * N];
+            jiz[k] = sc[(size_t)(SC_JIZ + k) * N]; jmot[k] = sc[(size_t)(SC_JMOT + k) * N];
+            motorMassK[k] = sc[(size_t)(SC_JOINT + k * SC_JOINT_FIELDS + 13) * N];
+            lim[k] = b.limit_state[(size_t)k * N + car];
+            on_road_next[k] = b.on_road_next[(size_t)k * N + car];      // loaded with everything else, stored at the end
         }
-        float rotn = h * w[i];
-        if (rotn * rotn > B2_MAX_ROTATION * B2_MAX_ROTATION) {
-            float ratio = B2_MAX_ROTATION / fabsf(rotn);
-            w[i] *= ratio;
-        }
-        cx[i] += h * vx[i]; cy[i] += h * vy[i];
-        ang[i] += h * w[i];
-    }
-    // SolvePositionConstraints, up to 60 iterations with Box2D's early exit
-    bool positionSolved = false;
-    for (int it = 0; it < MCR_POS_ITERS; ++it) {
-        bool jointsOkay = true;
-        // an iteration that leaves every position bit-identical is a fixed point of the remaining
-        // ones (e.g. a limit error that sits exactly at the angular slop): stopping there is exact
-        float p_cx[5], p_cy[5], p_an[5];
+        float px[5], py[5];
+        PK(1);
+        if (coupled) {
+            // coupled_kernel already integrated, position-solved and took the sleep decision for this car
 #pragma unroll
-        for (int i = 0; i < 5; ++i) { p_cx[i] = cx[i]; p_cy[i] = cy[i]; p_an[i] = ang[i]; }
-        jointsOkay = joints_solve_pos(cc, cx, cy, ang, lim, motorMassK);
-        if (jointsOkay) { positionSolved = true; break; }
-        unsigned moved = 0u;
-#pragma unroll
-        for (int i = 0; i < 5; ++i)
-            moved |= (__float_as_uint(p_cx[i]) ^ __float_as_uint(cx[i])) | (__float_as_uint(p_cy[i]) ^ __float_as_uint(cy[i])) |
-                     (__float_as_uint(p_an[i]) ^ __float_as_uint(ang[i]));
-        if (moved == 0u) break;
-    }
-    // SynchronizeTransform + sleep
-    float minSleepTime = 3.402823466e+38f;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        rot_set(ang[i], qs[i], qc[i]);
-        float lx = i == 0 ? cc.hull_lcx : 0.0f, ly = i == 0 ? cc.hull_lcy : 0.0f;
-        px[i] = cx[i] - (qc[i] * lx - qs[i] * ly);
-        py[i] = cy[i] - (qs[i] * lx + qc[i] * ly);
-        if (w[i] * w[i] > B2_ANGULAR_SLEEP_TOL * B2_ANGULAR_SLEEP_TOL ||
-            vx[i] * vx[i] + vy[i] * vy[i] > B2_LINEAR_SLEEP_TOL * B2_LINEAR_SLEEP_TOL) {
-            slp[i] = 0.0f; minSleepTime = 0.0f;
+            for (int i = 0; i < 5; ++i) {
+                slp[i] = sc[(size_t)(SC_SLP + i) * N]; awake[i] = sc[(size_t)(SC_AWAKE + i) * N] != 0.0f;
+                rot_set(ang[i], qs[i], qc[i]);
+                float lx = i == 0 ? cc.hull_lcx : 0.0f, ly = i == 0 ? cc.hull_lcy : 0.0f;
+                px[i] = cx[i] - (qc[i] * lx - qs[i] * ly);
+                py[i] = cy[i] - (qs[i] * lx + qc[i] * ly);
+            }
         } else {
-            slp[i] += h; minSleepTime = fminf(minSleepTime, slp[i]);
+            if (!awake[0]) { awake[0] = true; slp[0] = 0.0f; }           // island DFS wakes the hull
+            // integrate positions
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                float tx = h * vx[i], ty = h * vy[i];
+                if (tx * tx + ty * ty > B2_MAX_TRANSLATION * B2_MAX_TRANSLATION) {
+                    float ratio = B2_MAX_TRANSLATION / sqrtf(tx * tx + ty * ty);
+                    vx[i] = ratio * vx[i]; vy[i] = ratio * vy[i];
+                }
+                float rotn = h * w[i];
+                if (rotn * rotn > B2_MAX_ROTATION * B2_MAX_ROTATION) {
+                    float ratio = B2_MAX_ROTATION / fabsf(rotn);
+                    w[i] *= ratio;
+                }
+                cx[i] += h * vx[i]; cy[i] += h * vy[i];
+                ang[i] += h * w[i];
+            }
+            // SolvePositionConstraints, up to 60 iterations with Box2D's early exit
+            bool positionSolved = false;
+            for (int it = 0; it < MCR_POS_ITERS; ++it) {
+                bool jointsOkay = true;
+                // an iteration that leaves every position bit-identical is a fixed point of the remaining
+                // ones (e.g. a limit error that sits exactly at the angular slop): stopping there is exact
+                float p_cx[5], p_cy[5], p_an[5];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) { p_cx[i] = cx[i]; p_cy[i] = cy[i]; p_an[i] = ang[i]; }
+                jointsOkay = joints_solve_pos(cc, cx, cy, ang, lim, motorMassK);
+                if (jointsOkay) { positionSolved = true; break; }
+                unsigned moved = 0u;
+#pragma unroll
+                for (int i = 0; i < 5; ++i)
+                    moved |= (__float_as_uint(p_cx[i]) ^ __float_as_uint(cx[i])) | (__float_as_uint(p_cy[i]) ^ __float_as_uint(cy[i])) |
+                             (__float_as_uint(p_an[i]) ^ __float_as_uint(ang[i]));
+                if (moved == 0u) break;
+            }
+            PK(2);
+            // SynchronizeTransform + sleep
+            float minSleepTime = 3.402823466e+38f;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                rot_set(ang[i], qs[i], qc[i]);
+                float lx = i == 0 ? cc.hull_lcx : 0.0f, ly = i == 0 ? cc.hull_lcy : 0.0f;
+                px[i] = cx[i] - (qc[i] * lx - qs[i] * ly);
+                py[i] = cy[i] - (qs[i] * lx + qc[i] * ly);
+                if (w[i] * w[i] > B2_ANGULAR_SLEEP_TOL * B2_ANGULAR_SLEEP_TOL ||
+                    vx[i] * vx[i] + vy[i] * vy[i] > B2_LINEAR_SLEEP_TOL * B2_LINEAR_SLEEP_TOL) {
+                    slp[i] = 0.0f; minSleepTime = 0.0f;
+                } else {
+                    slp[i] += h; minSleepTime = fminf(minSleepTime, slp[i]);
+                }
+            }
+            if (minSleepTime >= B2_TIME_TO_SLEEP && positionSolved) {
+#pragma unroll
+                for (int i = 0; i < 5; ++i) { awake[i] = false; slp[i] = 0.0f; vx[i] = 0.0f; vy[i] = 0.0f; w[i] = 0.0f; }
+            }
+        }   // !coupled
+        PK(3);
+        hull_px = px[0]; hull_py = py[0]; hull_ang = ang[0];
+        // ---- store ---------------------------------------------------------------------------
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            float* p = b.body + (size_t)(i * BODY_FIELDS) * N + car;
+            p[(size_t)BF_CX * N] = cx[i]; p[(size_t)BF_CY * N] = cy[i]; p[(size_t)BF_A * N] = ang[i];
+            p[(size_t)BF_VX * N] = vx[i]; p[(size_t)BF_VY * N] = vy[i]; p[(size_t)BF_W * N] = w[i];
+            p[(size_t)BF_PX * N] = px[i]; p[(size_t)BF_PY * N] = py[i];
+            p[(size_t)BF_QS * N] = qs[i]; p[(size_t)BF_QC * N] = qc[i];
+            b.sleep_time[(size_t)i * N + car] = slp[i];
+            b.awake[(size_t)i * N + car] = awake[i] ? 1 : 0;
         }
-    }
-    if (minSleepTime >= B2_TIME_TO_SLEEP && positionSolved) {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) { awake[i] = false; slp[i] = 0.0f; vx[i] = 0.0f; vy[i] = 0.0f; w[i] = 0.0f; }
+        for (int k = 0; k < 4; ++k) {
+            float* p = b.joint + (size_t)(k * JOINT_FIELDS) * N + car;
+            p[(size_t)JF_IX * N] = jix[k]; p[(size_t)JF_IY * N] = jiy[k]; p[(size_t)JF_IZ * N] = jiz[k];
+            p[(size_t)JF_MOTOR * N] = jmot[k];
+            // the contact pass of THIS step decides the friction of the NEXT Car.step
+            b.on_road[(size_t)k * N + car] = on_road_next[k];
+        }
+        PK(4);
     }
-    }   // !coupled
 
-    // ---- store ---------------------------------------------------------------------------
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        float* p = b.body + (size_t)(i * BODY_FIELDS) * N + car;
-        p[(size_t)BF_CX * N] = cx[i]; p[(size_t)BF_CY * N] = cy[i]; p[(size_t)BF_A * N] = ang[i];
-        p[(size_t)BF_VX * N] = vx[i]; p[(size_t)BF_VY * N] = vy[i]; p[(size_t)BF_W * N] = w[i];
-        p[(size_t)BF_PX * N] = px[i]; p[(size_t)BF_PY * N] = py[i];
-        p[(size_t)BF_QS * N] = qs[i]; p[(size_t)BF_QC * N] = qc[i];
-        b.sleep_time[(size_t)i * N + car] = slp[i];
-        b.awake[(size_t)i * N + car] = awake[i] ? 1 : 0;
+    // ================================ view lane ====================================================
+    // what the camera and the backward test read of the hull: its FINAL velocity.  The view lane restates the few
+    // operations that produce it (integration clamp, island-wide sleep) from the same inputs, bit for bit.
+    double angle_fast = 0.0, cos_a = 1.0, sin_a = 0.0, cos_t = 1.0, sin_t = 0.0;   // cos / sin of the deg -> rad rounded angle and of the angle itself
+    bool fast = false, view_ready = false;
+    double t_new = 0.0;
+    if (live && view) {
+        float hvxf = sc[(size_t)(SC_VX + 0) * N], hvyf = sc[(size_t)(SC_VY + 0) * N];
+        const double t_old = b.time[car];
+        const double reward_now = b.reward[car];
+        const uint8_t backward_now = b.backward[car];
+        int steps_now = b.steps[car];
+        const bool counted = has_action && !(noact && noact[env]);
+        bool asleep;
+        if (coupled) {
+            asleep = sc[(size_t)(SC_AWAKE + 0) * N] == 0.0f;      // coupled_kernel: final velocities are in scratch, zeroed if asleep
+        } else {
+            // integration clamp of the hull (b2_maxTranslation), then the island's sleep decision: velocities are zeroed when
+            // every body has been below the sleep tolerances for b2_timeToSleep AND the position solve converged.  The
+            // view lane cannot know the latter early, so for the (rare) cars about to fall asleep it waits for the solver
+            // lane's verdict instead (fast = false path below is then taken with the final angle anyway).
+            const float tx = h * hvxf, ty = h * hvyf;
+            if (tx * tx + ty * ty > B2_MAX_TRANSLATION * B2_MAX_TRANSLATION) {
+                const float ratio = B2_MAX_TRANSLATION / sqrtf(tx * tx + ty * ty);
+                hvxf = ratio * hvxf; hvyf = ratio * hvyf;
+            }
+            asleep = false;
+        }
+        const double hvx = hvxf, hvy = hvyf;
+        fast = !asleep && sqrt(hvx * hvx + hvy * hvy) > 0.5;
+        if (fast) {
+            // a hull faster than 0.5 is far above b2_linearSleepTolerance (0.01): the island cannot fall asleep this step,
+            // so this velocity is final whatever the solver lane decides
+            angle_fast = atan2(hvx, hvy);
+            const float fdeg = (float)(57.29577951308232 * angle_fast);
+            const double rad = (double)fdeg * (3.14159265358979323846 / 180.0);
+            cos_a = cos(rad); sin_a = sin(rad);
+            cos_t = cos(angle_fast); sin_t = sin(angle_fast);
+            view_ready = true;
+        }
+        // what the reference's render() of this step sees: env.reward before `reward -= 0.1` (score label)
+        // and the backward flag of the previous step (mcr:431 precedes mcr:436-495)
+        b.score_snap[car] = reward_now;
+        b.backward_snap[car] = backward_now;
+        t_new = t_old + 1.0 / 50;                                  // mcr:429
+        b.time[car] = t_new;
+        if (counted) b.steps[car] = steps_now + 1;                 // TimeLimit counts step() calls only
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        float* p = b.joint + (size_t)(k * JOINT_FIELDS) * N + car;
-        p[(size_t)JF_IX * N] = jix[k]; p[(size_t)JF_IY * N] = jiy[k]; p[(size_t)JF_IZ * N] = jiz[k];
-        p[(size_t)JF_MOTOR * N] = jmot[k];
-        // the contact pass of THIS step decides the friction of the NEXT Car.step
-        b.on_road[(size_t)k * N + car] = b.on_road_next[(size_t)k * N + car];
-    }
-    // what the reference's render() of this step sees: env.reward before `reward -= 0.1` (score label)
-    // and the backward flag of the previous step (mcr:431 precedes mcr:436-495)
-    b.score_snap[car] = b.reward[car];
-    b.backward_snap[car] = b.backward[car];
-    // ---- per-view values the rasteriser needs, evaluated once here (fp64 trig is serial latency) --
-    const double t = b.time[car] + 1.0 / 50;                      // mcr:429
-    b.time[car] = t;
-    if (has_action && !(noact && noact[env])) b.steps[car] += 1;                                // TimeLimit counts step() calls only
-    {   // camera, mcr:540-556 + Transform.enable + glViewport(0,0,96,96) under glOrtho(0,1000,0,800)
+    // the pair is converged here: every lane of the warp executes the shuffles (lanes that are not live carry zeros)
+    const unsigned full = 0xffffffffu;
+    const int solver_lane = (threadIdx.x & 31) & ~1;
+    const float f_px = __shfl_sync(full, hull_px, solver_lane), f_py = __shfl_sync(full, hull_py, solver_lane);
+    const float f_ang = __shfl_sync(full, hull_ang, solver_lane);
+    if (live && view) {
+        // camera, mcr:540-556 + Transform.enable + glViewport(0,0,96,96) under glOrtho(0,1000,0,800)
         const double SCALE = 6.0, ZOOM = 2.7, WINDOW_W = 1000, WINDOW_H = 800;
-        const double zoom = 0.1 * SCALE * fmax(1 - t, 0.0) + ZOOM * SCALE * fmin(t, 1.0);
-        const double scroll_x = px[0], scroll_y = py[0];
-        double angle = -(double)ang[0];
-        const double hvx = vx[0], hvy = vy[0];
-        const bool fast = sqrt(hvx * hvx + hvy * hvy) > 0.5;
-        double at = 0.0;
-        if (fast) { at = atan2(hvx, hvy); angle = at; }
-        const double tx = WINDOW_W / 2 - (scroll_x * zoom * cos(angle) - scroll_y * zoom * sin(angle));
-        const double ty = WINDOW_H * h_ratio - (scroll_x * zoom * sin(angle) + scroll_y * zoom * cos(angle));
-        const float ftx = (float)tx, fty = (float)ty, fdeg = (float)(57.29577951308232 * angle), fzoom = (float)zoom;
-        const double rad = (double)fdeg * (3.14159265358979323846 / 180.0);
-        const double cs = cos(rad), sn = sin(rad);
+        const double zoom = 0.1 * SCALE * fmax(1 - t_new, 0.0) + ZOOM * SCALE * fmin(t_new, 1.0);
+        const double scroll_x = f_px, scroll_y = f_py;
+        double angle = -(double)f_ang;
+        if (fast) angle = angle_fast;
+        if (!view_ready) {
+            const float fdeg = (float)(57.29577951308232 * angle);
+            const double rad = (double)fdeg * (3.14159265358979323846 / 180.0);
+            cos_a = cos(rad); sin_a = sin(rad);
+            cos_t = cos(angle); sin_t = sin(angle);
+        }
+        const double tx = WINDOW_W / 2 - (scroll_x * zoom * cos_t - scroll_y * zoom * sin_t);
+        const double ty = WINDOW_H * h_ratio - (scroll_x * zoom * sin_t + scroll_y * zoom * cos_t);
+        const float ftx = (float)tx, fty = (float)ty, fzoom = (float)zoom;
+        const double cs = cos_a, sn = sin_a;
         const double SX = 96.0 / 1000.0, SY = 96.0 / 800.0;
         b.camera[(size_t)0 * N + car] = (float)(cs * (double)fzoom * SX);
         b.camera[(size_t)1 * N + car] = (float)(-sn * (double)fzoom * SX);
@@ -512,11 +600,16 @@ post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
         b.camera[(size_t)5 * N + car] = (float)((double)fty * SY);
         // car_angle of the backward test, mcr:449-456
         const double PI = 3.141592653589793;
-        double car_angle = fast ? -at : (double)ang[0];
+        double car_angle = fast ? -angle_fast : (double)f_ang;
         car_angle = fmod(car_angle + 2 * PI, 2 * PI);
         if (car_angle != 0 && car_angle < 0) car_angle += 2 * PI;
         b.heading[car] = car_angle;
     }
+    PK(5);
+    if (cls != 2 && threadIdx.x == 0) atomicMax(b.timeline + TL_POST_END, mcr_globaltimer());
+#ifdef MCR_PHASE_CLOCKS
+    if (threadIdx.x == 0) atomicAdd(&g_post_clk[7], 1ull);
+#endif
 }
 
 // Car.draw's wheel stripe (gym car_dynamics: a1 = phase, a2 = phase + 1.2, ...), evaluated once per
@@ -612,7 +705,7 @@ int launch_presweep(const Dims& d, const DevBuffers& b, const CarConst& cc, cons
 // start poses and writing on_road_next (the API joins the side stream before calling this).
 int launch_physics_post(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* noact,
                         int has_action, double h_ratio, int cls, void* stream) {
-    const int pb = pre_block(), nb = (d.N + pb - 1) / pb;
+    const int pb = pre_block(), nb = (2 * d.N + pb - 1) / pb;      // two lanes per car
     mcr_launch_pdl(post_kernel, dim3(nb), dim3(pb), 0, (cudaStream_t)stream, d, b, cc, mask, noact, has_action, h_ratio, cls);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

@@ -10,7 +10,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 WARM = int(sys.argv[3]) if len(sys.argv) > 3 else 60      # e.g. 900: late-episode steps (cars collide more)
 A = int(sys.argv[4]) if len(sys.argv) > 4 else 2
-names = ["head", "contacts", "stripes", "sweep", "coupled", "post", "score", "render", "render_end", "post2", "render2", "sweep_end_percar", "sweep_end_packed", "coupled_vel_end", "coupled_pos_end", "fill"]
+names = ["head", "contacts", "stripes", "sweep", "coupled", "post", "score", "render", "render_end", "post2", "render2", "sweep_end_percar", "sweep_end_packed", "coupled_vel_end", "coupled_pos_end", "fill", "post_end", "project_end", "head_end"]
 np.random.seed(1234)
 venv = mcr.BatchedMultiCarRacing(B, num_agents=A, auto_reset="next_step", max_episode_steps=1000, seed=1234)
 venv.reset(device_tracks=True)
