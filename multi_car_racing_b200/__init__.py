@@ -33,14 +33,29 @@ def make(id=ENV_ID, **kwargs):
     return TimeLimit(MultiCarRacing(**kwargs), MAX_EPISODE_STEPS)
 
 
+REGISTERED_WITH = []       # the gym packages the id was registered with at import time
+
+
 def _register():
+    """register(id='MultiCarRacing-v0', max_episode_steps=1000, reward_threshold=900) with every gym package that is
+    importable (reference gym_multi_car_racing/__init__.py:5-10).  A missing package is skipped silently; a package that
+    is present but refuses the registration (other than "already registered") is reported as a warning, not swallowed."""
+    import importlib
+    import warnings
     for modname in ("gym", "gymnasium"):
         try:
-            mod = __import__(modname + ".envs.registration", fromlist=["register"])
+            mod = importlib.import_module(modname + ".envs.registration")
+        except ImportError:
+            continue
+        try:
             mod.register(id=ENV_ID, entry_point="multi_car_racing_b200:MultiCarRacing",
                          max_episode_steps=MAX_EPISODE_STEPS, reward_threshold=REWARD_THRESHOLD)
-        except Exception:
-            pass
+            REGISTERED_WITH.append(modname)
+        except Exception as e:      # gym raises gym.error.Error on a duplicate id: a re-import, fine
+            if "registered" in str(e).lower() or "re-register" in str(e).lower():
+                REGISTERED_WITH.append(modname)
+            else:
+                warnings.warn("multi_car_racing_b200: could not register %s with %s: %r" % (ENV_ID, modname, e))
 
 
 _register()

@@ -242,3 +242,33 @@ def test_batched_seeding_matches_np_random(mcr):
         rng, _ = np_random(sd)
         st = rng.get_state()
         assert np.array_equal(states[i, :624], st[1]) and states[i, 624] == st[2], "seed %d" % sd
+
+
+def test_gym_registration_path(monkeypatch):
+    """reference gym_multi_car_racing/__init__.py:5-10: register(id, entry_point, max_episode_steps=1000,
+    reward_threshold=900).  gym is not installable here, so a stand-in `gym.envs.registration` module records the call
+    the package makes at import time; a package that refuses the registration produces a warning instead of silence."""
+    import importlib, sys, types, warnings
+    calls = []
+    gym = types.ModuleType("gym"); envs = types.ModuleType("gym.envs"); reg = types.ModuleType("gym.envs.registration")
+    reg.register = lambda **kw: calls.append(kw)
+    gym.envs = envs; envs.registration = reg
+    for name, mod in (("gym", gym), ("gym.envs", envs), ("gym.envs.registration", reg)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    import multi_car_racing_b200 as pkg
+    pkg = importlib.reload(pkg)
+    assert calls == [dict(id="MultiCarRacing-v0", entry_point="multi_car_racing_b200:MultiCarRacing",
+                          max_episode_steps=1000, reward_threshold=900)]
+    assert "gym" in pkg.REGISTERED_WITH
+    entry_mod, entry_cls = calls[0]["entry_point"].split(":")
+    assert getattr(importlib.import_module(entry_mod), entry_cls) is pkg.MultiCarRacing
+
+    def refuse(**kw):
+        raise RuntimeError("registry is read-only")
+    reg.register = refuse
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        pkg = importlib.reload(pkg)
+    assert any("could not register" in str(x.message) for x in w) and "gym" not in pkg.REGISTERED_WITH
+    monkeypatch.undo()
+    importlib.reload(pkg)
