@@ -538,6 +538,7 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
     set_spec(h, BUF_TRK_PRODUCED, "trk_produced", MCR_I32, {B});
     set_spec(h, BUF_TRK_LOCK, "trk_lock", MCR_I32, {B});
     set_spec(h, BUF_TG_SCRATCH, "tg_scratch", MCR_U8, {cfg->fresh_tracks > 0 ? B : 1, mcr_trackgen_scratch_bytes()});
+    set_spec(h, BUF_READY, "ready", MCR_I32, {(int64_t)READY_WORDS(N)});
     *out = h;
     return 0;
 }
@@ -633,6 +634,7 @@ extern "C" int mcr_bind_buffer(mcr_handle h, int i, void* p) {
         case BUF_TRK_PRODUCED: b.trk_produced = (int32_t*)p; break;
         case BUF_TRK_LOCK: b.trk_lock = (int32_t*)p; break;
         case BUF_TG_SCRATCH: b.tg_scratch = (unsigned char*)p; break;
+        case BUF_READY: b.ready = (int32_t*)p; break;
     }
     return 0;
 }
@@ -799,6 +801,8 @@ extern "C" int mcr_tracks_generate_device(mcr_handle h, int32_t n, uint32_t* d_m
 static int ensure_side(mcr_handle h) {
     if (!h->side_ready) {
         CUDA_OK(cudaSetDevice(h->cfg.device));
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CUDA_OK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
         CUDA_OK(cudaStreamCreateWithFlags(&h->cap, cudaStreamNonBlocking));
         CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -814,8 +818,6 @@ static int ensure_side(mcr_handle h) {
         CUDA_OK(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
         for (int i = 0; i < 8; ++i) CUDA_OK(cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
         CUDA_OK(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
-        int prio_lo = 0, prio_hi = 0;
-        CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CUDA_OK(cudaStreamCreateWithPriority(&h->refill, cudaStreamNonBlocking, prio_lo));
         CUDA_OK(cudaEventCreateWithFlags(&h->ev_refill, cudaEventDisableTiming));
         CUDA_OK(cudaEventCreateWithFlags(&h->ev_refill_go, cudaEventDisableTiming));
@@ -950,6 +952,14 @@ static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, con
     // for the per-car head): measured slower at every batch size, 1 k to 16 k envs (profiles/README r02) -- diagnostics only.
     static const char* head_env = std::getenv("MCR_HEAD_SPLIT");
     const bool head_split = head_env && head_env[0] == '1';
+    // Hand-offs of the main chain by per-car / per-frame ready flags instead of grid-wide dependencies (DevBuffers::ready):
+    //   1  sweep -> post -> project -> fill: the consumer is launched early and each CTA waits for its own cars / frame
+    //   2  also contacts / stripes -> post, so that post_kernel's only stream dependency is the sweep and it is placed while
+    //      the sweep runs (a second dependency costs the programmatic launch).  Only while post_kernel's grid is small: it
+    //      then waits, resident, for kernels that are launched after it.
+    // MCR_FLAG_HANDOFF=0|1|2 overrides (A/B); read per pass, i.e. once per graph capture.
+    int handoff = d.N <= 2304 ? 2 : 1;
+    if (const char* e = std::getenv("MCR_FLAG_HANDOFF")) handoff = std::min(handoff, std::max(0, atoi(e)));
     if (reset_flags) {
         // next-step auto reset: the flagged envs are respawned first, so the contact pass (which reads the start poses)
         // has to follow it
@@ -957,12 +967,12 @@ static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, con
         else LAUNCH(launch_head(d, b, cc, mask, reset_flags, ar, action, action_dtype, h->cfg.collisions, s));
         CUDA_OK(cudaEventRecord(h->ev_fork, s));
         CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-        LAUNCH(launch_contacts(d, b, cc, mask, h->side));
+        LAUNCH(launch_contacts(d, b, cc, mask, h->side, handoff == 2));
         if (head_split) LAUNCH(launch_presweep(d, b, cc, mask, noact, action, action_dtype, h->cfg.collisions, 0, s));
     } else {
         CUDA_OK(cudaEventRecord(h->ev_fork, s));
         CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-        LAUNCH(launch_contacts(d, b, cc, mask, h->side));
+        LAUNCH(launch_contacts(d, b, cc, mask, h->side, handoff == 2));
         if (noact || head_split) LAUNCH(launch_presweep(d, b, cc, mask, noact, action, action_dtype, h->cfg.collisions, 0, s));
         else LAUNCH(launch_head(d, b, cc, mask, nullptr, ar, action, action_dtype, h->cfg.collisions, s));
     }
@@ -970,7 +980,7 @@ static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, con
     // wheel stripes for the rasteriser: they need pre_kernel's phase and nothing else, so they ride on
     // the side stream behind the contact pass; ev_contacts (which every post_kernel waits for) covers both
     CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_pre, 0));
-    LAUNCH(launch_stripes(d, b, mask, h->side));
+    LAUNCH(launch_stripes(d, b, mask, h->side, handoff == 2));
     CUDA_OK(cudaEventRecord(h->ev_contacts, h->side));
     if (split) {
         CUDA_OK(cudaStreamWaitEvent(h->side2, h->ev_pre, 0));
@@ -990,10 +1000,11 @@ static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, con
         if (post_step) CUDA_OK(cudaStreamWaitEvent(h->side2, h->ev_score2, 0));
         CUDA_OK(cudaEventRecord(h->ev_chain2, h->side2));
     }
-    LAUNCH(launch_presweep(d, b, cc, mask, noact, action, action_dtype, h->cfg.collisions, 1, s));
-    CUDA_OK(cudaStreamWaitEvent(s, h->ev_contacts, 0));
+    LAUNCH(launch_presweep(d, b, cc, mask, noact, action, action_dtype, h->cfg.collisions, 1, s, handoff >= 1));
+    if (handoff < 2) CUDA_OK(cudaStreamWaitEvent(s, h->ev_contacts, 0));
     const int cls = split ? 1 : 0;
-    LAUNCH(launch_physics_post(d, b, cc, mask, noact, action != nullptr, h->cfg.h_ratio, cls, s));
+    const int flag_handoff = handoff >= 1;
+    LAUNCH(launch_physics_post(d, b, cc, mask, noact, action != nullptr, h->cfg.h_ratio, cls, s, handoff));
     // the reward / done block: inside the projector's launch (nothing between post_kernel and it in this stream, so the
     // programmatic dependent launch holds), or -- fused rasteriser -- as its own kernel on the side stream
     const bool score_in_render = post_step && render_runs_score(cls);
@@ -1010,7 +1021,7 @@ static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, con
         // mcr_step_host: the frames go to the host in up to 8 ranges of envs; the copy of a range starts as soon as it is
         // filled, beside the fill of the next ranges -- only the physics and the first range's fill are not hidden
         // behind the PCIe transfer.  (The touching-car chain's frames lie scattered in every range: wait for it first.)
-        LAUNCH(launch_project(d, b, cc, mask, h->cfg.backwards_flag, h->cfg.use_ego_color, cls, s, noact, sc_reward, done, h->cfg.max_episode_steps));
+        LAUNCH(launch_project(d, b, cc, mask, h->cfg.backwards_flag, h->cfg.use_ego_color, cls, s, noact, sc_reward, done, h->cfg.max_episode_steps, flag_handoff));
         if (split) CUDA_OK(cudaStreamWaitEvent(h->copy, h->ev_chain2, 0));
         // ranges grow geometrically (B/16, B/16, B/8, B/4, B/2): the first copy starts after a sixteenth of the fill, and
         // the later, larger copies keep the per-copy set-up cost off the link
@@ -1028,9 +1039,10 @@ static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, con
         CUDA_OK(cudaEventRecord(h->ev_copy, h->copy));
     } else {
         LAUNCH(launch_render(d, b, cc, mask, obs, h->cfg.backwards_flag, h->cfg.use_ego_color, cls, h->obs_format, h->stack_k, s,
-                             noact, sc_reward, done, h->cfg.max_episode_steps));
+                             noact, sc_reward, done, h->cfg.max_episode_steps, flag_handoff));
     }
     if (post_step && !score_in_render) CUDA_OK(cudaStreamWaitEvent(s, h->ev_score, 0));
+    if (handoff == 2) CUDA_OK(cudaStreamWaitEvent(s, h->ev_contacts, 0));      // the side stream joins here instead of in front of post_kernel
     if (split) CUDA_OK(cudaStreamWaitEvent(s, h->ev_chain2, 0));
     if (ho) {
         if (!chunked) CUDA_OK(cudaMemcpyAsync(ho->h_obs, obs, (size_t)d.N * frame_bytes, cudaMemcpyDeviceToHost, s));

@@ -330,6 +330,7 @@ head_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
     __shared__ float s_old[CC_WARPS][MAXM * MW];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * CC_WARPS + warp;
+    if (blockIdx.x == 0 && threadIdx.x == 0) b.ready[READY_EPOCH(d.N)] += 1;      // a new pass, see pre_kernel
     if (env >= d.B) return;
     if (mask && !mask[env]) return;
     bool respawned = false;

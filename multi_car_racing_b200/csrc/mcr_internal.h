@@ -47,7 +47,7 @@ enum {
     BUF_TRK_T, BUF_TRK_Q, BUF_TRK_NODE, BUF_TRK_TILE, BUF_TRK_TILE_AABB, BUF_TRK_QUAD, BUF_TRK_QUAD_COL,
     BUF_TRK_QUAD_TILE, BUF_TRK_SLOT_POSE, BUF_TRK_CHUNK, BUF_TRK_QUAD64,
     BUF_DL_HDR, BUF_DL_META, BUF_DL_EDGE, BUF_DL_OCT,
-    BUF_MT_STATE, BUF_TRK_CONSUMED, BUF_TRK_PRODUCED, BUF_TRK_LOCK, BUF_TG_SCRATCH,
+    BUF_MT_STATE, BUF_TRK_CONSUMED, BUF_TRK_PRODUCED, BUF_TRK_LOCK, BUF_TG_SCRATCH, BUF_READY,
     BUF_COUNT
 };
 
@@ -113,8 +113,22 @@ struct DevBuffers {
     uint32_t* mt_state;                  // [B][625] numpy RandomState of every env (624 words + position)
     int32_t* trk_consumed; int32_t* trk_produced; int32_t* trk_lock;   // [B]
     unsigned char* tg_scratch;           // [B][mcr_trackgen_scratch_bytes()] generator scratch (one element when fresh_tracks = 0)
+    // per-car / per-frame hand-off flags of the step's critical chain (release / acquire at GPU scope): the consumer kernel
+    // is launched early (programmatic dependent launch, the producer triggers at its start) and each of its CTAs only
+    // waits for the cars / the frame it reads, not for the producer's slowest CTA:
+    //   ready[car]           == ready[READY_EPOCH]: post_kernel stored car's final pose, camera and snapshots in this pass
+    //                        (contacts_kernel counts the passes; several CTAs read the flag, nobody takes it back)
+    //   ready[N + f]         project_kernel stored frame f's display list (taken back by the fill_kernel CTA that consumed it)
+    //   ready[2N + car]      sweep_kernel stored car's solved velocities      } set only inside mcr_step's pipeline, taken back
+    //   ready[3N + car]      contacts_kernel is done with car's env           } by the post_kernel lane pair of the car
+    //   ready[(4+k)N + car]  stripe_kernel stored the stripe of wheel k       }
+    // A consumer only triggers the launch of ITS consumer after its own waits: whatever a waiting grid depends on is
+    // complete by the time it can be placed, so a grid that does not fit the GPU never holds back its own producers.
+    int32_t* ready;
 };
 
+#define READY_EPOCH(N) (8 * (size_t)(N))
+#define READY_WORDS(N) (8 * (size_t)(N) + 32)
 struct Dims { int B, A, N, Tmax, Qmax, P; int particles; int dl_cap; };
 // display-list capacity per frame: every candidate of a state frame (playfield, 100 checker squares, road_poly, 12 parts per car, 9 HUD polygons)
 #define MCR_DL_CAP(Qmax, A) ((1 + 100 + (Qmax) + 12 * (A) + 9 + 7) & ~7)
@@ -124,13 +138,24 @@ struct Dims { int B, A, N, Tmax, Qmax, P; int particles; int dl_cap; };
 // skid_meta[wheel] bits: 0 skid_start valid, 1 skid_particle valid, 2 its grass flag, 8-15 its length, 16-23 its ring slot + 1 (0 = popped from Car.particles)
 // timeline slots: kernel start stamps (block 0, thread 0) and the latest CTA end of the rasteriser
 enum { TL_HEAD = 0, TL_CONTACTS, TL_STRIPES, TL_SWEEP, TL_COUPLED, TL_POST, TL_SCORE, TL_RENDER, TL_RENDER_END, TL_POST2, TL_RENDER2, TL_SWEEP_END, TL_SWEEP_END_PACKED, TL_COUPLED_VEL_END, TL_COUPLED_POS_END, TL_FILL = 15 /* fill_kernel start (cls != 2) */,
-       TL_POST_END = 16, TL_PROJECT_END = 17, TL_HEAD_END = 18 /* latest CTA end of post (cls != 2) / project / head */, TL_COUNT = 24 };
+       TL_POST_END = 16, TL_PROJECT_END = 17, TL_HEAD_END = 18 /* latest CTA end of post (cls != 2) / project / head */,
+       // hand-off diagnostics; "first" slots hold ~t (atomicMax of the complement = earliest stamp)
+       TL_FILL_FIRST_IN = 19 /* first fill CTA placed */, TL_FILL_FIRST_GO = 20 /* first fill CTA past its flag */, TL_PROJECT_FIRST_END = 21,
+       TL_PROJECT_LAST_GO = 22 /* last project CTA past post's flags */, TL_FILL_LAST_IN = 23 /* last fill CTA placed */, TL_COUNT = 24 };
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned long long mcr_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void tl_stamp_any(const unsigned long long* tl_base, int slot) { const_cast<unsigned long long*>(tl_base)[slot] = mcr_globaltimer(); }
 __device__ __forceinline__ void tl_stamp(const unsigned long long* tl_base, int slot) {
     if ((blockIdx.x | blockIdx.y | threadIdx.x) == 0) const_cast<unsigned long long*>(tl_base)[slot] = mcr_globaltimer();
 }
+// hand-off flags (DevBuffers::ready): release store after the producer's data stores, acquire load before the consumer's
+// data loads, both at GPU scope (the acquire also drops the SM's L1 lines, so weak loads after it see the producer's data)
+__device__ __forceinline__ void flag_release(int32_t* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+// polling uses relaxed loads (no L1 invalidation per poll); one acquire fence after the flags have been seen orders the
+// data loads behind them and drops the SM's L1 lines once
+__device__ __forceinline__ int flag_peek(const int32_t* p) { int v; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void flag_fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void flag_wait(const int32_t* p, unsigned ns = 40) { while (flag_peek(p) == 0) __nanosleep(ns); flag_fence_acquire(); }
 #endif
 
 // Programmatic dependent launch for the kernels of the critical chain (head -> sweep -> post -> render): the
@@ -153,32 +178,33 @@ static inline cudaError_t mcr_launch_pdl(void (*kernel)(KArgs...), dim3 grid, di
 #endif
 
 // kernel launchers (each returns the number of kernels it launched, or < 0 on error)
-int launch_contacts(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, void* stream);
+int launch_contacts(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, void* stream, int set_flags = 0);   // set_flags: see DevBuffers::ready
 // noact[env] != 0: that env takes the action=None path of mcr:421 this step (next-step auto reset)
 int launch_physics(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* noact,
                    const void* action, int action_dtype, double h_ratio, int collisions, void* stream);
 // wheel-stripe extents for the rasteriser (needs pre_kernel's phase; launch_physics issues it itself)
-int launch_stripes(const Dims& d, const DevBuffers& b, const uint8_t* mask, void* stream);
+int launch_stripes(const Dims& d, const DevBuffers& b, const uint8_t* mask, void* stream, int set_flags = 0);
 int launch_carcontacts(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, void* stream);
 int launch_coupled(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, int early_exit, void* stream);
 // cls selects envs by their car-car contact state this step: 0 = all, 1 = only envs without
 // manifolds (per-car solver), 2 = only envs with manifolds (coupled_kernel) -- the two classes
 // flow through post / score / render on separate streams
 int launch_physics_post(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* noact,
-                        int has_action, double h_ratio, int cls, void* stream);
+                        int has_action, double h_ratio, int cls, void* stream, int wait_sweep = 0);   // wait_sweep: right behind sweep_kernel, which swept every car this launch takes
 int launch_presweep(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* noact,
-                    const void* action, int action_dtype, int collisions, int with_sweep, void* stream);
+                    const void* action, int action_dtype, int collisions, int with_sweep, void* stream, int set_flags = 0);
 // score_reward != NULL (only when render_runs_score(cls)): the reward / done block (launch_score's work) runs inside the launch
 int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* obs,
                   int backwards_flag, int use_ego_color, int cls, int obs_format, int stack_k, void* stream,
-                  const uint8_t* score_noact = nullptr, double* score_reward = nullptr, uint8_t* score_done = nullptr, int max_episode_steps = 0);
+                  const uint8_t* score_noact = nullptr, double* score_reward = nullptr, uint8_t* score_done = nullptr, int max_episode_steps = 0,
+                  int wait_post = 0);   // wait_post: launched right behind post_kernel in the same stream -- the projector waits for post's per-car ready flags
 bool render_runs_score(int cls);
 int launch_score(const Dims& d, const DevBuffers& b, const uint8_t* mask, const uint8_t* noact, double* reward, uint8_t* done,
                  int max_episode_steps, int cls, void* stream);
 bool render_is_split();
 int launch_project(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, int backwards_flag, int use_ego_color,
                    int cls, void* stream, const uint8_t* score_noact = nullptr, double* score_reward = nullptr, uint8_t* score_done = nullptr,
-                   int max_episode_steps = 0);
+                   int max_episode_steps = 0, int wait_post = 0);
 int launch_fill(const Dims& d, const DevBuffers& b, const uint8_t* mask, uint8_t* obs, int cls, int obs_format, int stack_k,
                 int env0, int nenv, bool pdl, void* stream);
 // render(mode) for a vw x vh viewport (rgb_array: 600 x 400): camera_kernel + tiled render_kernel<true>

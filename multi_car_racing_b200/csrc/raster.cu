@@ -920,6 +920,7 @@ __device__ __forceinline__ void score_car(const Dims& d, const DevBuffers& b, co
     const float posxf = b.body[(size_t)BF_PX * N + car], posyf = b.body[(size_t)BF_PY * N + car];
     const double* node = b.trk_node + (size_t)slot * d.Tmax * 3;
     float best2 = 3.0e38f;
+#pragma unroll 4
     for (int i = lane; i < T; i += 32) {
         const float dx = posxf - (float)node[(size_t)i * 3 + 1], dy = posyf - (float)node[(size_t)i * 3 + 2];
         best2 = fminf(best2, dx * dx + dy * dy);
@@ -1112,15 +1113,18 @@ struct ScoreArgs { const uint8_t* noact; double* out_reward; uint8_t* out_done; 
 template <int PJ_W>
 __global__ void __launch_bounds__(PJ_W * 32, 32 / PJ_W)
 project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, int backwards_flag, int use_ego_color, int cls,
-               ScoreArgs sa) {
+               ScoreArgs sa, int wait_post) {
     __shared__ uint8_t s_vis_chunk[MAX_CHUNKS];
     __shared__ int s_nvis;
     __shared__ unsigned long long s_pre[PJ_MAX_PASS + 1];   // prefix BEFORE pass p: entries << 32 | span slots; ~0 = not published yet
     __shared__ __align__(16) uint8_t s_touched[2048];   // this env's "tile colour was reset" flags (Tmax <= Qmax <= 2048): loaded
                                                         // beside the camera, so the road passes do not wait for a dependent load
     PJCLK_T0();
-    cudaGridDependencySynchronize();               // programmatic dependent launch behind post_kernel (mcr_launch_pdl)
-    tl_stamp(b.timeline, cls == 2 ? TL_RENDER2 : TL_RENDER);
+    // wait_post (the step's main chain): post_kernel triggered this launch at its start and publishes every car with a
+    // ready flag; the CTA waits below for the cars of its own env only.  Otherwise: plain programmatic dependent launch
+    // behind whatever precedes in the stream.  Either way fill_kernel may be launched from here on -- its CTAs wait for
+    // their own frame's flag (set at the end of this kernel).
+    if (!wait_post || (int)blockIdx.x >= d.N) cudaGridDependencySynchronize();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if ((int)blockIdx.x >= d.N) {                  // score CTAs
         __shared__ int s_cand[PJ_W][32];
@@ -1134,8 +1138,23 @@ project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
     PJCLK(9);
     const int env = frame / d.A, agent = frame - env * d.A;
     if (mask && !mask[env]) return;
-    if (cls && (cls == 2) != (b.n_manifold[env] > 0)) return;
+    if (cls && (cls == 2) != (b.n_manifold[env] > 0)) return;      // (written by the head of the chain: complete long ago)
     const int N = d.N, car = frame;
+    if (wait_post) {
+        // every car of the env is drawn in this frame: lanes 0..A-1 of each warp wait for one car each
+        const int epoch = flag_peek(b.ready + READY_EPOCH(N));
+        if (lane < d.A) { while (flag_peek(b.ready + env * d.A + lane) != epoch) __nanosleep(40); }
+        flag_fence_acquire();
+        __syncwarp();
+    }
+    // fill_kernel may be launched once every CTA of this grid is here (or has left).  Not earlier: its CTAs wait for
+    // registers until CTAs of this kernel retire, and the hardware places grids in launch order -- launched at the top of
+    // this kernel (measured, profiles/README r02) the pending grid held score_kernel, which is launched when post_kernel
+    // completes, back by 30 us; a persistent score grid launched ahead of it and waiting for post_kernel's flags took
+    // project_kernel's one-wave residency instead.  Here post_kernel is complete, so score_kernel is launched first.
+    cudaTriggerProgrammaticLaunchCompletion();
+    tl_stamp(b.timeline, cls == 2 ? TL_RENDER2 : TL_RENDER);
+    if (cls != 2 && threadIdx.x == 0) atomicMax(b.timeline + TL_PROJECT_LAST_GO, mcr_globaltimer());
     const int slot = b.env_track[env];
     Affine M;
     M.m00 = b.camera[(size_t)0 * N + car]; M.m01 = b.camera[(size_t)1 * N + car]; M.m02 = b.camera[(size_t)2 * N + car];
@@ -1287,7 +1306,10 @@ project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
             *reinterpret_cast<int4*>(b.dl_hdr + (size_t)frame * 4) = make_int4(lc + __popc(bal), pc + pass_rows, V.grass_full, 0);
         PJCLK(13);
     }
-    if (cls != 2 && threadIdx.x == 0) atomicMax(b.timeline + TL_PROJECT_END, mcr_globaltimer());
+    // the frame's display list is complete when every warp has stored its passes: publish it (ready[N + frame])
+    __syncthreads();                               // (barrier + release store: the release is cumulative over the other threads' stores)
+    if (threadIdx.x == 0) flag_release(b.ready + N + frame, 1);
+    if (cls != 2 && threadIdx.x == 0) { const unsigned long long t = mcr_globaltimer(); atomicMax(b.timeline + TL_PROJECT_END, t); atomicMax(b.timeline + TL_PROJECT_FIRST_END, ~t); }
 #ifdef MCR_PHASE_CLOCKS
     if (threadIdx.x == 0) atomicAdd(&g_phase_clk[14], 1ull);
 #endif
@@ -1311,10 +1333,16 @@ fill_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, uint8_t* __r
     }
     if (tid < 256) S.prmt_sel[tid] = prmt_selector(tid);
     if (tid >= 128 && tid < 128 + SPAN_POOL / 32) S.startbits[tid - 128] = 0;
-    cudaGridDependencySynchronize();
-    if (cls != 2) tl_stamp(b.timeline, TL_FILL);
     if (mask && !mask[env]) return;
     if (cls && (cls == 2) != (b.n_manifold[env] > 0)) return;
+    // project_kernel triggered this launch at its start: wait for this frame's display list only (and take the flag back)
+    if (tid == 0) {
+        if (cls != 2) { const unsigned long long t = mcr_globaltimer(); atomicMax(b.timeline + TL_FILL_FIRST_IN, ~t); atomicMax(b.timeline + TL_FILL_LAST_IN, t); }
+        flag_wait(b.ready + d.N + frame); b.ready[d.N + frame] = 0;
+        if (cls != 2) atomicMax(b.timeline + TL_FILL_FIRST_GO, ~mcr_globaltimer());
+    }
+    __syncthreads();
+    if (cls != 2) tl_stamp(b.timeline, TL_FILL);
     const uint2* __restrict__ meta = reinterpret_cast<const uint2*>(b.dl_meta) + (size_t)frame * d.dl_cap;
     const float4* __restrict__ edge = reinterpret_cast<const float4*>(b.dl_edge) + (size_t)frame * d.dl_cap * 4;
     const float4* __restrict__ oct = reinterpret_cast<const float4*>(b.dl_oct) + (size_t)frame * d.A * 4;
@@ -1418,21 +1446,21 @@ static bool configure_render() {
 }
 
 static void launch_project_impl(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, int backwards_flag,
-                                int use_ego_color, int cls, const ScoreArgs& sa, cudaStream_t stream) {
+                                int use_ego_color, int cls, const ScoreArgs& sa, int wait_post, cudaStream_t stream) {
     if (d.N <= PJ_SMALL_FRAMES) {
         const int score_ctas = sa.enabled ? (d.N + PJ_W_SMALL - 1) / PJ_W_SMALL : 0;
         mcr_launch_pdl(project_kernel<PJ_W_SMALL>, dim3(d.N + score_ctas), dim3(PJ_W_SMALL * 32), 0, stream,
-                       d, b, cc, mask, backwards_flag, use_ego_color, cls, sa);
+                       d, b, cc, mask, backwards_flag, use_ego_color, cls, sa, wait_post);
     } else {
         const int score_ctas = sa.enabled ? d.N : 0;
         mcr_launch_pdl(project_kernel<1>, dim3(d.N + score_ctas), dim3(32), 0, stream,
-                       d, b, cc, mask, backwards_flag, use_ego_color, cls, sa);
+                       d, b, cc, mask, backwards_flag, use_ego_color, cls, sa, wait_post);
     }
 }
 
 int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* obs,
                   int backwards_flag, int use_ego_color, int cls, int obs_format, int stack_k, void* stream,
-                  const uint8_t* score_noact, double* score_reward, uint8_t* score_done, int max_episode_steps) {
+                  const uint8_t* score_noact, double* score_reward, uint8_t* score_done, int max_episode_steps, int wait_post) {
     if (!configure_render()) return -1;
     // score_reward != NULL: the step's reward / done block runs inside this launch (project_kernel's extra CTAs); callers
     // must check render_runs_score(cls) first -- the fused kernel has no such CTAs
@@ -1445,7 +1473,7 @@ int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const 
                        d, b, cc, mask, obs, backwards_flag, use_ego_color, cls, obs_format, stack_k, VpParams{});
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
     }
-    launch_project_impl(d, b, cc, mask, backwards_flag, use_ego_color, cls, sa, (cudaStream_t)stream);
+    launch_project_impl(d, b, cc, mask, backwards_flag, use_ego_color, cls, sa, wait_post, (cudaStream_t)stream);
     mcr_launch_pdl(fill_kernel, dim3(d.B, d.A), dim3(RS_THREADS), sizeof(RasterSmem), (cudaStream_t)stream,
                    d, b, mask, obs, cls, obs_format, stack_k, 0);
     return cudaGetLastError() == cudaSuccess ? 2 : -1;
@@ -1467,10 +1495,11 @@ bool render_runs_score(int cls) {
 }
 
 int launch_project(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, int backwards_flag, int use_ego_color,
-                   int cls, void* stream, const uint8_t* score_noact, double* score_reward, uint8_t* score_done, int max_episode_steps) {
+                   int cls, void* stream, const uint8_t* score_noact, double* score_reward, uint8_t* score_done, int max_episode_steps,
+                   int wait_post) {
     if (!configure_render()) return -1;
     const ScoreArgs sa{score_noact, score_reward, score_done, max_episode_steps, score_reward != nullptr ? 1 : 0};
-    launch_project_impl(d, b, cc, mask, backwards_flag, use_ego_color, cls, sa, (cudaStream_t)stream);
+    launch_project_impl(d, b, cc, mask, backwards_flag, use_ego_color, cls, sa, wait_post, (cudaStream_t)stream);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

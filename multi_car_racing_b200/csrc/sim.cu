@@ -245,7 +245,7 @@ __device__ void contacts_warp(const Dims& d, const DevBuffers& b, const CarConst
 #define CT_WARPS 4
 
 __global__ void __launch_bounds__(CT_WARPS * 32)
-contacts_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, size_t smem_per_warp) {
+contacts_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, size_t smem_per_warp, int set_flags) {
     extern __shared__ __align__(16) unsigned char sim_smem[];
     tl_stamp(b.timeline, TL_CONTACTS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -253,6 +253,10 @@ contacts_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ m
     if (env >= d.B) return;
     if (mask && !mask[env]) return;
     contacts_warp(d, b, cc, env, lane, sim_smem + (size_t)warp * smem_per_warp);
+    if (set_flags) {                               // publish the env's cars to post_kernel (ready[3N + car])
+        __syncwarp();
+        if (lane < d.A) flag_release(b.ready + 3 * d.N + env * d.A + lane, 1);
+    }
 }
 
 // pre/post are per-thread latency chains (fp64 division / sqrt / sincos); block size 32..128 measured equal
@@ -265,6 +269,9 @@ __global__ void __launch_bounds__(128)
 pre_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ noact,
            const ActT* __restrict__ action) {
     const int car = blockIdx.x * blockDim.x + threadIdx.x;
+    // a new pass: post_kernel publishes a car by writing the pass number into ready[car] (READY_EPOCH, see DevBuffers); counted
+    // by the first kernel of the main chain, which everything that reads the number follows in stream order
+    if (car == 0) b.ready[READY_EPOCH(d.N)] += 1;
     if (car >= d.N) return;
     const int env = car / d.A;
     if (mask && !mask[env]) return;
@@ -314,8 +321,9 @@ __device__ __forceinline__ void sweep_store(const DevBuffers& b, int car, int N,
 //   CTAs [packed, ...)    one WARP per car for the few cars with an active limit: code specialised
 //                         to the limit pattern, no divergence inside the sweep, own early exit.
 __global__ void __launch_bounds__(SWEEP_BLOCK)
-sweep_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, int early_exit, int packed_ctas) {
+sweep_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, int early_exit, int packed_ctas, int set_flags) {
     cudaGridDependencySynchronize();               // programmatic dependent launch behind head_kernel
+    cudaTriggerProgrammaticLaunchCompletion();     // post_kernel may be placed from here on: its lanes wait for their own car's flag (ready[2N + car])
     const int N = d.N;
     tl_stamp(b.timeline, TL_SWEEP);
     const float h = (float)(1.0 / 50);
@@ -343,6 +351,7 @@ sweep_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask
         sweep_load(b, car, N, s, J);
         solve_velocity<0>(s, J, m, early_exit != 0, peers);
         sweep_store(b, car, N, s);
+        if (set_flags) flag_release(b.ready + 2 * N + car, 1);
         if ((threadIdx.x & 31) == 0) atomicMax(b.timeline + TL_SWEEP_END_PACKED, mcr_globaltimer());
     } else {
         if (!mine || pat == 0) return;
@@ -355,7 +364,7 @@ sweep_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask
             case 3: solve_velocity<3>(s, J, m, early_exit != 0); break;
             default: solve_velocity<-1>(s, J, m, early_exit != 0); break;   // a rear joint at its limit: rare
         }
-        if ((threadIdx.x & 31) == 0) { sweep_store(b, car, N, s); atomicMax(b.timeline + TL_SWEEP_END, mcr_globaltimer()); }
+        if ((threadIdx.x & 31) == 0) { sweep_store(b, car, N, s); if (set_flags) flag_release(b.ready + 2 * N + car, 1); atomicMax(b.timeline + TL_SWEEP_END, mcr_globaltimer()); }
     }
 }
 
@@ -383,9 +392,13 @@ extern "C" int mcr_debug_post_clocks(unsigned long long* out8, int reset) {
 // chains; side by side the kernel is as long as the longer one instead of their sum.
 __global__ void __launch_bounds__(128)
 post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ noact, int has_action,
-            double h_ratio, int cls) {
+            double h_ratio, int cls, int wait_sweep) {
     PK_T0();
-    cudaGridDependencySynchronize();               // programmatic dependent launch behind the sweep / coupled kernel
+    // wait_sweep (the step's main chain, launched right behind sweep_kernel, which triggers at its start): each lane pair
+    // waits below for its own car's flags only -- 1: the sweep's; 2: also the contact pass's and the wheel stripes' (the
+    // launch then has no other dependency than the sweep and is placed while the sweep runs).
+    // Otherwise: programmatic dependent launch behind the sweep / coupled kernel.
+    if (!wait_sweep) cudaGridDependencySynchronize();
     PK(0);
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int car_raw = gt >> 1;
@@ -399,34 +412,77 @@ post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
     const bool coupled = b.n_manifold[env] > 0;
     if (cls && (cls == 2) != coupled) live = false;
     const int N = d.N;
-    const float h = (float)(1.0 / 50);
-    const float mA = cc.hull_invMass, iA = cc.hull_invI, mB = cc.wheel_invMass, iB = cc.wheel_invI;
-    (void)mA; (void)iA; (void)mB; (void)iB;
     const float* sc = b.scratch + car;
-    float hull_px = 0.0f, hull_py = 0.0f, hull_ang = 0.0f;       // the solver lane's result the view lane needs
-
+    if (wait_sweep > 1 && live) {
+        // the contact pass and the stripes end long before the sweep: their five flags are polled together, first
+        for (;;) {
+            int ok = flag_peek(b.ready + 3 * N + car);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ok &= flag_peek(b.ready + (size_t)(4 + k) * N + car);
+            if (ok) break;
+            __nanosleep(200);
+        }
+        flag_fence_acquire();
+    }
+    // what does not come from the sweep is loaded before the wait for it (the step's L2-cold loads leave the critical chain)
+    float cx[5], cy[5], ang[5], slp[5];
+    bool awake[5];
+    float motorMassK[4];
+    int lim[4];
+    uint8_t on_road_next[4];
+    double t_old = 0.0, reward_now = 0.0;
+    uint8_t backward_now = 0;
+    int steps_now = 0;
     if (live && !view) {
-        // ================================ solver lane ================================================
-        float cx[5], cy[5], ang[5], vx[5], vy[5], w[5], qs[5], qc[5], slp[5];
-        bool awake[5];
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
             const float* p = b.body + (size_t)(i * BODY_FIELDS) * N + car;
             cx[i] = p[(size_t)BF_CX * N]; cy[i] = p[(size_t)BF_CY * N]; ang[i] = p[(size_t)BF_A * N];
-            vx[i] = sc[(size_t)(SC_VX + i) * N]; vy[i] = sc[(size_t)(SC_VY + i) * N]; w[i] = sc[(size_t)(SC_W + i) * N];
             slp[i] = b.sleep_time[(size_t)i * N + car];
             awake[i] = b.awake[(size_t)i * N + car] != 0;
         }
-        float jix[4], jiy[4], jiz[4], jmot[4], motorMassK[4];
-        int lim[4];
-        uint8_t on_road_next[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            motorMassK[k] = sc[(size_t)(SC_JOINT + k * SC_JOINT_FIELDS + 13) * N];
+            lim[k] = b.limit_state[(size_t)k * N + car];
+            on_road_next[k] = b.on_road_next[(size_t)k * N + car];      // stored at the end
+        }
+    }
+    int epoch = 0;
+    if (live && view) {
+        t_old = b.time[car]; reward_now = b.reward[car]; backward_now = b.backward[car]; steps_now = b.steps[car];
+        epoch = flag_peek(b.ready + READY_EPOCH(N));       // (the contact pass that counted it is complete: flags above / stream order)
+    }
+    if (wait_sweep) {
+        if (live) { while (flag_peek(b.ready + 2 * N + car) == 0) __nanosleep(60); flag_fence_acquire(); }
+        __syncwarp(0xffffffffu);                   // both lanes of a pair have seen the flags before they are taken back
+    }
+    if (live && !view) {
+        // (also without waits -- the producers are complete then: a car that changes class between steps must not find
+        // the flags of an earlier pass)
+        b.ready[2 * N + car] = 0; b.ready[3 * N + car] = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) b.ready[(size_t)(4 + k) * N + car] = 0;
+    }
+    // the projector may be launched once every CTA is here (everything this kernel waits for is done by then, so the
+    // projector's grid cannot hold back a launch this kernel depends on): its CTAs wait for the ready flags of the cars
+    // they draw (set below) -- a frame is projected as soon as its own env is done, not when this kernel's slowest car is
+    cudaTriggerProgrammaticLaunchCompletion();
+    const float h = (float)(1.0 / 50);
+    const float mA = cc.hull_invMass, iA = cc.hull_invI, mB = cc.wheel_invMass, iB = cc.wheel_invI;
+    (void)mA; (void)iA; (void)mB; (void)iB;
+    float hull_px = 0.0f, hull_py = 0.0f, hull_ang = 0.0f;       // the solver lane's result the view lane needs
+
+    if (live && !view) {
+        // ================================ solver lane ================================================
+        float vx[5], vy[5], w[5], qs[5], qc[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { vx[i] = sc[(size_t)(SC_VX + i) * N]; vy[i] = sc[(size_t)(SC_VY + i) * N]; w[i] = sc[(size_t)(SC_W + i) * N]; }
+        float jix[4], jiy[4], jiz[4], jmot[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             jix[k] = sc[(size_t)(SC_JIX + k) * N]; jiy[k] = sc[(size_t)(SC_JIY + k) * N];
             jiz[k] = sc[(size_t)(SC_JIZ + k) * N]; jmot[k] = sc[(size_t)(SC_JMOT + k) * N];
-            motorMassK[k] = sc[(size_t)(SC_JOINT + k * SC_JOINT_FIELDS + 13) * N];
-            lim[k] = b.limit_state[(size_t)k * N + car];
-            on_road_next[k] = b.on_road_next[(size_t)k * N + car];      // loaded with everything else, stored at the end
         }
         float px[5], py[5];
         PK(1);
@@ -529,10 +585,6 @@ post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
     double t_new = 0.0;
     if (live && view) {
         float hvxf = sc[(size_t)(SC_VX + 0) * N], hvyf = sc[(size_t)(SC_VY + 0) * N];
-        const double t_old = b.time[car];
-        const double reward_now = b.reward[car];
-        const uint8_t backward_now = b.backward[car];
-        int steps_now = b.steps[car];
         const bool counted = has_action && !(noact && noact[env]);
         bool asleep;
         if (coupled) {
@@ -606,6 +658,9 @@ post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
         b.heading[car] = car_angle;
     }
     PK(5);
+    // both lanes of the pair have stored: publish the car (ready[car], see DevBuffers)
+    __syncwarp(full);                              // (warp barrier + release store: the release is cumulative over the solver lane's stores)
+    if (live && view) flag_release(b.ready + car, epoch);
     if (cls != 2 && threadIdx.x == 0) atomicMax(b.timeline + TL_POST_END, mcr_globaltimer());
 #ifdef MCR_PHASE_CLOCKS
     if (threadIdx.x == 0) atomicAdd(&g_post_clk[7], 1ull);
@@ -617,7 +672,7 @@ post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
 // (wheel, car) instead of a serial tail of post_kernel; phase is final once pre_kernel has run, so
 // mcr_step issues this beside the solver (side stream) and the rasteriser finds the result ready.
 __global__ void __launch_bounds__(128)
-stripe_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask) {
+stripe_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, int set_flags) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int N = d.N;
     if (idx >= 4 * N) return;
@@ -636,17 +691,18 @@ stripe_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask) {
     }
     b.stripe[(size_t)(k * 2 + 0) * N + car] = y1;
     b.stripe[(size_t)(k * 2 + 1) * N + car] = y2;
+    if (set_flags) flag_release(b.ready + (size_t)(4 + k) * N + car, 1);      // ready[(4 + wheel) N + car], taken back by post_kernel
 }
 
-int launch_stripes(const Dims& d, const DevBuffers& b, const uint8_t* mask, void* stream) {
-    stripe_kernel<<<(4 * d.N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d, b, mask);
+int launch_stripes(const Dims& d, const DevBuffers& b, const uint8_t* mask, void* stream, int set_flags) {
+    stripe_kernel<<<(4 * d.N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d, b, mask, set_flags);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 // ---------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------
-int launch_contacts(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, void* stream) {
+int launch_contacts(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, void* stream, int set_flags) {
     static bool configured[64] = {};       // per device: function attributes belong to the device's context
     const size_t per_warp = (sim_smem_bytes(d.A) + 15) & ~(size_t)15;
     const size_t smem = per_warp * CT_WARPS;
@@ -657,7 +713,7 @@ int launch_contacts(const Dims& d, const DevBuffers& b, const CarConst& cc, cons
         if (cudaFuncSetAttribute(contacts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) != cudaSuccess) return -1;
         configured[dev] = true;
     }
-    contacts_kernel<<<(d.B + CT_WARPS - 1) / CT_WARPS, CT_WARPS * 32, smem, (cudaStream_t)stream>>>(d, b, cc, mask, per_warp);
+    contacts_kernel<<<(d.B + CT_WARPS - 1) / CT_WARPS, CT_WARPS * 32, smem, (cudaStream_t)stream>>>(d, b, cc, mask, per_warp, set_flags);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -672,8 +728,8 @@ int launch_physics(const Dims& d, const DevBuffers& b, const CarConst& cc, const
     else pre_kernel<float><<<nb, pb, 0, s>>>(d, b, cc, mask, noact, (const float*)action);
     const int sb = sweep_block();
     const int packed_ctas = (d.N + sb - 1) / sb, percar_ctas = (d.N + sb / 32 - 1) / (sb / 32);
-    stripe_kernel<<<(4 * d.N + 127) / 128, 128, 0, s>>>(d, b, mask);
-    sweep_kernel<<<packed_ctas + percar_ctas, sb, 0, s>>>(d, b, cc, mask, early_exit, packed_ctas);
+    stripe_kernel<<<(4 * d.N + 127) / 128, 128, 0, s>>>(d, b, mask, 0);
+    sweep_kernel<<<packed_ctas + percar_ctas, sb, 0, s>>>(d, b, cc, mask, early_exit, packed_ctas, 0);
     launched += 3;
     if (collisions && d.A > 1) { if (launch_coupled(d, b, cc, mask, early_exit, stream) < 0) return -1; ++launched; }
     return cudaGetLastError() == cudaSuccess ? launched : -1;
@@ -682,7 +738,7 @@ int launch_physics(const Dims& d, const DevBuffers& b, const CarConst& cc, const
 // carcontacts -> pre (with_sweep = 0) or the sweep alone (with_sweep = 1): the pieces mcr_step's
 // two-chain pipeline issues itself (coupled_kernel goes to its own stream there).
 int launch_presweep(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* noact,
-                    const void* action, int action_dtype, int collisions, int with_sweep, void* stream) {
+                    const void* action, int action_dtype, int collisions, int with_sweep, void* stream, int set_flags) {
     static const int early_exit = (getenv("MCR_NO_EARLY_EXIT") ? 0 : 1);   // diagnostics only
     cudaStream_t s = (cudaStream_t)stream;
     int launched = 0;
@@ -695,7 +751,7 @@ int launch_presweep(const Dims& d, const DevBuffers& b, const CarConst& cc, cons
     } else {
         const int sb = sweep_block();
         const int packed_ctas = (d.N + sb - 1) / sb, percar_ctas = (d.N + sb / 32 - 1) / (sb / 32);
-        mcr_launch_pdl(sweep_kernel, dim3(packed_ctas + percar_ctas), dim3(sb), 0, s, d, b, cc, mask, early_exit, packed_ctas);
+        mcr_launch_pdl(sweep_kernel, dim3(packed_ctas + percar_ctas), dim3(sb), 0, s, d, b, cc, mask, early_exit, packed_ctas, set_flags);
         ++launched;
     }
     return cudaGetLastError() == cudaSuccess ? launched : -1;
@@ -704,8 +760,8 @@ int launch_presweep(const Dims& d, const DevBuffers& b, const CarConst& cc, cons
 // post_kernel must not start before the contacts pass of the same step has finished reading the
 // start poses and writing on_road_next (the API joins the side stream before calling this).
 int launch_physics_post(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* noact,
-                        int has_action, double h_ratio, int cls, void* stream) {
+                        int has_action, double h_ratio, int cls, void* stream, int wait_sweep) {
     const int pb = pre_block(), nb = (2 * d.N + pb - 1) / pb;      // two lanes per car
-    mcr_launch_pdl(post_kernel, dim3(nb), dim3(pb), 0, (cudaStream_t)stream, d, b, cc, mask, noact, has_action, h_ratio, cls);
+    mcr_launch_pdl(post_kernel, dim3(nb), dim3(pb), 0, (cudaStream_t)stream, d, b, cc, mask, noact, has_action, h_ratio, cls, wait_sweep);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

@@ -1,0 +1,20 @@
+#!/bin/bash
+OUT=gpurun_out/r4e; mkdir -p $OUT
+run() { # name, env...
+  name=$1; shift
+  env "$@" timeout 300 python scripts/timeline.py 1024 200 60 > $OUT/timeline_mid_$name.txt 2>&1
+  env "$@" timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e > $OUT/bench20_$name.json 2>$OUT/bench20_$name.err
+  echo "== $name"; head -28 $OUT/timeline_mid_$name.txt | tail -27
+  python - $OUT/bench20_$name.json <<'PY'
+import json, sys
+for f in sys.argv[1:]:
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1]); r = d.get("roofline") or {}
+        print(f.split("/")[-1], "value %.4g" % d["value"], "ms/step %.4f" % d["ms_per_step"], r.get("kernel_ms"), "frac %.3f" % r.get("frac", 0))
+    except Exception as e:
+        print(f, "unreadable", e)
+PY
+}
+run l2 A=1
+run l2_early MCR_PROJECT_TRIGGER_EARLY=1
+run l2_early_noprio MCR_PROJECT_TRIGGER_EARLY=1 MCR_SCORE_PRIO_OFF=1

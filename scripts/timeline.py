@@ -10,7 +10,8 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 WARM = int(sys.argv[3]) if len(sys.argv) > 3 else 60      # e.g. 900: late-episode steps (cars collide more)
 A = int(sys.argv[4]) if len(sys.argv) > 4 else 2
-names = ["head", "contacts", "stripes", "sweep", "coupled", "post", "score", "render", "render_end", "post2", "render2", "sweep_end_percar", "sweep_end_packed", "coupled_vel_end", "coupled_pos_end", "fill", "post_end", "project_end", "head_end"]
+names = ["head", "contacts", "stripes", "sweep", "coupled", "post", "score", "render", "render_end", "post2", "render2", "sweep_end_percar", "sweep_end_packed", "coupled_vel_end", "coupled_pos_end", "fill", "post_end", "project_end", "head_end",
+         "fill_first_in~", "fill_first_go~", "project_first_end~", "project_last_go", "fill_last_in"]     # "~": stored complemented (earliest stamp)
 np.random.seed(1234)
 venv = mcr.BatchedMultiCarRacing(B, num_agents=A, auto_reset="next_step", max_episode_steps=1000, seed=1234)
 venv.reset(device_tracks=True)
@@ -26,7 +27,10 @@ for s in range(STEPS):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); venv.step(tape[(WARM + s) % 128]); e1.record()
     torch.cuda.synchronize()
-    t = tl.cpu().numpy()[:len(names)].astype(np.float64)
+    ti = tl.cpu().numpy()[:len(names)].copy()
+    for k, nm_ in enumerate(names):
+        if nm_.endswith("~") and ti[k] != 0: ti[k] = ~ti[k]
+    t = ti.astype(np.float64)
     acc += np.where(t > 0, (t - t[0]) / 1e3, np.nan); n += 1; tot += e0.elapsed_time(e1) * 1e3
 nm = venv.buffers["n_manifold"].cpu().numpy()
 print("envs with car-car manifolds in the last step: %d of %d (max manifolds %d)" % ((nm > 0).sum(), B, nm.max()))

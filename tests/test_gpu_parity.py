@@ -72,6 +72,30 @@ def test_step_parity_300(oracle, mcr, A, B, seed):
     assert not venv.status().any()
 
 
+@pytest.mark.parametrize("level", ["0", "1", "2"])
+def test_flag_handoff_levels(oracle, mcr, level, monkeypatch):
+    """The step's critical chain hands over by per-car / per-frame ready flags (DevBuffers::ready, csrc/mcr_internal.h):
+    level 0 = plain stream order, 1 = sweep -> post -> project -> fill by flags, 2 = also contacts / stripes -> post (the
+    default for small batches).  Every level, replayed from its CUDA graph with cars that touch (both classes of envs in
+    flight), reproduces the oracle bit for bit."""
+    import torch
+    monkeypatch.setenv("MCR_FLAG_HANDOFF", level)
+    B, A, seed = 6, 2, 21
+    venv, worlds, tracks, obs0, oobs0 = _setup(oracle, mcr, B=B, A=A, seed=seed)
+    tape = action_tape(seed, 120, B, A)
+    tape[:, :, :, 0] *= 0.2; tape[:, :, 1, 1] = 1.0; tape[:, :, 1, 2] = 0.0; tape[:, :, 0, 1] = 0.1    # the rear car runs into the front one
+    touched_cars = False
+    for s in range(120):
+        obs, rew, done, _ = venv.step(torch.from_numpy(tape[s]).to(venv.device))
+        oo = [w.step(tape[s, e].astype(np.float64)) for e, w in enumerate(worlds)]
+        touched_cars = touched_cars or bool((venv.buffers["n_manifold"] > 0).any().item())
+        assert np.array_equal(rew.cpu().numpy(), np.stack([x[1] for x in oo])), "step_reward, step %d" % s
+        assert np.array_equal(obs.cpu().numpy(), np.stack([x[0] for x in oo])), "observation pixels, step %d" % s
+        if s % 20 == 0 or s == 119:
+            _compare_state(venv, worlds, tracks, s)
+    assert not venv.status().any()
+
+
 def test_pose_after_1000_steps(oracle, mcr):
     """north_star: tile visits + rewards bit-exact and pose within 1e-4 relative after 1000 steps."""
     import torch
