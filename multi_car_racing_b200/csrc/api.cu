@@ -435,7 +435,12 @@ struct mcr_handle_t {
     bool side_ready;
     // mcr_step replays a captured CUDA graph of its launches (one graph per argument tuple)
     struct StepGraph { int32_t dtype, flags; uint8_t* obs; double* reward; uint8_t* done; uint8_t* h_obs; double* h_reward; uint8_t* h_done;
-                       cudaGraphExec_t exec; int64_t launches; };
+                       cudaGraphExec_t exec; int64_t launches;
+                       // the kernel nodes that read the step's action: their pointer argument is patched per step
+                       // (cudaGraphExecKernelNodeSetParams) instead of copying the action into action_stage first -- the
+                       // copy was 3.5 us of every step (profiles/README r02).  `graph` stays alive: the nodes' argument
+                       // storage belongs to it.
+                       cudaGraph_t graph; std::vector<std::pair<cudaGraphNode_t, int>> action_nodes; const void* cur_action; };
     std::vector<StepGraph> graphs;
     int64_t eager_steps;
     bool use_graphs;
@@ -443,6 +448,49 @@ struct mcr_handle_t {
     int stack_k;                 // ring depth of MCR_OBS_GRAY_STACK
 };
 
+
+static void destroy_step_graph(mcr_handle_t::StepGraph& g) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.graph) cudaGraphDestroy(g.graph);
+    g.exec = nullptr; g.graph = nullptr; g.action_nodes.clear();
+}
+
+// The kernel nodes of a captured step that take `stage` as their action argument.
+static void find_action_nodes(cudaGraph_t graph, const void* stage, std::vector<std::pair<cudaGraphNode_t, int>>& out) {
+    size_t n = 0;
+    if (cudaGraphGetNodes(graph, nullptr, &n) != cudaSuccess || n == 0) { (void)cudaGetLastError(); return; }
+    std::vector<cudaGraphNode_t> nodes(n);
+    if (cudaGraphGetNodes(graph, nodes.data(), &n) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    for (size_t i = 0; i < n; ++i) {
+        cudaGraphNodeType ty;
+        if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp = {};
+        if (cudaGraphKernelNodeGetParams(nodes[i], &kp) != cudaSuccess || !kp.kernelParams) { (void)cudaGetLastError(); continue; }
+        int nargs = 0, idx = head_action_arg(kp.func, &nargs);
+        if (idx < 0) idx = pre_action_arg(kp.func, &nargs);
+        if (idx < 0) continue;
+        if (*reinterpret_cast<const void* const*>(kp.kernelParams[idx]) == stage) out.emplace_back(nodes[i], idx);
+    }
+}
+
+// Point the action argument of the step graph's kernels at `action` (no-op when it already is).
+static int patch_action(mcr_handle_t::StepGraph& g, const void* action) {
+    if (g.cur_action == action) return 0;
+    for (auto& na : g.action_nodes) {
+        cudaKernelNodeParams kp = {};
+        CUDA_OK(cudaGraphKernelNodeGetParams(na.first, &kp));
+        int nargs = 0;
+        if (head_action_arg(kp.func, &nargs) < 0) (void)pre_action_arg(kp.func, &nargs);
+        void* args[16];
+        for (int i = 0; i < nargs && i < 16; ++i) args[i] = kp.kernelParams[i];
+        const void* a = action;
+        args[na.second] = (void*)&a;
+        kp.kernelParams = args; kp.extra = nullptr;
+        CUDA_OK(cudaGraphExecKernelNodeSetParams(g.exec, na.first, &kp));
+    }
+    g.cur_action = action;
+    return 0;
+}
 
 static void set_spec(mcr_handle_t* h, int id, const char* name, int dtype, std::initializer_list<int64_t> dims) {
     BufSpec& s = h->spec[id];
@@ -544,7 +592,7 @@ extern "C" int mcr_create(const mcr_config* cfg, mcr_handle* out) {
 }
 
 extern "C" int mcr_destroy(mcr_handle h) {
-    if (h) for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+    if (h) for (auto& g : h->graphs) destroy_step_graph(g);
     if (h && h->side_ready) {
         cudaStreamDestroy(h->side); cudaStreamDestroy(h->cap); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
         cudaStreamDestroy(h->side3); cudaEventDestroy(h->ev_post2); cudaEventDestroy(h->ev_score2);
@@ -669,7 +717,7 @@ extern "C" int mcr_set_obs_format(mcr_handle h, int32_t format) {
         return fail(-1, "mcr_set_obs_format: unknown format %d", format);
     if (format != h->obs_format) {
         // captured step graphs bake the layout in
-        for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+        for (auto& g : h->graphs) destroy_step_graph(g);
         h->graphs.clear();
         h->obs_format = format;
     }
@@ -680,7 +728,7 @@ extern "C" int mcr_set_frame_stack(mcr_handle h, int32_t k) {
     if (!h) return fail(-1, "null handle");
     if (k < 1 || k > 16) return fail(-1, "mcr_set_frame_stack: depth must be in [1, 16]");
     if (k != h->stack_k) {
-        for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);    // captured step graphs bake the depth in
+        for (auto& g : h->graphs) destroy_step_graph(g);    // captured step graphs bake the depth in
         h->graphs.clear();
         h->stack_k = k;
     }
@@ -1126,7 +1174,7 @@ static int step_impl(mcr_handle h, const void* action, bool action_on_host, int3
         if (c.dtype == action_dtype && c.flags == flags && c.obs == obs && c.reward == reward && c.done == done &&
             c.h_obs == (ho ? ho->h_obs : nullptr) && c.h_reward == (ho ? ho->h_reward : nullptr) && c.h_done == (ho ? ho->h_done : nullptr)) { g = &c; break; }
     if (!g) {
-        if (h->graphs.size() >= 16) { cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
+        if (h->graphs.size() >= 16) { destroy_step_graph(h->graphs.front()); h->graphs.erase(h->graphs.begin()); }
         rc = ensure_side(h); if (rc) return rc;
         const int64_t before = h->launches;
         CUDA_OK(cudaStreamBeginCapture(h->cap, cudaStreamCaptureModeRelaxed));
@@ -1138,7 +1186,7 @@ static int step_impl(mcr_handle h, const void* action, bool action_on_host, int3
         cudaGraphExec_t exec = nullptr;
         cudaError_t ie = cudaErrorUnknown;
         if (!rc && ce == cudaSuccess && graph) ie = cudaGraphInstantiate(&exec, graph, 0);
-        if (graph) cudaGraphDestroy(graph);
+        if (ie != cudaSuccess && graph) { cudaGraphDestroy(graph); graph = nullptr; }
         if (ie != cudaSuccess) {
             // graphs are an optimisation of the launch path only: issue this and all later steps directly
             (void)cudaGetLastError();
@@ -1148,11 +1196,17 @@ static int step_impl(mcr_handle h, const void* action, bool action_on_host, int3
             return rc;
         }
         h->graphs.push_back(mcr_handle_t::StepGraph{action_dtype, flags, obs, reward, done, ho ? ho->h_obs : nullptr,
-                                                    ho ? ho->h_reward : nullptr, ho ? ho->h_done : nullptr, exec, per_step});
+                                                    ho ? ho->h_reward : nullptr, ho ? ho->h_done : nullptr, exec, per_step,
+                                                    graph, {}, (const void*)h->buf.action_stage});
         g = &h->graphs.back();
+        static const bool no_patch = std::getenv("MCR_ACTION_COPY") != nullptr;      // A/B: the device-to-device copy instead
+        if (!no_patch) find_action_nodes(graph, h->buf.action_stage, g->action_nodes);
     }
-    if (action != (const void*)h->buf.action_stage)
+    if (!g->action_nodes.empty()) {
+        rc = patch_action(*g, action); if (rc) return rc;
+    } else if (action != (const void*)h->buf.action_stage) {
         CUDA_OK(cudaMemcpyAsync(h->buf.action_stage, action, abytes, cudaMemcpyDeviceToDevice, s));
+    }
     CUDA_OK(cudaGraphLaunch(g->exec, s));
     h->launches += g->launches;
     if (refill_now) { rc = kick_refill(h, nullptr); if (rc) return rc; }

@@ -849,6 +849,14 @@ int launch_head(const Dims& d, const DevBuffers& b, const CarConst& cc, const ui
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
+// head_kernel's `action` argument for the captured step graph (api.cu patches it per step instead of copying the action)
+int head_action_arg(const void* func, int* nargs) {
+    const bool mine = func == (const void*)head_kernel<double, true> || func == (const void*)head_kernel<double, false> ||
+                      func == (const void*)head_kernel<float, true> || func == (const void*)head_kernel<float, false>;
+    if (nargs) *nargs = 8;
+    return mine ? 6 : -1;
+}
+
 int launch_coupled(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, int early_exit, void* stream) {
     coupled_kernel<<<d.B, 32, 0, (cudaStream_t)stream>>>(d, b, cc, mask, early_exit);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;

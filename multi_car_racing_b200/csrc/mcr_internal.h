@@ -220,5 +220,8 @@ int launch_ring_refill(const Dims& d, const DevBuffers& b, int R, void* stream);
 // auto reset (reset_flags != NULL: respawn the flagged envs, write reset_mask) + carcontacts + pre in one launch
 int launch_head(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* reset_flags,
                 const AutoResetCfg& ar, const void* action, int action_dtype, int collisions, void* stream);
+// index of the `action` argument if func is head_kernel / pre_kernel (any instantiation), else -1; *nargs = argument count
+int head_action_arg(const void* func, int* nargs);
+int pre_action_arg(const void* func, int* nargs);
 int launch_auto_reset(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* done,
                       const AutoResetCfg& cfg, void* stream);

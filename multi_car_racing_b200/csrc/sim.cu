@@ -278,6 +278,12 @@ pre_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, 
     pre_car<ActT>(d, b, cc, car, env, action && !(noact && noact[env]), action);
 }
 
+// pre_kernel's `action` argument for the captured step graph (api.cu patches it per step instead of copying the action)
+int pre_action_arg(const void* func, int* nargs) {
+    if (nargs) *nargs = 6;
+    return (func == (const void*)pre_kernel<float> || func == (const void*)pre_kernel<double>) ? 5 : -1;
+}
+
 #define SWEEP_BLOCK 128
 static int sweep_block() { const char* e = getenv("MCR_SWEEP_BLOCK"); const int v = e ? atoi(e) : SWEEP_BLOCK; return (v == 32 || v == 64 || v == 128) ? v : SWEEP_BLOCK; }   // tuning knob
 

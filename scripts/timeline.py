@@ -25,7 +25,11 @@ for s in range(STEPS):
     if not os.environ.get("NOFLUSH"): flush.zero_()      # NOFLUSH=1: leave the previous step's lines in L2
     tl.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); venv.step(tape[(WARM + s) % 128]); e1.record()
+    act = tape[(WARM + s) % 128]
+    if os.environ.get("ACTION_INPLACE"):              # the action already lies in the library's staging buffer: no device-to-device copy in the step
+        stage = venv.buffers["action_stage"].view(torch.float32).view(-1)[:B * A * 3].view(B, A, 3)
+        stage.copy_(act); act = stage
+    e0.record(); venv.step(act); e1.record()
     torch.cuda.synchronize()
     ti = tl.cpu().numpy()[:len(names)].copy()
     for k, nm_ in enumerate(names):
