@@ -378,11 +378,18 @@ sweep_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask
 // (0 grid-dependency wait, 1 loads, 2 integrate + position iterations, 3 transforms + sleep, 4 stores, 5 camera; 7 = CTAs).
 #ifdef MCR_PHASE_CLOCKS
 __device__ unsigned long long g_post_clk[8];
+__device__ unsigned long long g_post_iter_hist[64];      // position iterations a car needed (all cars, not just thread 0)
+__device__ unsigned long long g_post_warp_t[4][1024];    // per warp of the last cls != 2 launch: %globaltimer at entry, past the early flags, past the sweep flag, at the end
 #define PK_T0() long long pk_t_ = clock64()
 #define PK(k) do { if (threadIdx.x == 0) { const long long n_ = clock64(); atomicAdd(&g_post_clk[k], (unsigned long long)(n_ - pk_t_)); pk_t_ = n_; } } while (0)
 extern "C" int mcr_debug_post_clocks(unsigned long long* out8, int reset) {
     if (out8 && cudaMemcpyFromSymbol(out8, g_post_clk, sizeof(g_post_clk)) != cudaSuccess) return -1;
     if (reset) { unsigned long long z[8] = {}; if (cudaMemcpyToSymbol(g_post_clk, z, sizeof(z)) != cudaSuccess) return -1; }
+    if (reset == -2) return out8 && cudaMemcpyFromSymbol(out8, g_post_warp_t, sizeof(g_post_warp_t)) == cudaSuccess ? 0 : -1;   // out8: 4096 entries
+    if (reset < 0) {                              // reset = -1: out8 is a 64-entry buffer for the iteration histogram instead
+        if (out8 && cudaMemcpyFromSymbol(out8, g_post_iter_hist, sizeof(g_post_iter_hist)) != cudaSuccess) return -1;
+        unsigned long long z[64] = {}; if (cudaMemcpyToSymbol(g_post_iter_hist, z, sizeof(z)) != cudaSuccess) return -1;
+    }
     return 0;
 }
 #else
@@ -419,6 +426,13 @@ post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
     if (cls && (cls == 2) != coupled) live = false;
     const int N = d.N;
     const float* sc = b.scratch + car;
+#ifdef MCR_PHASE_CLOCKS
+    const int wid_ = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+#define PWT(k) do { if (cls != 2 && (threadIdx.x & 31) == 0 && wid_ < 1024) g_post_warp_t[k][wid_] = mcr_globaltimer(); } while (0)
+#else
+#define PWT(k) do {} while (0)
+#endif
+    PWT(0);
     if (wait_sweep > 1 && live) {
         // the contact pass and the stripes end long before the sweep: their five flags are polled together, first
         for (;;) {
@@ -459,10 +473,12 @@ post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
         t_old = b.time[car]; reward_now = b.reward[car]; backward_now = b.backward[car]; steps_now = b.steps[car];
         epoch = flag_peek(b.ready + READY_EPOCH(N));       // (the contact pass that counted it is complete: flags above / stream order)
     }
+    PWT(1);
     if (wait_sweep) {
         if (live) { while (flag_peek(b.ready + 2 * N + car) == 0) __nanosleep(60); flag_fence_acquire(); }
         __syncwarp(0xffffffffu);                   // both lanes of a pair have seen the flags before they are taken back
     }
+    PWT(2);
     if (live && !view) {
         // (also without waits -- the producers are complete then: a car that changes class between steps must not find
         // the flags of an earlier pass)
@@ -522,7 +538,13 @@ post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
             }
             // SolvePositionConstraints, up to 60 iterations with Box2D's early exit
             bool positionSolved = false;
+#ifdef MCR_PHASE_CLOCKS
+            int n_iter_ = 0;
+#endif
             for (int it = 0; it < MCR_POS_ITERS; ++it) {
+#ifdef MCR_PHASE_CLOCKS
+                ++n_iter_;
+#endif
                 bool jointsOkay = true;
                 // an iteration that leaves every position bit-identical is a fixed point of the remaining
                 // ones (e.g. a limit error that sits exactly at the angular slop): stopping there is exact
@@ -538,6 +560,9 @@ post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
                              (__float_as_uint(p_an[i]) ^ __float_as_uint(ang[i]));
                 if (moved == 0u) break;
             }
+#ifdef MCR_PHASE_CLOCKS
+            atomicAdd(&g_post_iter_hist[n_iter_ < 63 ? n_iter_ : 63], 1ull);
+#endif
             PK(2);
             // SynchronizeTransform + sleep
             float minSleepTime = 3.402823466e+38f;
@@ -667,6 +692,8 @@ post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
     // both lanes of the pair have stored: publish the car (ready[car], see DevBuffers)
     __syncwarp(full);                              // (warp barrier + release store: the release is cumulative over the solver lane's stores)
     if (live && view) flag_release(b.ready + car, epoch);
+    __syncwarp(full);
+    PWT(3);
     if (cls != 2 && threadIdx.x == 0) atomicMax(b.timeline + TL_POST_END, mcr_globaltimer());
 #ifdef MCR_PHASE_CLOCKS
     if (threadIdx.x == 0) atomicAdd(&g_post_clk[7], 1ull);

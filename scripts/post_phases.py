@@ -26,3 +26,18 @@ v = np.array(list(buf), np.float64); n = max(v[7], 1)
 for k, nm in enumerate(["grid-dependency wait", "loads", "integrate + position iterations", "transforms + sleep", "stores", "camera + heading"]):
     print("  %-34s %7.0f cycles per CTA" % (nm, v[k] / n))
 print("  total                              %7.0f   (%d CTA samples)" % (v[:6].sum() / n, n))
+hist = (ctypes.c_ulonglong * 64)()
+L.mcr_debug_post_clocks(hist, -1)
+hv = np.array(list(hist), np.float64)
+if hv.sum() > 0:
+    print("position iterations per car-step (all cars):", " ".join("%d:%.4f" % (k, hv[k] / hv.sum()) for k in range(64) if hv[k] > 0))
+wt = (ctypes.c_ulonglong * 4096)()
+if L.mcr_debug_post_clocks(wt, -2) == 0:
+    w = np.array(list(wt), np.float64).reshape(4, 1024)[:, :(2 * B * A + 31) // 32] / 1e3
+    t0 = w[0].min()
+    for k, nm in enumerate(["entry", "past contacts / stripes flags", "past the sweep flag", "end (car published)"]):
+        x = np.sort(w[k] - t0)
+        print("  post warps, %-30s min %.1f  median %.1f  p90 %.1f  p99 %.1f  max %.1f us" % (nm, x[0], x[len(x) // 2], x[int(len(x) * .9)], x[int(len(x) * .99)], x[-1]))
+    dur = np.sort(w[3] - w[2])
+    print("  per-warp time from the sweep flag to the end: median %.1f p90 %.1f p99 %.1f max %.1f us; slowest warps:" % (dur[len(dur) // 2], dur[int(len(dur) * .9)], dur[int(len(dur) * .99)], dur[-1]),
+          np.argsort(w[3] - w[2])[-8:].tolist())
