@@ -154,7 +154,10 @@ int mcr_reset(mcr_handle h, const uint8_t* d_env_mask, const int32_t* d_track_sl
  * done at step k keeps its terminal observation; the call for step k+1 ignores that env's action,
  * respawns it and runs reset()'s implicit step(None) (mcr:408) inside the same single pass, and
  * returns the new episode's first frame with reward 0, done 0.
- * Bit1 of d_done[env] marks TimeLimit truncation. */
+ * Bit1 of d_done[env] marks TimeLimit truncation.
+ * d_action is read by the step's first kernel in `stream` order (no staging copy: the replayed CUDA graph's kernel node
+ * is pointed at it): like any stream-ordered argument it must stay valid, and unchanged by other streams / the host,
+ * until the step has run. */
 int mcr_step(mcr_handle h, const void* d_action, int32_t action_dtype, uint8_t* d_obs, double* d_reward,
              uint8_t* d_done, int32_t flags, void* stream);
 
