@@ -1077,7 +1077,7 @@ static int pipeline(mcr_handle h, const uint8_t* mask, const uint8_t* noact, con
         for (int c = 0; c < 5 && env0 < d.B; ++c) {
             const int want = std::max(1, c == 0 ? d.B / 16 : (d.B >> (5 - c)));
             const int nenv = c == 4 ? d.B - env0 : std::min(want, d.B - env0);
-            LAUNCH(launch_fill(d, b, mask, obs, cls, h->obs_format, h->stack_k, env0, nenv, true, s));
+            LAUNCH(launch_fill(d, b, mask, obs, cls, h->obs_format, h->stack_k, env0, nenv, true, s, flag_handoff));
             CUDA_OK(cudaEventRecord(h->ev_chunk[c], s));
             CUDA_OK(cudaStreamWaitEvent(h->copy, h->ev_chunk[c], 0));
             const size_t off = (size_t)env0 * d.A * frame_bytes;

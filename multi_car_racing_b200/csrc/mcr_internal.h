@@ -206,7 +206,7 @@ int launch_project(const Dims& d, const DevBuffers& b, const CarConst& cc, const
                    int cls, void* stream, const uint8_t* score_noact = nullptr, double* score_reward = nullptr, uint8_t* score_done = nullptr,
                    int max_episode_steps = 0, int wait_post = 0);
 int launch_fill(const Dims& d, const DevBuffers& b, const uint8_t* mask, uint8_t* obs, int cls, int obs_format, int stack_k,
-                int env0, int nenv, bool pdl, void* stream);
+                int env0, int nenv, bool pdl, void* stream, int wait_flags = 0);
 // render(mode) for a vw x vh viewport (rgb_array: 600 x 400): camera_kernel + tiled render_kernel<true>
 int launch_render_viewport(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, uint8_t* out, float* cam,
                            int vw, int vh, double h_ratio, int backwards_flag, int use_ego_color, void* stream);

@@ -1102,6 +1102,7 @@ __device__ __forceinline__ CheckerRange checker_range(float m00, float m01, floa
 // throughput bound and do less redundant set-up work with one
 #define PJ_W_SMALL 2
 #define PJ_SMALL_FRAMES 8192
+#define PJ_ONE_WAVE 2304        // frames whose CTAs are all resident at once (148 SMs x 16 CTAs, less what post_kernel still holds)
 #define PJ_MAX_PASS 96           // (1 + 100) / 32 + 2048 / 32 + (12 * 16 + 9) / 32 + slack
 
 // The reward / done block of the step (score_car, mcr:433-507) rides in the same launch: CTAs past the last frame take
@@ -1152,7 +1153,13 @@ project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
     // this kernel (measured, profiles/README r02) the pending grid held score_kernel, which is launched when post_kernel
     // completes, back by 30 us; a persistent score grid launched ahead of it and waiting for post_kernel's flags took
     // project_kernel's one-wave residency instead.  Here post_kernel is complete, so score_kernel is launched first.
-    cudaTriggerProgrammaticLaunchCompletion();
+    // Only while this grid is a single wave: with more frames, fill_kernel's CTAs would be placed while later waves of
+    // this kernel are still to come and sit on their shared memory and registers waiting for their frame (measured:
+    // the rasteriser alone 7-10 % slower from 4096 envs up); there fill_kernel starts when this grid has completed.
+    // (and only on the step's chain: for a stand-alone render pass -- every CTA of this grid ends at about the same time --
+    // the early launch buys nothing and the flag costs fill_kernel's CTAs an L2 round trip each)
+    const bool flag_to_fill = wait_post && d.N <= PJ_ONE_WAVE;      // launch_fill takes the same decision (fill_kernel's wait_flags)
+    if (flag_to_fill) cudaTriggerProgrammaticLaunchCompletion();
     tl_stamp(b.timeline, cls == 2 ? TL_RENDER2 : TL_RENDER);
     if (cls != 2 && threadIdx.x == 0) atomicMax(b.timeline + TL_PROJECT_LAST_GO, mcr_globaltimer());
     const int slot = b.env_track[env];
@@ -1307,8 +1314,10 @@ project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
         PJCLK(13);
     }
     // the frame's display list is complete when every warp has stored its passes: publish it (ready[N + frame])
-    __syncthreads();                               // (barrier + release store: the release is cumulative over the other threads' stores)
-    if (threadIdx.x == 0) flag_release(b.ready + N + frame, 1);
+    if (flag_to_fill) {
+        __syncthreads();                           // (barrier + release store: the release is cumulative over the other threads' stores)
+        if (threadIdx.x == 0) flag_release(b.ready + N + frame, 1);
+    }
     if (cls != 2 && threadIdx.x == 0) { const unsigned long long t = mcr_globaltimer(); atomicMax(b.timeline + TL_PROJECT_END, t); atomicMax(b.timeline + TL_PROJECT_FIRST_END, ~t); }
 #ifdef MCR_PHASE_CLOCKS
     if (threadIdx.x == 0) atomicAdd(&g_phase_clk[14], 1ull);
@@ -1318,7 +1327,8 @@ project_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ ma
 // One CTA per agent-frame.  (Measured and dropped, profiles/README r02: persistent CTAs with a frame queue or a static
 // stride, register prefetch of the next frame's list, 5 CTAs per SM at 40 registers -- none beat this plain form.)
 __global__ void __launch_bounds__(RS_THREADS, FILL_CTAS)
-fill_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, uint8_t* __restrict__ obs, int cls, int obs_format, int stack_k, int env0) {
+fill_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, uint8_t* __restrict__ obs, int cls, int obs_format, int stack_k, int env0,
+            int wait_flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
     const int env = env0 + (int)blockIdx.x, agent = (int)blockIdx.y, frame = env * d.A + agent;   // env0: launches over a range of envs (step_host chunks)
@@ -1335,13 +1345,16 @@ fill_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, uint8_t* __r
     if (tid >= 128 && tid < 128 + SPAN_POOL / 32) S.startbits[tid - 128] = 0;
     if (mask && !mask[env]) return;
     if (cls && (cls == 2) != (b.n_manifold[env] > 0)) return;
-    // project_kernel triggered this launch at its start: wait for this frame's display list only (and take the flag back)
-    if (tid == 0) {
+    // wait_flags (project_kernel's grid is one wave and triggers this launch before it ends): wait for this frame's display
+    // list only, and take the flag back.  Otherwise project_kernel has completed when this grid is placed, and the plain
+    // grid dependency spares every CTA the flag's L2 round trip in front of its loads (10 % of the rasteriser from 4096 envs up).
+    if (!wait_flags) cudaGridDependencySynchronize();
+    else if (tid == 0) {
         if (cls != 2) { const unsigned long long t = mcr_globaltimer(); atomicMax(b.timeline + TL_FILL_FIRST_IN, ~t); atomicMax(b.timeline + TL_FILL_LAST_IN, t); }
         flag_wait(b.ready + d.N + frame); b.ready[d.N + frame] = 0;
         if (cls != 2) atomicMax(b.timeline + TL_FILL_FIRST_GO, ~mcr_globaltimer());
     }
-    __syncthreads();
+    if (wait_flags) __syncthreads();
     if (cls != 2) tl_stamp(b.timeline, TL_FILL);
     const uint2* __restrict__ meta = reinterpret_cast<const uint2*>(b.dl_meta) + (size_t)frame * d.dl_cap;
     const float4* __restrict__ edge = reinterpret_cast<const float4*>(b.dl_edge) + (size_t)frame * d.dl_cap * 4;
@@ -1475,7 +1488,7 @@ int launch_render(const Dims& d, const DevBuffers& b, const CarConst& cc, const 
     }
     launch_project_impl(d, b, cc, mask, backwards_flag, use_ego_color, cls, sa, wait_post, (cudaStream_t)stream);
     mcr_launch_pdl(fill_kernel, dim3(d.B, d.A), dim3(RS_THREADS), sizeof(RasterSmem), (cudaStream_t)stream,
-                   d, b, mask, obs, cls, obs_format, stack_k, 0);
+                   d, b, mask, obs, cls, obs_format, stack_k, 0, (wait_post && d.N <= PJ_ONE_WAVE) ? 1 : 0);
     return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
 
@@ -1503,12 +1516,13 @@ int launch_project(const Dims& d, const DevBuffers& b, const CarConst& cc, const
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
+// wait_flags: project_kernel was launched with wait_post (the step's chain) -- see fill_kernel
 int launch_fill(const Dims& d, const DevBuffers& b, const uint8_t* mask, uint8_t* obs, int cls, int obs_format, int stack_k,
-                int env0, int nenv, bool pdl, void* stream) {
+                int env0, int nenv, bool pdl, void* stream, int wait_flags) {
     if (!configure_render()) return -1;
     if (pdl) mcr_launch_pdl(fill_kernel, dim3(nenv, d.A), dim3(RS_THREADS), sizeof(RasterSmem), (cudaStream_t)stream,
-                            d, b, mask, obs, cls, obs_format, stack_k, env0);
-    else fill_kernel<<<dim3(nenv, d.A), RS_THREADS, sizeof(RasterSmem), (cudaStream_t)stream>>>(d, b, mask, obs, cls, obs_format, stack_k, env0);
+                            d, b, mask, obs, cls, obs_format, stack_k, env0, (wait_flags && d.N <= PJ_ONE_WAVE) ? 1 : 0);
+    else fill_kernel<<<dim3(nenv, d.A), RS_THREADS, sizeof(RasterSmem), (cudaStream_t)stream>>>(d, b, mask, obs, cls, obs_format, stack_k, env0, (wait_flags && d.N <= PJ_ONE_WAVE) ? 1 : 0);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
