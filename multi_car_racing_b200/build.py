@@ -62,6 +62,8 @@ def build(force=False, verbose=False, out=None, extra=()):
 if __name__ == "__main__":
     if "--stg-store" in sys.argv:
         path = build(out="libmcr_stg.so", extra=["-DMCR_FILL_STG_STORE"], verbose="--verbose" in sys.argv)
+    elif "--lane-bulk" in sys.argv:
+        path = build(out="libmcr_lb.so", extra=["-DMCR_FILL_LANE_BULK"], verbose="--verbose" in sys.argv)
     elif "--phase-clocks" in sys.argv:
         path = build(out="libmcr_clk.so", extra=["-DMCR_PHASE_CLOCKS"], verbose="--verbose" in sys.argv)
     else:

@@ -1375,14 +1375,16 @@ fill_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, uint8_t* __r
     PHASE(0);
     int e0 = 0;
     uint32_t rs0 = 0u;                     // first span slot of the chunk (the frame's first polygon starts at slot 0)
+    const bool whole = n <= LIST_CAP && hdr.y <= SPAN_POOL;     // the whole frame fits one list (the header holds both totals)
     do {
         // this chunk = the longest run of entries from e0 that fits the shared-memory list and the span pool
         if (e0 > 0) {
             rs0 = meta[e0].y;
             if (tid < LIST_CAP) mt = meta[min(e0 + tid, d.dl_cap - 1)];
         }
+        // the common case -- the whole frame fits one list (the header holds its entry and span-slot totals): no count, no barrier
         const bool fits = tid < LIST_CAP && e0 + tid < n && mt.y + ((mt.x >> 8) & 0xffu) - rs0 <= (uint32_t)SPAN_POOL;
-        const int cnt = __syncthreads_count(fits);         // slot offsets are monotone: the entries that fit are a prefix
+        const int cnt = whole ? n : __syncthreads_count(fits);         // slot offsets are monotone: the entries that fit are a prefix
         if (tid < cnt) {
             const int y0 = (int)(mt.x & 0xffu), rows = (int)((mt.x >> 8) & 0xffu), ne = (int)(mt.x >> 24);
             const int first = (int)(mt.y - rs0);
@@ -1403,6 +1405,22 @@ fill_kernel(Dims d, DevBuffers b, const uint8_t* __restrict__ mask, uint8_t* __r
         flush_list<false>(S, tid, pix, cnt, -1, last, 0, 0, SW);
         e0 += cnt;
     } while (e0 < n);
+#ifdef MCR_FILL_LANE_BULK
+    // A/B build (python -m multi_car_racing_b200.build --lane-bulk -> libmcr_lb.so): every thread sends its own 96 staged bytes
+    // with its own cp.async.bulk -- no block barrier in front of the store, 288 small TMA requests per frame instead of one
+    if (obs_format == MCR_OBS_RGB_HWC) {
+        unsigned char* stage = reinterpret_cast<unsigned char*>(&S.edge[0][0]);
+        finish_frame<false>(S, tid, pix, stage, 0, obs_format, 0, 0, SW, SH, 1, 0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const int my_seg = tid / SH, my_y = tid - SH * my_seg;
+        const unsigned off = (unsigned)((SH - 1 - my_y) * (SW * 3) + my_seg * 96);
+        const unsigned long long gdst = (unsigned long long)(obs + (size_t)frame * MCR_OBS_BYTES + off);
+        const unsigned ssrc = (unsigned)__cvta_generic_to_shared(stage + off);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(ssrc), "r"(96u) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    } else
+#endif
 #ifndef MCR_FILL_STG_STORE
     // The reference's RGB HWC frame is staged in shared memory (over the display list / span pool / row masks, which
     // are dead by now) and leaves as ONE cp.async.bulk (TMA, UBLKCP.G.S) of 27 648 contiguous bytes issued by thread 0.
