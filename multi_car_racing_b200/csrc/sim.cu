@@ -397,12 +397,14 @@ extern "C" int mcr_debug_post_clocks(unsigned long long* out8, int reset) {
 #define PK(k) do {} while (0)
 #endif
 
-// Two lanes per car (even lane = solver, odd lane = view): the solver lane integrates the positions, runs the position
-// iterations, synchronises the transforms, takes the sleep decision and stores the bodies and joints; the view lane
-// meanwhile evaluates what only depends on the solved VELOCITIES -- the camera's angle (atan2 + two sincos, mcr:544-556)
-// and the heading of the backward test (mcr:449-456) --, takes the score / backward snapshots, advances the env clock,
-// and finishes the camera once the solver lane hands it the final hull pose (one shuffle).  Both are serial fp64-trig
-// chains; side by side the kernel is as long as the longer one instead of their sum.
+// Two THREADS per car in two different warps of the CTA (warps [0, P) = solver, warps [P, 2P) = view, P = blockDim / 64;
+// solver warp p and view warp P + p hold the same 32 cars, lane = car): the solver thread integrates the positions, runs
+// the position iterations, synchronises the transforms, takes the sleep decision and stores the bodies and joints; the
+// view thread meanwhile evaluates what only depends on the solved VELOCITIES -- the camera's angle (atan2 + two sincos,
+// mcr:544-556) and the heading of the backward test (mcr:449-456) --, takes the score / backward snapshots, advances the
+// env clock, and finishes the camera once the solver thread hands it the final hull pose (shared memory, a named barrier of
+// the two warps).  Both are serial fp64-trig chains; on two warp schedulers they really run side by side (as two lanes
+// of one warp -- the form before -- the divergent halves only interleaved: 10 us per warp, now the longer of the two).
 __global__ void __launch_bounds__(128)
 post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ noact, int has_action,
             double h_ratio, int cls, int wait_sweep) {
@@ -413,11 +415,15 @@ post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
     // Otherwise: programmatic dependent launch behind the sweep / coupled kernel.
     if (!wait_sweep) cudaGridDependencySynchronize();
     PK(0);
-    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
-    const int car_raw = gt >> 1;
-    const bool view = (gt & 1) != 0;
+    const int lane_ = threadIdx.x & 31, wrp_ = threadIdx.x >> 5, pairs_ = blockDim.x >> 6;
+    const bool view = wrp_ >= pairs_;
+    const int pair_ = view ? wrp_ - pairs_ : wrp_;
+    const int car_raw = blockIdx.x * (pairs_ * 32) + pair_ * 32 + lane_;
+    __shared__ float s_pose[2][3][32];             // hull origin x, y and angle, solver warp -> view warp
+    // named barriers of a warp pair (64 threads; every thread of both warps executes them, live or not)
+#define PAIR_SYNC(k) asm volatile("bar.sync %0, 64;" :: "r"(1 + 3 * pair_ + (k)) : "memory")
+#define PAIR_ARRIVE(k) asm volatile("bar.arrive %0, 64;" :: "r"(1 + 3 * pair_ + (k)) : "memory")
     tl_stamp(b.timeline, cls == 2 ? TL_POST2 : TL_POST);
-    // both lanes of a pair take the same early exits, so the pair's shuffle below is always executed by both or none
     bool live = car_raw < d.N;
     const int car = live ? car_raw : d.N - 1;
     const int env = car / d.A;
@@ -476,7 +482,7 @@ post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
     PWT(1);
     if (wait_sweep) {
         if (live) { while (flag_peek(b.ready + 2 * N + car) == 0) __nanosleep(60); flag_fence_acquire(); }
-        __syncwarp(0xffffffffu);                   // both lanes of a pair have seen the flags before they are taken back
+        PAIR_SYNC(0);                              // both threads of a car have seen the flags before they are taken back
     }
     PWT(2);
     if (live && !view) {
@@ -493,20 +499,19 @@ post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
     const float h = (float)(1.0 / 50);
     const float mA = cc.hull_invMass, iA = cc.hull_invI, mB = cc.wheel_invMass, iB = cc.wheel_invI;
     (void)mA; (void)iA; (void)mB; (void)iB;
-    float hull_px = 0.0f, hull_py = 0.0f, hull_ang = 0.0f;       // the solver lane's result the view lane needs
+    float hull_px = 0.0f, hull_py = 0.0f, hull_ang = 0.0f;       // the solver thread's result the view thread needs
+    float vx[5], vy[5], w[5], qs[5], qc[5], px[5], py[5];
+    float jix[4], jiy[4], jiz[4], jmot[4];
 
     if (live && !view) {
-        // ================================ solver lane ================================================
-        float vx[5], vy[5], w[5], qs[5], qc[5];
+        // ================================ solver thread ==============================================
 #pragma unroll
         for (int i = 0; i < 5; ++i) { vx[i] = sc[(size_t)(SC_VX + i) * N]; vy[i] = sc[(size_t)(SC_VY + i) * N]; w[i] = sc[(size_t)(SC_W + i) * N]; }
-        float jix[4], jiy[4], jiz[4], jmot[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             jix[k] = sc[(size_t)(SC_JIX + k) * N]; jiy[k] = sc[(size_t)(SC_JIY + k) * N];
             jiz[k] = sc[(size_t)(SC_JIZ + k) * N]; jmot[k] = sc[(size_t)(SC_JMOT + k) * N];
         }
-        float px[5], py[5];
         PK(1);
         if (coupled) {
             // coupled_kernel already integrated, position-solved and took the sleep decision for this car
@@ -586,6 +591,14 @@ post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
         }   // !coupled
         PK(3);
         hull_px = px[0]; hull_py = py[0]; hull_ang = ang[0];
+    }
+    if (!view) {
+        // hand the hull pose to the view warp and go on storing (arrive, no wait)
+        s_pose[pair_][0][lane_] = hull_px; s_pose[pair_][1][lane_] = hull_py; s_pose[pair_][2][lane_] = hull_ang;
+        __threadfence_block();
+        PAIR_ARRIVE(1);
+    }
+    if (live && !view) {
         // ---- store ---------------------------------------------------------------------------
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
@@ -652,11 +665,11 @@ post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
         b.time[car] = t_new;
         if (counted) b.steps[car] = steps_now + 1;                 // TimeLimit counts step() calls only
     }
-    // the pair is converged here: every lane of the warp executes the shuffles (lanes that are not live carry zeros)
-    const unsigned full = 0xffffffffu;
-    const int solver_lane = (threadIdx.x & 31) & ~1;
-    const float f_px = __shfl_sync(full, hull_px, solver_lane), f_py = __shfl_sync(full, hull_py, solver_lane);
-    const float f_ang = __shfl_sync(full, hull_ang, solver_lane);
+    float f_px = 0.0f, f_py = 0.0f, f_ang = 0.0f;
+    if (view) {
+        PAIR_SYNC(1);                              // the solver warp's hull poses are in shared memory
+        f_px = s_pose[pair_][0][lane_]; f_py = s_pose[pair_][1][lane_]; f_ang = s_pose[pair_][2][lane_];
+    }
     if (live && view) {
         // camera, mcr:540-556 + Transform.enable + glViewport(0,0,96,96) under glOrtho(0,1000,0,800)
         const double SCALE = 6.0, ZOOM = 2.7, WINDOW_W = 1000, WINDOW_H = 800;
@@ -689,11 +702,12 @@ post_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
         b.heading[car] = car_angle;
     }
     PK(5);
-    // both lanes of the pair have stored: publish the car (ready[car], see DevBuffers)
-    __syncwarp(full);                              // (warp barrier + release store: the release is cumulative over the solver lane's stores)
+    // both threads of the car have stored: publish it (ready[car], see DevBuffers)
+    PAIR_SYNC(2);                                  // (barrier + release store: the release is cumulative over the solver thread's stores)
     if (live && view) flag_release(b.ready + car, epoch);
-    __syncwarp(full);
     PWT(3);
+#undef PAIR_SYNC
+#undef PAIR_ARRIVE
     if (cls != 2 && threadIdx.x == 0) atomicMax(b.timeline + TL_POST_END, mcr_globaltimer());
 #ifdef MCR_PHASE_CLOCKS
     if (threadIdx.x == 0) atomicAdd(&g_post_clk[7], 1ull);
@@ -794,7 +808,7 @@ int launch_presweep(const Dims& d, const DevBuffers& b, const CarConst& cc, cons
 // start poses and writing on_road_next (the API joins the side stream before calling this).
 int launch_physics_post(const Dims& d, const DevBuffers& b, const CarConst& cc, const uint8_t* mask, const uint8_t* noact,
                         int has_action, double h_ratio, int cls, void* stream, int wait_sweep) {
-    const int pb = pre_block(), nb = (2 * d.N + pb - 1) / pb;      // two lanes per car
+    const int pb = pre_block() < 128 ? 64 : 128, cars = pb / 2, nb = (d.N + cars - 1) / cars;      // two threads per car: a solver warp and a view warp per 32 cars
     mcr_launch_pdl(post_kernel, dim3(nb), dim3(pb), 0, (cudaStream_t)stream, d, b, cc, mask, noact, has_action, h_ratio, cls, wait_sweep);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
