@@ -20,6 +20,23 @@
 //                       decision through lane masks.  Envs without manifolds never enter here:
 //                       their cars take the per-car fast path of sim.cu.
 #include "solver.cuh"
+// Diagnostics build (-DMCR_PHASE_CLOCKS): lane 0 of every head_kernel warp adds the SM cycles of each part to g_head_clk
+// (0-3 pre_car: loads, controls + tyre model, integrate + joints_init, stores; 4 entry + auto-reset check, 5 narrow phase; 7 = warps)
+#ifdef MCR_PHASE_CLOCKS
+__device__ unsigned long long g_head_clk[8];
+#define PRE_CLK_T0() long long pc_t_ = clock64()
+#define PRE_CLK(k) do { if ((threadIdx.x & 31) == 0) { const long long n_ = clock64(); atomicAdd(&g_head_clk[k], (unsigned long long)(n_ - pc_t_)); pc_t_ = n_; } } while (0)
+#define HEAD_CLK_DECL long long hc_t_ = clock64()
+#define HEAD_CLK(k) do { if ((threadIdx.x & 31) == 0) { const long long n_ = clock64(); atomicAdd(&g_head_clk[k], (unsigned long long)(n_ - hc_t_)); hc_t_ = n_; } } while (0)
+extern "C" int mcr_debug_head_clocks(unsigned long long* out8, int reset) {
+    if (out8 && cudaMemcpyFromSymbol(out8, g_head_clk, sizeof(g_head_clk)) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[8] = {}; if (cudaMemcpyToSymbol(g_head_clk, z, sizeof(z)) != cudaSuccess) return -1; }
+    return 0;
+}
+#else
+#define HEAD_CLK_DECL do {} while (0)
+#define HEAD_CLK(k) do {} while (0)
+#endif
 #include "pre.cuh"
 #include "reset.cuh"
 
@@ -324,7 +341,7 @@ carcontacts_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict_
 // per-car head of the step (pre.cuh) on lanes 0 .. A-1.  Three dependent latency-bound launches
 // (auto_reset -> carcontacts -> pre, 3 + 7 + 9 us plus two launch gaps) become one.
 template <typename ActT, bool MANY>
-__global__ void __launch_bounds__(CC_WARPS * 32)
+__global__ void __launch_bounds__(CC_WARPS * 32, 2)      // (two CTAs per SM hold the bench batch; the register cap this implies leaves the per-car head without spills)
 head_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ reset_flags,
             AutoResetCfg ar, const ActT* __restrict__ action, int collisions) {
     __shared__ float s_old[CC_WARPS][MAXM * MW];
@@ -335,8 +352,42 @@ head_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
     if (mask && !mask[env]) return;
     bool respawned = false;
     tl_stamp(b.timeline, TL_HEAD);
+    HEAD_CLK_DECL;
+    // The control loads of the three stages, issued together (they used to be dependent round trips: reset flag ->
+    // manifold count -> hull origins, each from DRAM when the L2 is cold), and the lines pre_car will read prefetched
+    // into the L2 beside them.
+    const int car_l = env * d.A + (lane < d.A ? lane : 0);
+    // (volatile asm: the loads are issued HERE -- the compiler otherwise sinks them to their first use, behind the reset check)
+    unsigned rf_u = 0u; int nold_early = 0; float hx_early = 0.0f, hy_early = 0.0f, hs_early = 0.0f, hc_early = 1.0f;
+    const bool cc_on = collisions && d.A > 1;
+    if (reset_flags) asm volatile("ld.global.u8 %0, [%1];" : "=r"(rf_u) : "l"(reset_flags + env));
+    if (cc_on) {
+        asm volatile("ld.global.s32 %0, [%1];" : "=r"(nold_early) : "l"(b.n_manifold + env));
+        if (lane < d.A) {
+            asm volatile("ld.global.f32 %0, [%1];" : "=f"(hx_early) : "l"(b.body + (size_t)BF_PX * d.N + car_l));
+            asm volatile("ld.global.f32 %0, [%1];" : "=f"(hy_early) : "l"(b.body + (size_t)BF_PY * d.N + car_l));
+            asm volatile("ld.global.f32 %0, [%1];" : "=f"(hs_early) : "l"(b.body + (size_t)BF_QS * d.N + car_l));
+            asm volatile("ld.global.f32 %0, [%1];" : "=f"(hc_early) : "l"(b.body + (size_t)BF_QC * d.N + car_l));
+        }
+    }
+    const uint8_t rf_early = (uint8_t)rf_u;
+    if (warp == 0) {
+        // one warp per CTA prefetches for the CTA's CC_WARPS envs (consecutive cars: the same 128-byte line of every field,
+        // but for a batch boundary), one field per lane and round -- every redundant request queues in front of real loads
+        const size_t N_ = (size_t)d.N;
+        const int car0 = env * d.A;
+#define PF_L2(p) asm volatile("prefetch.global.L2 [%0];" :: "l"(p))
+        for (int f = lane; f < 5 * BODY_FIELDS; f += 32) PF_L2(b.body + f * N_ + car0);
+        if (lane < 4 * JOINT_FIELDS) PF_L2(b.joint + lane * N_ + car0);
+        if (lane < 4 * WHEEL_FIELDS) PF_L2(b.wheel + lane * N_ + car0);
+        if (lane < CTRL_FIELDS) PF_L2(b.ctrl + lane * N_ + car0);
+        if (lane < 5) { PF_L2(b.sleep_time + lane * N_ + car0); PF_L2(b.awake + lane * N_ + car0); }
+        if (lane < 4) { PF_L2(b.limit_state + lane * N_ + car0); PF_L2(b.on_road + lane * N_ + car0); }
+        if (action && lane == 0) PF_L2(action + (size_t)car0 * 3);
+#undef PF_L2
+    }
     if (reset_flags) {
-        respawned = reset_flags[env] != 0;
+        respawned = rf_early != 0;
         if (lane == 0) b.reset_mask[env] = respawned ? 1 : 0;
         if (respawned) {
             const uint32_t episode = b.env_episode[env] + 1u;
@@ -345,11 +396,64 @@ head_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
         }
         __syncwarp();                                  // the respawned poses are visible to every lane
     }
-    if (collisions && d.A > 1) carcontacts_warp<MANY>(d, b, cc, env, lane, s_old[warp]);
+    HEAD_CLK(4);
+    int coupled_known = cc_on ? -1 : 0;
+    if (cc_on) {
+        // The common case is decided right here, on the preloaded values: no manifold to carry over and every pair of
+        // hull origins more than 7 m apart (see carcontacts_warp) -- no fixture can touch.  carcontacts_warp is a real
+        // call whose struct arguments are copied to local memory first (~1.4 KB per thread: 5.8 of the kernel's 9.7 us
+        // when it was called for every env, scripts/head_phases.py); only the envs that need it pay for that now.
+        bool need = respawned || nold_early != 0;      // (a respawned env was just rewritten: the narrow phase loads it itself)
+        if (!__any_sync(0xffffffffu, need)) {
+            const int A = d.A, ncp = A * (A - 1) / 2;
+            bool close = false;
+            for (int cp0 = 0; cp0 < ncp; cp0 += 32) {
+                const int cp = cp0 + lane;
+                int a = 0, rem = cp < ncp ? cp : 0;
+                while (rem >= A - 1 - a) { rem -= A - 1 - a; ++a; }
+                const int bc = a + 1 + rem;
+                const float ax = __shfl_sync(0xffffffffu, hx_early, a), ay = __shfl_sync(0xffffffffu, hy_early, a);
+                const float bx = __shfl_sync(0xffffffffu, hx_early, bc), by = __shfl_sync(0xffffffffu, hy_early, bc);
+                const float as_ = __shfl_sync(0xffffffffu, hs_early, a), ac = __shfl_sync(0xffffffffu, hc_early, a);
+                const float bs = __shfl_sync(0xffffffffu, hs_early, bc), bcq = __shfl_sync(0xffffffffu, hc_early, bc);
+                const float dx = bx - ax, dy = by - ay;
+                bool near = !(dx * dx + dy * dy > 49.0f);
+                if (near) {
+                    // Inside 7 m: the two cars' bounding rectangles in their hull frames.  Every fixture point lies within
+                    // |x| <= 1.71 (wheel anchor 1.1 + wheel half diagonal 0.61), -2.4 <= y <= 2.6 (hull polygons) of the
+                    // hull origin; with 0.5 m for joint slack, polygon radii and rounding: half extents 2.21 x 3.1.  Cars on
+                    // the start grid stand 6.67 m apart side by side -- inside the 7 m circle test for the first part of
+                    // every episode, which sent most envs through the fixture-pair sweep (5 of the head's 8 us).
+                    const float EX = 2.21f, EY = 3.1f;
+                    // axes: A's (ac, as_), (-as_, ac); B's (bcq, bs), (-bs, bcq)
+                    const float c = ac * bcq + as_ * bs, sn = ac * bs - as_ * bcq;      // cos / sin of the relative angle
+                    const float ca = fabsf(c), sa = fabsf(sn);
+                    const float dAx = dx * ac + dy * as_, dAy = -dx * as_ + dy * ac;     // centre offset in A's frame
+                    const float dBx = dx * bcq + dy * bs, dBy = -dx * bs + dy * bcq;     // ... in B's frame
+                    const bool sep = fabsf(dAx) > EX + (EX * ca + EY * sa) || fabsf(dAy) > EY + (EX * sa + EY * ca) ||
+                                     fabsf(dBx) > EX + (EX * ca + EY * sa) || fabsf(dBy) > EY + (EX * sa + EY * ca);
+                    near = !sep;
+                }
+                close = close || (cp < ncp && near);
+            }
+            need = __any_sync(0xffffffffu, close);
+        }
+        if (need) carcontacts_warp<MANY>(d, b, cc, env, lane, s_old[warp]);
+        else if (lane == 0) b.n_manifold[env] = 0;
+        coupled_known = need ? -1 : 0;                 // (the common case: pre_car4 does not wait for the store above)
+    }
     __syncwarp();                                      // n_manifold[env]
+    HEAD_CLK(5);
     // a respawned env takes reset()'s implicit step(None) (mcr:408): its action is ignored
-    if (lane < d.A) pre_car<ActT>(d, b, cc, env * d.A + lane, env, action != nullptr && !respawned, action);
+    if (4 * d.A <= 32) {
+        // four lanes per car (wheel / joint k = lane & 3): a quarter of the wheel and joint code per warp
+        const unsigned gmask = 4 * d.A == 32 ? 0xffffffffu : ((1u << (4 * d.A)) - 1u);
+        if (lane < 4 * d.A) pre_car4<ActT>(d, b, cc, env * d.A + (lane >> 2), env, lane & 3, gmask, action != nullptr && !respawned, action, coupled_known);
+    } else if (lane < d.A) pre_car<ActT>(d, b, cc, env * d.A + lane, env, action != nullptr && !respawned, action);
     if (threadIdx.x == 0) atomicMax(b.timeline + TL_HEAD_END, mcr_globaltimer());
+#ifdef MCR_PHASE_CLOCKS
+    if (lane == 0) atomicAdd(&g_head_clk[7], 1ull);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------
@@ -839,6 +943,7 @@ int launch_head(const Dims& d, const DevBuffers& b, const CarConst& cc, const ui
     const int nb = (d.B + CC_WARPS - 1) / CC_WARPS;
     cudaStream_t s = (cudaStream_t)stream;
     const bool many = d.A > 3;
+    if (std::getenv("MCR_DEBUG_NO_NARROW")) collisions = 0;      // timing experiments only: the head without its narrow phase
     if (action_dtype == MCR_F64) {
         if (many) head_kernel<double, true><<<nb, CC_WARPS * 32, 0, s>>>(d, b, cc, mask, reset_flags, ar, (const double*)action, collisions);
         else head_kernel<double, false><<<nb, CC_WARPS * 32, 0, s>>>(d, b, cc, mask, reset_flags, ar, (const double*)action, collisions);
