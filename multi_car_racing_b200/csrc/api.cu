@@ -164,6 +164,13 @@ bool build_car_const(CarConst& cc) {
         if (lc.x != 0.0f || lc.y != 0.0f) return false;
     }
     for (int w = 0; w < 4; ++w) { cc.anchor_x[w] = (float)(kWHEELPOS[w][0] * kSIZE); cc.anchor_y[w] = (float)(kWHEELPOS[w][1] * kSIZE); }
+    {   // the rectangle of head_kernel's narrow-phase prefilter must hold the car with its margin (a wheel turns about its anchor)
+        float ex = 0.0f, ey = 0.0f;
+        for (int f = 0; f < 4; ++f) for (auto& v : hull[f]) { ex = std::max(ex, std::fabs(v.x)); ey = std::max(ey, std::fabs(v.y)); }
+        const float wheel_diag = (float)(std::sqrt(kWHEEL_R * kWHEEL_R + kWHEEL_W * kWHEEL_W) * kSIZE);
+        for (int w = 0; w < 4; ++w) { ex = std::max(ex, std::fabs(cc.anchor_x[w]) + wheel_diag); ey = std::max(ey, std::fabs(cc.anchor_y[w]) + wheel_diag); }
+        if (ex + 0.45f > CAR_OBB_EX || ey + 0.45f > CAR_OBB_EY) return false;
+    }
     cc.max_motor_torque = (float)(180 * 900 * kSIZE * kSIZE);
     cc.lower = (float)-0.4; cc.upper = (float)+0.4;
     // the sweep kernels have no e_equalLimits path (b2RevoluteJoint: |upper - lower| < 2 * angularSlop)

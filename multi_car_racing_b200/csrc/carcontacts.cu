@@ -424,7 +424,7 @@ head_kernel(Dims d, DevBuffers b, CarConst cc, const uint8_t* __restrict__ mask,
                     // hull origin; with 0.5 m for joint slack, polygon radii and rounding: half extents 2.21 x 3.1.  Cars on
                     // the start grid stand 6.67 m apart side by side -- inside the 7 m circle test for the first part of
                     // every episode, which sent most envs through the fixture-pair sweep (5 of the head's 8 us).
-                    const float EX = 2.21f, EY = 3.1f;
+                    const float EX = CAR_OBB_EX, EY = CAR_OBB_EY;
                     // axes: A's (ac, as_), (-as_, ac); B's (bcq, bs), (-bs, bcq)
                     const float c = ac * bcq + as_ * bs, sn = ac * bs - as_ * bcq;      // cos / sin of the relative angle
                     const float ca = fabsf(c), sa = fabsf(sn);

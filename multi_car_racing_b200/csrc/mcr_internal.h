@@ -127,6 +127,10 @@ struct DevBuffers {
     int32_t* ready;
 };
 
+// half extents, in the hull frame and about the hull origin, of a rectangle that holds every fixture point of a car with
+// 0.5 m to spare (joint slack, polygon radii, rounding): head_kernel's narrow-phase prefilter; checked at mcr_create
+#define CAR_OBB_EX 2.21f
+#define CAR_OBB_EY 3.1f
 #define READY_EPOCH(N) (8 * (size_t)(N))
 #define READY_WORDS(N) (8 * (size_t)(N) + 32)
 struct Dims { int B, A, N, Tmax, Qmax, P; int particles; int dl_cap; };
