@@ -62,6 +62,9 @@ def build(force=False, verbose=False, out=None, extra=()):
 if __name__ == "__main__":
     if "--stg-store" in sys.argv:
         path = build(out="libmcr_stg.so", extra=["-DMCR_FILL_STG_STORE"], verbose="--verbose" in sys.argv)
+    elif "--sweep-check" in sys.argv:      # A/B: sweeps between two fixed-point comparisons (4 by default)
+        n = sys.argv[sys.argv.index("--sweep-check") + 1]
+        path = build(out="libmcr_sc%s.so" % n, extra=["-DSWEEP_CHECK=%s" % n], verbose="--verbose" in sys.argv)
     elif "--lane-bulk" in sys.argv:
         path = build(out="libmcr_lb.so", extra=["-DMCR_FILL_LANE_BULK"], verbose="--verbose" in sys.argv)
     elif "--phase-clocks" in sys.argv:

@@ -132,18 +132,26 @@ __device__ __forceinline__ unsigned state_diff(const VelState& a, const VelState
 }
 
 // Box2D runs all 180 sweeps.  A sweep is a deterministic map of (velocities, accumulated
-// impulses): when four sweeps leave that state bit-identical (a fixed point, a 2-cycle or a
-// 4-cycle, checked at multiples of 4 so the phase matches sweep 180) the remaining sweeps
+// impulses): when SWEEP_CHECK sweeps leave that state bit-identical (a fixed point or a cycle whose
+// length divides SWEEP_CHECK, checked at multiples of it so the phase matches sweep 180) the remaining sweeps
 // cannot change it, so stopping there is exact.
 template <int PAT>
 __device__ __forceinline__ void solve_velocity(VelState& s, const JointC (&J)[4], const Masses& m, bool early_exit,
                                                unsigned peers = 0u) {
     // one sweep per loop trip keeps the loop body (~3 KB of SASS) inside the L0 instruction cache
+    // SWEEP_CHECK sweeps between two comparisons (a divisor of MCR_VEL_ITERS: a state that repeats after SWEEP_CHECK sweeps
+    // repeats after every multiple of it, so the phase matches sweep 180)
+// (A/B builds: python -m multi_car_racing_b200.build --sweep-check N.  4 -> 12: the state copy + 62 compare instructions +
+// vote per check were 9 % of the chain: sweep 45.9 -> 41.8 us, step 127.0 -> 124.9 us; 20 measured equal to 12.)
+#ifndef SWEEP_CHECK
+#define SWEEP_CHECK 12
+#endif
+    static_assert(MCR_VEL_ITERS % SWEEP_CHECK == 0, "SWEEP_CHECK must divide the sweep count");
 #pragma unroll 1
-    for (int it = 0; it < MCR_VEL_ITERS; it += 4) {
+    for (int it = 0; it < MCR_VEL_ITERS; it += SWEEP_CHECK) {
         const VelState before = s;
 #pragma unroll 1
-        for (int r = 0; r < 4; ++r) sweep<PAT>(s, J, m);
+        for (int r = 0; r < SWEEP_CHECK; ++r) sweep<PAT>(s, J, m);
         // peers != 0: the lanes of `peers` hold one car each and leave together
         const bool settled = state_diff(before, s) == 0u;
         if (early_exit && (peers ? __all_sync(peers, settled) : settled)) break;

@@ -1,5 +1,5 @@
 #!/bin/bash
-OUT=gpurun_out/r4t; mkdir -p $OUT
+OUT=gpurun_out/r5c; mkdir -p $OUT
 timeout 300 python -m pytest tests -m gpu -x -q > $OUT/pytest.log 2>&1; rc=$?; tail -3 $OUT/pytest.log
 if [ $rc -ne 0 ]; then echo "pytest failed or hung rc=$rc"; tail -30 $OUT/pytest.log; exit 1; fi
 timeout 100 python scripts/timeline.py 1024 200 60 > $OUT/timeline_mid.txt 2>&1; head -28 $OUT/timeline_mid.txt | tr '\n' ';' | sed 's/  */ /g'; echo
