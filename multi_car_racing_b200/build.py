@@ -65,6 +65,9 @@ if __name__ == "__main__":
     elif "--sweep-check" in sys.argv:      # A/B: sweeps between two fixed-point comparisons (4 by default)
         n = sys.argv[sys.argv.index("--sweep-check") + 1]
         path = build(out="libmcr_sc%s.so" % n, extra=["-DSWEEP_CHECK=%s" % n], verbose="--verbose" in sys.argv)
+    elif "--sweep-unroll" in sys.argv:     # A/B: sweeps per trip of the inner loop (1 by default: the body stays in the L0 instruction cache)
+        n = sys.argv[sys.argv.index("--sweep-unroll") + 1]
+        path = build(out="libmcr_su%s.so" % n, extra=["-DSWEEP_UNROLL=%s" % n], verbose="--verbose" in sys.argv)
     elif "--lane-bulk" in sys.argv:
         path = build(out="libmcr_lb.so", extra=["-DMCR_FILL_LANE_BULK"], verbose="--verbose" in sys.argv)
     elif "--phase-clocks" in sys.argv:

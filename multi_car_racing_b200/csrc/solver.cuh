@@ -150,7 +150,11 @@ __device__ __forceinline__ void solve_velocity(VelState& s, const JointC (&J)[4]
 #pragma unroll 1
     for (int it = 0; it < MCR_VEL_ITERS; it += SWEEP_CHECK) {
         const VelState before = s;
-#pragma unroll 1
+#ifndef SWEEP_UNROLL
+#define SWEEP_UNROLL 1
+#endif
+        constexpr int kSweepUnroll = SWEEP_UNROLL;     // (A/B builds: --sweep-unroll N)
+#pragma unroll kSweepUnroll
         for (int r = 0; r < SWEEP_CHECK; ++r) sweep<PAT>(s, J, m);
         // peers != 0: the lanes of `peers` hold one car each and leave together
         const bool settled = state_diff(before, s) == 0u;
