@@ -23,15 +23,16 @@
 //                    are bit-reproducible -- no racing atomicAdds.  Runs on a side stream beside the
 //                    solver; it only reads the step's start poses.
 //   pre_kernel       one THREAD per car, SoA-coalesced: controls, the float64 tyre model, velocity
-//                    integration, InitVelocityConstraints + warm start.  Everything lane-parallel
-//                    (fp64 division/sqrt/sincos) lives here and in post_kernel, at full lane use.
-//   sweep_kernel     one WARP per car: the 180 Gauss-Seidel sweeps are a serial dependency chain
-//                    through the hull velocity (latency bound, ~650 cycles per sweep), so a car's
-//                    warp runs straight-line code specialised to its joints' limit pattern and
-//                    leaves the loop as soon as the car has reached an exact fixed point.
-//   post_kernel      one THREAD per car: position integration, <= 60 position iterations,
-//                    SynchronizeTransform, sleeping, and the per-view values the rasteriser needs
-//                    (camera affine, heading, wheel-stripe extents).
+//                    integration, InitVelocityConstraints + warm start (the split entry points; mcr_step's
+//                    head_kernel, carcontacts.cu, runs the same arithmetic with four lanes per car).
+//   sweep_kernel     the 180 Gauss-Seidel sweeps are a serial dependency chain through the hull velocity
+//                    (latency bound): one THREAD per car for the cars without an active joint limit (32 per
+//                    warp), one WARP per car -- straight-line code specialised to the limit pattern -- for
+//                    the rest; a warp leaves the loop when its cars sit on an exact fixed point / cycle.
+//   post_kernel      two threads per car in two warps (solver warp: position integration, <= 60 position
+//                    iterations, SynchronizeTransform, sleeping; view warp: the per-view values the
+//                    rasteriser needs -- camera affine, heading, snapshots).
+//   The kernels of mcr_step's chain hand over by per-car ready flags (DevBuffers::ready, mcr_internal.h).
 #include "mcr_internal.h"
 #include <cuda_runtime.h>
 #include <cstdlib>
