@@ -943,7 +943,6 @@ int launch_head(const Dims& d, const DevBuffers& b, const CarConst& cc, const ui
     const int nb = (d.B + CC_WARPS - 1) / CC_WARPS;
     cudaStream_t s = (cudaStream_t)stream;
     const bool many = d.A > 3;
-    if (std::getenv("MCR_DEBUG_NO_NARROW")) collisions = 0;      // timing experiments only: the head without its narrow phase
     if (action_dtype == MCR_F64) {
         if (many) head_kernel<double, true><<<nb, CC_WARPS * 32, 0, s>>>(d, b, cc, mask, reset_flags, ar, (const double*)action, collisions);
         else head_kernel<double, false><<<nb, CC_WARPS * 32, 0, s>>>(d, b, cc, mask, reset_flags, ar, (const double*)action, collisions);
