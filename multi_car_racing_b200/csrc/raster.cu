@@ -664,7 +664,7 @@ __device__ __forceinline__ void finish_frame(RasterSmem& S, int tid, uint32_t (&
             // one colour across the 32 pixels (grass, road, HUD bar: about half of all segments): the 12-byte
             // r g b pattern repeats, one palette lookup instead of 32
             const uint32_t c = S.pal32[p0 & 0xff];
-            const uint32_t w0 = c | (c << 24), w1 = (c >> 8) | (c << 16), w2 = (c >> 16) | (c << 8);
+            const uint32_t w0 = __byte_perm(c, c, 0x4210), w1 = __byte_perm(c, c, 0x5421), w2 = __byte_perm(c, c, 0x6542);
             const uint4 q0 = make_uint4(w0, w1, w2, w0), q1 = make_uint4(w1, w2, w0, w1), q2 = make_uint4(w2, w0, w1, w2);
             dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q0; dst[4] = q1; dst[5] = q2;
             return;
@@ -673,9 +673,10 @@ __device__ __forceinline__ void finish_frame(RasterSmem& S, int tid, uint32_t (&
         for (int k = 0; k < 8; ++k) {
             const uint32_t c0 = S.pal32[pix[k] & 0xff], c1 = S.pal32[(pix[k] >> 8) & 0xff];
             const uint32_t c2 = S.pal32[(pix[k] >> 16) & 0xff], c3 = S.pal32[pix[k] >> 24];
-            o[3 * k + 0] = c0 | (c1 << 24);
-            o[3 * k + 1] = (c1 >> 8) | (c2 << 16);
-            o[3 * k + 2] = (c2 >> 16) | (c3 << 8);
+            // (byte permutes: r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3 -- one instruction per word instead of shift, shift, or)
+            o[3 * k + 0] = __byte_perm(c0, c1, 0x4210);
+            o[3 * k + 1] = __byte_perm(c1, c2, 0x5421);
+            o[3 * k + 2] = __byte_perm(c2, c3, 0x6542);
         }
 #pragma unroll
         for (int v = 0; v < 6; ++v) dst[v] = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
